@@ -1,0 +1,176 @@
+"""oracle/bindings.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes bindings for the two CPU checkers:
+
+* ``liboracle.so``              plain-C restatement (oracle/convolver_oracle.c), always buildable;
+* ``_ref/libref_convolver.so``  the reference's own ``Convolver.cpp`` compiled verbatim over the
+                                restated ``lsp::dsp::`` kernels (only buildable where
+                                ``/root/reference`` exists; the prebuilt file travels to the GPU box).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product (``lsp-dsp-units_b200``) never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_FP = ctypes.POINTER(ctypes.c_float)
+_SZ = ctypes.c_size_t
+
+
+def build(quiet=True):
+    """Compile liboracle.so and (where the reference tree is present) _ref/libref_convolver.so."""
+    out = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if not quiet:
+        print(out.stdout)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_FP)
+
+
+class _State(ctypes.Structure):
+    _fields_ = [(n, _SZ) for n in ("data_buffer_size", "direct_size", "frame_size", "frame_off",
+                                   "conv_size", "levels", "blocks", "blocks_done", "rank",
+                                   "blk_init")] + [("blk_coef", ctypes.c_float)]
+
+
+def _load(path, prefix):
+    lib = ctypes.CDLL(path)
+    f = lambda n: getattr(lib, prefix + n)
+    f("create").restype = ctypes.c_void_p
+    f("create").argtypes = []
+    f("free").argtypes = [ctypes.c_void_p]
+    f("destroy").argtypes = [ctypes.c_void_p]
+    f("init").argtypes = [ctypes.c_void_p, _FP, _SZ, _SZ, ctypes.c_float]
+    f("init").restype = ctypes.c_int
+    f("process").argtypes = [ctypes.c_void_p, _FP, _FP, _SZ]
+    f("data_size").argtypes = [ctypes.c_void_p]
+    f("data_size").restype = _SZ
+    f("rank").argtypes = [ctypes.c_void_p]
+    f("rank").restype = _SZ
+    f("bench").argtypes = [_SZ] * 7 + [ctypes.POINTER(ctypes.c_double)]
+    f("bench").restype = ctypes.c_double
+    return lib
+
+
+class CpuConvolver:
+    """One CPU convolver with the reference's init/process/destroy surface.
+
+    ``impl="oracle"`` -> the plain-C restatement; ``impl="reference"`` -> the verbatim build.
+    """
+
+    _libs = {}
+
+    @classmethod
+    def lib(cls, impl):
+        if impl not in cls._libs:
+            if impl == "oracle":
+                path, prefix = os.path.join(_HERE, "liboracle.so"), "orc_"
+            elif impl == "reference":
+                path, prefix = os.path.join(_HERE, "_ref", "libref_convolver.so"), "refconv_"
+            else:
+                raise ValueError(impl)
+            if not os.path.exists(path):
+                if impl == "oracle":
+                    build()
+                else:
+                    raise FileNotFoundError(path)
+            cls._libs[impl] = (_load(path, prefix), prefix)
+        return cls._libs[impl]
+
+    @classmethod
+    def available(cls, impl):
+        try:
+            cls.lib(impl)
+            return True
+        except (OSError, RuntimeError):
+            return False
+
+    def __init__(self, impl="oracle"):
+        self._lib, self._p = self.lib(impl)
+        self.impl = impl
+        self._h = self._f("create")()
+
+    def _f(self, name):
+        return getattr(self._lib, self._p + name)
+
+    def init(self, ir, rank, phase=0.0):
+        ir = np.ascontiguousarray(ir, dtype=np.float32)
+        return bool(self._f("init")(self._h, _ptr(ir), ir.size, rank, phase))
+
+    def destroy(self):
+        self._f("destroy")(self._h)
+
+    def process(self, src, out=None):
+        """Convolver::process(dst, src, count) on a float32 array; returns dst."""
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        if out is None:
+            out = np.empty_like(src)
+        self._f("process")(self._h, _ptr(out), _ptr(src), src.size)
+        return out
+
+    def run(self, src, step):
+        """Feed ``src`` in calls of ``step`` samples (reference utest helper convolver.cpp:43-53)."""
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        out = np.zeros_like(src)
+        for i in range(0, src.size, step):
+            n = min(step, src.size - i)
+            self._f("process")(self._h, _ptr(out[i:]), _ptr(src[i:]), n)
+        return out
+
+    def data_size(self):
+        return int(self._f("data_size")(self._h))
+
+    def rank(self):
+        return int(self._f("rank")(self._h))
+
+    def state(self):
+        if self.impl != "oracle":
+            raise NotImplementedError
+        st = _State()
+        self._lib.orc_get_state.argtypes = [ctypes.c_void_p, ctypes.POINTER(_State)]
+        self._lib.orc_get_state(self._h, ctypes.byref(st))
+        return {n: getattr(st, n) for n, _ in _State._fields_}
+
+    def dump_names(self):
+        if self.impl != "reference":
+            raise NotImplementedError
+        buf = ctypes.create_string_buffer(1024)
+        self._lib.refconv_dump_names.argtypes = [ctypes.c_void_p, ctypes.c_char_p, _SZ]
+        self._lib.refconv_dump_names.restype = _SZ
+        n = self._lib.refconv_dump_names(self._h, buf, 1024)
+        return int(n), buf.value.decode().split(",")
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._f("free")(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def cpu_bench(impl, instances, taps, rank, block, warm_blocks, blocks, threads):
+    """Time ``blocks`` process() calls of ``block`` samples on ``instances`` CPU convolvers.
+
+    Returns (output samples per second over all instances, elapsed seconds)."""
+    lib, prefix = CpuConvolver.lib(impl)
+    chk = ctypes.c_double(0.0)
+    sec = getattr(lib, prefix + "bench")(instances, taps, rank, block, warm_blocks, blocks,
+                                         threads, ctypes.byref(chk))
+    if sec <= 0:
+        raise RuntimeError("cpu bench failed")
+    return instances * block * blocks / sec, sec
+
+
+def direct_convolve(src, ir, count=None):
+    """Naive direct convolution in float64 -- the identity the reference's utest pins against
+    (src/test/utest/util/convolver.cpp:32-40); computed with numpy for speed."""
+    y = np.convolve(np.asarray(src, dtype=np.float64), np.asarray(ir, dtype=np.float64))
+    return y if count is None else y[:count]

@@ -1,0 +1,35 @@
+/*
+ * oracle/shim -- TEST INFRASTRUCTURE.  Stand-in for lsp-common-lib's
+ * <lsp-plug.in/common/alloc.h>: alloc_aligned / free_aligned as used at
+ * reference Convolver.cpp:73,104.
+ */
+#ifndef ORACLE_SHIM_COMMON_ALLOC_H_
+#define ORACLE_SHIM_COMMON_ALLOC_H_
+
+#include <lsp-plug.in/common/types.h>
+#include <stdlib.h>
+
+namespace lsp
+{
+    template <class T>
+    inline T *alloc_aligned(uint8_t * &raw, size_t count, size_t align)
+    {
+        raw             = static_cast<uint8_t *>(::malloc(count * sizeof(T) + align));
+        if (raw == NULL)
+            return NULL;
+        uintptr_t p     = reinterpret_cast<uintptr_t>(raw);
+        uintptr_t rem   = p % align;
+        if (rem != 0)
+            p              += align - rem;
+        return reinterpret_cast<T *>(p);
+    }
+
+    inline void free_aligned(uint8_t * &raw)
+    {
+        if (raw != NULL)
+            ::free(raw);
+        raw             = NULL;
+    }
+}
+
+#endif /* ORACLE_SHIM_COMMON_ALLOC_H_ */
