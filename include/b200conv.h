@@ -1,0 +1,168 @@
+/*
+ * b200conv.h -- C ABI of the B200-native batched partitioned-FFT convolution engine.
+ *
+ * Drop-in boundary for ONE hot path of lsp-plugins/lsp-dsp-units: lsp::dspu::Convolver
+ * (reference include/lsp-plug.in/dsp-units/util/Convolver.h:35-114,
+ *  src/main/util/Convolver.cpp:36-340).  A "batch" is a set of independent convolver
+ * instances (one mono-in / mono-out dspu::Convolver each) that live on one GPU and are
+ * advanced together, one kernel sequence per audio block for all instances x partitions.
+ * The C++ facade lsp::dspu::Convolver (lsp-dsp-units_b200/host) is a batch of one.
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  Every function returns
+ * B200CONV_OK (0) or a negative error code; b200conv_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device every call fails with
+ * B200CONV_ERR_CUDA.
+ */
+#ifndef B200CONV_H_
+#define B200CONV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CONV_RANK_MIN       8       /* CONVOLVER_RANK_MIN, Convolver.h:28 */
+#define B200CONV_RANK_MAX       16      /* CONVOLVER_RANK_MAX, Convolver.h:29 */
+
+enum
+{
+    B200CONV_OK             =  0,
+    B200CONV_ERR_ARG        = -1,   /* bad argument (NULL handle, index out of range, rank mismatch) */
+    B200CONV_ERR_NOMEM      = -2,   /* host or device allocation failed; previous state is intact     */
+    B200CONV_ERR_CUDA       = -3,   /* CUDA runtime / launch failure, or no device                    */
+    B200CONV_ERR_STATE      = -4    /* call not valid in the current state                            */
+};
+
+typedef struct b200conv_batch b200conv_batch_t;
+
+/* Scheduler state of one instance; mirrors the observable part of Convolver.h:45-55. */
+typedef struct b200conv_state
+{
+    size_t  conv_size;      /* nConvSize : taps given to init, 0 when not initialised (data_size()) */
+    size_t  rank;           /* nRank     : clamped rank, 0 when not initialised (rank())            */
+    size_t  frame_size;     /* nFrameSize: F = 2^(rank-1)                                            */
+    size_t  frame_off;      /* nFrameOff : samples received in the current frame                    */
+    size_t  bins;           /* ceil(conv_size / F) (Convolver.cpp:93)                                */
+    size_t  partitions;     /* rows of IR spectra held on the device (bins + 1, folded overlap)      */
+    size_t  part_offset;    /* first global partition index (partition-range sharding), else 0      */
+    uint64_t frames;        /* complete frames received since init                                   */
+} b200conv_state_t;
+
+/* Counters since create (or the last b200conv_reset_stats). */
+typedef struct b200conv_stats
+{
+    uint64_t launches;          /* kernels of this library launched                                 */
+    uint64_t frames;            /* instance-frames pushed through the FFT -> MAC -> IFFT chain       */
+    uint64_t h2d_bytes;         /* bytes copied host -> device by b200conv_process / _init          */
+    uint64_t d2h_bytes;         /* bytes copied device -> host by b200conv_process                  */
+    uint64_t mac_launches;      /* launches of the partition MAC kernel                             */
+    uint64_t mac_algo_bytes;    /* algorithmic bytes of those launches (16*F*bins + 24*F per instance-frame) */
+} b200conv_stats_t;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Creates a batch of `instances` un-initialised convolvers on CUDA device `device`
+ * (-1 = the calling thread's current device).  Replaces N x Convolver::Convolver()
+ * (Convolver.cpp:36-39). */
+int     b200conv_create(b200conv_batch_t **out, int device, size_t instances);
+
+/* Releases everything (N x Convolver::~Convolver, Convolver.cpp:41-44).  NULL is allowed. */
+void    b200conv_free(b200conv_batch_t *h);
+
+/* ---- Convolver::init / destroy --------------------------------------------------------- */
+
+/* Convolver::init(data, count, rank, phase) for instance `idx` (Convolver.cpp:77-215):
+ *   count == 0      -> the instance is destroyed and the call succeeds (:80-84);
+ *   rank            -> clamped to [8, 16] (:87); all initialised instances of one batch must
+ *                      share the clamped rank (B200CONV_ERR_ARG otherwise);
+ *   phase           -> frame_off = size_t(phase * F) % F in fp32 (:140);
+ *   `data` is a HOST pointer, borrowed for the call only.
+ * The IR is transformed on the device.  All history of the instance is discarded (:110).
+ * On allocation failure the previous state of the instance is kept (:103-108). */
+int     b200conv_init(b200conv_batch_t *h, size_t idx, const float *data, size_t count,
+                      size_t rank, float phase);
+
+/* Same, for partition-range sharding of one long IR across GPUs: `data` holds the taps
+ * [part_offset * F, part_offset * F + count) of the full IR and this instance produces only
+ * their contribution; the full output is the sum over shards.  part_offset == 0
+ * is b200conv_init. */
+int     b200conv_init_range(b200conv_batch_t *h, size_t idx, const float *data, size_t count,
+                            size_t rank, float phase, size_t part_offset);
+
+/* Convolver::destroy for instance `idx` (Convolver.cpp:71-75); idempotent. */
+int     b200conv_destroy(b200conv_batch_t *h, size_t idx);
+
+/* ---- Convolver::process ---------------------------------------------------------------- */
+
+/* N x Convolver::process(dst[i], src[i], count) (Convolver.cpp:217-313) in one call: HOST
+ * pointers, one planar buffer of `count` floats per instance, any alignment, dst[i] == src[i]
+ * allowed, any count (0 = no-op), state carried across calls, zero latency.  Instances that
+ * are not initialised get zeros (:219-223).  Synchronous: dst is complete on return. */
+int     b200conv_process(b200conv_batch_t *h, float *const *dst, const float *const *src,
+                         size_t count);
+
+/* Same with DEVICE buffers laid out [instances][stride] floats (row i = instance i), enqueued
+ * on `stream` (a cudaStream_t; NULL = the batch's own stream) without host synchronisation.
+ * dst == src is allowed.  All calls on one batch must be ordered on one stream (or be
+ * separated by b200conv_sync). */
+int     b200conv_process_device(b200conv_batch_t *h, float *dst, const float *src,
+                                size_t stride, size_t count, void *stream);
+
+/* Waits for everything enqueued on the batch's own stream. */
+int     b200conv_sync(b200conv_batch_t *h);
+
+/* ---- queries (Convolver.h:101,107) ------------------------------------------------------ */
+
+size_t  b200conv_data_size(const b200conv_batch_t *h, size_t idx);
+size_t  b200conv_rank(const b200conv_batch_t *h, size_t idx);
+size_t  b200conv_instances(const b200conv_batch_t *h);
+int     b200conv_get_state(const b200conv_batch_t *h, size_t idx, b200conv_state_t *st);
+int     b200conv_get_stats(const b200conv_batch_t *h, b200conv_stats_t *st);
+int     b200conv_reset_stats(b200conv_batch_t *h);
+
+/* Per-launch timing of the partition MAC kernel (the roofline kernel): while enabled, every
+ * k_mac launch is bracketed by CUDA events on the launching stream.  b200conv_get_profile
+ * synchronises, returns the summed device time (ms) and launch count since the last call, and
+ * clears the record.  Costs two event records per launch -- keep it off in timed regions. */
+int     b200conv_set_profiling(b200conv_batch_t *h, int enable);
+int     b200conv_get_profile(b200conv_batch_t *h, double *mac_ms, uint64_t *mac_launches);
+
+/* The batch's own CUDA stream (cudaStream_t), for callers that time with CUDA events. */
+void   *b200conv_stream(b200conv_batch_t *h);
+
+/* Tuning knobs of the partition MAC kernel (0 = automatic): partition splits per
+ * instance-frame, shared-memory pipeline stages. */
+int     b200conv_set_tuning(b200conv_batch_t *h, int mac_splits, int mac_stages);
+
+/* ---- the fastconv primitives on the device (lsp::dsp:: contract) ---------- */
+
+/* Batched device restatements of dsp::fastconv_parse / _apply / _parse_apply / _restore for
+ * `count` independent problems at one rank (8..16).  All pointers are DEVICE pointers, rows are
+ * contiguous.  An "image" here is 2^rank floats: 2^(rank-1) packed complex bins of the real
+ * FFT, (DC, Nyquist) folded into bin 0 -- opaque to callers exactly like the reference's.
+ *   parse       : image[i]  = FFT_{2^rank}([src[i][0 .. 2^(rank-1)), zeros])
+ *   apply       : dst[i][0 .. 2^rank) += IFFT(c1[i] * c2[i]) / 2^rank
+ *   parse_apply : dst[i][0 .. 2^rank) += IFFT(c[i] * parse(src[i])) / 2^rank
+ *   restore     : dst[i][0 .. 2^rank)  = IFFT(image[i]) / 2^rank
+ * Enqueued on `stream` (NULL = default stream of `device`). */
+int     b200conv_fastconv_parse(int device, float *image, const float *src, size_t rank,
+                                size_t count, void *stream);
+int     b200conv_fastconv_apply(int device, float *dst, const float *c1, const float *c2,
+                                size_t rank, size_t count, void *stream);
+int     b200conv_fastconv_parse_apply(int device, float *dst, const float *c, const float *src,
+                                      size_t rank, size_t count, void *stream);
+int     b200conv_fastconv_restore(int device, float *dst, const float *image, size_t rank,
+                                  size_t count, void *stream);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+
+const char *b200conv_last_error(void);      /* thread-local text of the last failure */
+const char *b200conv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* B200CONV_H_ */

@@ -1,0 +1,262 @@
+"""lsp-dsp-units_b200 -- B200-native batched ``dspu::Convolver`` (host-side Python mirror).
+
+Thin ctypes layer over the C ABI in ``include/b200conv.h`` (``libb200conv.so``, hand-written
+sm_100a CUDA).  ``Convolver`` mirrors ``lsp::dspu::Convolver`` (reference
+``include/lsp-plug.in/dsp-units/util/Convolver.h:59-113``): same method names, argument meaning
+and error behaviour; ``ConvolverBatch`` is the many-instance form the engine is built for.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible,
+construction raises.  The directory name contains a hyphen, so import it through ``load()`` in
+``__graft_entry__.py`` (module name ``lsp_dsp_units_b200``).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libb200conv.so")
+
+RANK_MIN, RANK_MAX = 8, 16
+OK, ERR_ARG, ERR_NOMEM, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
+
+_SZ = ctypes.c_size_t
+_FP = ctypes.POINTER(ctypes.c_float)
+_VP = ctypes.c_void_p
+
+
+class State(ctypes.Structure):
+    _fields_ = [("conv_size", _SZ), ("rank", _SZ), ("frame_size", _SZ), ("frame_off", _SZ),
+                ("bins", _SZ), ("partitions", _SZ), ("part_offset", _SZ), ("frames", ctypes.c_uint64)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ("launches", "frames", "h2d_bytes", "d2h_bytes",
+                                               "mac_launches", "mac_algo_bytes")]
+
+
+class B200ConvError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("b200conv error %d: %s" % (code, text))
+        self.code = code
+
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build(verbose=False):
+    """Compile csrc/engine.cu for sm_100a into libb200conv.so (in-tree)."""
+    src = os.path.join(_HERE, "csrc", "engine.cu")
+    deps = [src, os.path.join(_HERE, "csrc", "kernels.cuh"), os.path.join(_ROOT, "include", "b200conv.h")]
+    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, src]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(" ".join(cmd))
+    return LIB_PATH
+
+
+_lib = None
+
+_SIGNATURES = {
+    "b200conv_create": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_int, _SZ]),
+    "b200conv_free": (None, [_VP]),
+    "b200conv_init": (ctypes.c_int, [_VP, _SZ, _FP, _SZ, _SZ, ctypes.c_float]),
+    "b200conv_init_range": (ctypes.c_int, [_VP, _SZ, _FP, _SZ, _SZ, ctypes.c_float, _SZ]),
+    "b200conv_destroy": (ctypes.c_int, [_VP, _SZ]),
+    "b200conv_process": (ctypes.c_int, [_VP, ctypes.POINTER(_FP), ctypes.POINTER(_FP), _SZ]),
+    "b200conv_process_device": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ, _VP]),
+    "b200conv_sync": (ctypes.c_int, [_VP]),
+    "b200conv_data_size": (_SZ, [_VP, _SZ]),
+    "b200conv_rank": (_SZ, [_VP, _SZ]),
+    "b200conv_instances": (_SZ, [_VP]),
+    "b200conv_get_state": (ctypes.c_int, [_VP, _SZ, ctypes.POINTER(State)]),
+    "b200conv_get_stats": (ctypes.c_int, [_VP, ctypes.POINTER(Stats)]),
+    "b200conv_reset_stats": (ctypes.c_int, [_VP]),
+    "b200conv_set_profiling": (ctypes.c_int, [_VP, ctypes.c_int]),
+    "b200conv_get_profile": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
+    "b200conv_stream": (_VP, [_VP]),
+    "b200conv_set_tuning": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int]),
+    "b200conv_fastconv_parse": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _SZ, _SZ, _VP]),
+    "b200conv_fastconv_apply": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _VP, _SZ, _SZ, _VP]),
+    "b200conv_fastconv_parse_apply": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _VP, _SZ, _SZ, _VP]),
+    "b200conv_fastconv_restore": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _SZ, _SZ, _VP]),
+    "b200conv_last_error": (ctypes.c_char_p, []),
+    "b200conv_version": (ctypes.c_char_p, []),
+}
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                "%s is missing: build it with __graft_entry__.build() (nvcc, sm_100a). "
+                "This engine has no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def _check(rc):
+    if rc != OK:
+        raise B200ConvError(rc, lib().b200conv_last_error().decode())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_FP)
+
+
+class ConvolverBatch:
+    """``instances`` independent convolvers on one GPU, advanced together (include/b200conv.h)."""
+
+    def __init__(self, instances, device=-1):
+        self._h = _VP()
+        _check(lib().b200conv_create(ctypes.byref(self._h), device, instances))
+        self.instances = instances
+
+    # -- Convolver::init / destroy ------------------------------------------------------------
+    def init(self, idx, data, rank, phase=0.0, part_offset=0):
+        """``Convolver::init(data, count, rank, phase)`` for instance ``idx``; True on success,
+        False only on allocation failure (previous state kept), like the reference."""
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        rc = lib().b200conv_init_range(self._h, idx, _ptr(data), data.size, rank, phase, part_offset)
+        if rc == ERR_NOMEM:
+            return False
+        _check(rc)
+        return True
+
+    def destroy(self, idx):
+        _check(lib().b200conv_destroy(self._h, idx))
+
+    # -- Convolver::process -------------------------------------------------------------------
+    def process(self, src, out=None):
+        """Host arrays ``[instances][count]`` float32 (rows are the planar per-instance buffers)."""
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        if src.ndim == 1:
+            src = src[None, :]
+        assert src.shape[0] == self.instances
+        if out is None:
+            out = np.empty_like(src)
+        n = src.shape[1]
+        srcs = (_FP * self.instances)(*[_ptr(src[i]) for i in range(self.instances)])
+        dsts = (_FP * self.instances)(*[_ptr(out[i]) for i in range(self.instances)])
+        _check(lib().b200conv_process(self._h, dsts, srcs, n))
+        return out
+
+    def process_device(self, dst_ptr, src_ptr, stride, count, stream=None):
+        """Device pointers (ints), ``[instances][stride]`` floats; asynchronous."""
+        _check(lib().b200conv_process_device(self._h, dst_ptr, src_ptr, stride, count, stream))
+
+    def sync(self):
+        _check(lib().b200conv_sync(self._h))
+
+    # -- queries ------------------------------------------------------------------------------
+    def data_size(self, idx):
+        return int(lib().b200conv_data_size(self._h, idx))
+
+    def rank(self, idx):
+        return int(lib().b200conv_rank(self._h, idx))
+
+    def state(self, idx):
+        st = State()
+        _check(lib().b200conv_get_state(self._h, idx, ctypes.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in State._fields_}
+
+    def stats(self):
+        st = Stats()
+        _check(lib().b200conv_get_stats(self._h, ctypes.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in Stats._fields_}
+
+    def reset_stats(self):
+        _check(lib().b200conv_reset_stats(self._h))
+
+    def set_profiling(self, enable):
+        _check(lib().b200conv_set_profiling(self._h, int(bool(enable))))
+
+    def profile(self):
+        """(summed k_mac device time in ms, k_mac launches) since the last call."""
+        ms, n = ctypes.c_double(0.0), ctypes.c_uint64(0)
+        _check(lib().b200conv_get_profile(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, int(n.value)
+
+    def stream(self):
+        return lib().b200conv_stream(self._h)
+
+    def set_tuning(self, mac_splits=0, mac_stages=0):
+        _check(lib().b200conv_set_tuning(self._h, mac_splits, mac_stages))
+
+    def close(self):
+        if self._h:
+            lib().b200conv_free(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Convolver:
+    """Mirror of ``lsp::dspu::Convolver``: a batch of one (Convolver.h:59-113)."""
+
+    def __init__(self, device=-1):
+        self._device = device
+        self._b = None
+
+    def init(self, data, rank, phase=0.0):
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        if data.size == 0:                      # Convolver.cpp:80-84
+            self.destroy()
+            return True
+        fresh = ConvolverBatch(1, self._device)
+        if not fresh.init(0, data, rank, phase):
+            fresh.close()
+            return False                        # previous state intact (Convolver.cpp:103-108)
+        self.destroy()
+        self._b = fresh
+        return True
+
+    def destroy(self):
+        if self._b is not None:
+            self._b.close()
+            self._b = None
+
+    def process(self, src, out=None):
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        if out is None:
+            out = np.empty_like(src)
+        if self._b is None:                     # Convolver.cpp:219-223
+            out[...] = 0.0
+            return out
+        if src.size:
+            self._b.process(src[None, :], out[None, :])
+        return out
+
+    def run(self, src, step):
+        """Feed ``src`` in calls of ``step`` samples (reference utest helper convolver.cpp:43-53)."""
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        out = np.zeros_like(src)
+        for i in range(0, src.size, step):
+            self.process(src[i:i + step], out[i:i + step])
+        return out
+
+    def data_size(self):
+        return self._b.data_size(0) if self._b is not None else 0
+
+    def rank(self):
+        return self._b.rank(0) if self._b is not None else 0
+
+    def state(self):
+        return self._b.state(0) if self._b is not None else None

@@ -1,0 +1,1206 @@
+/*
+ * engine.cu -- host side of the batched convolver: instance table, frame bookkeeping, ring
+ * indices, job lists, kernel launches, and the C ABI declared in include/b200conv.h.
+ *
+ * Frame bookkeeping follows lsp::dspu::Convolver (reference src/main/util/Convolver.cpp):
+ * rank clamp :87, frame offset from phase :140, bins :93, zero output when not initialised
+ * :219-223, zero latency for any call size :225-313.  What differs is the arithmetic plan:
+ * uniform partitions in folded-overlap form, an input-spectrum ring instead of a shifted
+ * time-domain tail (:304-311), one inverse FFT per frame instead of one per partition (:280-285).
+ */
+#include "b200conv.h"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace b200conv;
+
+/* ------------------------------------------------------------------------------------------- */
+/* errors                                                                                       */
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                            \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail((e_ == cudaErrorMemoryAllocation) ? B200CONV_ERR_NOMEM              \
+                                                          : B200CONV_ERR_CUDA,             \
+                        "%s failed: %s", #call, cudaGetErrorString(e_));                    \
+    } while (0)
+
+#define TRY(expr)   do { int rc_ = (expr); if (rc_ != B200CONV_OK) return rc_; } while (0)
+
+/* ------------------------------------------------------------------------------------------- */
+/* per-rank kernel dispatch                                                                     */
+
+static const int MAX_DEVICES = 64;
+
+/* function attributes are per device; the caller has made the batch's device current */
+static int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return ((dev >= 0) && (dev < MAX_DEVICES)) ? dev : 0;
+}
+
+template <int RANK>
+static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t st)
+{
+    using C = FftCfg<RANK>;
+    static bool attr_set[MAX_DEVICES] = { false };
+    int dev = current_device();
+    if ((!attr_set[dev]) && (C::SMEM > 48 * 1024))
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_fwd<RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM));
+        if (e != cudaSuccess)
+            return e;
+    }
+    attr_set[dev] = true;
+    k_fwd<RANK><<<grid, C::T, C::SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int RANK>
+static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t st)
+{
+    using C = FftCfg<RANK>;
+    static bool attr_set[MAX_DEVICES] = { false };
+    int dev = current_device();
+    if ((!attr_set[dev]) && (C::SMEM > 48 * 1024))
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_inv<RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM));
+        if (e != cudaSuccess)
+            return e;
+    }
+    attr_set[dev] = true;
+    k_inv<RANK><<<grid, C::T, C::SMEM, st>>>(a);
+    return cudaGetLastError();
+}
+
+#define RANK_SWITCH(fn, rank, ...)                                      \
+    switch (rank) {                                                     \
+        case 8:  return fn<8>(__VA_ARGS__);                             \
+        case 9:  return fn<9>(__VA_ARGS__);                             \
+        case 10: return fn<10>(__VA_ARGS__);                            \
+        case 11: return fn<11>(__VA_ARGS__);                            \
+        case 12: return fn<12>(__VA_ARGS__);                            \
+        case 13: return fn<13>(__VA_ARGS__);                            \
+        case 14: return fn<14>(__VA_ARGS__);                            \
+        case 15: return fn<15>(__VA_ARGS__);                            \
+        case 16: return fn<16>(__VA_ARGS__);                            \
+        default: return cudaErrorInvalidValue;                          \
+    }
+
+static cudaError_t launch_fwd(const StepArgs &a, uint32_t grid, cudaStream_t st)
+{
+    RANK_SWITCH(launch_fwd_r, a.rank, a, grid, st)
+}
+
+static cudaError_t launch_inv(const StepArgs &a, uint32_t grid, cudaStream_t st)
+{
+    RANK_SWITCH(launch_inv_r, a.rank, a, grid, st)
+}
+
+struct MacPlan
+{
+    MacShape    sh;
+    uint32_t    tiles, threads, splits;
+    size_t      smem;
+};
+
+static MacPlan plan_mac(uint32_t rank, uint32_t jobs, uint32_t max_nq, int sm_count,
+                        int tune_splits, int tune_stages)
+{
+    MacPlan p;
+    uint32_t M      = 1u << (rank - 1);
+    p.sh.TB         = (M < 1024) ? M : 1024;
+    p.sh.QB         = 1024 / p.sh.TB;
+    p.sh.NS         = (tune_stages > 0) ? uint32_t(tune_stages) : 3;
+    p.tiles         = M / p.sh.TB;
+    p.threads       = p.sh.TB / (2 * MAC_VPT);
+    p.smem          = size_t(2) * p.sh.NS * p.sh.QB * p.sh.TB * sizeof(float2) + p.sh.NS * sizeof(uint64_t);
+
+    uint32_t splits;
+    if (tune_splits > 0)
+        splits          = uint32_t(tune_splits);
+    else
+    {
+        /* aim at ~4 co-resident CTAs per SM so that all chunks stream concurrently */
+        uint32_t target = 4u * uint32_t(sm_count);
+        uint32_t ctas   = jobs * p.tiles;
+        splits          = (ctas > 0) ? (target / ctas) : 1;
+    }
+    uint32_t cap    = max_nq / (2 * p.sh.QB);           /* at least two stages of work per chunk */
+    if (splits > cap)   splits = cap;
+    if (splits > 32)    splits = 32;
+    if (splits < 1)     splits = 1;
+    p.splits        = splits;
+    return p;
+}
+
+static cudaError_t launch_mac_raw(const StepArgs &a, const MacPlan &p, uint32_t jobs, cudaStream_t st)
+{
+    static size_t attr_smem[MAX_DEVICES] = { 0 };
+    int dev = current_device();
+    if (p.smem > attr_smem[dev])
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_mac, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem));
+        if (e != cudaSuccess)
+            return e;
+        attr_smem[dev] = p.smem;
+    }
+    dim3 grid(jobs * p.splits, p.tiles);
+    k_mac<<<grid, p.threads, p.smem, st>>>(a, p.sh);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* twiddle tables: exp(-2 pi i j / N), j < N, computed in double                                 */
+
+static int make_twiddles(uint32_t rank, float2 **out)
+{
+    size_t N = size_t(1) << rank;
+    std::vector<float2> h(N);
+    for (size_t j = 0; j < N; ++j)
+    {
+        double ang  = -2.0 * M_PI * double(j) / double(N);
+        h[j]        = make_float2(float(cos(ang)), float(sin(ang)));
+    }
+    float2 *d = nullptr;
+    CU(cudaMalloc(&d, N * sizeof(float2)));
+    cudaError_t e = cudaMemcpy(d, h.data(), N * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess)
+    {
+        cudaFree(d);
+        return fail(B200CONV_ERR_CUDA, "twiddle upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = d;
+    return B200CONV_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* batch                                                                                        */
+
+struct Instance
+{
+    bool        active      = false;
+    size_t      conv_size   = 0;
+    size_t      rank        = 0;
+    size_t      F           = 0;
+    size_t      bins        = 0;
+    size_t      nq          = 0;
+    size_t      q_lo        = 0;
+    size_t      S           = 0;
+    size_t      off         = 0;        /* nFrameOff */
+    uint64_t    frames      = 0;
+    bool        pend_valid  = false;
+    float2     *G           = nullptr;
+    float2     *ring        = nullptr;
+    float      *aux         = nullptr;  /* cur | pend | head, F floats each */
+};
+
+static const size_t JOB_RING = size_t(1) << 15;
+
+struct b200conv_batch
+{
+    int                     device      = 0;
+    int                     sm_count    = 148;
+    size_t                  n           = 0;
+    std::vector<Instance>   inst;
+    size_t                  rank        = 0;        /* shared clamped rank, 0 = none active */
+    cudaStream_t            stream      = nullptr;
+
+    std::vector<InstDesc>   h_desc;
+    InstDesc               *d_desc      = nullptr;
+    std::vector<uint32_t>   active;
+    uint32_t               *d_active    = nullptr;
+    bool                    desc_dirty  = true;
+    uint64_t                t_batch     = 0;
+    size_t                  max_nq      = 0;
+
+    float2                 *tw[B200CONV_RANK_MAX + 1] = { nullptr };
+    float2                 *ypart       = nullptr;
+    size_t                  ypart_bytes = 0;
+
+    Job                    *h_jobs      = nullptr;  /* pinned */
+    Job                    *d_jobs      = nullptr;
+    size_t                  job_pos     = 0;
+
+    float                  *h_in = nullptr, *h_out = nullptr;   /* pinned staging */
+    float                  *d_in = nullptr, *d_out = nullptr;
+    size_t                  stage_floats = 0;
+
+    b200conv_stats_t        stats       = {};
+    int                     tune_splits = 0, tune_stages = 0;
+
+    bool                    profiling   = false;
+    std::vector<cudaEvent_t> prof_events;           /* pairs: before / after each k_mac */
+    size_t                  prof_used   = 0;
+};
+
+typedef b200conv_batch Batch;
+
+static cudaError_t launch_mac(Batch *b, const StepArgs &a, const MacPlan &p, uint32_t jobs, cudaStream_t st)
+{
+    if (!b->profiling)
+        return launch_mac_raw(a, p, jobs, st);
+    while (b->prof_events.size() < b->prof_used + 2)
+    {
+        cudaEvent_t ev;
+        cudaError_t e = cudaEventCreate(&ev);
+        if (e != cudaSuccess)
+            return e;
+        b->prof_events.push_back(ev);
+    }
+    cudaError_t e = cudaEventRecord(b->prof_events[b->prof_used], st);
+    if (e == cudaSuccess) e = launch_mac_raw(a, p, jobs, st);
+    if (e == cudaSuccess) e = cudaEventRecord(b->prof_events[b->prof_used + 1], st);
+    b->prof_used += 2;
+    return e;
+}
+
+static int set_device(const Batch *b)
+{
+    CU(cudaSetDevice(b->device));
+    return B200CONV_OK;
+}
+
+static void free_instance_buffers(Instance &in)
+{
+    if (in.G)       cudaFree(in.G);
+    if (in.ring)    cudaFree(in.ring);
+    if (in.aux)     cudaFree(in.aux);
+    in.G = nullptr; in.ring = nullptr; in.aux = nullptr;
+}
+
+static void rebuild_tables(Batch *b)
+{
+    b->active.clear();
+    b->max_nq   = 0;
+    b->rank     = 0;
+    for (size_t i = 0; i < b->n; ++i)
+    {
+        const Instance &in = b->inst[i];
+        InstDesc &d = b->h_desc[i];
+        memset(&d, 0, sizeof(d));
+        if (!in.active)
+            continue;
+        b->active.push_back(uint32_t(i));
+        b->rank     = in.rank;
+        if (in.nq > b->max_nq)
+            b->max_nq   = in.nq;
+        d.G         = in.G;
+        d.ring      = in.ring;
+        d.cur       = in.aux;
+        d.pend      = in.aux + in.F;
+        d.head      = in.aux + 2 * in.F;
+        d.t_delta   = int64_t(in.frames) - int64_t(b->t_batch);
+        d.nq        = uint32_t(in.nq);
+        d.q_lo      = uint32_t(in.q_lo);
+        d.S         = uint32_t(in.S);
+    }
+    b->desc_dirty = true;
+}
+
+static int upload_tables(Batch *b, cudaStream_t st)
+{
+    if (!b->desc_dirty)
+        return B200CONV_OK;
+    for (size_t i = 0; i < b->n; ++i)
+        if (b->inst[i].active)
+            b->h_desc[i].t_delta = int64_t(b->inst[i].frames) - int64_t(b->t_batch);
+    /* pageable sources: cudaMemcpyAsync stages them before returning */
+    CU(cudaMemcpyAsync(b->d_desc, b->h_desc.data(), b->n * sizeof(InstDesc), cudaMemcpyHostToDevice, st));
+    if (!b->active.empty())
+        CU(cudaMemcpyAsync(b->d_active, b->active.data(), b->active.size() * sizeof(uint32_t),
+                           cudaMemcpyHostToDevice, st));
+    b->desc_dirty = false;
+    return B200CONV_OK;
+}
+
+static int ensure_ypart(Batch *b, size_t bytes, cudaStream_t st)
+{
+    if (bytes <= b->ypart_bytes)
+        return B200CONV_OK;
+    CU(cudaStreamSynchronize(st));
+    if (b->ypart)
+        cudaFree(b->ypart);
+    b->ypart        = nullptr;
+    b->ypart_bytes  = 0;
+    size_t want     = bytes + bytes / 4;
+    CU(cudaMalloc(&b->ypart, want));
+    b->ypart_bytes  = want;
+    return B200CONV_OK;
+}
+
+/* Reserves `count` consecutive slots of the job upload ring and returns their index. */
+static int reserve_jobs(Batch *b, size_t count, cudaStream_t st, size_t *pos)
+{
+    if (count > JOB_RING)
+        return fail(B200CONV_ERR_ARG, "job list too long (%zu)", count);
+    if (b->job_pos + count > JOB_RING)
+    {
+        CU(cudaStreamSynchronize(st));      /* everything queued from the ring has been consumed */
+        b->job_pos  = 0;
+    }
+    *pos        = b->job_pos;
+    b->job_pos += count;
+    return B200CONV_OK;
+}
+
+static int push_jobs(Batch *b, size_t pos, size_t count, cudaStream_t st)
+{
+    if (count == 0)
+        return B200CONV_OK;
+    CU(cudaMemcpyAsync(b->d_jobs + pos, b->h_jobs + pos, count * sizeof(Job), cudaMemcpyHostToDevice, st));
+    return B200CONV_OK;
+}
+
+static StepArgs base_args(const Batch *b)
+{
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.inst      = b->d_desc;
+    a.active    = b->d_active;
+    a.tw        = b->tw[b->rank];
+    a.ypart     = b->ypart;
+    a.rank      = uint32_t(b->rank);
+    a.n_active  = uint32_t(b->active.size());
+    a.splits    = 1;
+    return a;
+}
+
+static uint64_t algo_bytes(const Batch *b, const Instance &in, size_t qa, size_t qb)
+{
+    /* 16*F*bins + 24*F per instance-frame, bins = partitions of F taps in range */
+    size_t lo   = (qa > in.q_lo) ? qa : in.q_lo;
+    size_t hi   = (qb < in.q_lo + in.nq) ? qb : in.q_lo + in.nq;
+    size_t rows = (hi > lo) ? hi - lo : 0;
+    size_t bins = (rows > 0) ? rows - 1 : 0;
+    (void)b;
+    return uint64_t(16) * in.F * bins + uint64_t(24) * in.F;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* create / free                                                                                */
+
+extern "C" int b200conv_create(b200conv_batch_t **out, int device, size_t instances)
+{
+    if ((out == nullptr) || (instances == 0) || (instances > (size_t(1) << 20)))
+        return fail(B200CONV_ERR_ARG, "b200conv_create: bad arguments");
+    *out = nullptr;
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if ((e != cudaSuccess) || (count == 0))
+        return fail(B200CONV_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0)
+        CU(cudaGetDevice(&device));
+    if (device >= count)
+        return fail(B200CONV_ERR_ARG, "device %d out of range (%d devices)", device, count);
+
+    Batch *b = new (std::nothrow) Batch();
+    if (b == nullptr)
+        return fail(B200CONV_ERR_NOMEM, "out of host memory");
+    b->device   = device;
+    b->n        = instances;
+    b->inst.resize(instances);
+    b->h_desc.resize(instances);
+    memset(b->h_desc.data(), 0, instances * sizeof(InstDesc));
+
+    int rc = B200CONV_OK;
+    do
+    {
+        if ((rc = set_device(b)) != B200CONV_OK) break;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+            b->sm_count = prop.multiProcessorCount;
+        #define CU_BRK(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(B200CONV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); break; } }
+        CU_BRK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+        CU_BRK(cudaMalloc(&b->d_desc, instances * sizeof(InstDesc)));
+        CU_BRK(cudaMalloc(&b->d_active, instances * sizeof(uint32_t)));
+        CU_BRK(cudaMallocHost(&b->h_jobs, JOB_RING * sizeof(Job)));
+        CU_BRK(cudaMalloc(&b->d_jobs, JOB_RING * sizeof(Job)));
+        CU_BRK(cudaMemset(b->d_desc, 0, instances * sizeof(InstDesc)));
+        #undef CU_BRK
+    } while (false);
+
+    if (rc != B200CONV_OK)
+    {
+        std::string keep = g_last_error;
+        b200conv_free(b);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = b;
+    return B200CONV_OK;
+}
+
+extern "C" void b200conv_free(b200conv_batch_t *b)
+{
+    if (b == nullptr)
+        return;
+    cudaSetDevice(b->device);
+    if (b->stream)
+        cudaStreamSynchronize(b->stream);
+    for (Instance &in : b->inst)
+        free_instance_buffers(in);
+    for (float2 *t : b->tw)
+        if (t) cudaFree(t);
+    if (b->ypart)       cudaFree(b->ypart);
+    if (b->d_desc)      cudaFree(b->d_desc);
+    if (b->d_active)    cudaFree(b->d_active);
+    if (b->d_jobs)      cudaFree(b->d_jobs);
+    if (b->h_jobs)      cudaFreeHost(b->h_jobs);
+    if (b->h_in)        cudaFreeHost(b->h_in);
+    if (b->h_out)       cudaFreeHost(b->h_out);
+    if (b->d_in)        cudaFree(b->d_in);
+    if (b->d_out)       cudaFree(b->d_out);
+    for (cudaEvent_t ev : b->prof_events)
+        cudaEventDestroy(ev);
+    if (b->stream)      cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* init / destroy                                                                               */
+
+extern "C" int b200conv_destroy(b200conv_batch_t *b, size_t idx)
+{
+    if ((b == nullptr) || (idx >= b->n))
+        return fail(B200CONV_ERR_ARG, "b200conv_destroy: bad handle or index");
+    Instance &in = b->inst[idx];
+    if (!in.active)
+        return B200CONV_OK;
+    TRY(set_device(b));
+    CU(cudaStreamSynchronize(b->stream));
+    free_instance_buffers(in);
+    in = Instance();
+    rebuild_tables(b);
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float *data, size_t count,
+                                   size_t rank, float phase, size_t part_offset)
+{
+    if ((b == nullptr) || (idx >= b->n))
+        return fail(B200CONV_ERR_ARG, "b200conv_init: bad handle or index");
+    if (count == 0)                                         /* Convolver.cpp:80-84 */
+        return b200conv_destroy(b, idx);
+    if (data == nullptr)
+        return fail(B200CONV_ERR_ARG, "b200conv_init: NULL impulse response");
+
+    /* Convolver.cpp:87 : clamp through a signed value */
+    long r = long(rank);
+    if (r < B200CONV_RANK_MIN) r = B200CONV_RANK_MIN;
+    if (r > B200CONV_RANK_MAX) r = B200CONV_RANK_MAX;
+    rank = size_t(r);
+
+    for (size_t i = 0; i < b->n; ++i)
+        if ((i != idx) && b->inst[i].active && (b->inst[i].rank != rank))
+            return fail(B200CONV_ERR_ARG, "all instances of a batch share one rank (%zu active, %zu requested)",
+                        b->inst[i].rank, rank);
+
+    TRY(set_device(b));
+    cudaStream_t st = b->stream;
+
+    const size_t F      = size_t(1) << (rank - 1);
+    const size_t bins   = (count + F - 1) >> (rank - 1);    /* Convolver.cpp:93 */
+    const size_t nq     = bins + 1;                         /* folded overlap: one extra row */
+    const size_t S      = part_offset + nq;
+    if ((part_offset + nq) >= (size_t(1) << 31))
+        return fail(B200CONV_ERR_ARG, "impulse response too long");
+
+    if (b->tw[rank] == nullptr)
+        TRY(make_twiddles(uint32_t(rank), &b->tw[rank]));
+
+    /* Allocate everything new before touching the old state (Convolver.cpp:103-108). */
+    Instance fresh;
+    float *irdev = nullptr;
+    float2 *H = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&fresh.G, nq * F * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&fresh.ring, S * F * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&fresh.aux, 3 * F * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&irdev, bins * F * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&H, bins * F * sizeof(float2));
+    if (e != cudaSuccess)
+    {
+        free_instance_buffers(fresh);
+        if (irdev) cudaFree(irdev);
+        if (H)     cudaFree(H);
+        cudaGetLastError();
+        return fail(B200CONV_ERR_NOMEM, "device allocation failed for %zu taps: %s", count, cudaGetErrorString(e));
+    }
+
+    int rc = B200CONV_OK;
+    do
+    {
+        #define CU_BRK(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(B200CONV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); break; } }
+        CU_BRK(cudaMemsetAsync(irdev, 0, bins * F * sizeof(float), st));
+        CU_BRK(cudaMemcpyAsync(irdev, data, count * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU_BRK(cudaMemsetAsync(fresh.ring, 0, S * F * sizeof(float2), st));
+        CU_BRK(cudaMemsetAsync(fresh.aux, 0, 3 * F * sizeof(float), st));
+        b->stats.h2d_bytes += count * sizeof(float);
+
+        /* H_p = spectrum of taps [pF, (p+1)F) zero padded -- the per-partition fastconv_parse of
+         * Convolver.cpp:183-197, batched over partitions on the device */
+        StepArgs a  = base_args(b);
+        a.rank      = uint32_t(rank);
+        a.tw        = b->tw[rank];
+        for (size_t p0 = 0; p0 < bins; p0 += JOB_RING)
+        {
+            size_t cnt  = (bins - p0 < JOB_RING) ? bins - p0 : JOB_RING;
+            size_t pos  = 0;
+            if ((rc = reserve_jobs(b, cnt, st, &pos)) != B200CONV_OK) break;
+            for (size_t p = 0; p < cnt; ++p)
+            {
+                Job &j  = b->h_jobs[pos + p];
+                memset(&j, 0, sizeof(j));
+                j.src   = irdev + (p0 + p) * F;
+                j.spec  = H + (p0 + p) * F;
+            }
+            if ((rc = push_jobs(b, pos, cnt, st)) != B200CONV_OK) break;
+            a.jobs      = b->d_jobs + pos;
+            a.n_jobs    = uint32_t(cnt);
+            CU_BRK(launch_fwd(a, uint32_t(cnt), st));
+            b->stats.launches++;
+        }
+        if (rc != B200CONV_OK) break;
+
+        dim3 grid(uint32_t((F + 255) / 256), uint32_t(nq));
+        k_fold<<<grid, 256, 0, st>>>(fresh.G, H, uint32_t(bins), uint32_t(F));
+        CU_BRK(cudaGetLastError());
+        b->stats.launches++;
+
+        if (part_offset == 0)
+            CU_BRK(cudaMemcpyAsync(fresh.aux + 2 * F, irdev, F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CU_BRK(cudaStreamSynchronize(st));
+        #undef CU_BRK
+    } while (false);
+
+    cudaFree(irdev);
+    cudaFree(H);
+    if (rc != B200CONV_OK)
+    {
+        free_instance_buffers(fresh);
+        return rc;
+    }
+
+    /* swap in (Convolver.cpp:108-142) */
+    Instance &in    = b->inst[idx];
+    free_instance_buffers(in);
+    in              = fresh;
+    in.active       = true;
+    in.conv_size    = count;
+    in.rank         = rank;
+    in.F            = F;
+    in.bins         = bins;
+    in.nq           = nq;
+    in.q_lo         = part_offset;
+    in.S            = S;
+    float fo        = phase * float(F);                     /* Convolver.cpp:140, fp32 */
+    in.off          = ((fo > 0.0f) && (fo < 1.8e19f)) ? (size_t(fo) % F) : 0;
+    in.frames       = 0;
+    in.pend_valid   = false;
+    rebuild_tables(b);
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_init(b200conv_batch_t *b, size_t idx, const float *data, size_t count,
+                             size_t rank, float phase)
+{
+    return b200conv_init_range(b, idx, data, count, rank, phase, 0);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* process                                                                                      */
+
+/* All active instances sit on a frame boundary and `frames` whole frames arrive: derive the
+ * jobs on the device, three launches per frame for all instances x partitions. */
+static int process_uniform(Batch *b, float *dst, const float *src, size_t stride, size_t frames,
+                           cudaStream_t st)
+{
+    const uint32_t nact = uint32_t(b->active.size());
+    TRY(upload_tables(b, st));
+    MacPlan plan    = plan_mac(uint32_t(b->rank), nact, uint32_t(b->max_nq), b->sm_count,
+                               b->tune_splits, b->tune_stages);
+    const size_t F  = size_t(1) << (b->rank - 1);
+    TRY(ensure_ypart(b, size_t(nact) * plan.splits * F * sizeof(float2), st));
+
+    uint64_t per_frame_bytes = 0;
+    for (uint32_t i : b->active)
+        per_frame_bytes += algo_bytes(b, b->inst[i], 0, size_t(-1));
+
+    StepArgs a      = base_args(b);
+    a.src           = src;
+    a.dst           = dst;
+    a.stride        = stride;
+    a.splits        = plan.splits;
+    a.n_jobs        = nact;
+    a.t_base        = b->t_batch;
+    for (size_t f = 0; f < frames; ++f)
+    {
+        a.frame0        = uint32_t(f);
+        CU(launch_fwd(a, nact, st));
+        CU(launch_mac(b, a, plan, nact, st));
+        CU(launch_inv(a, nact, st));
+        b->stats.launches       += 3;
+        b->stats.mac_launches   += 1;
+        b->stats.mac_algo_bytes += per_frame_bytes;
+        b->stats.frames         += nact;
+    }
+    b->t_batch     += frames;
+    for (uint32_t i : b->active)
+    {
+        b->inst[i].frames      += frames;
+        b->inst[i].pend_valid   = false;
+    }
+    return B200CONV_OK;
+}
+
+static inline uint32_t slot_of(const Instance &in, uint64_t t)
+{
+    uint64_t tm = t % in.S;
+    return uint32_t((tm == 0) ? 0 : in.S - tm);
+}
+
+/* Any call size / any phase: explicit job lists, one segment per instance per step. */
+static int process_general(Batch *b, float *dst, const float *src, size_t stride, size_t count,
+                           cudaStream_t st)
+{
+    const size_t F      = size_t(1) << (b->rank - 1);
+    const size_t nact   = b->active.size();
+    TRY(upload_tables(b, st));
+    std::vector<size_t> pos(b->n, 0);
+    std::vector<Job> fft, mac, part;
+
+    for (;;)
+    {
+        fft.clear(); mac.clear(); part.clear();
+        uint64_t bytes = 0;
+        for (uint32_t i : b->active)
+        {
+            Instance &in = b->inst[i];
+            if (pos[i] >= count)
+                continue;
+            float *cur  = in.aux, *pend = in.aux + F;
+            Job j;
+
+            if (in.off == F)
+            {
+                /* the frame delivered in pieces is complete: its spectrum enters the ring */
+                memset(&j, 0, sizeof(j));
+                j.inst      = i;
+                j.src       = cur;
+                j.slot0     = slot_of(in, in.frames);
+                j.spec      = in.ring + size_t(j.slot0) * F;
+                fft.push_back(j);
+                in.frames  += 1;
+                in.off      = 0;
+                in.pend_valid = false;
+            }
+
+            size_t n    = count - pos[i];
+            if (n > F - in.off)
+                n           = F - in.off;
+            const float *s  = src + size_t(i) * stride + pos[i];
+            float *d        = dst + size_t(i) * stride + pos[i];
+
+            if ((in.off == 0) && (n == F))
+            {
+                /* a whole frame at once: FFT -> MAC over every partition -> IFFT -> out */
+                memset(&j, 0, sizeof(j));
+                j.inst      = i;
+                j.src       = s;
+                j.dst       = d;
+                j.slot0     = slot_of(in, in.frames);
+                j.spec      = in.ring + size_t(j.slot0) * F;
+                j.qa        = uint32_t(in.q_lo);
+                j.qb        = uint32_t(in.q_lo + in.nq);
+                fft.push_back(j);
+                mac.push_back(j);
+                bytes      += algo_bytes(b, in, j.qa, j.qb);
+                in.frames  += 1;
+                in.pend_valid = false;
+                b->stats.frames += 1;
+            }
+            else
+            {
+                if (!in.pend_valid)
+                {
+                    /* what the complete frames contribute to the frame in progress: q >= 1 */
+                    memset(&j, 0, sizeof(j));
+                    j.inst      = i;
+                    j.dst       = pend;
+                    j.slot0     = slot_of(in, in.frames);
+                    j.qa        = uint32_t((in.q_lo > 1) ? in.q_lo : 1);
+                    j.qb        = uint32_t(in.q_lo + in.nq);
+                    mac.push_back(j);
+                    bytes      += algo_bytes(b, in, j.qa, j.qb);
+                    in.pend_valid = true;
+                    b->stats.frames += 1;
+                }
+                memset(&j, 0, sizeof(j));
+                j.inst      = i;
+                j.src       = s;
+                j.dst       = d;
+                j.off       = uint32_t(in.off);
+                j.n         = uint32_t(n);
+                part.push_back(j);
+                in.off     += n;
+            }
+            pos[i]     += n;
+        }
+
+        size_t total = fft.size() + mac.size() + part.size();
+        if (total == 0)
+            break;
+
+        size_t at = 0;
+        TRY(reserve_jobs(b, total, st, &at));
+        Job *hj = b->h_jobs + at;
+        if (!fft.empty())   memcpy(hj, fft.data(), fft.size() * sizeof(Job));
+        if (!mac.empty())   memcpy(hj + fft.size(), mac.data(), mac.size() * sizeof(Job));
+        if (!part.empty())  memcpy(hj + fft.size() + mac.size(), part.data(), part.size() * sizeof(Job));
+        TRY(push_jobs(b, at, total, st));
+
+        StepArgs a  = base_args(b);
+        if (!fft.empty())
+        {
+            a.jobs      = b->d_jobs + at;
+            a.n_jobs    = uint32_t(fft.size());
+            CU(launch_fwd(a, a.n_jobs, st));
+            b->stats.launches++;
+        }
+        if (!mac.empty())
+        {
+            MacPlan plan = plan_mac(uint32_t(b->rank), uint32_t(mac.size()), uint32_t(b->max_nq),
+                                    b->sm_count, b->tune_splits, b->tune_stages);
+            TRY(ensure_ypart(b, mac.size() * plan.splits * F * sizeof(float2), st));
+            a.ypart     = b->ypart;
+            a.jobs      = b->d_jobs + at + fft.size();
+            a.n_jobs    = uint32_t(mac.size());
+            a.splits    = plan.splits;
+            CU(launch_mac(b, a, plan, a.n_jobs, st));
+            CU(launch_inv(a, a.n_jobs, st));
+            b->stats.launches       += 2;
+            b->stats.mac_launches   += 1;
+            b->stats.mac_algo_bytes += bytes;
+        }
+        if (!part.empty())
+        {
+            a.jobs      = b->d_jobs + at + fft.size() + mac.size();
+            a.n_jobs    = uint32_t(part.size());
+            size_t maxn = 0;
+            for (const Job &j : part)
+                if (j.n > maxn) maxn = j.n;
+            dim3 grid(uint32_t((maxn + 127) / 128), a.n_jobs);
+            k_store<<<grid, 128, 0, st>>>(a);
+            CU(cudaGetLastError());
+            k_partial<<<grid, 128, 0, st>>>(a);
+            CU(cudaGetLastError());
+            b->stats.launches += 2;
+        }
+    }
+
+    (void)nact;
+    b->desc_dirty = true;       /* per-instance frame counters moved independently of t_batch */
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_process_device(b200conv_batch_t *b, float *dst, const float *src,
+                                       size_t stride, size_t count, void *stream)
+{
+    if (b == nullptr)
+        return fail(B200CONV_ERR_ARG, "b200conv_process_device: NULL handle");
+    if (count == 0)
+        return B200CONV_OK;
+    if ((dst == nullptr) || (src == nullptr) || (stride < count))
+        return fail(B200CONV_ERR_ARG, "b200conv_process_device: bad buffers");
+    TRY(set_device(b));
+    cudaStream_t st = (stream != nullptr) ? cudaStream_t(stream) : b->stream;
+
+    /* not initialised -> zeros (Convolver.cpp:219-223) */
+    for (size_t i = 0; i < b->n; )
+    {
+        if (b->inst[i].active) { ++i; continue; }
+        size_t j = i;
+        while ((j < b->n) && (!b->inst[j].active))
+            ++j;
+        CU(cudaMemset2DAsync(dst + i * stride, stride * sizeof(float), 0, count * sizeof(float), j - i, st));
+        i = j;
+    }
+    if (b->active.empty())
+        return B200CONV_OK;
+
+    const size_t F = size_t(1) << (b->rank - 1);
+    bool uniform = (count % F) == 0;
+    for (uint32_t i : b->active)
+        if (b->inst[i].off != 0)
+            uniform = false;
+
+    if (uniform)
+        return process_uniform(b, dst, src, stride, count / F, st);
+    return process_general(b, dst, src, stride, count, st);
+}
+
+static int ensure_staging(Batch *b, size_t floats)
+{
+    if (floats <= b->stage_floats)
+        return B200CONV_OK;
+    CU(cudaStreamSynchronize(b->stream));
+    if (b->h_in)  cudaFreeHost(b->h_in);
+    if (b->h_out) cudaFreeHost(b->h_out);
+    if (b->d_in)  cudaFree(b->d_in);
+    if (b->d_out) cudaFree(b->d_out);
+    b->h_in = b->h_out = b->d_in = b->d_out = nullptr;
+    b->stage_floats = 0;
+    CU(cudaMallocHost(&b->h_in, floats * sizeof(float)));
+    CU(cudaMallocHost(&b->h_out, floats * sizeof(float)));
+    CU(cudaMalloc(&b->d_in, floats * sizeof(float)));
+    CU(cudaMalloc(&b->d_out, floats * sizeof(float)));
+    b->stage_floats = floats;
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_process(b200conv_batch_t *b, float *const *dst, const float *const *src,
+                                size_t count)
+{
+    if (b == nullptr)
+        return fail(B200CONV_ERR_ARG, "b200conv_process: NULL handle");
+    if (count == 0)
+        return B200CONV_OK;
+    if ((dst == nullptr) || (src == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_process: NULL buffer table");
+    for (size_t i = 0; i < b->n; ++i)
+        if ((dst[i] == nullptr) || (src[i] == nullptr))
+            return fail(B200CONV_ERR_ARG, "b200conv_process: NULL buffer for instance %zu", i);
+    TRY(set_device(b));
+
+    /* samples per instance per pass: bounded staging, at least one frame */
+    size_t cap = (size_t(1) << 24) / b->n;
+    if (cap > 65536)    cap = 65536;
+    size_t F   = (b->rank > 0) ? (size_t(1) << (b->rank - 1)) : 128;
+    if (cap < F)        cap = F;
+    cap        = (cap / F) * F;
+
+    for (size_t done = 0; done < count; )
+    {
+        size_t c = count - done;
+        if (c > cap)
+            c = cap;
+        TRY(ensure_staging(b, b->n * c));
+        for (size_t i = 0; i < b->n; ++i)
+            if (b->inst[i].active)
+                memcpy(b->h_in + i * c, src[i] + done, c * sizeof(float));
+        CU(cudaMemcpyAsync(b->d_in, b->h_in, b->n * c * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+        TRY(b200conv_process_device(b, b->d_out, b->d_in, c, c, b->stream));
+        CU(cudaMemcpyAsync(b->h_out, b->d_out, b->n * c * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+        for (size_t i = 0; i < b->n; ++i)
+            memcpy(dst[i] + done, b->h_out + i * c, c * sizeof(float));
+        b->stats.h2d_bytes += b->n * c * sizeof(float);
+        b->stats.d2h_bytes += b->n * c * sizeof(float);
+        done += c;
+    }
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_sync(b200conv_batch_t *b)
+{
+    if (b == nullptr)
+        return fail(B200CONV_ERR_ARG, "b200conv_sync: NULL handle");
+    TRY(set_device(b));
+    CU(cudaStreamSynchronize(b->stream));
+    return B200CONV_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* queries                                                                                      */
+
+extern "C" size_t b200conv_data_size(const b200conv_batch_t *b, size_t idx)
+{
+    return ((b != nullptr) && (idx < b->n)) ? b->inst[idx].conv_size : 0;
+}
+
+extern "C" size_t b200conv_rank(const b200conv_batch_t *b, size_t idx)
+{
+    return ((b != nullptr) && (idx < b->n)) ? b->inst[idx].rank : 0;
+}
+
+extern "C" size_t b200conv_instances(const b200conv_batch_t *b)
+{
+    return (b != nullptr) ? b->n : 0;
+}
+
+extern "C" int b200conv_get_state(const b200conv_batch_t *b, size_t idx, b200conv_state_t *st)
+{
+    if ((b == nullptr) || (idx >= b->n) || (st == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_get_state: bad arguments");
+    const Instance &in = b->inst[idx];
+    st->conv_size   = in.conv_size;
+    st->rank        = in.rank;
+    st->frame_size  = in.F;
+    st->frame_off   = (in.off == in.F) ? 0 : in.off;    /* a complete frame rolls over lazily */
+    st->bins        = in.bins;
+    st->partitions  = in.nq;
+    st->part_offset = in.q_lo;
+    st->frames      = in.frames + ((in.active && (in.off == in.F)) ? 1 : 0);
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_get_stats(const b200conv_batch_t *b, b200conv_stats_t *st)
+{
+    if ((b == nullptr) || (st == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_get_stats: bad arguments");
+    *st = b->stats;
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_reset_stats(b200conv_batch_t *b)
+{
+    if (b == nullptr)
+        return fail(B200CONV_ERR_ARG, "b200conv_reset_stats: NULL handle");
+    memset(&b->stats, 0, sizeof(b->stats));
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_set_profiling(b200conv_batch_t *b, int enable)
+{
+    if (b == nullptr)
+        return fail(B200CONV_ERR_ARG, "b200conv_set_profiling: NULL handle");
+    b->profiling    = (enable != 0);
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_get_profile(b200conv_batch_t *b, double *mac_ms, uint64_t *mac_launches)
+{
+    if (b == nullptr)
+        return fail(B200CONV_ERR_ARG, "b200conv_get_profile: NULL handle");
+    TRY(set_device(b));
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < b->prof_used; i += 2)
+    {
+        CU(cudaEventSynchronize(b->prof_events[i + 1]));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, b->prof_events[i], b->prof_events[i + 1]));
+        total += ms;
+    }
+    if (mac_ms != nullptr)          *mac_ms = total;
+    if (mac_launches != nullptr)    *mac_launches = b->prof_used / 2;
+    b->prof_used = 0;
+    return B200CONV_OK;
+}
+
+extern "C" void *b200conv_stream(b200conv_batch_t *b)
+{
+    return (b != nullptr) ? (void *)b->stream : nullptr;
+}
+
+extern "C" int b200conv_set_tuning(b200conv_batch_t *b, int mac_splits, int mac_stages)
+{
+    if ((b == nullptr) || (mac_splits < 0) || (mac_splits > 32) || (mac_stages < 0) || (mac_stages > 12))
+        return fail(B200CONV_ERR_ARG, "b200conv_set_tuning: bad arguments");
+    b->tune_splits  = mac_splits;
+    b->tune_stages  = mac_stages;
+    return B200CONV_OK;
+}
+
+extern "C" const char *b200conv_last_error(void)
+{
+    return g_last_error.c_str();
+}
+
+extern "C" const char *b200conv_version(void)
+{
+    return "b200conv 0.1 (sm_100a)";
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* fastconv primitives on the device                                                            */
+
+namespace
+{
+    struct PrimCtx
+    {
+        float2     *tw[B200CONV_RANK_MAX + 1] = { nullptr };
+        Job        *d_jobs      = nullptr;
+        size_t      job_cap     = 0;
+        float      *scratch     = nullptr;      /* images / time rows */
+        size_t      scratch_bytes = 0;
+    };
+    std::mutex  g_prim_lock;
+    PrimCtx     g_prim[64];
+
+    int prim_prepare(int device, size_t rank, size_t count, size_t scratch_bytes, PrimCtx **out)
+    {
+        if ((rank < B200CONV_RANK_MIN) || (rank > B200CONV_RANK_MAX) || (count == 0))
+            return fail(B200CONV_ERR_ARG, "fastconv: rank %zu / count %zu not supported", rank, count);
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if ((e != cudaSuccess) || (n == 0))
+            return fail(B200CONV_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
+        if (device < 0)
+            CU(cudaGetDevice(&device));
+        if ((device >= n) || (device >= 64))
+            return fail(B200CONV_ERR_ARG, "device %d out of range", device);
+        CU(cudaSetDevice(device));
+        PrimCtx &c = g_prim[device];
+        if (c.tw[rank] == nullptr)
+            TRY(make_twiddles(uint32_t(rank), &c.tw[rank]));
+        if (count > c.job_cap)
+        {
+            CU(cudaDeviceSynchronize());
+            if (c.d_jobs) cudaFree(c.d_jobs);
+            c.d_jobs = nullptr; c.job_cap = 0;
+            CU(cudaMalloc(&c.d_jobs, count * sizeof(Job)));
+            c.job_cap = count;
+        }
+        if (scratch_bytes > c.scratch_bytes)
+        {
+            CU(cudaDeviceSynchronize());
+            if (c.scratch) cudaFree(c.scratch);
+            c.scratch = nullptr; c.scratch_bytes = 0;
+            CU(cudaMalloc(&c.scratch, scratch_bytes));
+            c.scratch_bytes = scratch_bytes;
+        }
+        *out = &c;
+        return B200CONV_OK;
+    }
+
+    /* rows: job i reads src + i*src_step, writes spec + i*spec_step / dst + i*dst_step */
+    int prim_jobs(PrimCtx *c, size_t count, const float *src, size_t src_step, float2 *spec,
+                  size_t spec_step, float *dst, size_t dst_step, cudaStream_t st)
+    {
+        std::vector<Job> jobs(count);
+        for (size_t i = 0; i < count; ++i)
+        {
+            memset(&jobs[i], 0, sizeof(Job));
+            jobs[i].src     = (src != nullptr) ? src + i * src_step : nullptr;
+            jobs[i].spec    = (spec != nullptr) ? spec + i * spec_step : nullptr;
+            jobs[i].dst     = (dst != nullptr) ? dst + i * dst_step : nullptr;
+        }
+        CU(cudaMemcpyAsync(c->d_jobs, jobs.data(), count * sizeof(Job), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));      /* `jobs` is pageable and about to go out of scope */
+        return B200CONV_OK;
+    }
+
+    StepArgs prim_args(PrimCtx *c, size_t rank, size_t count)
+    {
+        StepArgs a;
+        memset(&a, 0, sizeof(a));
+        a.jobs      = c->d_jobs;
+        a.tw        = c->tw[rank];
+        a.rank      = uint32_t(rank);
+        a.n_jobs    = uint32_t(count);
+        a.splits    = 1;
+        return a;
+    }
+}
+
+extern "C" int b200conv_fastconv_parse(int device, float *image, const float *src, size_t rank,
+                                       size_t count, void *stream)
+{
+    std::lock_guard<std::mutex> lock(g_prim_lock);
+    PrimCtx *c = nullptr;
+    TRY(prim_prepare(device, rank, count, 0, &c));
+    cudaStream_t st = cudaStream_t(stream);
+    size_t F = size_t(1) << (rank - 1);
+    TRY(prim_jobs(c, count, src, F, reinterpret_cast<float2 *>(image), F, nullptr, 0, st));
+    StepArgs a = prim_args(c, rank, count);
+    CU(launch_fwd(a, uint32_t(count), st));
+    CU(cudaStreamSynchronize(st));
+    return B200CONV_OK;
+}
+
+static int prim_inverse(PrimCtx *c, float *dst, const float2 *images, size_t rank, size_t count,
+                        bool accumulate, float *time_scratch, cudaStream_t st)
+{
+    size_t N = size_t(1) << rank;
+    float *out = accumulate ? time_scratch : dst;
+    TRY(prim_jobs(c, count, nullptr, 0, nullptr, 0, out, N, st));
+    StepArgs a = prim_args(c, rank, count);
+    a.ypart     = const_cast<float2 *>(images);
+    a.flags     = INV_FULL;
+    CU(launch_inv(a, uint32_t(count), st));
+    if (accumulate)
+    {
+        uint64_t total = uint64_t(count) * N;
+        uint32_t grid = uint32_t((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+        k_accumulate<<<grid, 256, 0, st>>>(dst, time_scratch, total);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(st));
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_fastconv_restore(int device, float *dst, const float *image, size_t rank,
+                                         size_t count, void *stream)
+{
+    std::lock_guard<std::mutex> lock(g_prim_lock);
+    PrimCtx *c = nullptr;
+    TRY(prim_prepare(device, rank, count, 0, &c));
+    return prim_inverse(c, dst, reinterpret_cast<const float2 *>(image), rank, count, false, nullptr,
+                        cudaStream_t(stream));
+}
+
+extern "C" int b200conv_fastconv_apply(int device, float *dst, const float *c1, const float *c2,
+                                       size_t rank, size_t count, void *stream)
+{
+    std::lock_guard<std::mutex> lock(g_prim_lock);
+    size_t N = size_t(1) << rank, M = N / 2;
+    PrimCtx *c = nullptr;
+    /* scratch: product images (count*M float2) + time rows (count*N floats) */
+    TRY(prim_prepare(device, rank, count, count * M * sizeof(float2) + count * N * sizeof(float), &c));
+    cudaStream_t st = cudaStream_t(stream);
+    float2 *prod    = reinterpret_cast<float2 *>(c->scratch);
+    float *rows     = c->scratch + count * M * 2;
+    uint64_t total  = uint64_t(count) * M;
+    uint32_t grid   = uint32_t((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+    k_cmul<<<grid, 256, 0, st>>>(prod, reinterpret_cast<const float2 *>(c1),
+                                 reinterpret_cast<const float2 *>(c2), uint32_t(M), total);
+    CU(cudaGetLastError());
+    return prim_inverse(c, dst, prod, rank, count, true, rows, st);
+}
+
+extern "C" int b200conv_fastconv_parse_apply(int device, float *dst, const float *cimg, const float *src,
+                                             size_t rank, size_t count, void *stream)
+{
+    std::lock_guard<std::mutex> lock(g_prim_lock);
+    size_t N = size_t(1) << rank, M = N / 2;
+    PrimCtx *c = nullptr;
+    TRY(prim_prepare(device, rank, count, count * M * sizeof(float2) + count * N * sizeof(float), &c));
+    cudaStream_t st = cudaStream_t(stream);
+    float2 *prod    = reinterpret_cast<float2 *>(c->scratch);
+    float *rows     = c->scratch + count * M * 2;
+    TRY(prim_jobs(c, count, src, M, prod, M, nullptr, 0, st));
+    StepArgs a = prim_args(c, rank, count);
+    CU(launch_fwd(a, uint32_t(count), st));
+    uint64_t total  = uint64_t(count) * M;
+    uint32_t grid   = uint32_t((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+    k_cmul<<<grid, 256, 0, st>>>(prod, prod, reinterpret_cast<const float2 *>(cimg), uint32_t(M), total);
+    CU(cudaGetLastError());
+    return prim_inverse(c, dst, prod, rank, count, true, rows, st);
+}

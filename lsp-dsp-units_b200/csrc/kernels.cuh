@@ -1,0 +1,646 @@
+/*
+ * kernels.cuh -- sm_100a device code of the batched partitioned-FFT convolver.
+ *
+ * Kernel map (reference primitive it replaces -> kernel):
+ *   dsp::fastconv_parse  (Convolver.cpp:159,174,191,270)  -> k_fwd   : F reals -> M packed bins
+ *   dsp::fastconv_apply  (Convolver.cpp:280-285, the hot   -> k_mac   : sum_q G_q * X_{t-q}
+ *        loop: nBlocks x (spectrum multiply + IFFT + add)     k_inv   : ONE inverse FFT per frame
+ *   dsp::fastconv_parse_apply head (Convolver.cpp:256,293) -> folded into partition q = 0
+ *   dsp::convolve        (Convolver.cpp:295)               -> k_partial (unaligned call sizes)
+ *   dsp::copy/move/fill_zero (Convolver.cpp:291,296,308-310) -> ring indices, nothing moves
+ *
+ * Notation: rank R, N = 2^R, F = M = N/2 (frame length = packed complex bins), P = M/2.
+ *
+ * Spectrum layout: M float2 per row; bin k = 1..M-1 complex, bin 0 = (DC, Nyquist), both real.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200conv
+{
+
+/* ------------------------------------------------------------------------------------------- */
+/* Descriptors shared with the host                                                             */
+
+struct InstDesc                     /* one per instance, device resident */
+{
+    const float2   *G;              /* [nq][M]   folded IR spectra, row q_local = q - q_lo          */
+    float2         *ring;           /* [S][M]    input-spectrum ring; frame t lives in slot (-t) mod S */
+    float          *cur;            /* [F]       frame being received (partial-call path)           */
+    float          *pend;           /* [F]       contribution of complete frames to that frame      */
+    const float    *head;           /* [F]       taps [0, F) in the time domain                     */
+    int64_t         t_delta;        /* frames(instance) - frames(batch), uniform mode               */
+    uint32_t        nq;             /* rows in G                                                    */
+    uint32_t        q_lo;           /* global index of row 0                                        */
+    uint32_t        S;              /* ring slots                                                   */
+    uint32_t        pad;
+};
+
+struct Job                          /* explicit work item (general path and init) */
+{
+    const float    *src;            /* k_fwd: F input samples;  k_store/k_partial: call input       */
+    float          *dst;            /* k_inv / k_partial output                                     */
+    float2         *spec;           /* k_fwd output row                                             */
+    uint32_t        inst;
+    uint32_t        slot0;          /* ring slot of X_t for this job's frame index t                */
+    uint32_t        qa, qb;         /* global partition range of the MAC                            */
+    uint32_t        off, n;         /* partial path: first sample index in the frame, sample count  */
+};
+
+struct StepArgs                     /* by-value kernel argument */
+{
+    const InstDesc *inst;
+    const Job      *jobs;           /* NULL -> uniform mode: jobs are derived from the fields below */
+    const uint32_t *active;         /* uniform mode: instance ids                                   */
+    const float2   *tw;             /* N-point twiddle table exp(-2 pi i j / N)                     */
+    float2         *ypart;          /* [job][split][M] partial spectra                              */
+    const float    *src;            /* uniform mode: [instances][stride]                            */
+    float          *dst;
+    uint64_t        stride;
+    uint64_t        t_base;         /* uniform mode: batch frame counter of frame 0 of this launch  */
+    uint32_t        n_active;
+    uint32_t        n_jobs;
+    uint32_t        splits;
+    uint32_t        rank;
+    uint32_t        frame0;         /* uniform mode: first frame (within the call) of this launch   */
+    uint32_t        flags;
+};
+
+enum { INV_FULL = 1 };
+
+__device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
+{
+    if (a.jobs != nullptr)
+        return a.jobs[j];
+
+    /* uniform mode: every active instance sits on a frame boundary and receives whole frames */
+    const uint32_t F    = 1u << (a.rank - 1);
+    uint32_t ia         = j % a.n_active;
+    uint32_t f          = a.frame0 + j / a.n_active;
+    Job r;
+    r.inst              = a.active[ia];
+    const InstDesc &d   = a.inst[r.inst];
+    uint64_t t          = uint64_t(int64_t(a.t_base) + d.t_delta) + f;
+    uint32_t tm         = uint32_t(t % d.S);
+    r.slot0             = (tm == 0) ? 0 : d.S - tm;
+    r.src               = a.src + uint64_t(r.inst) * a.stride + uint64_t(f) * F;
+    r.dst               = a.dst + uint64_t(r.inst) * a.stride + uint64_t(f) * F;
+    r.spec              = d.ring + uint64_t(r.slot0) * F;
+    r.qa                = d.q_lo;
+    r.qb                = d.q_lo + d.nq;
+    r.off               = 0;
+    r.n                 = F;
+    return r;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Small complex helpers                                                                        */
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b)  { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b)  { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cconj(float2 a)           { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+/* a * conj(b) */
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Shared-memory Stockham FFT: NH independent P-point transforms laid out back to back.         */
+/* Radix 4, with one leading radix-2 pass when log2(P) is odd.  Each pass stages its inputs in   */
+/* registers, so one buffer is enough (load, barrier, store, barrier).                          */
+
+template <int RANK>
+struct FftCfg
+{
+    static constexpr int N      = 1 << RANK;
+    static constexpr int M      = N / 2;
+    static constexpr int P      = M / 2;
+    static constexpr int LOGP   = RANK - 2;
+    static constexpr int NH     = (RANK >= 16) ? 1 : 2;                 /* halves resident in smem */
+    static constexpr int BF     = NH * P / 4;                           /* radix-4 butterflies/pass */
+    static constexpr int T      = (BF >= 512) ? 512 : ((BF < 32) ? 32 : BF);
+    static constexpr int BPT    = (BF + T - 1) / T;                     /* butterflies per thread   */
+    static constexpr size_t SMEM = size_t(NH) * P * sizeof(float2);
+};
+
+template <int RANK, bool INV>
+__device__ __forceinline__ void fft_smem(float2 *sm, const float2 *__restrict__ tw, int tid)
+{
+    using C = FftCfg<RANK>;
+    constexpr int P = C::P, T = C::T, BPT = C::BPT, NH = C::NH, N = C::N;
+
+    int Ns = 1;
+    if (C::LOGP & 1)
+    {
+        /* radix-2, Ns = 1: twiddles are all 1.  NH*P/2 butterflies = 2*BPT per thread. */
+        float2 a[2 * BPT], b[2 * BPT];
+        #pragma unroll
+        for (int i = 0; i < 2 * BPT; ++i)
+        {
+            int idx = tid + i * T;
+            if (idx < NH * P / 2)
+            {
+                int h   = idx / (P / 2), j = idx % (P / 2);
+                a[i]    = sm[h * P + j];
+                b[i]    = sm[h * P + j + P / 2];
+            }
+        }
+        __syncthreads();
+        #pragma unroll
+        for (int i = 0; i < 2 * BPT; ++i)
+        {
+            int idx = tid + i * T;
+            if (idx < NH * P / 2)
+            {
+                int h   = idx / (P / 2), j = idx % (P / 2);
+                sm[h * P + 2 * j]       = cadd(a[i], b[i]);
+                sm[h * P + 2 * j + 1]   = csub(a[i], b[i]);
+            }
+        }
+        __syncthreads();
+        Ns = 2;
+    }
+
+    for ( ; Ns < P; Ns <<= 2)
+    {
+        float2 v[BPT][4];
+        #pragma unroll
+        for (int i = 0; i < BPT; ++i)
+        {
+            int idx = tid + i * T;
+            if (idx < NH * P / 4)
+            {
+                int h   = idx / (P / 4), j = idx % (P / 4);
+                #pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    v[i][r] = sm[h * P + j + r * (P / 4)];
+            }
+        }
+        __syncthreads();
+
+        const int step = N / (4 * Ns);          /* exp(-2 pi i k / (4 Ns)) = tw[k * step] */
+        #pragma unroll
+        for (int i = 0; i < BPT; ++i)
+        {
+            int idx = tid + i * T;
+            if (idx < NH * P / 4)
+            {
+                int h   = idx / (P / 4), j = idx % (P / 4);
+                int k   = j & (Ns - 1);
+                float2 x0 = v[i][0], x1 = v[i][1], x2 = v[i][2], x3 = v[i][3];
+                if (Ns > 1)
+                {
+                    float2 w1 = __ldg(&tw[k * step]);
+                    float2 w2 = __ldg(&tw[2 * k * step]);
+                    float2 w3 = __ldg(&tw[3 * k * step]);
+                    if (INV)    { x1 = cmulc(x1, w1); x2 = cmulc(x2, w2); x3 = cmulc(x3, w3); }
+                    else        { x1 = cmul(x1, w1);  x2 = cmul(x2, w2);  x3 = cmul(x3, w3);  }
+                }
+                float2 s0 = cadd(x0, x2), s1 = csub(x0, x2);
+                float2 s2 = cadd(x1, x3), s3 = csub(x1, x3);
+                /* forward: rot = -i * s3 ; inverse: rot = +i * s3 */
+                float2 rot = INV ? make_float2(-s3.y, s3.x) : make_float2(s3.y, -s3.x);
+                float2 *o  = sm + h * P + ((j - k) << 2) + k;
+                o[0]        = cadd(s0, s2);
+                o[Ns]       = cadd(s1, rot);
+                o[2 * Ns]   = csub(s0, s2);
+                o[3 * Ns]   = csub(s1, rot);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* k_fwd : one CTA per frame.  F real samples (zero padded to 2F) -> M packed complex bins.      */
+/*                                                                                             */
+/* z[m] = x[2m] + i x[2m+1], m < P (the upper half of the packed sequence is the zero padding).  */
+/* Even bins of its M-point transform are FFT_P(z), odd bins are FFT_P(z * w_M^m); the real-FFT  */
+/* split then needs Z[k] and Z[M-k], which have the same parity, so the two halves never mix.    */
+
+template <int RANK>
+__global__ void __launch_bounds__(FftCfg<RANK>::T)
+k_fwd(const StepArgs a)
+{
+    using C = FftCfg<RANK>;
+    constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH;
+    extern __shared__ float2 sm[];
+
+    const int tid           = threadIdx.x;
+    const Job job           = fetch_job(a, blockIdx.x);
+    const float *src        = job.src;
+    float2 *out             = job.spec;
+    const float2 *tw        = a.tw;
+
+    #pragma unroll 1
+    for (int pass = 0; pass < 2 / NH; ++pass)
+    {
+        for (int m = tid; m < P; m += T)
+        {
+            float2 z    = make_float2(src[2 * m], src[2 * m + 1]);
+            float2 zb   = cmul(z, __ldg(&tw[2 * m]));           /* w_M^m = w_N^(2m) */
+            if (NH == 2)    { sm[m] = z; sm[P + m] = zb; }
+            else            { sm[m] = (pass == 0) ? z : zb; }
+        }
+        __syncthreads();
+
+        fft_smem<RANK, false>(sm, tw, tid);
+
+        /* split post-pass over pairs (k, M-k), k = 0 .. M/2 */
+        for (int k = tid; k <= M / 2; k += T)
+        {
+            int par     = k & 1;
+            if ((NH == 1) && (par != pass))
+                continue;
+            const float2 *half  = sm + ((NH == 2) ? par * P : 0);
+            int ik      = k >> 1;
+            int im      = (k == 0) ? 0 : (par ? (P - 1 - ik) : (P - ik));
+            float2 zk   = half[ik], zm = half[im];
+            if (k == 0)
+            {
+                out[0]      = make_float2(zk.x + zk.y, zk.x - zk.y);
+                continue;
+            }
+            /* e = (zk + conj(zm))/2 ; o = (zk - conj(zm))/2 ; X[k] = e - i w^k o */
+            float2 e    = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+            float2 o    = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
+            float2 w    = __ldg(&tw[k]);
+            float2 wo   = cmul(w, o);
+            out[k]      = make_float2(e.x + wo.y, e.y - wo.x);
+            if (k != M - k)
+            {
+                /* X[M-k] = conj(e) - i conj(w) conj(o) = conj(e) - i conj(wo) */
+                out[M - k]  = make_float2(e.x - wo.y, -e.y - wo.x);
+            }
+        }
+        if (NH == 1)
+            __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* k_inv : one CTA per frame.  Sums the MAC's partial rows, merges the packed spectrum back into  */
+/* the P-point even/odd sub-sequences, runs two inverse FFTs and combines only the first F of the */
+/* 2F output samples (the second half is time-aliased garbage in the folded-overlap form).        */
+/* INV_FULL also emits samples [F, 2F) (used by the fastconv primitives).                          */
+
+template <int RANK>
+__global__ void __launch_bounds__(FftCfg<RANK>::T)
+k_inv(const StepArgs a)
+{
+    using C = FftCfg<RANK>;
+    constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH, N = C::N;
+    extern __shared__ float2 sm[];
+
+    const int tid           = threadIdx.x;
+    const Job job           = fetch_job(a, blockIdx.x);
+    float *dst              = job.dst;
+    const float2 *tw        = a.tw;
+    const float2 *yp        = a.ypart + uint64_t(blockIdx.x) * a.splits * M;
+    const uint32_t splits   = a.splits;
+    const float scale       = 1.0f / float(N);
+    const bool full         = (a.flags & INV_FULL) != 0;
+
+    #pragma unroll 1
+    for (int pass = 0; pass < 2 / NH; ++pass)
+    {
+        /* with one resident half the odd half goes first and is parked in dst */
+        const int want = (NH == 1) ? (1 - pass) : 0;
+
+        for (int k = tid; k <= M / 2; k += T)
+        {
+            int par     = k & 1;
+            if ((NH == 1) && (par != want))
+                continue;
+            float2 *half = sm + ((NH == 2) ? par * P : 0);
+            float2 yk   = make_float2(0.0f, 0.0f), ym = make_float2(0.0f, 0.0f);
+            for (uint32_t s = 0; s < splits; ++s)
+            {
+                yk          = cadd(yk, yp[uint64_t(s) * M + k]);
+                if ((k != 0) && (k != M - k))
+                    ym          = cadd(ym, yp[uint64_t(s) * M + (M - k)]);
+            }
+            if (k == 0)
+            {
+                /* (DC, Nyquist) -> Z[0] = (DC + Ny) + i (DC - Ny) */
+                half[0]     = make_float2(yk.x + yk.y, yk.x - yk.y);
+                continue;
+            }
+            if (k == M - k)
+                ym          = yk;
+            /* e = yk + conj(ym) ; o = conj(w^k) (yk - conj(ym)) ; Z[k] = e + i o ; Z[M-k] = conj(e) + i conj(o) */
+            float2 e    = make_float2(yk.x + ym.x, yk.y - ym.y);
+            float2 df   = make_float2(yk.x - ym.x, yk.y + ym.y);
+            float2 o    = cmulc(df, __ldg(&tw[k]));
+            int ik      = k >> 1;
+            half[ik]    = make_float2(e.x - o.y, e.y + o.x);
+            if (k != M - k)
+            {
+                int im      = par ? (P - 1 - ik) : (P - ik);
+                half[im]    = make_float2(e.x + o.y, o.x - e.y);
+            }
+        }
+        __syncthreads();
+
+        fft_smem<RANK, true>(sm, tw, tid);
+
+        /* z[m] = (A[m] + conj(w_M^m) B[m]) / N ; z[m + P] = (A[m] - conj(w_M^m) B[m]) / N */
+        for (int m = tid; m < P; m += T)
+        {
+            float2 lo, hi;
+            if (NH == 2)
+            {
+                float2 av   = sm[m];
+                float2 bv   = cmulc(sm[P + m], __ldg(&tw[2 * m]));
+                lo          = make_float2((av.x + bv.x) * scale, (av.y + bv.y) * scale);
+                hi          = make_float2((av.x - bv.x) * scale, (av.y - bv.y) * scale);
+            }
+            else if (pass == 0)
+            {
+                /* park conj(w) B / N where the result will go; the same thread reads it back */
+                float2 bv   = cmulc(sm[m], __ldg(&tw[2 * m]));
+                dst[2 * m]      = bv.x * scale;
+                dst[2 * m + 1]  = bv.y * scale;
+                continue;
+            }
+            else
+            {
+                float2 av   = sm[m];
+                float2 pk   = make_float2(dst[2 * m], dst[2 * m + 1]);
+                lo          = make_float2(av.x * scale + pk.x, av.y * scale + pk.y);
+                hi          = make_float2(av.x * scale - pk.x, av.y * scale - pk.y);
+            }
+
+            dst[2 * m]      = lo.x;
+            dst[2 * m + 1]  = lo.y;
+            if (full)
+            {
+                dst[2 * (m + P)]        = hi.x;
+                dst[2 * (m + P) + 1]    = hi.y;
+            }
+        }
+        if (NH == 1)
+            __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* k_mac : the roofline kernel.  Y[job][split][k] = sum_{q in chunk} G_q[k] * X_{t-q}[k].        */
+/*                                                                                             */
+/* Pure fp32 stream: 16 bytes in per complex MAC, no reuse (one frame per call), so the only job */
+/* is to keep enough bytes in flight.  One elected thread feeds an NS-deep shared-memory ring     */
+/* with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx); all threads drain it with     */
+/* conflict-free LDS.128 and FFMA.  No tensor cores: 0.5 flop/byte is far below any MMA ridge.    */
+/*                                                                                             */
+/* grid = (jobs * splits, M / TB).  Stage = QB consecutive partitions x TB bins of G and of the   */
+/* ring (QB > 1 only when TB == M, where consecutive rows are contiguous in memory).             */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return uint32_t(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do
+    {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+/* global -> shared bulk copy (TMA, 1-D); bytes % 16 == 0, both addresses 16-byte aligned */
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct MacShape
+{
+    uint32_t TB;        /* bins per CTA tile                 */
+    uint32_t QB;        /* partitions per stage              */
+    uint32_t NS;        /* stages                            */
+};
+
+constexpr int MAC_VPT = 2;      /* float4 columns per thread; blockDim.x = TB / (2 * MAC_VPT) */
+
+__global__ void __launch_bounds__(256)
+k_mac(const StepArgs a, const MacShape sh)
+{
+    extern __shared__ __align__(128) unsigned char smraw[];
+
+    const uint32_t M        = 1u << (a.rank - 1);
+    const uint32_t TB       = sh.TB, QB = sh.QB, NS = sh.NS;
+    const uint32_t T        = blockDim.x;
+    const uint32_t tid      = threadIdx.x;
+    const uint32_t jobi     = blockIdx.x / a.splits;
+    const uint32_t split    = blockIdx.x % a.splits;
+    const uint32_t tile     = blockIdx.y;
+
+    const uint32_t stage_elems = QB * TB;                           /* float2 per operand per stage */
+    float2 *sG              = reinterpret_cast<float2 *>(smraw);
+    float2 *sX              = sG + size_t(NS) * stage_elems;
+    uint64_t *full          = reinterpret_cast<uint64_t *>(sX + size_t(NS) * stage_elems);
+
+    const Job job           = fetch_job(a, jobi);
+    const InstDesc d        = a.inst[job.inst];
+
+    /* this CTA's partition chunk [q0, q1) in global partition indices */
+    uint32_t qa             = max(job.qa, d.q_lo);
+    uint32_t qb             = min(job.qb, d.q_lo + d.nq);
+    uint32_t nq             = (qb > qa) ? (qb - qa) : 0;
+    const uint32_t q0       = qa + uint32_t((uint64_t(nq) * split) / a.splits);
+    const uint32_t q1       = qa + uint32_t((uint64_t(nq) * (split + 1)) / a.splits);
+    const uint32_t n_iter   = (q1 - q0 + QB - 1) / QB;
+
+    const float2 *Gt        = d.G + uint64_t(tile) * TB;            /* row r at Gt + r * M */
+    const float2 *Xt        = d.ring + uint64_t(tile) * TB;
+    const uint32_t row_bytes = TB * uint32_t(sizeof(float2));
+
+    if (tid == 0)
+    {
+        for (uint32_t s = 0; s < NS; ++s)
+            mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t it)
+    {
+        uint32_t s      = it % NS;
+        uint32_t q      = q0 + it * QB;
+        uint32_t rows   = min(QB, q1 - q);
+        float2 *g       = sG + size_t(s) * stage_elems;
+        float2 *x       = sX + size_t(s) * stage_elems;
+        mbar_expect_tx(&full[s], 2u * rows * row_bytes);
+        /* IR rows q .. q+rows-1 are contiguous when TB == M (QB > 1 only then) */
+        bulk_g2s(g, Gt + uint64_t(q - d.q_lo) * M, rows * row_bytes, &full[s]);
+        /* ring slots (slot0 + q) mod S ascend with q: one copy, or two around the wrap */
+        uint32_t first  = uint32_t((uint64_t(job.slot0) + q) % d.S);
+        uint32_t n1     = min(rows, d.S - first);
+        bulk_g2s(x, Xt + uint64_t(first) * M, n1 * row_bytes, &full[s]);
+        if (n1 < rows)
+            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[s]);
+    };
+
+    if (tid == 0)
+    {
+        for (uint32_t it = 0; (it < NS) && (it < n_iter); ++it)
+            issue(it);
+    }
+
+    float4 acc[MAC_VPT];
+    #pragma unroll
+    for (int v = 0; v < MAC_VPT; ++v)
+        acc[v]      = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float dny       = 0.0f;         /* sum of Im*Im of the thread's first bin: Nyquist fix-up for bin 0 */
+
+    for (uint32_t it = 0; it < n_iter; ++it)
+    {
+        uint32_t s      = it % NS;
+        uint32_t rows   = min(QB, q1 - (q0 + it * QB));
+        mbar_wait(&full[s], (it / NS) & 1u);
+
+        const float4 *g4 = reinterpret_cast<const float4 *>(sG + size_t(s) * stage_elems);
+        const float4 *x4 = reinterpret_cast<const float4 *>(sX + size_t(s) * stage_elems);
+        for (uint32_t r = 0; r < rows; ++r)
+        {
+            #pragma unroll
+            for (int v = 0; v < MAC_VPT; ++v)
+            {
+                float4 g    = g4[r * (TB / 2) + tid + v * T];
+                float4 x    = x4[r * (TB / 2) + tid + v * T];
+                acc[v].x    = fmaf(g.x, x.x, acc[v].x);
+                acc[v].y    = fmaf(g.x, x.y, acc[v].y);
+                acc[v].z    = fmaf(g.z, x.z, acc[v].z);
+                acc[v].w    = fmaf(g.z, x.w, acc[v].w);
+                acc[v].x    = fmaf(-g.y, x.y, acc[v].x);
+                acc[v].y    = fmaf(g.y, x.x, acc[v].y);
+                acc[v].z    = fmaf(-g.w, x.w, acc[v].z);
+                acc[v].w    = fmaf(g.w, x.z, acc[v].w);
+                if (v == 0)
+                    dny         = fmaf(g.y, x.y, dny);
+            }
+        }
+
+        __syncthreads();            /* everyone is done with stage s: refill it */
+        if ((tid == 0) && (it + NS < n_iter))
+            issue(it + NS);
+    }
+
+    /* bin 0 holds (DC, Nyquist): both real, multiplied separately.  The complex MAC above gave
+     * x = sum(re*re - im*im), so re = x + sum(im*im), im = sum(im*im). */
+    if ((tile == 0) && (tid == 0))
+    {
+        acc[0].x   += dny;
+        acc[0].y    = dny;
+    }
+
+    float4 *yp      = reinterpret_cast<float4 *>(a.ypart + (uint64_t(jobi) * a.splits + split) * M
+                                                 + uint64_t(tile) * TB);
+    #pragma unroll
+    for (int v = 0; v < MAC_VPT; ++v)
+        yp[tid + v * T] = acc[v];
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Partial-call path (calls that do not complete whole frames, or a non-zero phase)              */
+
+/* cur[off .. off+n) = src[0 .. n) */
+__global__ void k_store(const StepArgs a)
+{
+    const Job job       = a.jobs[blockIdx.y];
+    float *cur          = a.inst[job.inst].cur;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x)
+        cur[job.off + i]    = job.src[i];
+}
+
+/* dst[m - off] = pend[m] + sum_{j <= m} cur[j] * head[m - j],  m in [off, off+n):
+ * zero latency for any call size -- the samples of the frame in progress against taps [0, F)
+ * in direct form (reference: dsp::convolve and the raising levels, Convolver.cpp:251-262,295). */
+__global__ void k_partial(const StepArgs a)
+{
+    const Job job       = a.jobs[blockIdx.y];
+    const InstDesc &d   = a.inst[job.inst];
+    const float *cur    = d.cur;
+    const float *head   = d.head;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x)
+    {
+        uint32_t m      = job.off + i;
+        double total    = 0.0;
+        for (uint32_t j0 = 0; j0 <= m; j0 += 128)
+        {
+            uint32_t j1     = min(j0 + 128, m + 1);
+            float part      = 0.0f;
+            for (uint32_t j = j0; j < j1; ++j)
+                part            = fmaf(cur[j], head[m - j], part);
+            total          += double(part);
+        }
+        job.dst[i]      = d.pend[m] + float(total);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* init helpers                                                                                 */
+
+/* G[q][k] = H[q][k] + (-1)^k H[q-1][k],  q = 0 .. bins, H[-1] = H[bins] = 0.  Packed bin 0 is
+ * (DC, Nyquist = bin M), both even, so it takes '+' like every even bin. */
+__global__ void k_fold(float2 *G, const float2 *H, uint32_t bins, uint32_t M)
+{
+    uint32_t q          = blockIdx.y;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < M; k += gridDim.x * blockDim.x)
+    {
+        float2 cur      = (q < bins) ? H[uint64_t(q) * M + k] : make_float2(0.0f, 0.0f);
+        float2 prev     = (q > 0) ? H[uint64_t(q - 1) * M + k] : make_float2(0.0f, 0.0f);
+        float sgn       = (k & 1) ? -1.0f : 1.0f;
+        G[uint64_t(q) * M + k] = make_float2(cur.x + sgn * prev.x, cur.y + sgn * prev.y);
+    }
+}
+
+/* dst[i] += add[i] (fastconv_apply accumulates) */
+__global__ void k_accumulate(float *dst, const float *add, uint64_t total)
+{
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += uint64_t(gridDim.x) * blockDim.x)
+        dst[i]     += add[i];
+}
+
+/* packed spectrum product for the fastconv primitives: y = a * b, bin 0 component-wise */
+__global__ void k_cmul(float2 *y, const float2 *a, const float2 *b, uint32_t M, uint64_t total)
+{
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += uint64_t(gridDim.x) * blockDim.x)
+    {
+        float2 u = a[i], v = b[i];
+        y[i]    = ((i % M) == 0) ? make_float2(u.x * v.x, u.y * v.y) : cmul(u, v);
+    }
+}
+
+} /* namespace b200conv */

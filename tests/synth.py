@@ -36,3 +36,16 @@ def utest_large(seed=7):
     src = np.zeros(0x20 + ir.size, dtype=np.float32)
     src[:0x20] = rng.uniform(-1.0, 1.0, 0x20).astype(np.float32)
     return ir, src
+
+
+def equals_relative(a, b, tol):
+    """lsp-test-fw's FloatBuffer::equals_relative as used at convolver.cpp:123 (recalled: the
+    test framework is not in the reference tree): when either value is exactly zero the other
+    must be below `tol` in magnitude, otherwise |a/b - 1| < tol."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    zero = (a == 0.0) | (b == 0.0)
+    ok_zero = np.maximum(np.abs(a), np.abs(b)) < tol
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ok_rel = np.abs(a / np.where(b == 0.0, 1.0, b) - 1.0) < tol
+    return bool(np.all(np.where(zero, ok_zero, ok_rel)))

@@ -1,0 +1,72 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and
+exports every symbol include/b200conv.h declares.  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import __graft_entry__ as ge
+
+ROOT = ge.ROOT
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    p = ge.load()
+    p.build()
+    return p
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200conv.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200conv_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_declares_the_convolver_surface():
+    names = declared_symbols()
+    for need in ("b200conv_create", "b200conv_free", "b200conv_init", "b200conv_init_range",
+                 "b200conv_destroy", "b200conv_process", "b200conv_process_device",
+                 "b200conv_data_size", "b200conv_rank", "b200conv_fastconv_parse",
+                 "b200conv_fastconv_apply", "b200conv_fastconv_parse_apply",
+                 "b200conv_fastconv_restore"):
+        assert need in names
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    # and the Python mirror binds exactly that set
+    assert sorted(pkg._SIGNATURES) == declared_symbols()
+
+
+def test_no_cpu_fallback_without_a_device(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.B200ConvError) as e:
+        pkg.ConvolverBatch(1, 0)
+    assert e.value.code == pkg.ERR_CUDA
+    # queries on a NULL handle are harmless
+    assert pkg.lib().b200conv_rank(None, 0) == 0
+    assert pkg.lib().b200conv_version().startswith(b"b200conv")
+
+
+def test_library_is_sm100a_sass(pkg):
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-lelf", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package may reference it."""
+    for dirpath, _, files in os.walk(ge.PKG_DIR):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, f)

@@ -1,0 +1,305 @@
+"""GPU parity: the CUDA engine, through the C ABI, against the CPU oracle (same seeded inputs).
+
+Tolerance (BASELINE.json north_star): max |gpu - ref| <= 1e-5 of the reference peak
+(<= -100 dB), zero latency, frame boundaries at the same sample indices.  Shapes mirror the
+reference's own unit test src/test/utest/util/convolver.cpp and the BASELINE configs.
+"""
+import numpy as np
+import pytest
+
+import synth
+from oracle.bindings import CpuConvolver, direct_convolve
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as ge
+    p = ge.load()
+    p.lib()         # fails loudly when the CUDA library has not been built
+    return p
+
+
+def rel_err(got, want):
+    return float(np.max(np.abs(np.asarray(got, np.float64) - want)) / np.max(np.abs(want)))
+
+
+def oracle_run(ir, src, rank, phase, step):
+    c = CpuConvolver("oracle")
+    assert c.init(ir, rank, phase)
+    return c.run(src, step)
+
+
+# ---- the reference's own unit test, re-expressed against the GPU engine ----------------------
+
+def test_utest_small(pkg):
+    # convolver.cpp:88-136 : rel 1e-4 vs naive direct convolution, calls of 31
+    ir, src = synth.utest_small()
+    c = pkg.Convolver(0)
+    assert c.init(ir, 9, 0.0)
+    out = c.run(src, 31)
+    want = direct_convolve(src, ir, src.size)
+    assert synth.equals_relative(out, want, 1e-4)
+    assert rel_err(out, want) <= TOL
+    c.destroy()
+    assert c.rank() == 0 and c.data_size() == 0
+
+
+def test_utest_large(pkg):
+    # convolver.cpp:184-223 : abs 1e-4, 8192 taps, rank 10, calls of 31
+    ir, src = synth.utest_large()
+    c = pkg.Convolver(0)
+    assert c.init(ir, 10, 0.0)
+    out = c.run(src, 31)
+    assert np.max(np.abs(out - direct_convolve(src, ir, src.size))) <= 1e-4
+    assert rel_err(out, oracle_run(ir, src, 10, 0.0, 31).astype(np.float64)) <= TOL
+
+
+def test_utest_collisions_subsampled(pkg):
+    # convolver.cpp:138-182 (disabled upstream): 65536 taps, rank 10, calls of 127, abs 1e-5,
+    # tail flushed with data_size()-1 zeros.  Larger calls here keep the runtime bounded; one
+    # offset also runs with the original 127-sample calls.
+    rng = np.random.Generator(np.random.PCG64(11))
+    L = 0x10000
+    ir = rng.uniform(-1.0, 1.0, L).astype(np.float32)
+    for i, step in ((1, 127 * 64), (513, 127 * 64), (40000, 127 * 64), (4095, 127)):
+        c = pkg.Convolver(0)
+        assert c.init(ir, 10, 0.0)
+        total = L + c.data_size() - 1
+        if step == 127:
+            total = 3 * 4096      # bounded: 127-sample calls are ~100 kernel launches each
+        src = np.zeros(total, dtype=np.float32)
+        src[0] = 1.0
+        src[i] = 1.0
+        out = c.run(src, step)
+        want = direct_convolve(src[:L], ir)[:total]
+        assert np.max(np.abs(out - want)) <= 1e-5, (i, step)
+
+
+def test_api_contract(pkg):
+    c = pkg.Convolver(0)
+    x = synth.noise(0, 300)
+    assert not c.process(x).any()                               # Convolver.cpp:219-223
+    assert c.init(np.ones(10, np.float32), 3, 0.0) and c.rank() == 8        # :87
+    assert c.init(np.ones(10, np.float32), 20, 0.0) and c.rank() == 16
+    assert c.data_size() == 10
+    assert c.init(np.zeros(0, np.float32), 10, 0.0)             # :80-84
+    assert c.rank() == 0 and c.data_size() == 0
+    assert not c.process(x).any()
+    c.init(np.ones(4, np.float32), 8, 0.0)
+    assert c.process(np.zeros(0, np.float32)).size == 0
+
+
+@pytest.mark.parametrize("taps,rank,phase,step", [(65536, 11, 0.0, 1024), (65536, 11, 0.37, 1000),
+                                                  (5000, 8, 0.0, 77), (5000, 16, 0.5, 4096),
+                                                  (70000, 13, 0.9, 333), (200, 12, 0.0, 256),
+                                                  (129, 9, 0.0, 64), (1, 8, 0.0, 5),
+                                                  (9000, 14, 0.0, 8192), (40000, 15, 0.1, 16384),
+                                                  (40000, 16, 0.0, 32768), (3000, 10, 0.0, 512),
+                                                  (3000, 12, 0.5, 2048)])
+def test_matches_oracle_any_rank_phase_call_size(pkg, taps, rank, phase, step):
+    ir = synth.decaying_ir(3, taps)
+    n = min(3 * taps + 500, 90000)
+    if step >= 4096:
+        n = ((n + step - 1) // step) * step
+    src = synth.noise(3, n)
+    c = pkg.Convolver(0)
+    assert c.init(ir, rank, phase)
+    out = c.run(src, step)
+    want = oracle_run(ir, src, rank, phase, step)
+    truth = direct_convolve(src, ir, src.size)
+    assert rel_err(out, want.astype(np.float64)) <= TOL
+    assert rel_err(out, truth) <= TOL
+    assert c.state()["frame_off"] == (int(np.float32(phase) * np.float32(1 << (c.rank() - 1)))
+                                      + src.size) % (1 << (c.rank() - 1))
+
+
+def test_golden_fixtures(pkg, golden):
+    """Outputs frozen from the reference's Convolver.cpp compiled verbatim (tests/golden)."""
+    for name in sorted({k.split(".")[0] for k in golden.files}):
+        rank, phase, step, eff_rank, size = golden[name + ".meta"]
+        c = pkg.Convolver(0)
+        assert c.init(golden[name + ".ir"], int(rank), float(phase))
+        assert (c.rank(), c.data_size()) == (int(eff_rank), int(size))
+        out = c.run(golden[name + ".src"], int(step))
+        want = golden[name + ".dst"].astype(np.float64)
+        assert rel_err(out, want) <= TOL, name
+
+
+def test_inplace_and_random_call_sizes(pkg):
+    ir = synth.decaying_ir(5, 5000)
+    src = synth.noise(5, 12000)
+    rng = np.random.Generator(np.random.PCG64(3))
+    c = pkg.Convolver(0)
+    assert c.init(ir, 9, 0.37)
+    buf = src.copy()
+    i = 0
+    while i < buf.size:
+        n = int(rng.integers(1, 700))
+        c.process(buf[i:i + n], out=buf[i:i + n])           # dst == src
+        i += n
+    assert rel_err(buf, direct_convolve(src, ir, src.size)) <= TOL
+
+
+# ---- batches ------------------------------------------------------------------------------------
+
+def test_config1_mono_65536_taps_1024_blocks(pkg):
+    # BASELINE config 1 (shortened to 3 s of input + the reference's flush of L-1 zeros)
+    L, rank, step = 65536, 11, 1024
+    ir = synth.decaying_ir(0, L)
+    x = synth.noise(0, 3 * 48000)
+    total = ((x.size + L - 1 + step - 1) // step) * step
+    src = np.zeros(total, np.float32)
+    src[:x.size] = x
+    c = pkg.Convolver(0)
+    assert c.init(ir, rank, 0.0)
+    out = c.run(src, step)
+    assert rel_err(out, oracle_run(ir, src, rank, 0.0, step).astype(np.float64)) <= TOL
+    assert rel_err(out, direct_convolve(src, ir, src.size)) <= TOL
+
+
+def test_config2_stereo_phases_256_blocks(pkg):
+    # BASELINE config 2 (IR shortened to 1 s): two instances, phases 0 and 0.5, rank 9 and 8
+    for rank in (9, 8):
+        L, step, n = 48000, 256, 256 * 400
+        b = pkg.ConvolverBatch(2, 0)
+        irs = [synth.decaying_ir(c, L) for c in range(2)]
+        src = np.stack([synth.noise(c, n) for c in range(2)])
+        for c, ph in enumerate((0.0, 0.5)):
+            assert b.init(c, irs[c], rank, ph)
+        out = np.empty_like(src)
+        for i in range(0, n, step):
+            out[:, i:i + step] = b.process(src[:, i:i + step])
+        for c, ph in enumerate((0.0, 0.5)):
+            assert rel_err(out[c], oracle_run(irs[c], src[c], rank, ph, step).astype(np.float64)) <= TOL
+            assert rel_err(out[c], direct_convolve(src[c], irs[c], n)) <= TOL
+        b.close()
+
+
+def test_config3_batch_subset(pkg):
+    # BASELINE config 3 at full IR length on 4 of the 64 channels (the CPU oracle is slow):
+    # 480000-tap IRs, rank 11, 1024-sample calls
+    L, rank, step, nblk, n = 480000, 11, 1024, 96, 4
+    b = pkg.ConvolverBatch(n, 0)
+    irs = [synth.decaying_ir(c, L) for c in range(n)]
+    src = np.stack([synth.noise(c, nblk * step) for c in range(n)])
+    for c in range(n):
+        assert b.init(c, irs[c], rank, 0.0)
+        assert b.state(c)["bins"] == 469
+    out = np.empty_like(src)
+    for i in range(0, nblk * step, step):
+        out[:, i:i + step] = b.process(src[:, i:i + step])
+    for c in range(n):
+        assert rel_err(out[c], oracle_run(irs[c], src[c], rank, 0.0, step).astype(np.float64)) <= TOL
+    b.close()
+
+
+def test_ragged_batch_mixed_lengths_and_uninitialised(pkg):
+    # ragged IR lengths in one batch, one instance never initialised, one destroyed mid-stream
+    rank, step, n = 10, 512, 512 * 12
+    lens = [1, 511, 512, 513, 7000, 0, 30000]
+    b = pkg.ConvolverBatch(len(lens), 0)
+    irs = [synth.decaying_ir(c, L) if L else None for c, L in enumerate(lens)]
+    src = np.stack([synth.noise(c, n) for c in range(len(lens))])
+    for c, ir in enumerate(irs):
+        if ir is not None:
+            assert b.init(c, ir, rank, 0.0)
+    out = np.empty_like(src)
+    half = n // 2
+    for i in range(0, half, step):
+        out[:, i:i + step] = b.process(src[:, i:i + step])
+    b.destroy(1)
+    for i in range(half, n, step):
+        out[:, i:i + step] = b.process(src[:, i:i + step])
+    for c, ir in enumerate(irs):
+        if ir is None:
+            assert not out[c].any()
+        elif c == 1:
+            assert rel_err(out[c][:half], direct_convolve(src[c][:half], ir, half)) <= TOL
+            assert not out[c][half:].any()
+        else:
+            assert rel_err(out[c], direct_convolve(src[c], ir, n)) <= TOL
+    # a different rank in a live batch is refused
+    with pytest.raises(pkg.B200ConvError):
+        b.init(5, np.ones(10, np.float32), 12, 0.0)
+    b.close()
+
+
+def test_reinit_discards_history(pkg):
+    ir1, ir2 = synth.decaying_ir(1, 4000), synth.decaying_ir(2, 900)
+    x = synth.noise(9, 4096)
+    c = pkg.Convolver(0)
+    assert c.init(ir1, 9, 0.0)
+    c.run(x, 256)
+    assert c.init(ir2, 9, 0.25)                 # Convolver.cpp:108-110: slab zeroed
+    out = c.run(x, 100)
+    assert rel_err(out, direct_convolve(x, ir2, x.size)) <= TOL
+
+
+def test_partition_range_shards_sum_to_full(pkg):
+    # SURVEY 8e / BASELINE config 5 in miniature: one IR split by partition range over 3 shards
+    rank, F, L, n, step = 9, 256, 9000, 256 * 40, 256
+    ir, x = synth.decaying_ir(2, L), synth.noise(2, n)
+    bins = (L + F - 1) // F
+    cuts = [0, 10, 23, bins]
+    total = np.zeros(n, np.float64)
+    for a, e in zip(cuts[:-1], cuts[1:]):
+        b = pkg.ConvolverBatch(1, 0)
+        assert b.init(0, ir[a * F:e * F], rank, 0.0, part_offset=a)
+        out = np.concatenate([b.process(x[None, i:i + step])[0] for i in range(0, n, step)])
+        total += out
+        b.close()
+    assert rel_err(total, direct_convolve(x, ir, n)) <= TOL
+
+
+def test_linearity_and_impulse_at_full_size(pkg):
+    """Size-independent properties on a full-length (10 s) IR: an impulse returns the IR itself
+    (bit-aligned: zero latency), and the response to a sum is the sum of the responses."""
+    L, rank, step = 480000, 11, 1024
+    ir = synth.decaying_ir(7, L)
+    nblk = 40
+    n = nblk * step
+    imp = np.zeros(n, np.float32)
+    imp[5] = 1.0
+    a, bsig = synth.noise(1, n), synth.noise(2, n)
+    batch = pkg.ConvolverBatch(4, 0)
+    for c in range(4):
+        assert batch.init(c, ir, rank, 0.0)
+    src = np.stack([imp, a, bsig, a + bsig])
+    out = np.empty_like(src)
+    for i in range(0, n, step):
+        out[:, i:i + step] = batch.process(src[:, i:i + step])
+    peak = np.abs(ir).max()
+    assert np.max(np.abs(out[0][5:] - ir[:n - 5])) <= TOL * peak
+    assert np.max(np.abs(out[0][:5])) <= TOL * peak          # nothing before the impulse (fp32 FFT noise only)
+    assert np.max(np.abs(out[1] + out[2] - out[3])) <= 4 * TOL * np.abs(out[3]).max()
+    batch.close()
+
+
+def test_device_pointer_api_and_stats(pkg):
+    torch = pytest.importorskip("torch")
+    n, L, rank, F, nblk = 8, 20000, 11, 1024, 24
+    b = pkg.ConvolverBatch(n, 0)
+    irs = [synth.decaying_ir(c, L) for c in range(n)]
+    for c in range(n):
+        assert b.init(c, irs[c], rank, 0.0)
+    src = np.stack([synth.noise(c, nblk * F) for c in range(n)])
+    dsrc = torch.from_numpy(src).cuda()
+    ddst = torch.empty_like(dsrc)
+    torch.cuda.synchronize()
+    b.reset_stats()
+    stride = dsrc.shape[1]
+    for i in range(nblk):
+        b.process_device(ddst.data_ptr() + 4 * i * F, dsrc.data_ptr() + 4 * i * F, stride, F)
+    b.sync()
+    st = b.stats()
+    assert st["launches"] == 3 * nblk and st["mac_launches"] == nblk
+    bins = (L + F - 1) // F
+    assert st["mac_algo_bytes"] == nblk * n * (16 * F * bins + 24 * F)
+    out = ddst.cpu().numpy()
+    for c in range(n):
+        assert rel_err(out[c], direct_convolve(src[c], irs[c], nblk * F)) <= TOL
+    b.close()

@@ -16,12 +16,7 @@ HAVE_REF = CpuConvolver.available("reference")
 IMPLS = ["oracle"] + (["reference"] if HAVE_REF else [])
 
 
-def equals_relative(a, b, tol):
-    """FloatBuffer::equals_relative as used at convolver.cpp:123 (|a-b| <= tol * max(|a|,|b|))."""
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
-    scale = np.maximum(np.abs(a), np.abs(b))
-    return bool(np.all(np.abs(a - b) <= tol * np.maximum(scale, 1e-30) + 1e-12))
+equals_relative = synth.equals_relative
 
 
 @pytest.mark.parametrize("impl", IMPLS)
