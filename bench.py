@@ -164,6 +164,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--bias", type=int, default=3)
+    ap.add_argument("--pdl", type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -195,7 +198,11 @@ def main():
     pkg = ge.load()
     pkg.lib()
     batch = pkg.ConvolverBatch(INSTANCES, device=local_rank)
-    batch.set_tuning(args.splits, args.stages)
+    batch.set_option("mac_splits", args.splits)
+    batch.set_option("mac_stages", args.stages)
+    batch.set_option("fused", args.fused)
+    batch.set_option("fft_bias", args.bias)
+    batch.set_option("pdl", args.pdl)
 
     # ---- synthetic data: decaying-noise IRs, white-noise input --------------------
     # A handful of distinct seeded IRs/inputs are cycled over the 64 instances: timing does not
@@ -305,7 +312,7 @@ def main():
             "gpu_launches": stats["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "k_mac", "launch_ms": mac_avg_ms, "launches_timed": mac_n,
+                         "kernel": "k_frame<11>" if args.fused else "k_mac", "launch_ms": mac_avg_ms, "launches_timed": mac_n,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src},
         }
         if (world == 1) and (not args.no_cpu_baseline):

@@ -132,9 +132,14 @@ int     b200conv_get_profile(b200conv_batch_t *h, double *mac_ms, uint64_t *mac_
 /* The batch's own CUDA stream (cudaStream_t), for callers that time with CUDA events. */
 void   *b200conv_stream(b200conv_batch_t *h);
 
-/* Tuning knobs of the partition MAC kernel (0 = automatic): partition splits per
- * instance-frame, shared-memory pipeline stages. */
-int     b200conv_set_tuning(b200conv_batch_t *h, int mac_splits, int mac_stages);
+/* Tuning / A-B knobs (value 0 = automatic unless stated):
+ *   "mac_splits"  partition splits per instance-frame (1..32)
+ *   "mac_stages"  shared-memory pipeline stages of the MAC stream (2..12)
+ *   "fused"       1 (default) = ranks 8..11 run FFT + MAC + IFFT as ONE launch per block
+ *                 (k_frame); 0 = always three launches (k_fwd, k_mac, k_inv)
+ *   "fft_bias"    partitions taken off the split that also transforms the input (default 3)
+ *   "pdl"         1 (default) = programmatic dependent launch between consecutive blocks */
+int     b200conv_set_option(b200conv_batch_t *h, const char *name, int value);
 
 /* ---- the fastconv primitives on the device (lsp::dsp:: contract) ---------- */
 

@@ -82,7 +82,7 @@ _SIGNATURES = {
     "b200conv_set_profiling": (ctypes.c_int, [_VP, ctypes.c_int]),
     "b200conv_get_profile": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
     "b200conv_stream": (_VP, [_VP]),
-    "b200conv_set_tuning": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int]),
+    "b200conv_set_option": (ctypes.c_int, [_VP, ctypes.c_char_p, ctypes.c_int]),
     "b200conv_fastconv_parse": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_fastconv_apply": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_fastconv_parse_apply": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _VP, _SZ, _SZ, _VP]),
@@ -193,8 +193,9 @@ class ConvolverBatch:
     def stream(self):
         return lib().b200conv_stream(self._h)
 
-    def set_tuning(self, mac_splits=0, mac_stages=0):
-        _check(lib().b200conv_set_tuning(self._h, mac_splits, mac_stages))
+    def set_option(self, name, value):
+        """Tuning / A-B knobs, see b200conv_set_option in include/b200conv.h."""
+        _check(lib().b200conv_set_option(self._h, name.encode(), int(value)))
 
     def close(self):
         if self._h:

@@ -138,7 +138,8 @@ static MacPlan plan_mac(uint32_t rank, uint32_t jobs, uint32_t max_nq, int sm_co
     p.sh.NS         = (tune_stages > 0) ? uint32_t(tune_stages) : 3;
     p.tiles         = M / p.sh.TB;
     p.threads       = p.sh.TB / (2 * MAC_VPT);
-    p.smem          = size_t(2) * p.sh.NS * p.sh.QB * p.sh.TB * sizeof(float2) + p.sh.NS * sizeof(uint64_t);
+    p.sh.bias       = 0;
+    p.smem          = size_t(2) * p.sh.NS * p.sh.QB * p.sh.TB * sizeof(float2) + p.sh.NS * sizeof(uint64_t) + 16;
 
     uint32_t splits;
     if (tune_splits > 0)
@@ -172,6 +173,46 @@ static cudaError_t launch_mac_raw(const StepArgs &a, const MacPlan &p, uint32_t 
     dim3 grid(jobs * p.splits, p.tiles);
     k_mac<<<grid, p.threads, p.smem, st>>>(a, p.sh);
     return cudaGetLastError();
+}
+
+template <int RANK>
+static cudaError_t launch_frame_r(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
+                                  bool pdl, cudaStream_t st)
+{
+    static size_t attr_smem[MAX_DEVICES] = { 0 };
+    int dev = current_device();
+    if (p.smem > attr_smem[dev])
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_frame<RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem));
+        if (e != cudaSuccess)
+            return e;
+        attr_smem[dev] = p.smem;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim             = dim3(jobs * p.splits);
+    cfg.blockDim            = dim3(p.threads);
+    cfg.dynamicSmemBytes    = p.smem;
+    cfg.stream              = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id              = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs               = attr;
+    cfg.numAttrs            = 1;
+    return cudaLaunchKernelEx(&cfg, k_frame<RANK>, a, p.sh, tickets);
+}
+
+static cudaError_t launch_frame(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
+                                bool pdl, cudaStream_t st)
+{
+    switch (a.rank)
+    {
+        case 8:  return launch_frame_r<8>(a, p, jobs, tickets, pdl, st);
+        case 9:  return launch_frame_r<9>(a, p, jobs, tickets, pdl, st);
+        case 10: return launch_frame_r<10>(a, p, jobs, tickets, pdl, st);
+        case 11: return launch_frame_r<11>(a, p, jobs, tickets, pdl, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -252,6 +293,8 @@ struct b200conv_batch
 
     b200conv_stats_t        stats       = {};
     int                     tune_splits = 0, tune_stages = 0;
+    int                     opt_fused   = 1, opt_bias = 3, opt_pdl = 1;
+    uint32_t               *d_tickets   = nullptr;  /* k_frame: one arrival counter per job */
 
     bool                    profiling   = false;
     std::vector<cudaEvent_t> prof_events;           /* pairs: before / after each k_mac */
@@ -260,10 +303,17 @@ struct b200conv_batch
 
 typedef b200conv_batch Batch;
 
-static cudaError_t launch_mac(Batch *b, const StepArgs &a, const MacPlan &p, uint32_t jobs, cudaStream_t st)
+static cudaError_t launch_mac(Batch *b, const StepArgs &a, const MacPlan &p, uint32_t jobs, cudaStream_t st,
+                              bool fused = false)
 {
-    if (!b->profiling)
+    auto go = [&]() -> cudaError_t
+    {
+        if (fused)
+            return launch_frame(a, p, jobs, b->d_tickets, (b->opt_pdl != 0) && (!b->profiling), st);
         return launch_mac_raw(a, p, jobs, st);
+    };
+    if (!b->profiling)
+        return go();
     while (b->prof_events.size() < b->prof_used + 2)
     {
         cudaEvent_t ev;
@@ -273,7 +323,7 @@ static cudaError_t launch_mac(Batch *b, const StepArgs &a, const MacPlan &p, uin
         b->prof_events.push_back(ev);
     }
     cudaError_t e = cudaEventRecord(b->prof_events[b->prof_used], st);
-    if (e == cudaSuccess) e = launch_mac_raw(a, p, jobs, st);
+    if (e == cudaSuccess) e = go();
     if (e == cudaSuccess) e = cudaEventRecord(b->prof_events[b->prof_used + 1], st);
     b->prof_used += 2;
     return e;
@@ -443,6 +493,8 @@ extern "C" int b200conv_create(b200conv_batch_t **out, int device, size_t instan
         CU_BRK(cudaMallocHost(&b->h_jobs, JOB_RING * sizeof(Job)));
         CU_BRK(cudaMalloc(&b->d_jobs, JOB_RING * sizeof(Job)));
         CU_BRK(cudaMemset(b->d_desc, 0, instances * sizeof(InstDesc)));
+        CU_BRK(cudaMalloc(&b->d_tickets, instances * sizeof(uint32_t)));
+        CU_BRK(cudaMemset(b->d_tickets, 0, instances * sizeof(uint32_t)));
         #undef CU_BRK
     } while (false);
 
@@ -471,6 +523,7 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     if (b->ypart)       cudaFree(b->ypart);
     if (b->d_desc)      cudaFree(b->d_desc);
     if (b->d_active)    cudaFree(b->d_active);
+    if (b->d_tickets)   cudaFree(b->d_tickets);
     if (b->d_jobs)      cudaFree(b->d_jobs);
     if (b->h_jobs)      cudaFreeHost(b->h_jobs);
     if (b->h_in)        cudaFreeHost(b->h_in);
@@ -660,13 +713,24 @@ static int process_uniform(Batch *b, float *dst, const float *src, size_t stride
     a.splits        = plan.splits;
     a.n_jobs        = nact;
     a.t_base        = b->t_batch;
+    const bool fused = (b->opt_fused != 0) && (b->rank <= 11);
+    plan.sh.bias    = fused ? uint32_t(b->opt_bias) : 0;
     for (size_t f = 0; f < frames; ++f)
     {
         a.frame0        = uint32_t(f);
-        CU(launch_fwd(a, nact, st));
-        CU(launch_mac(b, a, plan, nact, st));
-        CU(launch_inv(a, nact, st));
-        b->stats.launches       += 3;
+        if (fused)
+        {
+            /* one launch per block for all instances x partitions */
+            CU(launch_mac(b, a, plan, nact, st, true));
+            b->stats.launches       += 1;
+        }
+        else
+        {
+            CU(launch_fwd(a, nact, st));
+            CU(launch_mac(b, a, plan, nact, st));
+            CU(launch_inv(a, nact, st));
+            b->stats.launches       += 3;
+        }
         b->stats.mac_launches   += 1;
         b->stats.mac_algo_bytes += per_frame_bytes;
         b->stats.frames         += nact;
@@ -1019,12 +1083,17 @@ extern "C" void *b200conv_stream(b200conv_batch_t *b)
     return (b != nullptr) ? (void *)b->stream : nullptr;
 }
 
-extern "C" int b200conv_set_tuning(b200conv_batch_t *b, int mac_splits, int mac_stages)
+extern "C" int b200conv_set_option(b200conv_batch_t *b, const char *name, int value)
 {
-    if ((b == nullptr) || (mac_splits < 0) || (mac_splits > 32) || (mac_stages < 0) || (mac_stages > 12))
-        return fail(B200CONV_ERR_ARG, "b200conv_set_tuning: bad arguments");
-    b->tune_splits  = mac_splits;
-    b->tune_stages  = mac_stages;
+    if ((b == nullptr) || (name == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_set_option: bad arguments");
+    if (!strcmp(name, "mac_splits") && (value >= 0) && (value <= 32))       b->tune_splits = value;
+    else if (!strcmp(name, "mac_stages") && ((value == 0) || ((value >= 2) && (value <= 12)))) b->tune_stages = value;
+    else if (!strcmp(name, "fused") && (value >= 0) && (value <= 1))        b->opt_fused = value;
+    else if (!strcmp(name, "fft_bias") && (value >= 0) && (value <= 64))    b->opt_bias = value;
+    else if (!strcmp(name, "pdl") && (value >= 0) && (value <= 1))          b->opt_pdl = value;
+    else
+        return fail(B200CONV_ERR_ARG, "b200conv_set_option: unknown option or bad value: %s = %d", name, value);
     return B200CONV_OK;
 }
 

@@ -113,8 +113,9 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b)
 
 /* ------------------------------------------------------------------------------------------- */
 /* Shared-memory Stockham FFT: NH independent P-point transforms laid out back to back.         */
-/* Radix 4, with one leading radix-2 pass when log2(P) is odd.  Each pass stages its inputs in   */
-/* registers, so one buffer is enough (load, barrier, store, barrier).                          */
+/* Radix 4, with one leading radix-2 pass when log2(P) is odd.  Every pass stages its inputs in  */
+/* registers.  With a second buffer (PP) a pass is load A -> butterflies -> store B -> barrier;  */
+/* without it, load -> barrier -> store -> barrier in place.                                    */
 
 template <int RANK>
 struct FftCfg
@@ -127,15 +128,21 @@ struct FftCfg
     static constexpr int BF     = NH * P / 4;                           /* radix-4 butterflies/pass */
     static constexpr int T      = (BF >= 512) ? 512 : ((BF < 32) ? 32 : BF);
     static constexpr int BPT    = (BF + T - 1) / T;                     /* butterflies per thread   */
-    static constexpr size_t SMEM = size_t(NH) * P * sizeof(float2);
+    static constexpr bool PP    = (RANK <= 12);                         /* ping-pong work buffers   */
+    static constexpr bool TWS   = (RANK <= 12);                         /* twiddle table in smem    */
+    static constexpr int WORK   = NH * P;                               /* float2 per work buffer   */
+    static constexpr size_t SMEM = (size_t(WORK) * (PP ? 2 : 1) + (TWS ? N : 0)) * sizeof(float2);
 };
 
-template <int RANK, bool INV>
-__device__ __forceinline__ void fft_smem(float2 *sm, const float2 *__restrict__ tw, int tid)
+/* Transforms the NH sequences held in A; returns the buffer that holds the result (A or B). */
+template <int RANK, bool INV, bool PP>
+__device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *tw, int tid)
 {
     using C = FftCfg<RANK>;
     constexpr int P = C::P, T = C::T, BPT = C::BPT, NH = C::NH, N = C::N;
 
+    float2 *in  = A;
+    float2 *out = PP ? B : A;
     int Ns = 1;
     if (C::LOGP & 1)
     {
@@ -148,11 +155,12 @@ __device__ __forceinline__ void fft_smem(float2 *sm, const float2 *__restrict__ 
             if (idx < NH * P / 2)
             {
                 int h   = idx / (P / 2), j = idx % (P / 2);
-                a[i]    = sm[h * P + j];
-                b[i]    = sm[h * P + j + P / 2];
+                a[i]    = in[h * P + j];
+                b[i]    = in[h * P + j + P / 2];
             }
         }
-        __syncthreads();
+        if (!PP)
+            __syncthreads();
         #pragma unroll
         for (int i = 0; i < 2 * BPT; ++i)
         {
@@ -160,11 +168,12 @@ __device__ __forceinline__ void fft_smem(float2 *sm, const float2 *__restrict__ 
             if (idx < NH * P / 2)
             {
                 int h   = idx / (P / 2), j = idx % (P / 2);
-                sm[h * P + 2 * j]       = cadd(a[i], b[i]);
-                sm[h * P + 2 * j + 1]   = csub(a[i], b[i]);
+                out[h * P + 2 * j]      = cadd(a[i], b[i]);
+                out[h * P + 2 * j + 1]  = csub(a[i], b[i]);
             }
         }
         __syncthreads();
+        if (PP) { float2 *t = in; in = out; out = t; }
         Ns = 2;
     }
 
@@ -180,10 +189,11 @@ __device__ __forceinline__ void fft_smem(float2 *sm, const float2 *__restrict__ 
                 int h   = idx / (P / 4), j = idx % (P / 4);
                 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-                    v[i][r] = sm[h * P + j + r * (P / 4)];
+                    v[i][r] = in[h * P + j + r * (P / 4)];
             }
         }
-        __syncthreads();
+        if (!PP)
+            __syncthreads();
 
         const int step = N / (4 * Ns);          /* exp(-2 pi i k / (4 Ns)) = tw[k * step] */
         #pragma unroll
@@ -197,9 +207,9 @@ __device__ __forceinline__ void fft_smem(float2 *sm, const float2 *__restrict__ 
                 float2 x0 = v[i][0], x1 = v[i][1], x2 = v[i][2], x3 = v[i][3];
                 if (Ns > 1)
                 {
-                    float2 w1 = __ldg(&tw[k * step]);
-                    float2 w2 = __ldg(&tw[2 * k * step]);
-                    float2 w3 = __ldg(&tw[3 * k * step]);
+                    float2 w1 = tw[k * step];
+                    float2 w2 = tw[2 * k * step];
+                    float2 w3 = tw[3 * k * step];
                     if (INV)    { x1 = cmulc(x1, w1); x2 = cmulc(x2, w2); x3 = cmulc(x3, w3); }
                     else        { x1 = cmul(x1, w1);  x2 = cmul(x2, w2);  x3 = cmul(x3, w3);  }
                 }
@@ -207,7 +217,7 @@ __device__ __forceinline__ void fft_smem(float2 *sm, const float2 *__restrict__ 
                 float2 s2 = cadd(x1, x3), s3 = csub(x1, x3);
                 /* forward: rot = -i * s3 ; inverse: rot = +i * s3 */
                 float2 rot = INV ? make_float2(-s3.y, s3.x) : make_float2(s3.y, -s3.x);
-                float2 *o  = sm + h * P + ((j - k) << 2) + k;
+                float2 *o  = out + h * P + ((j - k) << 2) + k;
                 o[0]        = cadd(s0, s2);
                 o[Ns]       = cadd(s1, rot);
                 o[2 * Ns]   = csub(s0, s2);
@@ -215,29 +225,26 @@ __device__ __forceinline__ void fft_smem(float2 *sm, const float2 *__restrict__ 
             }
         }
         __syncthreads();
+        if (PP) { float2 *t = in; in = out; out = t; }
     }
+    return in;
 }
 
 /* ------------------------------------------------------------------------------------------- */
-/* k_fwd : one CTA per frame.  F real samples (zero padded to 2F) -> M packed complex bins.      */
+/* fwd_body : F real samples (zero padded to 2F) -> M packed complex bins.                       */
 /*                                                                                             */
 /* z[m] = x[2m] + i x[2m+1], m < P (the upper half of the packed sequence is the zero padding).  */
 /* Even bins of its M-point transform are FFT_P(z), odd bins are FFT_P(z * w_M^m); the real-FFT  */
 /* split then needs Z[k] and Z[M-k], which have the same parity, so the two halves never mix.    */
+/* twg = twiddle table in global memory (used next to the global loads), tw = the table the      */
+/* transform passes read (shared-memory copy when the caller staged one, else twg).              */
 
-template <int RANK>
-__global__ void __launch_bounds__(FftCfg<RANK>::T)
-k_fwd(const StepArgs a)
+template <int RANK, bool PP>
+__device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src, float2 *out,
+                                         const float2 *twg, const float2 *tw, int tid)
 {
     using C = FftCfg<RANK>;
     constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH;
-    extern __shared__ float2 sm[];
-
-    const int tid           = threadIdx.x;
-    const Job job           = fetch_job(a, blockIdx.x);
-    const float *src        = job.src;
-    float2 *out             = job.spec;
-    const float2 *tw        = a.tw;
 
     #pragma unroll 1
     for (int pass = 0; pass < 2 / NH; ++pass)
@@ -245,68 +252,100 @@ k_fwd(const StepArgs a)
         for (int m = tid; m < P; m += T)
         {
             float2 z    = make_float2(src[2 * m], src[2 * m + 1]);
-            float2 zb   = cmul(z, __ldg(&tw[2 * m]));           /* w_M^m = w_N^(2m) */
-            if (NH == 2)    { sm[m] = z; sm[P + m] = zb; }
-            else            { sm[m] = (pass == 0) ? z : zb; }
+            float2 zb   = cmul(z, twg[2 * m]);                  /* w_M^m = w_N^(2m) */
+            if (NH == 2)    { A[m] = z; A[P + m] = zb; }
+            else            { A[m] = (pass == 0) ? z : zb; }
         }
         __syncthreads();
 
-        fft_smem<RANK, false>(sm, tw, tid);
+        const float2 *R = fft_smem<RANK, false, PP>(A, B, tw, tid);
 
-        /* split post-pass over pairs (k, M-k), k = 0 .. M/2 */
-        for (int k = tid; k <= M / 2; k += T)
+        /* split post-pass over pairs (k, M-k), k = 0 .. M/2; thread 0 takes k = 0 and k = M/2 */
+        for (int k = tid; k < M / 2; k += T)
         {
+            if (k == 0)
+            {
+                if ((NH == 2) || (pass == 0))
+                {
+                    float2 z0   = R[0];                         /* Z[0]: (DC, Nyquist) */
+                    out[0]      = make_float2(z0.x + z0.y, z0.x - z0.y);
+                    float2 zh   = R[P / 2];                     /* Z[M/2] pairs with itself: X = conj(Z) */
+                    out[M / 2]  = make_float2(zh.x, -zh.y);
+                }
+                continue;
+            }
             int par     = k & 1;
             if ((NH == 1) && (par != pass))
                 continue;
-            const float2 *half  = sm + ((NH == 2) ? par * P : 0);
+            const float2 *half  = R + ((NH == 2) ? par * P : 0);
             int ik      = k >> 1;
-            int im      = (k == 0) ? 0 : (par ? (P - 1 - ik) : (P - ik));
+            int im      = par ? (P - 1 - ik) : (P - ik);
             float2 zk   = half[ik], zm = half[im];
-            if (k == 0)
-            {
-                out[0]      = make_float2(zk.x + zk.y, zk.x - zk.y);
-                continue;
-            }
             /* e = (zk + conj(zm))/2 ; o = (zk - conj(zm))/2 ; X[k] = e - i w^k o */
             float2 e    = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
             float2 o    = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
-            float2 w    = __ldg(&tw[k]);
-            float2 wo   = cmul(w, o);
+            float2 wo   = cmul(tw[k], o);
             out[k]      = make_float2(e.x + wo.y, e.y - wo.x);
-            if (k != M - k)
-            {
-                /* X[M-k] = conj(e) - i conj(w) conj(o) = conj(e) - i conj(wo) */
-                out[M - k]  = make_float2(e.x - wo.y, -e.y - wo.x);
-            }
+            /* X[M-k] = conj(e) - i conj(w) conj(o) = conj(e) - i conj(wo) */
+            out[M - k]  = make_float2(e.x - wo.y, -e.y - wo.x);
         }
         if (NH == 1)
             __syncthreads();
     }
 }
 
-/* ------------------------------------------------------------------------------------------- */
-/* k_inv : one CTA per frame.  Sums the MAC's partial rows, merges the packed spectrum back into  */
-/* the P-point even/odd sub-sequences, runs two inverse FFTs and combines only the first F of the */
-/* 2F output samples (the second half is time-aliased garbage in the folded-overlap form).        */
-/* INV_FULL also emits samples [F, 2F) (used by the fastconv primitives).                          */
-
 template <int RANK>
 __global__ void __launch_bounds__(FftCfg<RANK>::T)
-k_inv(const StepArgs a)
+k_fwd(const StepArgs a)
+{
+    using C = FftCfg<RANK>;
+    extern __shared__ float2 sm[];
+    float2 *A               = sm;
+    float2 *B               = C::PP ? sm + C::WORK : nullptr;
+    const float2 *tw        = a.tw;
+    if (C::TWS)
+    {
+        float2 *tws         = sm + C::WORK * (C::PP ? 2 : 1);
+        for (int i = threadIdx.x; i < C::N; i += C::T)
+            tws[i]              = a.tw[i];
+        tw                  = tws;          /* visible after fwd_body's first barrier */
+    }
+    const Job job           = fetch_job(a, blockIdx.x);
+    fwd_body<RANK, C::PP>(A, B, job.src, job.spec, a.tw, tw, threadIdx.x);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* inv_body : sums the MAC's partial rows, merges the packed spectrum back into the P-point      */
+/* even/odd sub-sequences, runs two inverse FFTs and combines only the first F of the 2F output  */
+/* samples (the second half is time-aliased garbage in the folded-overlap form).  `full` also    */
+/* emits samples [F, 2F) (used by the fastconv primitives).                                      */
+
+template <int RANK>
+__device__ __forceinline__ float2 sum_rows(const float2 *yp, uint32_t splits, uint32_t k)
+{
+    constexpr uint32_t M = FftCfg<RANK>::M;
+    float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, s2 = s0, s3 = s0;
+    uint32_t s = 0;
+    for ( ; s + 4 <= splits; s += 4)
+    {
+        float2 v0 = __ldcg(&yp[uint64_t(s) * M + k]);
+        float2 v1 = __ldcg(&yp[uint64_t(s + 1) * M + k]);
+        float2 v2 = __ldcg(&yp[uint64_t(s + 2) * M + k]);
+        float2 v3 = __ldcg(&yp[uint64_t(s + 3) * M + k]);
+        s0 = cadd(s0, v0); s1 = cadd(s1, v1); s2 = cadd(s2, v2); s3 = cadd(s3, v3);
+    }
+    for ( ; s < splits; ++s)
+        s0 = cadd(s0, __ldcg(&yp[uint64_t(s) * M + k]));
+    return cadd(cadd(s0, s1), cadd(s2, s3));
+}
+
+template <int RANK, bool PP>
+__device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp, uint32_t splits,
+                                         float *dst, const float2 *twg, const float2 *tw, bool full, int tid)
 {
     using C = FftCfg<RANK>;
     constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH, N = C::N;
-    extern __shared__ float2 sm[];
-
-    const int tid           = threadIdx.x;
-    const Job job           = fetch_job(a, blockIdx.x);
-    float *dst              = job.dst;
-    const float2 *tw        = a.tw;
-    const float2 *yp        = a.ypart + uint64_t(blockIdx.x) * a.splits * M;
-    const uint32_t splits   = a.splits;
     const float scale       = 1.0f / float(N);
-    const bool full         = (a.flags & INV_FULL) != 0;
 
     #pragma unroll 1
     for (int pass = 0; pass < 2 / NH; ++pass)
@@ -314,42 +353,38 @@ k_inv(const StepArgs a)
         /* with one resident half the odd half goes first and is parked in dst */
         const int want = (NH == 1) ? (1 - pass) : 0;
 
-        for (int k = tid; k <= M / 2; k += T)
+        for (int k = tid; k < M / 2; k += T)
         {
+            if (k == 0)
+            {
+                if ((NH == 2) || (want == 0))
+                {
+                    /* (DC, Nyquist) -> Z[0] = (DC + Ny) + i (DC - Ny);  Z[M/2] = 2 conj(Y[M/2]) */
+                    float2 y0   = sum_rows<RANK>(yp, splits, 0);
+                    float2 yh   = sum_rows<RANK>(yp, splits, M / 2);
+                    A[0]        = make_float2(y0.x + y0.y, y0.x - y0.y);
+                    A[P / 2]    = make_float2(2.0f * yh.x, -2.0f * yh.y);
+                }
+                continue;
+            }
             int par     = k & 1;
             if ((NH == 1) && (par != want))
                 continue;
-            float2 *half = sm + ((NH == 2) ? par * P : 0);
-            float2 yk   = make_float2(0.0f, 0.0f), ym = make_float2(0.0f, 0.0f);
-            for (uint32_t s = 0; s < splits; ++s)
-            {
-                yk          = cadd(yk, yp[uint64_t(s) * M + k]);
-                if ((k != 0) && (k != M - k))
-                    ym          = cadd(ym, yp[uint64_t(s) * M + (M - k)]);
-            }
-            if (k == 0)
-            {
-                /* (DC, Nyquist) -> Z[0] = (DC + Ny) + i (DC - Ny) */
-                half[0]     = make_float2(yk.x + yk.y, yk.x - yk.y);
-                continue;
-            }
-            if (k == M - k)
-                ym          = yk;
+            float2 *half = A + ((NH == 2) ? par * P : 0);
+            float2 yk   = sum_rows<RANK>(yp, splits, k);
+            float2 ym   = sum_rows<RANK>(yp, splits, M - k);
             /* e = yk + conj(ym) ; o = conj(w^k) (yk - conj(ym)) ; Z[k] = e + i o ; Z[M-k] = conj(e) + i conj(o) */
             float2 e    = make_float2(yk.x + ym.x, yk.y - ym.y);
             float2 df   = make_float2(yk.x - ym.x, yk.y + ym.y);
-            float2 o    = cmulc(df, __ldg(&tw[k]));
+            float2 o    = cmulc(df, twg[k]);
             int ik      = k >> 1;
+            int im      = par ? (P - 1 - ik) : (P - ik);
             half[ik]    = make_float2(e.x - o.y, e.y + o.x);
-            if (k != M - k)
-            {
-                int im      = par ? (P - 1 - ik) : (P - ik);
-                half[im]    = make_float2(e.x + o.y, o.x - e.y);
-            }
+            half[im]    = make_float2(e.x + o.y, o.x - e.y);
         }
         __syncthreads();
 
-        fft_smem<RANK, true>(sm, tw, tid);
+        const float2 *R = fft_smem<RANK, true, PP>(A, B, tw, tid);
 
         /* z[m] = (A[m] + conj(w_M^m) B[m]) / N ; z[m + P] = (A[m] - conj(w_M^m) B[m]) / N */
         for (int m = tid; m < P; m += T)
@@ -357,22 +392,22 @@ k_inv(const StepArgs a)
             float2 lo, hi;
             if (NH == 2)
             {
-                float2 av   = sm[m];
-                float2 bv   = cmulc(sm[P + m], __ldg(&tw[2 * m]));
+                float2 av   = R[m];
+                float2 bv   = cmulc(R[P + m], tw[2 * m]);
                 lo          = make_float2((av.x + bv.x) * scale, (av.y + bv.y) * scale);
                 hi          = make_float2((av.x - bv.x) * scale, (av.y - bv.y) * scale);
             }
             else if (pass == 0)
             {
                 /* park conj(w) B / N where the result will go; the same thread reads it back */
-                float2 bv   = cmulc(sm[m], __ldg(&tw[2 * m]));
+                float2 bv   = cmulc(R[m], tw[2 * m]);
                 dst[2 * m]      = bv.x * scale;
                 dst[2 * m + 1]  = bv.y * scale;
                 continue;
             }
             else
             {
-                float2 av   = sm[m];
+                float2 av   = R[m];
                 float2 pk   = make_float2(dst[2 * m], dst[2 * m + 1]);
                 lo          = make_float2(av.x * scale + pk.x, av.y * scale + pk.y);
                 hi          = make_float2(av.x * scale - pk.x, av.y * scale - pk.y);
@@ -389,6 +424,27 @@ k_inv(const StepArgs a)
         if (NH == 1)
             __syncthreads();
     }
+}
+
+template <int RANK>
+__global__ void __launch_bounds__(FftCfg<RANK>::T)
+k_inv(const StepArgs a)
+{
+    using C = FftCfg<RANK>;
+    extern __shared__ float2 sm[];
+    float2 *A               = sm;
+    float2 *B               = C::PP ? sm + C::WORK : nullptr;
+    const float2 *tw        = a.tw;
+    if (C::TWS)
+    {
+        float2 *tws         = sm + C::WORK * (C::PP ? 2 : 1);
+        for (int i = threadIdx.x; i < C::N; i += C::T)
+            tws[i]              = a.tw[i];
+        tw                  = tws;          /* visible after inv_body's first barrier */
+    }
+    const Job job           = fetch_job(a, blockIdx.x);
+    inv_body<RANK, C::PP>(A, B, a.ypart + uint64_t(blockIdx.x) * a.splits * C::M, a.splits, job.dst,
+                          a.tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -446,7 +502,38 @@ struct MacShape
     uint32_t TB;        /* bins per CTA tile                 */
     uint32_t QB;        /* partitions per stage              */
     uint32_t NS;        /* stages                            */
+    uint32_t bias;      /* k_frame: partitions taken off split 0, which also transforms the input */
 };
+
+/* Partition chunk [c0, c1) (relative to the job's first partition) of split `split`. */
+__device__ __forceinline__ void chunk_range(uint32_t nq, uint32_t split, uint32_t splits, uint32_t bias,
+                                            uint32_t &c0, uint32_t &c1)
+{
+    uint32_t even   = nq / splits;
+    if (nq < splits)
+    {
+        /* one partition each for the first nq splits: split 0 always owns partition 0 */
+        c0          = min(split, nq);
+        c1          = min(split + 1, nq);
+        return;
+    }
+    if ((splits <= 1) || (bias == 0) || (even <= bias + 1))
+    {
+        c0          = uint32_t((uint64_t(nq) * split) / splits);
+        c1          = uint32_t((uint64_t(nq) * (split + 1)) / splits);
+        return;
+    }
+    uint32_t len0   = even - bias;
+    uint32_t rest   = nq - len0;
+    if (split == 0)
+    {
+        c0          = 0;
+        c1          = len0;
+        return;
+    }
+    c0              = len0 + uint32_t((uint64_t(rest) * (split - 1)) / (splits - 1));
+    c1              = len0 + uint32_t((uint64_t(rest) * split) / (splits - 1));
+}
 
 constexpr int MAC_VPT = 2;      /* float4 columns per thread; blockDim.x = TB / (2 * MAC_VPT) */
 
@@ -475,8 +562,9 @@ k_mac(const StepArgs a, const MacShape sh)
     uint32_t qa             = max(job.qa, d.q_lo);
     uint32_t qb             = min(job.qb, d.q_lo + d.nq);
     uint32_t nq             = (qb > qa) ? (qb - qa) : 0;
-    const uint32_t q0       = qa + uint32_t((uint64_t(nq) * split) / a.splits);
-    const uint32_t q1       = qa + uint32_t((uint64_t(nq) * (split + 1)) / a.splits);
+    uint32_t c0, c1;
+    chunk_range(nq, split, a.splits, 0, c0, c1);
+    const uint32_t q0       = qa + c0, q1 = qa + c1;
     const uint32_t n_iter   = (q1 - q0 + QB - 1) / QB;
 
     const float2 *Gt        = d.G + uint64_t(tile) * TB;            /* row r at Gt + r * M */
@@ -568,6 +656,207 @@ k_mac(const StepArgs a, const MacShape sh)
     #pragma unroll
     for (int v = 0; v < MAC_VPT; ++v)
         yp[tid + v * T] = acc[v];
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* k_frame : ranks 8..11 (one bin tile per instance), whole frames for every instance -- the     */
+/* block scheduler's "one launch per block".  grid = jobs * splits, M/4 threads.                 */
+/*                                                                                             */
+/*   split 0 of each job  : transforms the input frame (fwd_body) into the ring while its first  */
+/*                          TMA stages are in flight, and handles partition q = qa (which needs   */
+/*                          that spectrum) LAST;                                                 */
+/*   every split          : streams its partition chunk exactly like k_mac and writes one        */
+/*                          partial row;                                                        */
+/*   the last split to    : (atomic ticket per job) sums the partial rows out of L2 and runs the  */
+/*   finish a job           inverse transform (inv_body) -> output block.                        */
+/*                                                                                             */
+/* Launched with programmatic stream serialisation: the prologue overlaps the previous frame's   */
+/* tail; nothing global is touched before griddepcontrol.wait.                                   */
+
+template <int RANK>
+__global__ void __launch_bounds__(FftCfg<RANK>::T)
+k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
+{
+    using C = FftCfg<RANK>;
+    constexpr uint32_t M = C::M, T = C::T, N = C::N;
+    static_assert(C::T == C::M / 4, "k_frame: FFT and MAC thread counts must agree (ranks 8..11)");
+    static_assert(C::NH == 2, "k_frame: both FFT halves resident");
+
+    extern __shared__ __align__(128) unsigned char smraw[];
+
+    const uint32_t QB       = sh.QB, NS = sh.NS;                    /* TB == M */
+    const uint32_t tid      = threadIdx.x;
+    const uint32_t jobi     = blockIdx.x / a.splits;
+    const uint32_t split    = blockIdx.x % a.splits;
+
+    /* stage s = [ G rows : stage_elems float2 | ring rows : stage_elems float2 ], back to back */
+    const uint32_t stage_elems = QB * M;                            /* 1024 float2 for ranks 8..11 */
+    float2 *stages          = reinterpret_cast<float2 *>(smraw);
+    uint64_t *full          = reinterpret_cast<uint64_t *>(stages + size_t(NS) * 2 * stage_elems);
+    uint32_t *flag          = reinterpret_cast<uint32_t *>(full + NS);
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0)
+    {
+        for (uint32_t s = 0; s < NS; ++s)
+            mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const Job job           = fetch_job(a, jobi);
+    const InstDesc d        = a.inst[job.inst];
+
+    uint32_t qa             = max(job.qa, d.q_lo);
+    uint32_t qb             = min(job.qb, d.q_lo + d.nq);
+    uint32_t nq             = (qb > qa) ? (qb - qa) : 0;
+    uint32_t c0, c1;
+    chunk_range(nq, split, a.splits, sh.bias, c0, c1);
+    const uint32_t q0       = qa + c0, q1 = qa + c1;
+    const uint32_t n_iter   = (q1 - q0 + QB - 1) / QB;
+    const bool fft_cta      = (split == 0);
+    /* the stage holding partition qa goes last in the FFT CTA */
+    const uint32_t shift    = (fft_cta && (n_iter > 1)) ? 1 : 0;
+
+    const float2 *Gt        = d.G;
+    const float2 *Xt        = d.ring;
+    const uint32_t row_bytes = M * uint32_t(sizeof(float2));
+
+    auto issue = [&](uint32_t it)
+    {
+        uint32_t s      = it % NS;
+        uint32_t stg    = (it + shift) % n_iter;
+        uint32_t q      = q0 + stg * QB;
+        uint32_t rows   = min(QB, q1 - q);
+        float2 *g       = stages + size_t(s) * 2 * stage_elems;
+        float2 *x       = g + stage_elems;
+        mbar_expect_tx(&full[s], 2u * rows * row_bytes);
+        bulk_g2s(g, Gt + uint64_t(q - d.q_lo) * M, rows * row_bytes, &full[s]);
+        uint32_t first  = uint32_t((uint64_t(job.slot0) + q) % d.S);
+        uint32_t n1     = min(rows, d.S - first);
+        bulk_g2s(x, Xt + uint64_t(first) * M, n1 * row_bytes, &full[s]);
+        if (n1 < rows)
+            bulk_g2s(x + size_t(n1) * M, Xt, (rows - n1) * row_bytes, &full[s]);
+    };
+
+    /* prologue: the FFT CTA keeps the last SCR stage buffers as transform scratch (two work
+     * buffers, and the twiddle table when a second buffer can be spared) and must not fetch its
+     * final stage yet -- that one reads the spectrum which is about to be written */
+    const uint32_t SCR      = ((NS >= 3) && (2 * stage_elems >= N)) ? 2 : 1;
+    uint32_t pre            = min(NS, n_iter);
+    if (fft_cta)
+        pre                 = (n_iter > 0) ? min(NS - SCR, n_iter - 1) : 0;
+    if (tid == 0)
+    {
+        for (uint32_t it = 0; it < pre; ++it)
+            issue(it);
+    }
+    if (fft_cta)
+    {
+        float2 *scr         = stages + size_t(NS - SCR) * 2 * stage_elems;
+        float2 *wa          = scr, *wb = scr + stage_elems;
+        const float2 *tw    = a.tw;
+        if (SCR == 2)
+        {
+            float2 *tws         = scr + 2 * stage_elems;
+            for (uint32_t i = tid; i < N; i += T)
+                tws[i]              = a.tw[i];
+            tw                  = tws;          /* visible after fwd_body's first barrier */
+        }
+        fwd_body<RANK, true>(wa, wb, job.src, job.spec, a.tw, tw, int(tid));
+        /* generic-proxy global writes -> visible to the TMA (async proxy) reads issued below */
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (uint32_t it = pre; (it < NS) && (it < n_iter); ++it)
+                issue(it);
+        }
+    }
+
+    float4 acc[MAC_VPT];
+    #pragma unroll
+    for (int v = 0; v < MAC_VPT; ++v)
+        acc[v]      = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float dny       = 0.0f;
+
+    for (uint32_t it = 0; it < n_iter; ++it)
+    {
+        uint32_t s      = it % NS;
+        uint32_t stg    = (it + shift) % n_iter;
+        uint32_t rows   = min(QB, q1 - (q0 + stg * QB));
+        mbar_wait(&full[s], (it / NS) & 1u);
+
+        const float4 *g4 = reinterpret_cast<const float4 *>(stages + size_t(s) * 2 * stage_elems);
+        const float4 *x4 = g4 + stage_elems / 2;
+        for (uint32_t r = 0; r < rows; ++r)
+        {
+            #pragma unroll
+            for (int v = 0; v < MAC_VPT; ++v)
+            {
+                float4 g    = g4[r * (M / 2) + tid + v * T];
+                float4 x    = x4[r * (M / 2) + tid + v * T];
+                acc[v].x    = fmaf(g.x, x.x, acc[v].x);
+                acc[v].y    = fmaf(g.x, x.y, acc[v].y);
+                acc[v].z    = fmaf(g.z, x.z, acc[v].z);
+                acc[v].w    = fmaf(g.z, x.w, acc[v].w);
+                acc[v].x    = fmaf(-g.y, x.y, acc[v].x);
+                acc[v].y    = fmaf(g.y, x.x, acc[v].y);
+                acc[v].z    = fmaf(-g.w, x.w, acc[v].z);
+                acc[v].w    = fmaf(g.w, x.z, acc[v].w);
+                if (v == 0)
+                    dny         = fmaf(g.y, x.y, dny);
+            }
+        }
+
+        __syncthreads();
+        if ((tid == 0) && (it + NS < n_iter))
+            issue(it + NS);
+    }
+
+    if (tid == 0)
+    {
+        acc[0].x   += dny;
+        acc[0].y    = dny;
+    }
+
+    float2 *yrow    = a.ypart + uint64_t(jobi) * a.splits * M;
+    float4 *yp      = reinterpret_cast<float4 *>(yrow + uint64_t(split) * M);
+    #pragma unroll
+    for (int v = 0; v < MAC_VPT; ++v)
+        __stcg(&yp[tid + v * T], acc[v]);
+
+    /* ticket: the last split of this job to get here finishes the frame */
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+    {
+        uint32_t old    = atomicAdd(&tickets[jobi], 1u);
+        uint32_t last   = (old == a.splits - 1) ? 1u : 0u;
+        if (last)
+            tickets[jobi]   = 0;                /* ready for the next launch */
+        *flag           = last;
+    }
+    __syncthreads();
+    if (*flag == 0)
+        return;
+    __threadfence();
+
+    /* The inverse transform is the exposed tail of the launch: twiddles go to shared memory
+     * (the stage buffers are idle now) so that its dependent loads stay on chip. */
+    float2 *wa      = stages, *wb = stages + stage_elems;
+    const float2 *tw = a.tw;
+    if ((NS >= 2) && (2 * stage_elems >= N))
+    {
+        float2 *tws     = stages + 2 * stage_elems;
+        for (uint32_t i = tid; i < N; i += T)
+            tws[i]          = a.tw[i];
+        tw              = tws;                  /* visible after inv_body's first barrier */
+    }
+    inv_body<RANK, true>(wa, wb, yrow, a.splits, job.dst, a.tw, tw, false, int(tid));
 }
 
 /* ------------------------------------------------------------------------------------------- */

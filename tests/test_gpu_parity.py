@@ -279,10 +279,12 @@ def test_linearity_and_impulse_at_full_size(pkg):
     batch.close()
 
 
-def test_device_pointer_api_and_stats(pkg):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_device_pointer_api_and_stats(pkg, fused):
     torch = pytest.importorskip("torch")
     n, L, rank, F, nblk = 8, 20000, 11, 1024, 24
     b = pkg.ConvolverBatch(n, 0)
+    b.set_option("fused", fused)
     irs = [synth.decaying_ir(c, L) for c in range(n)]
     for c in range(n):
         assert b.init(c, irs[c], rank, 0.0)
@@ -296,10 +298,39 @@ def test_device_pointer_api_and_stats(pkg):
         b.process_device(ddst.data_ptr() + 4 * i * F, dsrc.data_ptr() + 4 * i * F, stride, F)
     b.sync()
     st = b.stats()
-    assert st["launches"] == 3 * nblk and st["mac_launches"] == nblk
+    assert st["launches"] == (1 if fused else 3) * nblk and st["mac_launches"] == nblk
     bins = (L + F - 1) // F
     assert st["mac_algo_bytes"] == nblk * n * (16 * F * bins + 24 * F)
     out = ddst.cpu().numpy()
     for c in range(n):
         assert rel_err(out[c], direct_convolve(src[c], irs[c], nblk * F)) <= TOL
+    b.close()
+
+
+@pytest.mark.parametrize("rank", [8, 9, 10, 11])
+@pytest.mark.parametrize("opts", [dict(fused=1), dict(fused=0), dict(fused=1, pdl=0, fft_bias=0),
+                                  dict(fused=1, mac_splits=7, mac_stages=2),
+                                  dict(fused=1, mac_splits=1, mac_stages=5)])
+def test_one_launch_per_block_matches_three_kernel_path(pkg, rank, opts):
+    """k_frame (FFT + MAC + IFFT in one launch, ranks 8..11) against direct convolution on a ragged
+    batch: IRs shorter than the number of partition splits, exactly one frame, many frames."""
+    F = 1 << (rank - 1)
+    lens = [1, F - 1, F, F + 1, 5 * F + 3, 40 * F + 7, 0, 200 * F]
+    nblk = 24
+    b = pkg.ConvolverBatch(len(lens), 0)
+    for k, v in opts.items():
+        b.set_option(k, v)
+    irs = [synth.decaying_ir(c, L) if L else None for c, L in enumerate(lens)]
+    for c, ir in enumerate(irs):
+        if ir is not None:
+            assert b.init(c, ir, rank, 0.0)
+    src = np.stack([synth.noise(40 + c, nblk * F) for c in range(len(lens))])
+    out = np.empty_like(src)
+    for i in range(0, nblk * F, 2 * F):                      # two frames per call
+        out[:, i:i + 2 * F] = b.process(src[:, i:i + 2 * F])
+    for c, ir in enumerate(irs):
+        if ir is None:
+            assert not out[c].any()
+        else:
+            assert rel_err(out[c], direct_convolve(src[c], ir, nblk * F)) <= TOL, (c, lens[c])
     b.close()
