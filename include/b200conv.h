@@ -103,6 +103,12 @@ int     b200conv_destroy(b200conv_batch_t *h, size_t idx);
 int     b200conv_process(b200conv_batch_t *h, float *const *dst, const float *const *src,
                          size_t count);
 
+/* Same for HOST buffers laid out as one planar matrix [instances][stride] floats (row i =
+ * instance i): no per-instance pointer table, the rows go to the device with one strided copy
+ * (a true DMA when the matrix is page-locked).  dst == src is allowed.  Synchronous. */
+int     b200conv_process_planar(b200conv_batch_t *h, float *dst, const float *src,
+                                size_t stride, size_t count);
+
 /* Same with DEVICE buffers laid out [instances][stride] floats (row i = instance i), enqueued
  * on `stream` (a cudaStream_t; NULL = the batch's own stream) without host synchronisation.
  * dst == src is allowed.  All calls on one batch must be ordered on one stream (or be
@@ -137,7 +143,7 @@ void   *b200conv_stream(b200conv_batch_t *h);
  *   "mac_stages"  shared-memory pipeline stages of the MAC stream (2..12)
  *   "fused"       1 (default) = ranks 8..11 run FFT + MAC + IFFT as ONE launch per block
  *                 (k_frame); 0 = always three launches (k_fwd, k_mac, k_inv)
- *   "fft_bias"    partitions taken off the split that also transforms the input (default 3)
+ *   "fft_bias"    partitions taken off the split that also transforms the input (default 6)
  *   "pdl"         1 (default) = programmatic dependent launch between consecutive blocks */
 int     b200conv_set_option(b200conv_batch_t *h, const char *name, int value);
 

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "b200conv_init_range": (ctypes.c_int, [_VP, _SZ, _FP, _SZ, _SZ, ctypes.c_float, _SZ]),
     "b200conv_destroy": (ctypes.c_int, [_VP, _SZ]),
     "b200conv_process": (ctypes.c_int, [_VP, ctypes.POINTER(_FP), ctypes.POINTER(_FP), _SZ]),
+    "b200conv_process_planar": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ]),
     "b200conv_process_device": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_sync": (ctypes.c_int, [_VP]),
     "b200conv_data_size": (_SZ, [_VP, _SZ]),
@@ -141,18 +142,38 @@ class ConvolverBatch:
 
     # -- Convolver::process -------------------------------------------------------------------
     def process(self, src, out=None):
-        """Host arrays ``[instances][count]`` float32 (rows are the planar per-instance buffers)."""
-        src = np.ascontiguousarray(src, dtype=np.float32)
+        """Host arrays ``[instances][count]`` float32 (rows are the planar per-instance buffers).
+
+        Row-contiguous 2-D arrays go through ``b200conv_process_planar`` (one strided copy each
+        way); anything else through the per-instance pointer table of ``b200conv_process``."""
+        src = np.asarray(src, dtype=np.float32)
         if src.ndim == 1:
             src = src[None, :]
         assert src.shape[0] == self.instances
         if out is None:
-            out = np.empty_like(src)
+            out = np.empty(src.shape, dtype=np.float32)
         n = src.shape[1]
+        planar = (src.strides[1] == 4 and out.strides[1] == 4 and out.shape == src.shape
+                  and (self.instances == 1 or (src.strides[0] == out.strides[0] and src.strides[0] % 4 == 0
+                                               and src.strides[0] >= 4 * n)))
+        if planar:
+            stride = (src.strides[0] // 4) if self.instances > 1 else n
+            _check(lib().b200conv_process_planar(self._h, out.ctypes.data, src.ctypes.data, stride, n))
+            return out
+        src = np.ascontiguousarray(src)
+        tmp = out if out.flags.c_contiguous else np.empty(src.shape, dtype=np.float32)
         srcs = (_FP * self.instances)(*[_ptr(src[i]) for i in range(self.instances)])
-        dsts = (_FP * self.instances)(*[_ptr(out[i]) for i in range(self.instances)])
+        dsts = (_FP * self.instances)(*[_ptr(tmp[i]) for i in range(self.instances)])
         _check(lib().b200conv_process(self._h, dsts, srcs, n))
+        if tmp is not out:
+            out[...] = tmp
         return out
+
+    def process_pointers(self, dsts, srcs, count):
+        """``b200conv_process`` with explicit per-instance host arrays (any alignment)."""
+        sp = (_FP * self.instances)(*[_ptr(a) for a in srcs])
+        dp = (_FP * self.instances)(*[_ptr(a) for a in dsts])
+        _check(lib().b200conv_process(self._h, dp, sp, count))
 
     def process_device(self, dst_ptr, src_ptr, stride, count, stream=None):
         """Device pointers (ints), ``[instances][stride]`` floats; asynchronous."""

@@ -135,7 +135,7 @@ static MacPlan plan_mac(uint32_t rank, uint32_t jobs, uint32_t max_nq, int sm_co
     uint32_t M      = 1u << (rank - 1);
     p.sh.TB         = (M < 1024) ? M : 1024;
     p.sh.QB         = 1024 / p.sh.TB;
-    p.sh.NS         = (tune_stages > 0) ? uint32_t(tune_stages) : 3;
+    p.sh.NS         = (tune_stages > 0) ? uint32_t(tune_stages) : 2;      /* measured: 2 x 16 KiB beats 3 (profiles/) */
     p.tiles         = M / p.sh.TB;
     p.threads       = p.sh.TB / (2 * MAC_VPT);
     p.sh.bias       = 0;
@@ -146,8 +146,8 @@ static MacPlan plan_mac(uint32_t rank, uint32_t jobs, uint32_t max_nq, int sm_co
         splits          = uint32_t(tune_splits);
     else
     {
-        /* aim at ~4 co-resident CTAs per SM so that all chunks stream concurrently */
-        uint32_t target = 4u * uint32_t(sm_count);
+        /* aim at ~3.5 co-resident CTAs per SM so that all chunks stream concurrently (4 fit) */
+        uint32_t target = (7u * uint32_t(sm_count)) / 2u;
         uint32_t ctas   = jobs * p.tiles;
         splits          = (ctas > 0) ? (target / ctas) : 1;
     }
@@ -293,8 +293,13 @@ struct b200conv_batch
 
     b200conv_stats_t        stats       = {};
     int                     tune_splits = 0, tune_stages = 0;
-    int                     opt_fused   = 1, opt_bias = 3, opt_pdl = 1;
+    int                     opt_fused   = 1, opt_bias = 6, opt_pdl = 1;
     uint32_t               *d_tickets   = nullptr;  /* k_frame: one arrival counter per job */
+    uint32_t               *d_ring_head = nullptr;  /* k_frame: frames published per instance */
+    uint32_t               *d_stream_done = nullptr; /* k_frame: CTAs done reading the ring, cumulative */
+    uint32_t                done_prev   = 0;        /* cumulative CTAs per instance through the previous launch */
+    uint32_t                done_prev2  = 0;        /* ... through the launch before that */
+    std::vector<uint32_t>   h_ring_head;
 
     bool                    profiling   = false;
     std::vector<cudaEvent_t> prof_events;           /* pairs: before / after each k_mac */
@@ -377,8 +382,15 @@ static int upload_tables(Batch *b, cudaStream_t st)
     if (!b->desc_dirty)
         return B200CONV_OK;
     for (size_t i = 0; i < b->n; ++i)
+    {
+        b->h_ring_head[i]   = uint32_t(b->inst[i].frames);
         if (b->inst[i].active)
             b->h_desc[i].t_delta = int64_t(b->inst[i].frames) - int64_t(b->t_batch);
+    }
+    CU(cudaMemcpyAsync(b->d_ring_head, b->h_ring_head.data(), b->n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    /* the memset is a full stream dependency: every earlier launch has completed when it runs */
+    CU(cudaMemsetAsync(b->d_stream_done, 0, b->n * sizeof(uint32_t), st));
+    b->done_prev = b->done_prev2 = 0;
     /* pageable sources: cudaMemcpyAsync stages them before returning */
     CU(cudaMemcpyAsync(b->d_desc, b->h_desc.data(), b->n * sizeof(InstDesc), cudaMemcpyHostToDevice, st));
     if (!b->active.empty())
@@ -434,6 +446,8 @@ static StepArgs base_args(const Batch *b)
     a.active    = b->d_active;
     a.tw        = b->tw[b->rank];
     a.ypart     = b->ypart;
+    a.ring_head = b->d_ring_head;
+    a.stream_done = b->d_stream_done;
     a.rank      = uint32_t(b->rank);
     a.n_active  = uint32_t(b->active.size());
     a.splits    = 1;
@@ -477,6 +491,7 @@ extern "C" int b200conv_create(b200conv_batch_t **out, int device, size_t instan
     b->n        = instances;
     b->inst.resize(instances);
     b->h_desc.resize(instances);
+    b->h_ring_head.assign(instances, 0);
     memset(b->h_desc.data(), 0, instances * sizeof(InstDesc));
 
     int rc = B200CONV_OK;
@@ -495,6 +510,10 @@ extern "C" int b200conv_create(b200conv_batch_t **out, int device, size_t instan
         CU_BRK(cudaMemset(b->d_desc, 0, instances * sizeof(InstDesc)));
         CU_BRK(cudaMalloc(&b->d_tickets, instances * sizeof(uint32_t)));
         CU_BRK(cudaMemset(b->d_tickets, 0, instances * sizeof(uint32_t)));
+        CU_BRK(cudaMalloc(&b->d_stream_done, instances * sizeof(uint32_t)));
+        CU_BRK(cudaMemset(b->d_stream_done, 0, instances * sizeof(uint32_t)));
+        CU_BRK(cudaMalloc(&b->d_ring_head, instances * sizeof(uint32_t)));
+        CU_BRK(cudaMemset(b->d_ring_head, 0, instances * sizeof(uint32_t)));
         #undef CU_BRK
     } while (false);
 
@@ -524,6 +543,8 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     if (b->d_desc)      cudaFree(b->d_desc);
     if (b->d_active)    cudaFree(b->d_active);
     if (b->d_tickets)   cudaFree(b->d_tickets);
+    if (b->d_ring_head) cudaFree(b->d_ring_head);
+    if (b->d_stream_done) cudaFree(b->d_stream_done);
     if (b->d_jobs)      cudaFree(b->d_jobs);
     if (b->h_jobs)      cudaFreeHost(b->h_jobs);
     if (b->h_in)        cudaFreeHost(b->h_in);
@@ -581,7 +602,7 @@ extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float 
     const size_t F      = size_t(1) << (rank - 1);
     const size_t bins   = (count + F - 1) >> (rank - 1);    /* Convolver.cpp:93 */
     const size_t nq     = bins + 1;                         /* folded overlap: one extra row */
-    const size_t S      = part_offset + nq;
+    const size_t S      = part_offset + nq + 1;             /* one spare slot, see k_frame */
     if ((part_offset + nq) >= (size_t(1) << 31))
         return fail(B200CONV_ERR_ARG, "impulse response too long");
 
@@ -720,8 +741,12 @@ static int process_uniform(Batch *b, float *dst, const float *src, size_t stride
         a.frame0        = uint32_t(f);
         if (fused)
         {
-            /* one launch per block for all instances x partitions */
+            /* one launch per block for all instances x partitions; the ring slot it overwrites
+             * was last read by the launch before the previous one */
+            a.need_done     = b->done_prev2;
             CU(launch_mac(b, a, plan, nact, st, true));
+            b->done_prev2   = b->done_prev;
+            b->done_prev   += plan.splits;
             b->stats.launches       += 1;
         }
         else
@@ -992,6 +1017,42 @@ extern "C" int b200conv_process(b200conv_batch_t *b, float *const *dst, const fl
     return B200CONV_OK;
 }
 
+extern "C" int b200conv_process_planar(b200conv_batch_t *b, float *dst, const float *src,
+                                       size_t stride, size_t count)
+{
+    if (b == nullptr)
+        return fail(B200CONV_ERR_ARG, "b200conv_process_planar: NULL handle");
+    if (count == 0)
+        return B200CONV_OK;
+    if ((dst == nullptr) || (src == nullptr) || (stride < count))
+        return fail(B200CONV_ERR_ARG, "b200conv_process_planar: bad buffers");
+    TRY(set_device(b));
+
+    size_t cap = (size_t(1) << 24) / b->n;
+    if (cap > 65536)    cap = 65536;
+    size_t F   = (b->rank > 0) ? (size_t(1) << (b->rank - 1)) : 128;
+    if (cap < F)        cap = F;
+    cap        = (cap / F) * F;
+
+    for (size_t done = 0; done < count; )
+    {
+        size_t c = count - done;
+        if (c > cap)
+            c = cap;
+        TRY(ensure_staging(b, b->n * c));
+        CU(cudaMemcpy2DAsync(b->d_in, c * sizeof(float), src + done, stride * sizeof(float),
+                             c * sizeof(float), b->n, cudaMemcpyHostToDevice, b->stream));
+        TRY(b200conv_process_device(b, b->d_out, b->d_in, c, c, b->stream));
+        CU(cudaMemcpy2DAsync(dst + done, stride * sizeof(float), b->d_out, c * sizeof(float),
+                             c * sizeof(float), b->n, cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+        b->stats.h2d_bytes += b->n * c * sizeof(float);
+        b->stats.d2h_bytes += b->n * c * sizeof(float);
+        done += c;
+    }
+    return B200CONV_OK;
+}
+
 extern "C" int b200conv_sync(b200conv_batch_t *b)
 {
     if (b == nullptr)
@@ -1094,6 +1155,7 @@ extern "C" int b200conv_set_option(b200conv_batch_t *b, const char *name, int va
     else if (!strcmp(name, "pdl") && (value >= 0) && (value <= 1))          b->opt_pdl = value;
     else
         return fail(B200CONV_ERR_ARG, "b200conv_set_option: unknown option or bad value: %s = %d", name, value);
+    b->desc_dirty   = true;     /* the hand-shake counters are re-seeded before the next launch */
     return B200CONV_OK;
 }
 

@@ -47,6 +47,8 @@ struct Job                          /* explicit work item (general path and init
     uint32_t        slot0;          /* ring slot of X_t for this job's frame index t                */
     uint32_t        qa, qb;         /* global partition range of the MAC                            */
     uint32_t        off, n;         /* partial path: first sample index in the frame, sample count  */
+    uint32_t        tlo;            /* low 32 bits of the job's frame index t                       */
+    uint32_t        pad;
 };
 
 struct StepArgs                     /* by-value kernel argument */
@@ -56,6 +58,10 @@ struct StepArgs                     /* by-value kernel argument */
     const uint32_t *active;         /* uniform mode: instance ids                                   */
     const float2   *tw;             /* N-point twiddle table exp(-2 pi i j / N)                     */
     float2         *ypart;          /* [job][split][M] partial spectra                              */
+    uint32_t       *ring_head;      /* [instance] frames whose spectrum is in the ring (low 32 bits) */
+    uint32_t       *stream_done;    /* [instance] k_frame CTAs that finished reading the ring, cumulative */
+    uint32_t        need_done;      /* k_frame: stream_done value after which ring slot (-t) mod S is free */
+    uint32_t        pad0;
     const float    *src;            /* uniform mode: [instances][stride]                            */
     float          *dst;
     uint64_t        stride;
@@ -85,6 +91,8 @@ __device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
     uint64_t t          = uint64_t(int64_t(a.t_base) + d.t_delta) + f;
     uint32_t tm         = uint32_t(t % d.S);
     r.slot0             = (tm == 0) ? 0 : d.S - tm;
+    r.tlo               = uint32_t(t);
+    r.pad               = 0;
     r.src               = a.src + uint64_t(r.inst) * a.stride + uint64_t(f) * F;
     r.dst               = a.dst + uint64_t(r.inst) * a.stride + uint64_t(f) * F;
     r.spec              = d.ring + uint64_t(r.slot0) * F;
@@ -105,6 +113,16 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+/* L2-coherent 16-byte load; volatile so that a group of them stays in program order (all issued
+ * before the first use) instead of being sunk next to their consumers */
+__device__ __forceinline__ float4 ld_cg_f4(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 /* a * conj(b) */
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b)
 {
@@ -320,31 +338,14 @@ k_fwd(const StepArgs a)
 /* samples (the second half is time-aliased garbage in the folded-overlap form).  `full` also    */
 /* emits samples [F, 2F) (used by the fastconv primitives).                                      */
 
-template <int RANK>
-__device__ __forceinline__ float2 sum_rows(const float2 *yp, uint32_t splits, uint32_t k)
-{
-    constexpr uint32_t M = FftCfg<RANK>::M;
-    float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, s2 = s0, s3 = s0;
-    uint32_t s = 0;
-    for ( ; s + 4 <= splits; s += 4)
-    {
-        float2 v0 = __ldcg(&yp[uint64_t(s) * M + k]);
-        float2 v1 = __ldcg(&yp[uint64_t(s + 1) * M + k]);
-        float2 v2 = __ldcg(&yp[uint64_t(s + 2) * M + k]);
-        float2 v3 = __ldcg(&yp[uint64_t(s + 3) * M + k]);
-        s0 = cadd(s0, v0); s1 = cadd(s1, v1); s2 = cadd(s2, v2); s3 = cadd(s3, v3);
-    }
-    for ( ; s < splits; ++s)
-        s0 = cadd(s0, __ldcg(&yp[uint64_t(s) * M + k]));
-    return cadd(cadd(s0, s1), cadd(s2, s3));
-}
-
-template <int RANK, bool PP>
+template <int RANK, bool PP, int RG = 8>     /* RG: partial rows loaded per round (registers) */
 __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp, uint32_t splits,
                                          float *dst, const float2 *twg, const float2 *tw, bool full, int tid)
 {
     using C = FftCfg<RANK>;
     constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH, N = C::N;
+    constexpr int ITER = (M / 2) / T;           /* bins k = tid + it*T handled by this thread; even */
+    static_assert((ITER >= 2) && ((ITER & 1) == 0), "inv_body: two bins per round");
     const float scale       = 1.0f / float(N);
 
     #pragma unroll 1
@@ -353,34 +354,106 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
         /* with one resident half the odd half goes first and is parked in dst */
         const int want = (NH == 1) ? (1 - pass) : 0;
 
-        for (int k = tid; k < M / 2; k += T)
+        if (PP)
         {
-            if (k == 0)
+            /* Reduce the partial rows first, as coalesced float4 columns, into the second work
+             * buffer.  The loads are volatile asm so that a whole group is in flight before the
+             * first add: this is the exposed tail of the launch. */
+            float4 *ysum = reinterpret_cast<float4 *>(B);
+            #pragma unroll 1
+            for (int c0 = 0; c0 < M / 2; c0 += 2 * T)
             {
-                if ((NH == 2) || (want == 0))
+                const int ca = c0 + tid, cb = c0 + T + tid;
+                float4 sa = make_float4(0.0f, 0.0f, 0.0f, 0.0f), sb = sa;
+                for (uint32_t s0 = 0; s0 < splits; s0 += RG)
+                {
+                    float4 va[RG], vb[RG];
+                    #pragma unroll
+                    for (int r = 0; r < RG; ++r)
+                    {
+                        uint32_t row = min(s0 + r, splits - 1);     /* clamp: the extra loads are dropped below */
+                        const float4 *rp = reinterpret_cast<const float4 *>(yp + uint64_t(row) * M);
+                        va[r]       = ld_cg_f4(rp + ca);
+                        vb[r]       = ld_cg_f4(rp + cb);
+                    }
+                    #pragma unroll
+                    for (int r = 0; r < RG; ++r)
+                    {
+                        if (s0 + r < splits)
+                        {
+                            sa.x += va[r].x; sa.y += va[r].y; sa.z += va[r].z; sa.w += va[r].w;
+                            sb.x += vb[r].x; sb.y += vb[r].y; sb.z += vb[r].z; sb.w += vb[r].w;
+                        }
+                    }
+                }
+                ysum[ca]    = sa;
+                ysum[cb]    = sb;
+            }
+            __syncthreads();
+        }
+
+        #pragma unroll 1
+        for (int it0 = 0; it0 < ITER; it0 += 2)
+        {
+            /* Two bins per round, each with its mirror (k = 0 pairs with M/2: both self-paired
+             * specials ride in thread 0's first slot). */
+            int k[2], km[2];
+            #pragma unroll
+            for (int u = 0; u < 2; ++u)
+            {
+                k[u]        = tid + (it0 + u) * T;
+                km[u]       = (k[u] == 0) ? (M / 2) : (M - k[u]);
+            }
+            float2 yk[2], ym[2];
+            if (PP)
+            {
+                #pragma unroll
+                for (int u = 0; u < 2; ++u)
+                {
+                    yk[u]       = B[k[u]];
+                    ym[u]       = B[km[u]];
+                }
+            }
+            else
+            {
+                #pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    yk[u] = ym[u] = make_float2(0.0f, 0.0f);
+                for (uint32_t s = 0; s < splits; ++s)
+                {
+                    const float2 *row = yp + uint64_t(s) * M;
+                    #pragma unroll
+                    for (int u = 0; u < 2; ++u)
+                    {
+                        yk[u]       = cadd(yk[u], __ldcg(row + k[u]));
+                        ym[u]       = cadd(ym[u], __ldcg(row + km[u]));
+                    }
+                }
+            }
+
+            #pragma unroll
+            for (int u = 0; u < 2; ++u)
+            {
+                int par     = k[u] & 1;
+                if ((NH == 1) && (par != want))
+                    continue;
+                float2 *half = A + ((NH == 2) ? par * P : 0);
+                if (k[u] == 0)
                 {
                     /* (DC, Nyquist) -> Z[0] = (DC + Ny) + i (DC - Ny);  Z[M/2] = 2 conj(Y[M/2]) */
-                    float2 y0   = sum_rows<RANK>(yp, splits, 0);
-                    float2 yh   = sum_rows<RANK>(yp, splits, M / 2);
-                    A[0]        = make_float2(y0.x + y0.y, y0.x - y0.y);
-                    A[P / 2]    = make_float2(2.0f * yh.x, -2.0f * yh.y);
+                    half[0]     = make_float2(yk[u].x + yk[u].y, yk[u].x - yk[u].y);
+                    half[P / 2] = make_float2(2.0f * ym[u].x, -2.0f * ym[u].y);
+                    continue;
                 }
-                continue;
+                /* e = yk + conj(ym) ; o = conj(w^k) (yk - conj(ym)) ; Z[k] = e + i o ; Z[M-k] = conj(e) + i conj(o) */
+                float2 e    = make_float2(yk[u].x + ym[u].x, yk[u].y - ym[u].y);
+                float2 df   = make_float2(yk[u].x - ym[u].x, yk[u].y + ym[u].y);
+                float2 o    = cmulc(df, twg[k[u]]);
+                int ik      = k[u] >> 1;
+                int im      = par ? (P - 1 - ik) : (P - ik);
+                half[ik]    = make_float2(e.x - o.y, e.y + o.x);
+                half[im]    = make_float2(e.x + o.y, o.x - e.y);
             }
-            int par     = k & 1;
-            if ((NH == 1) && (par != want))
-                continue;
-            float2 *half = A + ((NH == 2) ? par * P : 0);
-            float2 yk   = sum_rows<RANK>(yp, splits, k);
-            float2 ym   = sum_rows<RANK>(yp, splits, M - k);
-            /* e = yk + conj(ym) ; o = conj(w^k) (yk - conj(ym)) ; Z[k] = e + i o ; Z[M-k] = conj(e) + i conj(o) */
-            float2 e    = make_float2(yk.x + ym.x, yk.y - ym.y);
-            float2 df   = make_float2(yk.x - ym.x, yk.y + ym.y);
-            float2 o    = cmulc(df, twg[k]);
-            int ik      = k >> 1;
-            int im      = par ? (P - 1 - ik) : (P - ik);
-            half[ik]    = make_float2(e.x - o.y, e.y + o.x);
-            half[im]    = make_float2(e.x + o.y, o.x - e.y);
         }
         __syncthreads();
 
@@ -674,7 +747,7 @@ k_mac(const StepArgs a, const MacShape sh)
 /* tail; nothing global is touched before griddepcontrol.wait.                                   */
 
 template <int RANK>
-__global__ void __launch_bounds__(FftCfg<RANK>::T)
+__global__ void __launch_bounds__(FftCfg<RANK>::T, (FftCfg<RANK>::T >= 256) ? 4 : 8)
 k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
 {
     using C = FftCfg<RANK>;
@@ -695,6 +768,12 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
     uint64_t *full          = reinterpret_cast<uint64_t *>(stages + size_t(NS) * 2 * stage_elems);
     uint32_t *flag          = reinterpret_cast<uint32_t *>(full + NS);
 
+    /* Let the next block's launch become resident as soon as this one frees SM slots.  What the
+     * next launch may touch before this one has completed is ordered explicitly below:
+     *   - its MAC chunks read only IR spectra and ring slots of frames already published through
+     *     ring_head (release/acquire), so they stream while this launch's inverse-FFT tail runs;
+     *   - its split-0 CTAs (input block, ring write) and every CTA's partial-row / ticket /
+     *     output writes sit behind griddepcontrol.wait, i.e. after this launch has completed. */
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0)
     {
@@ -704,8 +783,8 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
 
+    /* the instance / job tables are written by stream-ordered memcpys, never by a kernel */
     const Job job           = fetch_job(a, jobi);
     const InstDesc d        = a.inst[job.inst];
 
@@ -746,12 +825,45 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
      * final stage yet -- that one reads the spectrum which is about to be written */
     const uint32_t SCR      = ((NS >= 3) && (2 * stage_elems >= N)) ? 2 : 1;
     uint32_t pre            = min(NS, n_iter);
+    uint32_t issued         = 0;            /* thread 0: stages fetched so far */
     if (fft_cta)
-        pre                 = (n_iter > 0) ? min(NS - SCR, n_iter - 1) : 0;
-    if (tid == 0)
     {
-        for (uint32_t it = 0; it < pre; ++it)
-            issue(it);
+        /* Its partitions q >= 1 need the spectra of frames <= t - 1.  In steady state they were
+         * published long ago and the first stages are fetched right away; if the previous
+         * launch's split-0 CTA is still at work, fetching waits until after the transform. */
+        pre                 = (n_iter > 0) ? min(NS - SCR, n_iter - 1) : 0;
+        if (tid == 0)
+        {
+            uint32_t have;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(a.ring_head + job.inst) : "memory");
+            if (int32_t(have - job.tlo) >= 0)
+            {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                for ( ; issued < pre; ++issued)
+                    issue(issued);
+            }
+        }
+    }
+    else if (tid == 0)
+    {
+        if (n_iter > 0)
+        {
+            /* partitions q >= q0 >= 1 need the spectra of frames <= t - q0; the newest of them may
+             * still be in flight in the previous launch's split-0 CTA */
+            const uint32_t need = job.tlo - q0 + 1u;
+            const uint32_t *hp  = a.ring_head + job.inst;
+            uint32_t have;
+            for (;;)
+            {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(hp) : "memory");
+                if (int32_t(have - need) >= 0)
+                    break;
+                __nanosleep(100);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        for ( ; issued < pre; ++issued)
+            issue(issued);
     }
     if (fft_cta)
     {
@@ -765,6 +877,22 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
                 tws[i]              = a.tw[i];
             tw                  = tws;          /* visible after fwd_body's first barrier */
         }
+        /* The ring keeps one spare slot: slot (-t) mod S was last read two launches ago.  Those
+         * reads are over once every CTA of that launch has bumped stream_done (they may not be
+         * when only the PREVIOUS launch is known to have started).  The input block is the
+         * caller's and final: an early (programmatic) start only ever follows a k_frame. */
+        if (tid == 0)
+        {
+            const uint32_t *dp  = a.stream_done + job.inst;
+            uint32_t have;
+            for (;;)
+            {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(dp) : "memory");
+                if (int32_t(have - a.need_done) >= 0)
+                    break;
+                __nanosleep(100);
+            }
+        }
         fwd_body<RANK, true>(wa, wb, job.src, job.spec, a.tw, tw, int(tid));
         /* generic-proxy global writes -> visible to the TMA (async proxy) reads issued below */
         __threadfence();
@@ -772,8 +900,24 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
         __syncthreads();
         if (tid == 0)
         {
-            for (uint32_t it = pre; (it < NS) && (it < n_iter); ++it)
-                issue(it);
+            /* Publish "frames 0 .. t are in the ring" -- strictly in frame order: the split-0
+             * CTAs of consecutive launches run independently, and a later frame must not be
+             * announced before an earlier one has landed.  (The acquire/release chain also makes
+             * every older spectrum formally visible to whoever acquires the new value.) */
+            uint32_t *hp    = a.ring_head + job.inst;
+            uint32_t have;
+            for (;;)
+            {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(hp) : "memory");
+                if (int32_t(have - job.tlo) >= 0)
+                    break;
+                __nanosleep(100);
+            }
+            const uint32_t head = job.tlo + 1u;
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(hp), "r"(head) : "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+            for ( ; (issued < NS) && (issued < n_iter); ++issued)
+                issue(issued);
         }
     }
 
@@ -823,6 +967,16 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
         acc[0].y    = dny;
     }
 
+    /* partial rows, tickets and the output block are shared with the previous launch's tail */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    /* This CTA is done reading the ring.  Counted only now, after every earlier launch has
+     * completed, so that the counter advances in launch order: stream_done >= (CTAs of launches
+     * 0..L) holds exactly when all of them have finished streaming, however the CTAs of the
+     * launches in flight interleave. */
+    if (tid == 0)
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(a.stream_done + job.inst), "r"(1u) : "memory");
+
     float2 *yrow    = a.ypart + uint64_t(jobi) * a.splits * M;
     float4 *yp      = reinterpret_cast<float4 *>(yrow + uint64_t(split) * M);
     #pragma unroll
@@ -856,7 +1010,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
             tws[i]          = a.tw[i];
         tw              = tws;                  /* visible after inv_body's first barrier */
     }
-    inv_body<RANK, true>(wa, wb, yrow, a.splits, job.dst, a.tw, tw, false, int(tid));
+    inv_body<RANK, true, 4>(wa, wb, yrow, a.splits, job.dst, a.tw, tw, false, int(tid));
 }
 
 /* ------------------------------------------------------------------------------------------- */
