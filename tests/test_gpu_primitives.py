@@ -1,0 +1,80 @@
+"""The batched device restatements of lsp::dsp::fastconv_* (include/b200conv.h) against their
+contract and the CPU oracle's restated primitives."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle.bindings import CpuConvolver
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as ge
+    p = ge.load()
+    p.lib()
+    return p
+
+
+def _check(pkg, rc):
+    assert rc == 0, pkg.lib().b200conv_last_error().decode()
+
+
+@pytest.mark.parametrize("rank", [8, 9, 10, 11, 12, 13, 14, 15, 16])
+def test_parse_apply_restore(pkg, rank):
+    lib = pkg.lib()
+    n, F = 1 << rank, 1 << (rank - 1)
+    count = 5 if rank <= 13 else 2
+    rng = np.random.Generator(np.random.PCG64(rank))
+    a = rng.uniform(-1, 1, (count, F)).astype(np.float32)
+    b = rng.uniform(-1, 1, (count, F)).astype(np.float32)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    ia = torch.empty((count, n), device="cuda", dtype=torch.float32)     # image: 2^rank floats
+    ib = torch.empty_like(ia)
+    _check(pkg, lib.b200conv_fastconv_parse(0, ia.data_ptr(), da.data_ptr(), rank, count, None))
+    _check(pkg, lib.b200conv_fastconv_parse(0, ib.data_ptr(), db.data_ptr(), rank, count, None))
+
+    want = np.stack([np.convolve(a[i].astype(np.float64), b[i].astype(np.float64)) for i in range(count)])
+    want = np.concatenate([want, np.zeros((count, 1))], axis=1)          # length 2F
+    tol = 1e-5 * np.abs(want).max()
+
+    # apply ACCUMULATES into dst (the reference depends on it, Convolver.cpp:278-283)
+    dst = torch.ones((count, n), device="cuda", dtype=torch.float32)
+    _check(pkg, lib.b200conv_fastconv_apply(0, dst.data_ptr(), ia.data_ptr(), ib.data_ptr(), rank, count, None))
+    torch.cuda.synchronize()
+    assert np.max(np.abs(dst.cpu().numpy() - 1.0 - want)) <= tol
+
+    # parse_apply == parse + apply
+    dst2 = torch.full((count, n), 2.0, device="cuda", dtype=torch.float32)
+    _check(pkg, lib.b200conv_fastconv_parse_apply(0, dst2.data_ptr(), ia.data_ptr(), db.data_ptr(), rank, count, None))
+    torch.cuda.synchronize()
+    assert np.max(np.abs(dst2.cpu().numpy() - 2.0 - want)) <= tol
+
+    # restore(parse(a)) == [a, 0 ...] and STORES
+    dst3 = torch.full((count, n), 7.0, device="cuda", dtype=torch.float32)
+    _check(pkg, lib.b200conv_fastconv_restore(0, dst3.data_ptr(), ia.data_ptr(), rank, count, None))
+    torch.cuda.synchronize()
+    got = dst3.cpu().numpy()
+    assert np.max(np.abs(got[:, :F] - a)) <= 2e-6 and np.max(np.abs(got[:, F:])) <= 2e-6
+
+    # same numbers as the oracle's restated primitives (different image layout, same contract)
+    olib = CpuConvolver.lib("oracle")[0]
+    fp = ctypes.POINTER(ctypes.c_float)
+    P = lambda x: x.ctypes.data_as(fp)
+    oa, ob, tmp = (np.zeros(2 * n, np.float32) for _ in range(3))
+    olib.rs_fastconv_parse(P(oa), P(a[0]), ctypes.c_size_t(rank))
+    olib.rs_fastconv_parse(P(ob), P(b[0]), ctypes.c_size_t(rank))
+    od = np.ones(n, np.float32)
+    olib.rs_fastconv_apply(P(od), P(tmp), P(oa), P(ob), ctypes.c_size_t(rank))
+    assert np.max(np.abs(dst.cpu().numpy()[0] - od)) <= tol
+
+
+def test_primitives_reject_bad_arguments(pkg):
+    lib = pkg.lib()
+    x = torch.zeros(4096, device="cuda")
+    assert lib.b200conv_fastconv_parse(0, x.data_ptr(), x.data_ptr(), 7, 1, None) == pkg.ERR_ARG
+    assert lib.b200conv_fastconv_parse(0, x.data_ptr(), x.data_ptr(), 17, 1, None) == pkg.ERR_ARG
+    assert lib.b200conv_fastconv_restore(0, x.data_ptr(), x.data_ptr(), 9, 0, None) == pkg.ERR_ARG
