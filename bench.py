@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--fused", type=int, default=1)
     ap.add_argument("--bias", type=int, default=6)
     ap.add_argument("--pdl", type=int, default=1)
+    ap.add_argument("--zero-copy", type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -203,6 +204,7 @@ def main():
     batch.set_option("fused", args.fused)
     batch.set_option("fft_bias", args.bias)
     batch.set_option("pdl", args.pdl)
+    batch.set_option("zero_copy", args.zero_copy)
 
     # ---- synthetic data: decaying-noise IRs, white-noise input --------------------
     # A handful of distinct seeded IRs/inputs are cycled over the 64 instances: timing does not
@@ -315,7 +317,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io_bytes,
                     "d2h_bytes_per_step": io_bytes,
-                    "api": "b200conv_process_planar (pinned host buffers, synchronous per 1024-sample call)"},
+                    "api": "b200conv_process_planar (pinned host buffers, synchronous per 1024-sample call; %s)" % ("kernels read/write the pinned buffers over PCIe" if args.zero_copy else "staged H2D/D2H copies")},
             "gpu_launches": stats["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,

@@ -144,7 +144,9 @@ void   *b200conv_stream(b200conv_batch_t *h);
  *   "fused"       1 (default) = ranks 8..11 run FFT + MAC + IFFT as ONE launch per block
  *                 (k_frame); 0 = always three launches (k_fwd, k_mac, k_inv)
  *   "fft_bias"    partitions taken off the split that also transforms the input (default 6)
- *   "pdl"         1 (default) = programmatic dependent launch between consecutive blocks */
+ *   "pdl"         1 (default) = programmatic dependent launch between consecutive blocks
+ *   "zero_copy"   1 (default) = b200conv_process_planar lets the kernels read / write page-locked
+ *                 host matrices directly (no staging copies); 0 = always stage */
 int     b200conv_set_option(b200conv_batch_t *h, const char *name, int value);
 
 /* ---- the fastconv primitives on the device (lsp::dsp:: contract) ---------- */

@@ -267,9 +267,11 @@ __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src,
     #pragma unroll 1
     for (int pass = 0; pass < 2 / NH; ++pass)
     {
+        const bool src8 = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
         for (int m = tid; m < P; m += T)
         {
-            float2 z    = make_float2(src[2 * m], src[2 * m + 1]);
+            float2 z    = src8 ? reinterpret_cast<const float2 *>(src)[m]
+                               : make_float2(src[2 * m], src[2 * m + 1]);
             float2 zb   = cmul(z, twg[2 * m]);                  /* w_M^m = w_N^(2m) */
             if (NH == 2)    { A[m] = z; A[P + m] = zb; }
             else            { A[m] = (pass == 0) ? z : zb; }
@@ -486,12 +488,21 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
                 hi          = make_float2(av.x * scale - pk.x, av.y * scale - pk.y);
             }
 
-            dst[2 * m]      = lo.x;
-            dst[2 * m + 1]  = lo.y;
-            if (full)
+            if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)
             {
-                dst[2 * (m + P)]        = hi.x;
-                dst[2 * (m + P) + 1]    = hi.y;
+                reinterpret_cast<float2 *>(dst)[m]  = lo;
+                if (full)
+                    reinterpret_cast<float2 *>(dst)[m + P]  = hi;
+            }
+            else
+            {
+                dst[2 * m]      = lo.x;
+                dst[2 * m + 1]  = lo.y;
+                if (full)
+                {
+                    dst[2 * (m + P)]        = hi.x;
+                    dst[2 * (m + P) + 1]    = hi.y;
+                }
             }
         }
         if (NH == 1)
