@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Secondary measurements: the five BASELINE.json configs on ONE GPU (bench.py stays the headline,
+config 3).  Per config: device-resident throughput of back-to-back process calls (CUDA events),
+its share of the HBM roofline (16*bins+24 bytes per output sample per instance), and
+the host-visible latency of one synchronous b200conv_process_planar call on pinned buffers
+(median / p99 wall time) -- the number a real-time caller sees.
+
+    python tools/bench_configs.py [--configs 1,2,3,4,5] > profiles/rN_configs.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+
+import __graft_entry__ as ge
+import synth
+
+#        name                                   instances taps      rank block phases        note
+CONFIGS = {
+    1: ("cfg1 mono 65536 taps, 1024 blocks",          1,   65536,   11, 1024, (0.0,),        ""),
+    2: ("cfg2 stereo 4 s IR, 256 blocks, rank 9",     2,   192000,  9,  256,  (0.0, 0.5),    "phases 0 / 0.5: second instance takes the partial-frame path"),
+    3: ("cfg3 64 ch x 10 s IR, 1024 blocks",          64,  480000,  11, 1024, (0.0,),        ""),
+    4: ("cfg4 4096 mono x 1 s IR, 1024 blocks",       4096, 48000,  11, 1024, (0.0,),        "one frame per launch (no IR reuse across frames yet)"),
+    5: ("cfg5 8 ch x 120 s IR on ONE GPU",            8,   5760000, 11, 1024, (0.0,),        "all 5625 partitions on one GPU; the 8-way split is 1/8 of this per GPU + a 32 KiB all-reduce"),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,3,5,4")
+    ap.add_argument("--seconds", type=float, default=0.4)
+    args = ap.parse_args()
+    pkg = ge.load()
+    peak = 6546.2
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+
+    for cid in [int(c) for c in args.configs.split(",")]:
+        name, n, taps, rank, block, phases, note = CONFIGS[cid]
+        F = 1 << (rank - 1)
+        bins = (taps + F - 1) // F
+        b = pkg.ConvolverBatch(n, 0)
+        irs = [synth.decaying_ir(c, taps) for c in range(min(n, 4))]
+        for c in range(n):
+            assert b.init(c, irs[c % len(irs)], rank, phases[c % len(phases)])
+        bytes_per_sample = 16 * bins + 24
+
+        # device-resident throughput
+        frames = max(8, min(512, int(2e8 // (n * block))))
+        src = torch.rand((n, frames * block), device="cuda") * 2 - 1
+        dst = torch.empty_like(src)
+        st = torch.cuda.Stream()
+        def run():
+            for i in range(frames):
+                b.process_device(dst.data_ptr() + 4 * i * block, src.data_ptr() + 4 * i * block,
+                                 frames * block, block, st.cuda_stream)
+        with torch.cuda.stream(st):
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps, t0 = 0, time.time()
+            e0.record(st)
+            while reps < 3 or time.time() - t0 < args.seconds:
+                run()
+                reps += 1
+            e1.record(st)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        rate = reps * frames * block * n / (ms * 1e-3)
+        us_per_call = ms * 1e3 / (reps * frames)
+
+        # host-visible latency of one synchronous call on pinned buffers
+        hs = torch.zeros((n, block)).pin_memory()
+        hs.copy_(src[:, :block].cpu())
+        hd = torch.zeros((n, block)).pin_memory()
+        a, o = hs.numpy(), hd.numpy()
+        for _ in range(20):
+            b.process(a, o)
+        lat = []
+        t_end = time.time() + args.seconds
+        while len(lat) < 200 or time.time() < t_end:
+            t0 = time.perf_counter()
+            b.process(a, o)
+            lat.append(time.perf_counter() - t0)
+            if len(lat) >= 5000:
+                break
+        lat = np.sort(np.array(lat)) * 1e6
+        line = {
+            "config": name, "instances": n, "taps": taps, "rank": rank, "block": block, "partitions": bins,
+            "device_samples_per_s": rate, "device_us_per_call": us_per_call,
+            "hbm_roofline_samples_per_s": peak * 1e9 / bytes_per_sample,
+            "share_of_hbm_roofline": rate * bytes_per_sample / (peak * 1e9),
+            "realtime_factor": rate / (n * 48000.0),
+            "host_call_us_median": float(lat[len(lat) // 2]), "host_call_us_p99": float(lat[int(len(lat) * 0.99)]),
+            "host_samples_per_s": n * block / (float(lat[len(lat) // 2]) * 1e-6),
+            "block_duration_us_at_48k": block / 48000.0 * 1e6, "note": note,
+        }
+        print(json.dumps(line), flush=True)
+        b.close()
+        del src, dst
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
