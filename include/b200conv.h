@@ -145,6 +145,8 @@ void   *b200conv_stream(b200conv_batch_t *h);
  *                 (k_frame); 0 = always three launches (k_fwd, k_mac, k_inv)
  *   "fft_bias"    partitions taken off the split that also transforms the input (default 6)
  *   "pdl"         1 (default) = programmatic dependent launch between consecutive blocks
+ *   "multi_frame" frames served by one pass over the IR spectra when a call brings several whole
+ *                 frames: 8 (default), 4, 2, or 1 = off (one launch per frame)
  *   "zero_copy"   1 (default) = b200conv_process_planar lets the kernels read / write page-locked
  *                 host matrices directly (no staging copies); 0 = always stage */
 int     b200conv_set_option(b200conv_batch_t *h, const char *name, int value);

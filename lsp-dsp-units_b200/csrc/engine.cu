@@ -175,6 +175,34 @@ static cudaError_t launch_mac_raw(const StepArgs &a, const MacPlan &p, uint32_t 
     return cudaGetLastError();
 }
 
+template <int TF>
+static cudaError_t launch_mac_multi_t(const StepArgs &a, const MacPlan &p, uint32_t jobs, cudaStream_t st)
+{
+    static size_t attr_smem[MAX_DEVICES] = { 0 };
+    int dev = current_device();
+    if (p.smem > attr_smem[dev])
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_mac_multi<TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem));
+        if (e != cudaSuccess)
+            return e;
+        attr_smem[dev] = p.smem;
+    }
+    dim3 grid(jobs * p.splits, p.tiles);
+    k_mac_multi<TF><<<grid, p.threads, p.smem, st>>>(a, p.sh);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_mac_multi(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t tf, cudaStream_t st)
+{
+    switch (tf)
+    {
+        case 2:  return launch_mac_multi_t<2>(a, p, jobs, st);
+        case 4:  return launch_mac_multi_t<4>(a, p, jobs, st);
+        case 8:  return launch_mac_multi_t<8>(a, p, jobs, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <int RANK>
 static cudaError_t launch_frame_r(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
                                   bool pdl, cudaStream_t st)
@@ -261,6 +289,7 @@ struct Instance
 };
 
 static const size_t JOB_RING = size_t(1) << 15;
+static const size_t RING_SPARE = 8;
 
 struct b200conv_batch
 {
@@ -293,7 +322,7 @@ struct b200conv_batch
 
     b200conv_stats_t        stats       = {};
     int                     tune_splits = 0, tune_stages = 0;
-    int                     opt_fused   = 1, opt_bias = 6, opt_pdl = 1, opt_zero_copy = 1;
+    int                     opt_fused   = 1, opt_bias = 6, opt_pdl = 1, opt_zero_copy = 1, opt_multi = 8;
     uint32_t               *d_tickets   = nullptr;  /* k_frame: one arrival counter per job */
     uint32_t               *d_ring_head = nullptr;  /* k_frame: frames published per instance */
     uint32_t               *d_stream_done = nullptr; /* k_frame: CTAs done reading the ring, cumulative */
@@ -602,7 +631,9 @@ extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float 
     const size_t F      = size_t(1) << (rank - 1);
     const size_t bins   = (count + F - 1) >> (rank - 1);    /* Convolver.cpp:93 */
     const size_t nq     = bins + 1;                         /* folded overlap: one extra row */
-    const size_t S      = part_offset + nq + 1;             /* one spare slot, see k_frame */
+    /* spare slots: one for the overlapped single-frame launches (k_frame), RING_SPARE - 1 so that
+     * up to RING_SPARE frames can be transformed ahead of one multi-frame MAC pass */
+    const size_t S      = part_offset + nq + RING_SPARE;
     if ((part_offset + nq) >= (size_t(1) << 31))
         return fail(B200CONV_ERR_ARG, "impulse response too long");
 
@@ -736,10 +767,39 @@ static int process_uniform(Batch *b, float *dst, const float *src, size_t stride
     a.t_base        = b->t_batch;
     const bool fused = (b->opt_fused != 0) && (b->rank <= 11);
     plan.sh.bias    = fused ? uint32_t(b->opt_bias) : 0;
-    for (size_t f = 0; f < frames; ++f)
+    bool used_multi = false;
+    for (size_t f = 0; f < frames; )
     {
         a.frame0        = uint32_t(f);
-        if (fused)
+        a.n_jobs        = nact;
+        /* several whole frames in one call: transform them all, then ONE pass over the IR
+         * spectra serves tf frames (k_mac_multi), then all inverse transforms */
+        uint32_t tf     = 0;
+        for (uint32_t c = uint32_t(b->opt_multi); c >= 2; c >>= 1)
+            if (frames - f >= c) { tf = c; break; }
+        if (tf >= 2)
+        {
+            MacPlan mp      = plan;
+            mp.sh.bias      = 0;
+            /* the register window limits occupancy (8 frames: 1 CTA/SM, 4: 2, 2: 3), so the
+             * bytes in flight come from a deeper shared-memory ring instead */
+            mp.sh.NS        = (tf == 8) ? 8 : (tf == 4) ? 6 : 4;
+            mp.smem         = size_t(2) * mp.sh.NS * mp.sh.QB * mp.sh.TB * sizeof(float2) + mp.sh.NS * sizeof(uint64_t) + 16;
+            TRY(ensure_ypart(b, size_t(nact) * tf * mp.splits * F * sizeof(float2), st));
+            a.ypart         = b->ypart;
+            a.n_jobs        = nact * tf;
+            CU(launch_fwd(a, nact * tf, st));
+            CU(launch_mac_multi(a, mp, nact, tf, st));
+            CU(launch_inv(a, nact * tf, st));
+            b->stats.launches       += 3;
+            b->stats.mac_launches   += 1;
+            b->stats.mac_algo_bytes += per_frame_bytes * tf;
+            b->stats.frames         += uint64_t(nact) * tf;
+            used_multi      = true;
+            f              += tf;
+            continue;
+        }
+        if (fused && (!used_multi))
         {
             /* one launch per block for all instances x partitions; the ring slot it overwrites
              * was last read by the launch before the previous one */
@@ -751,15 +811,20 @@ static int process_uniform(Batch *b, float *dst, const float *src, size_t stride
         }
         else
         {
+            MacPlan sp      = plan;
+            sp.sh.bias      = 0;
             CU(launch_fwd(a, nact, st));
-            CU(launch_mac(b, a, plan, nact, st));
+            CU(launch_mac(b, a, sp, nact, st));
             CU(launch_inv(a, nact, st));
             b->stats.launches       += 3;
         }
         b->stats.mac_launches   += 1;
         b->stats.mac_algo_bytes += per_frame_bytes;
         b->stats.frames         += nact;
+        f              += 1;
     }
+    if (used_multi)
+        b->desc_dirty   = true;     /* ring_head / stream_done were bypassed: re-seed before the next k_frame */
     b->t_batch     += frames;
     for (uint32_t i : b->active)
     {
@@ -1175,6 +1240,8 @@ extern "C" int b200conv_set_option(b200conv_batch_t *b, const char *name, int va
     else if (!strcmp(name, "fft_bias") && (value >= 0) && (value <= 64))    b->opt_bias = value;
     else if (!strcmp(name, "pdl") && (value >= 0) && (value <= 1))          b->opt_pdl = value;
     else if (!strcmp(name, "zero_copy") && (value >= 0) && (value <= 1))    b->opt_zero_copy = value;
+    else if (!strcmp(name, "multi_frame") && ((value == 0) || (value == 1) || (value == 2) || (value == 4) || (value == 8)))
+        b->opt_multi = (value == 1) ? 0 : value;
     else
         return fail(B200CONV_ERR_ARG, "b200conv_set_option: unknown option or bad value: %s = %d", name, value);
     b->desc_dirty   = true;     /* the hand-shake counters are re-seeded before the next launch */

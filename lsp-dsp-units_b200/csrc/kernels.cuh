@@ -743,6 +743,195 @@ k_mac(const StepArgs a, const MacShape sh)
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* k_mac_multi<TF> : TF consecutive frames of every instance in ONE pass over the IR spectra      */
+/* (calls that bring several whole frames: offline rendering, BASELINE config 4).                */
+/*                                                                                             */
+/*   Y_{t+j}[k] = sum_q G_q[k] X_{t+j-q}[k],  j = 0 .. TF-1                                       */
+/*                                                                                             */
+/* For a fixed q the TF frames need the ring rows X_{t-q} .. X_{t-q+TF-1}; stepping q -> q+1      */
+/* slides that window by one row.  Every thread keeps the window for its bins in registers        */
+/* (a rotating register file, statically indexed: the step loop is dispatched on step % TF), so a */
+/* step still loads just one IR row and ONE ring row from shared memory -- the HBM bytes per      */
+/* output sample drop by TF, the shared-memory traffic per step does not grow.                    */
+/* Partial rows go to ypart[(j * n_active + job) * splits + split], the order k_inv expects for   */
+/* a launch over TF * n_active frame-jobs.                                                       */
+
+template <int TF, int PH>
+__device__ __forceinline__ void multi_step(float4 (&acc)[TF][MAC_VPT], float4 (&win)[TF][MAC_VPT],
+                                           float (&dny)[TF], const float4 *g4, const float4 *x4,
+                                           uint32_t tid, uint32_t T)
+{
+    /* the row that enters the window at this step is frame 0's operand */
+    constexpr int NEW = (TF - PH) % TF;
+    float4 g[MAC_VPT];
+    #pragma unroll
+    for (int v = 0; v < MAC_VPT; ++v)
+    {
+        g[v]            = g4[tid + v * T];
+        win[NEW][v]     = x4[tid + v * T];
+    }
+    #pragma unroll
+    for (int j = 0; j < TF; ++j)
+    {
+        const int w = (j + TF - PH) % TF;
+        #pragma unroll
+        for (int v = 0; v < MAC_VPT; ++v)
+        {
+            const float4 x  = win[w][v];
+            acc[j][v].x     = fmaf(g[v].x, x.x, acc[j][v].x);
+            acc[j][v].y     = fmaf(g[v].x, x.y, acc[j][v].y);
+            acc[j][v].z     = fmaf(g[v].z, x.z, acc[j][v].z);
+            acc[j][v].w     = fmaf(g[v].z, x.w, acc[j][v].w);
+            acc[j][v].x     = fmaf(-g[v].y, x.y, acc[j][v].x);
+            acc[j][v].y     = fmaf(g[v].y, x.x, acc[j][v].y);
+            acc[j][v].z     = fmaf(-g[v].w, x.w, acc[j][v].z);
+            acc[j][v].w     = fmaf(g[v].w, x.z, acc[j][v].w);
+            if (v == 0)
+                dny[j]          = fmaf(g[v].y, x.y, dny[j]);
+        }
+    }
+}
+
+template <int TF>
+__global__ void __launch_bounds__(256)
+k_mac_multi(const StepArgs a, const MacShape sh)
+{
+    static_assert((TF == 2) || (TF == 4) || (TF == 8), "k_mac_multi: TF must be 2, 4 or 8");
+    extern __shared__ __align__(128) unsigned char smraw[];
+
+    const uint32_t M        = 1u << (a.rank - 1);
+    const uint32_t TB       = sh.TB, QB = sh.QB, NS = sh.NS;
+    const uint32_t T        = blockDim.x;
+    const uint32_t tid      = threadIdx.x;
+    const uint32_t jobi     = blockIdx.x / a.splits;        /* = index into the active list */
+    const uint32_t split    = blockIdx.x % a.splits;
+    const uint32_t tile     = blockIdx.y;
+
+    const uint32_t stage_elems = QB * TB;
+    float2 *sG              = reinterpret_cast<float2 *>(smraw);
+    float2 *sX              = sG + size_t(NS) * stage_elems;
+    uint64_t *full          = reinterpret_cast<uint64_t *>(sX + size_t(NS) * stage_elems);
+
+    /* job of the FIRST frame of the group: slot0 = ring slot of X_t */
+    const Job job           = fetch_job(a, jobi);
+    const InstDesc d        = a.inst[job.inst];
+
+    uint32_t qa             = max(job.qa, d.q_lo);
+    uint32_t qb             = min(job.qb, d.q_lo + d.nq);
+    uint32_t nq             = (qb > qa) ? (qb - qa) : 0;
+    uint32_t c0, c1;
+    chunk_range(nq, split, a.splits, 0, c0, c1);
+    const uint32_t q0       = qa + c0, q1 = qa + c1;
+    const uint32_t n_iter   = (q1 - q0 + QB - 1) / QB;
+
+    const float2 *Gt        = d.G + uint64_t(tile) * TB;
+    const float2 *Xt        = d.ring + uint64_t(tile) * TB;
+    const uint32_t row_bytes = TB * uint32_t(sizeof(float2));
+
+    if (tid == 0)
+    {
+        for (uint32_t s = 0; s < NS; ++s)
+            mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t it)
+    {
+        uint32_t s      = it % NS;
+        uint32_t q      = q0 + it * QB;
+        uint32_t rows   = min(QB, q1 - q);
+        float2 *g       = sG + size_t(s) * stage_elems;
+        float2 *x       = sX + size_t(s) * stage_elems;
+        mbar_expect_tx(&full[s], 2u * rows * row_bytes);
+        bulk_g2s(g, Gt + uint64_t(q - d.q_lo) * M, rows * row_bytes, &full[s]);
+        uint32_t first  = uint32_t((uint64_t(job.slot0) + q) % d.S);
+        uint32_t n1     = min(rows, d.S - first);
+        bulk_g2s(x, Xt + uint64_t(first) * M, n1 * row_bytes, &full[s]);
+        if (n1 < rows)
+            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[s]);
+    };
+
+    if (tid == 0)
+    {
+        for (uint32_t it = 0; (it < NS) && (it < n_iter); ++it)
+            issue(it);
+    }
+
+    float4 acc[TF][MAC_VPT], win[TF][MAC_VPT];
+    float dny[TF];
+    #pragma unroll
+    for (int j = 0; j < TF; ++j)
+    {
+        dny[j]          = 0.0f;
+        #pragma unroll
+        for (int v = 0; v < MAC_VPT; ++v)
+            acc[j][v]       = win[j][v] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+
+    /* window rows of the later frames at the first step: frame j needs X_{t+j-q0}, which sits
+     * j slots BEFORE the slot of X_{t-q0} (newer frames live in lower slots) */
+    if (n_iter > 0)
+    {
+        #pragma unroll
+        for (int j = 1; j < TF; ++j)
+        {
+            uint32_t slot   = uint32_t((uint64_t(job.slot0) + q0 + uint64_t(d.S) * TF - uint32_t(j)) % d.S);
+            const float4 *xr = reinterpret_cast<const float4 *>(Xt + uint64_t(slot) * M);
+            #pragma unroll
+            for (int v = 0; v < MAC_VPT; ++v)
+                win[j][v]       = __ldg(xr + tid + v * T);
+        }
+    }
+
+    uint32_t step = 0;
+    for (uint32_t it = 0; it < n_iter; ++it)
+    {
+        uint32_t s      = it % NS;
+        uint32_t rows   = min(QB, q1 - (q0 + it * QB));
+        mbar_wait(&full[s], (it / NS) & 1u);
+
+        const float4 *g4 = reinterpret_cast<const float4 *>(sG + size_t(s) * stage_elems);
+        const float4 *x4 = reinterpret_cast<const float4 *>(sX + size_t(s) * stage_elems);
+        for (uint32_t r = 0; r < rows; ++r, ++step)
+        {
+            const float4 *gr = g4 + r * (TB / 2), *xr = x4 + r * (TB / 2);
+            switch (step & (TF - 1))
+            {
+                case 0: multi_step<TF, 0>(acc, win, dny, gr, xr, tid, T); break;
+                case 1: multi_step<TF, 1 % TF>(acc, win, dny, gr, xr, tid, T); break;
+                case 2: multi_step<TF, 2 % TF>(acc, win, dny, gr, xr, tid, T); break;
+                case 3: multi_step<TF, 3 % TF>(acc, win, dny, gr, xr, tid, T); break;
+                case 4: multi_step<TF, 4 % TF>(acc, win, dny, gr, xr, tid, T); break;
+                case 5: multi_step<TF, 5 % TF>(acc, win, dny, gr, xr, tid, T); break;
+                case 6: multi_step<TF, 6 % TF>(acc, win, dny, gr, xr, tid, T); break;
+                default: multi_step<TF, 7 % TF>(acc, win, dny, gr, xr, tid, T); break;
+            }
+        }
+
+        __syncthreads();
+        if ((tid == 0) && (it + NS < n_iter))
+            issue(it + NS);
+    }
+
+    #pragma unroll
+    for (int j = 0; j < TF; ++j)
+    {
+        if ((tile == 0) && (tid == 0))
+        {
+            acc[j][0].x    += dny[j];
+            acc[j][0].y     = dny[j];
+        }
+        float4 *yp      = reinterpret_cast<float4 *>(
+            a.ypart + ((uint64_t(j) * a.n_active + jobi) * a.splits + split) * M + uint64_t(tile) * TB);
+        #pragma unroll
+        for (int v = 0; v < MAC_VPT; ++v)
+            yp[tid + v * T] = acc[j][v];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* k_frame : ranks 8..11 (one bin tile per instance), whole frames for every instance -- the     */
 /* block scheduler's "one launch per block".  grid = jobs * splits, M/4 threads.                 */
 /*                                                                                             */

@@ -318,6 +318,7 @@ def test_one_launch_per_block_matches_three_kernel_path(pkg, rank, opts):
     lens = [1, F - 1, F, F + 1, 5 * F + 3, 40 * F + 7, 0, 200 * F]
     nblk = 24
     b = pkg.ConvolverBatch(len(lens), 0)
+    b.set_option("multi_frame", 1)                           # two-frame calls as two single launches
     for k, v in opts.items():
         b.set_option(k, v)
     irs = [synth.decaying_ir(c, L) if L else None for c, L in enumerate(lens)]
@@ -404,3 +405,33 @@ def test_planar_zero_copy_from_pinned_host_memory(pkg):
     assert np.array_equal(outs[0], outs[1])
     for c in range(n):
         assert rel_err(outs[0][c], direct_convolve(src[c], irs[c], nblk * F)) <= TOL
+
+
+@pytest.mark.parametrize("rank", [8, 10, 11, 12])
+@pytest.mark.parametrize("multi", [8, 4, 2])
+def test_multi_frame_calls_share_one_pass_over_the_ir(pkg, rank, multi):
+    """Calls that bring several whole frames (offline rendering) run k_mac_multi: one pass over
+    the IR spectra serves up to 8 frames.  Mixed call lengths (groups of 8/4/2 and single-frame
+    launches, then back to one-frame calls) on a ragged batch, against direct convolution."""
+    F = 1 << (rank - 1)
+    lens = [1, F, 3 * F + 5, 37 * F + 11, 0, 150 * F]
+    b = pkg.ConvolverBatch(len(lens), 0)
+    b.set_option("multi_frame", multi)
+    irs = [synth.decaying_ir(c, L) if L else None for c, L in enumerate(lens)]
+    for c, ir in enumerate(irs):
+        if ir is not None:
+            assert b.init(c, ir, rank, 0.0)
+    calls = [3, 8, 13, 1, 1, 21, 2, 1, 16, 5]
+    total = sum(calls) * F
+    src = np.stack([synth.noise(80 + c, total) for c in range(len(lens))])
+    out = np.empty_like(src)
+    i = 0
+    for nf in calls:
+        out[:, i:i + nf * F] = b.process(src[:, i:i + nf * F])
+        i += nf * F
+    for c, ir in enumerate(irs):
+        if ir is None:
+            assert not out[c].any()
+        else:
+            assert rel_err(out[c], direct_convolve(src[c], ir, total)) <= TOL, (c, lens[c])
+    b.close()

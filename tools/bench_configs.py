@@ -28,15 +28,19 @@ CONFIGS = {
     1: ("cfg1 mono 65536 taps, 1024 blocks",          1,   65536,   11, 1024, (0.0,),        ""),
     2: ("cfg2 stereo 4 s IR, 256 blocks, rank 9",     2,   192000,  9,  256,  (0.0, 0.5),    "phases 0 / 0.5: second instance takes the partial-frame path"),
     3: ("cfg3 64 ch x 10 s IR, 1024 blocks",          64,  480000,  11, 1024, (0.0,),        ""),
-    4: ("cfg4 4096 mono x 1 s IR, 1024 blocks",       4096, 48000,  11, 1024, (0.0,),        "one frame per launch (no IR reuse across frames yet)"),
+    4: ("cfg4 4096 mono x 1 s IR, 1024 blocks",       4096, 48000,  11, 1024, (0.0,),        "one frame per call"),
+    6: ("cfg4 4096 mono x 1 s IR, 8192-sample calls", 4096, 48000,  11, 8192, (0.0,),        "offline render: 8 frames per call share one pass over the IR spectra (k_mac_multi<8>)"),
+    7: ("cfg3 64 ch x 10 s IR, 8192-sample calls",    64,  480000,  11, 8192, (0.0,),        "offline render of config 3: 8 frames per call"),
     5: ("cfg5 8 ch x 120 s IR on ONE GPU",            8,   5760000, 11, 1024, (0.0,),        "all 5625 partitions on one GPU; the 8-way split is 1/8 of this per GPU + a 32 KiB all-reduce"),
 }
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,2,3,5,4")
+    ap.add_argument("--configs", default="1,2,3,5,4,6,7")
     ap.add_argument("--seconds", type=float, default=0.4)
+    ap.add_argument("--multi", type=int, default=8)
+    ap.add_argument("--no-host", action="store_true")
     args = ap.parse_args()
     pkg = ge.load()
     peak = 6546.2
@@ -50,10 +54,11 @@ def main():
         F = 1 << (rank - 1)
         bins = (taps + F - 1) // F
         b = pkg.ConvolverBatch(n, 0)
+        b.set_option("multi_frame", args.multi)
         irs = [synth.decaying_ir(c, taps) for c in range(min(n, 4))]
         for c in range(n):
             assert b.init(c, irs[c % len(irs)], rank, phases[c % len(phases)])
-        bytes_per_sample = 16 * bins + 24
+        bytes_per_sample = 16 * bins + 24           # per-frame model: one pass over the IR per frame
 
         # device-resident throughput
         frames = max(8, min(512, int(2e8 // (n * block))))
@@ -84,11 +89,11 @@ def main():
         hs.copy_(src[:, :block].cpu())
         hd = torch.zeros((n, block)).pin_memory()
         a, o = hs.numpy(), hd.numpy()
-        for _ in range(20):
+        for _ in range(20 if not args.no_host else 1):
             b.process(a, o)
         lat = []
         t_end = time.time() + args.seconds
-        while len(lat) < 200 or time.time() < t_end:
+        while (len(lat) < 200 or time.time() < t_end) and not (args.no_host and len(lat) >= 3):
             t0 = time.perf_counter()
             b.process(a, o)
             lat.append(time.perf_counter() - t0)
