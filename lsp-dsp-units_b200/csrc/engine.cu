@@ -188,7 +188,8 @@ static cudaError_t launch_mac_multi_t(const StepArgs &a, const MacPlan &p, uint3
         attr_smem[dev] = p.smem;
     }
     dim3 grid(jobs * p.splits, p.tiles);
-    k_mac_multi<TF><<<grid, p.threads, p.smem, st>>>(a, p.sh);
+    /* TB/2 consumer threads (one float4 column each) + one producer warp */
+    k_mac_multi<TF><<<grid, p.sh.TB / 2 + 32, p.smem, st>>>(a, p.sh);
     return cudaGetLastError();
 }
 
@@ -784,7 +785,7 @@ static int process_uniform(Batch *b, float *dst, const float *src, size_t stride
             /* the register window limits occupancy (8 frames: 1 CTA/SM, 4: 2, 2: 3), so the
              * bytes in flight come from a deeper shared-memory ring instead */
             mp.sh.NS        = (tf == 8) ? 8 : (tf == 4) ? 6 : 4;
-            mp.smem         = size_t(2) * mp.sh.NS * mp.sh.QB * mp.sh.TB * sizeof(float2) + mp.sh.NS * sizeof(uint64_t) + 16;
+            mp.smem         = size_t(2) * mp.sh.NS * mp.sh.QB * mp.sh.TB * sizeof(float2) + 2 * mp.sh.NS * sizeof(uint64_t) + 16;
             TRY(ensure_ypart(b, size_t(nact) * tf * mp.splits * F * sizeof(float2), st));
             a.ypart         = b->ypart;
             a.n_jobs        = nact * tf;

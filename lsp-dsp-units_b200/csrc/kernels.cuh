@@ -664,28 +664,34 @@ k_mac(const StepArgs a, const MacShape sh)
     }
     __syncthreads();
 
-    auto issue = [&](uint32_t it)
+    /* Stage-ring bookkeeping is incremental (next stage buffer, next partition, next ring slot):
+     * no integer division inside the streaming loop. */
+    uint32_t f_it = 0, f_s = 0, f_q = q0;
+    uint32_t f_slot         = uint32_t((uint64_t(job.slot0) + q0) % d.S);
+    auto issue_next = [&]()
     {
-        uint32_t s      = it % NS;
-        uint32_t q      = q0 + it * QB;
-        uint32_t rows   = min(QB, q1 - q);
-        float2 *g       = sG + size_t(s) * stage_elems;
-        float2 *x       = sX + size_t(s) * stage_elems;
-        mbar_expect_tx(&full[s], 2u * rows * row_bytes);
+        uint32_t rows   = min(QB, q1 - f_q);
+        float2 *g       = sG + size_t(f_s) * stage_elems;
+        float2 *x       = sX + size_t(f_s) * stage_elems;
+        mbar_expect_tx(&full[f_s], 2u * rows * row_bytes);
         /* IR rows q .. q+rows-1 are contiguous when TB == M (QB > 1 only then) */
-        bulk_g2s(g, Gt + uint64_t(q - d.q_lo) * M, rows * row_bytes, &full[s]);
+        bulk_g2s(g, Gt + uint64_t(f_q - d.q_lo) * M, rows * row_bytes, &full[f_s]);
         /* ring slots (slot0 + q) mod S ascend with q: one copy, or two around the wrap */
-        uint32_t first  = uint32_t((uint64_t(job.slot0) + q) % d.S);
-        uint32_t n1     = min(rows, d.S - first);
-        bulk_g2s(x, Xt + uint64_t(first) * M, n1 * row_bytes, &full[s]);
+        uint32_t n1     = min(rows, d.S - f_slot);
+        bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s]);
         if (n1 < rows)
-            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[s]);
+            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s]);
+        ++f_it;
+        f_q            += QB;
+        f_slot         += QB;
+        if (f_slot >= d.S)  f_slot -= d.S;
+        if (++f_s == NS)    f_s = 0;
     };
 
     if (tid == 0)
     {
-        for (uint32_t it = 0; (it < NS) && (it < n_iter); ++it)
-            issue(it);
+        while ((f_it < NS) && (f_it < n_iter))
+            issue_next();
     }
 
     float4 acc[MAC_VPT];
@@ -694,14 +700,14 @@ k_mac(const StepArgs a, const MacShape sh)
         acc[v]      = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float dny       = 0.0f;         /* sum of Im*Im of the thread's first bin: Nyquist fix-up for bin 0 */
 
+    uint32_t c_s = 0, c_par = 0, c_q = q0;
     for (uint32_t it = 0; it < n_iter; ++it)
     {
-        uint32_t s      = it % NS;
-        uint32_t rows   = min(QB, q1 - (q0 + it * QB));
-        mbar_wait(&full[s], (it / NS) & 1u);
+        uint32_t rows   = min(QB, q1 - c_q);
+        mbar_wait(&full[c_s], c_par);
 
-        const float4 *g4 = reinterpret_cast<const float4 *>(sG + size_t(s) * stage_elems);
-        const float4 *x4 = reinterpret_cast<const float4 *>(sX + size_t(s) * stage_elems);
+        const float4 *g4 = reinterpret_cast<const float4 *>(sG + size_t(c_s) * stage_elems);
+        const float4 *x4 = reinterpret_cast<const float4 *>(sX + size_t(c_s) * stage_elems);
         for (uint32_t r = 0; r < rows; ++r)
         {
             #pragma unroll
@@ -721,10 +727,12 @@ k_mac(const StepArgs a, const MacShape sh)
                     dny         = fmaf(g.y, x.y, dny);
             }
         }
+        c_q            += QB;
+        if (++c_s == NS)    { c_s = 0; c_par ^= 1u; }
 
-        __syncthreads();            /* everyone is done with stage s: refill it */
-        if ((tid == 0) && (it + NS < n_iter))
-            issue(it + NS);
+        __syncthreads();            /* everyone is done with that stage: refill it */
+        if ((tid == 0) && (f_it < n_iter))
+            issue_next();
     }
 
     /* bin 0 holds (DC, Nyquist): both real, multiplied separately.  The complex MAC above gave
@@ -757,43 +765,40 @@ k_mac(const StepArgs a, const MacShape sh)
 /* a launch over TF * n_active frame-jobs.                                                       */
 
 template <int TF, int PH>
-__device__ __forceinline__ void multi_step(float4 (&acc)[TF][MAC_VPT], float4 (&win)[TF][MAC_VPT],
-                                           float (&dny)[TF], const float4 *g4, const float4 *x4,
-                                           uint32_t tid, uint32_t T)
+__device__ __forceinline__ void multi_step(float4 (&acc)[TF], float4 (&win)[TF], float (&dny)[TF],
+                                           const float4 *g4, const float4 *x4, uint32_t col)
 {
     /* the row that enters the window at this step is frame 0's operand */
     constexpr int NEW = (TF - PH) % TF;
-    float4 g[MAC_VPT];
-    #pragma unroll
-    for (int v = 0; v < MAC_VPT; ++v)
-    {
-        g[v]            = g4[tid + v * T];
-        win[NEW][v]     = x4[tid + v * T];
-    }
+    const float4 g  = g4[col];
+    win[NEW]        = x4[col];
     #pragma unroll
     for (int j = 0; j < TF; ++j)
     {
-        const int w = (j + TF - PH) % TF;
-        #pragma unroll
-        for (int v = 0; v < MAC_VPT; ++v)
-        {
-            const float4 x  = win[w][v];
-            acc[j][v].x     = fmaf(g[v].x, x.x, acc[j][v].x);
-            acc[j][v].y     = fmaf(g[v].x, x.y, acc[j][v].y);
-            acc[j][v].z     = fmaf(g[v].z, x.z, acc[j][v].z);
-            acc[j][v].w     = fmaf(g[v].z, x.w, acc[j][v].w);
-            acc[j][v].x     = fmaf(-g[v].y, x.y, acc[j][v].x);
-            acc[j][v].y     = fmaf(g[v].y, x.x, acc[j][v].y);
-            acc[j][v].z     = fmaf(-g[v].w, x.w, acc[j][v].z);
-            acc[j][v].w     = fmaf(g[v].w, x.z, acc[j][v].w);
-            if (v == 0)
-                dny[j]          = fmaf(g[v].y, x.y, dny[j]);
-        }
+        const float4 x  = win[(j + TF - PH) % TF];
+        acc[j].x        = fmaf(g.x, x.x, acc[j].x);
+        acc[j].y        = fmaf(g.x, x.y, acc[j].y);
+        acc[j].z        = fmaf(g.z, x.z, acc[j].z);
+        acc[j].w        = fmaf(g.z, x.w, acc[j].w);
+        acc[j].x        = fmaf(-g.y, x.y, acc[j].x);
+        acc[j].y        = fmaf(g.y, x.x, acc[j].y);
+        acc[j].z        = fmaf(-g.w, x.w, acc[j].z);
+        acc[j].w        = fmaf(g.w, x.z, acc[j].w);
+        dny[j]          = fmaf(g.y, x.y, dny[j]);
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+/* blockDim.x = TB/2 consumer threads (one float4 column = 2 bins each) + one producer warp.
+ * The register window limits occupancy to one CTA per SM at TF = 8, so latency is hidden inside
+ * the CTA instead: a dedicated producer warp keeps an NS-deep TMA ring full, consumers hand
+ * stages back through per-stage "empty" mbarriers, and there is no CTA-wide barrier in the loop. */
 template <int TF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(544)
 k_mac_multi(const StepArgs a, const MacShape sh)
 {
     static_assert((TF == 2) || (TF == 4) || (TF == 8), "k_mac_multi: TF must be 2, 4 or 8");
@@ -801,7 +806,7 @@ k_mac_multi(const StepArgs a, const MacShape sh)
 
     const uint32_t M        = 1u << (a.rank - 1);
     const uint32_t TB       = sh.TB, QB = sh.QB, NS = sh.NS;
-    const uint32_t T        = blockDim.x;
+    const uint32_t CONS     = blockDim.x - 32;              /* consumer threads = TB / 2 */
     const uint32_t tid      = threadIdx.x;
     const uint32_t jobi     = blockIdx.x / a.splits;        /* = index into the active list */
     const uint32_t split    = blockIdx.x % a.splits;
@@ -811,6 +816,7 @@ k_mac_multi(const StepArgs a, const MacShape sh)
     float2 *sG              = reinterpret_cast<float2 *>(smraw);
     float2 *sX              = sG + size_t(NS) * stage_elems;
     uint64_t *full          = reinterpret_cast<uint64_t *>(sX + size_t(NS) * stage_elems);
+    uint64_t *empty         = full + NS;
 
     /* job of the FIRST frame of the group: slot0 = ring slot of X_t */
     const Job job           = fetch_job(a, jobi);
@@ -831,43 +837,52 @@ k_mac_multi(const StepArgs a, const MacShape sh)
     if (tid == 0)
     {
         for (uint32_t s = 0; s < NS; ++s)
+        {
             mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONS / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](uint32_t it)
+    if (tid >= CONS)
     {
-        uint32_t s      = it % NS;
-        uint32_t q      = q0 + it * QB;
-        uint32_t rows   = min(QB, q1 - q);
-        float2 *g       = sG + size_t(s) * stage_elems;
-        float2 *x       = sX + size_t(s) * stage_elems;
-        mbar_expect_tx(&full[s], 2u * rows * row_bytes);
-        bulk_g2s(g, Gt + uint64_t(q - d.q_lo) * M, rows * row_bytes, &full[s]);
-        uint32_t first  = uint32_t((uint64_t(job.slot0) + q) % d.S);
-        uint32_t n1     = min(rows, d.S - first);
-        bulk_g2s(x, Xt + uint64_t(first) * M, n1 * row_bytes, &full[s]);
-        if (n1 < rows)
-            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[s]);
-    };
-
-    if (tid == 0)
-    {
-        for (uint32_t it = 0; (it < NS) && (it < n_iter); ++it)
-            issue(it);
+        /* ---- producer warp: one lane feeds the ring ---- */
+        if (tid == CONS)
+        {
+            uint32_t f_s = 0, f_par = 1, f_q = q0;
+            uint32_t f_slot = uint32_t((uint64_t(job.slot0) + q0) % d.S);
+            for (uint32_t it = 0; it < n_iter; ++it)
+            {
+                if (it >= NS)
+                    mbar_wait(&empty[f_s], f_par);                  /* consumers released use it - NS */
+                uint32_t rows   = min(QB, q1 - f_q);
+                float2 *g       = sG + size_t(f_s) * stage_elems;
+                float2 *x       = sX + size_t(f_s) * stage_elems;
+                mbar_expect_tx(&full[f_s], 2u * rows * row_bytes);
+                bulk_g2s(g, Gt + uint64_t(f_q - d.q_lo) * M, rows * row_bytes, &full[f_s]);
+                uint32_t n1     = min(rows, d.S - f_slot);
+                bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s]);
+                if (n1 < rows)
+                    bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s]);
+                f_q            += QB;
+                f_slot         += QB;
+                if (f_slot >= d.S)  f_slot -= d.S;
+                if (++f_s == NS)    { f_s = 0; f_par ^= 1u; }       /* parity of use (it/NS - 1) */
+            }
+        }
+        return;
     }
 
-    float4 acc[TF][MAC_VPT], win[TF][MAC_VPT];
+    /* ---- consumers ---- */
+    float4 acc[TF], win[TF];
     float dny[TF];
     #pragma unroll
     for (int j = 0; j < TF; ++j)
     {
         dny[j]          = 0.0f;
-        #pragma unroll
-        for (int v = 0; v < MAC_VPT; ++v)
-            acc[j][v]       = win[j][v] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        acc[j]          = win[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 
     /* window rows of the later frames at the first step: frame j needs X_{t+j-q0}, which sits
@@ -878,19 +893,16 @@ k_mac_multi(const StepArgs a, const MacShape sh)
         for (int j = 1; j < TF; ++j)
         {
             uint32_t slot   = uint32_t((uint64_t(job.slot0) + q0 + uint64_t(d.S) * TF - uint32_t(j)) % d.S);
-            const float4 *xr = reinterpret_cast<const float4 *>(Xt + uint64_t(slot) * M);
-            #pragma unroll
-            for (int v = 0; v < MAC_VPT; ++v)
-                win[j][v]       = __ldg(xr + tid + v * T);
+            win[j]          = __ldg(reinterpret_cast<const float4 *>(Xt + uint64_t(slot) * M) + tid);
         }
     }
 
-    uint32_t step = 0;
+    uint32_t step = 0, c_s = 0, c_par = 0, c_q = q0;
     for (uint32_t it = 0; it < n_iter; ++it)
     {
-        uint32_t s      = it % NS;
-        uint32_t rows   = min(QB, q1 - (q0 + it * QB));
-        mbar_wait(&full[s], (it / NS) & 1u);
+        const uint32_t s = c_s;
+        uint32_t rows   = min(QB, q1 - c_q);
+        mbar_wait(&full[s], c_par);
 
         const float4 *g4 = reinterpret_cast<const float4 *>(sG + size_t(s) * stage_elems);
         const float4 *x4 = reinterpret_cast<const float4 *>(sX + size_t(s) * stage_elems);
@@ -899,20 +911,24 @@ k_mac_multi(const StepArgs a, const MacShape sh)
             const float4 *gr = g4 + r * (TB / 2), *xr = x4 + r * (TB / 2);
             switch (step & (TF - 1))
             {
-                case 0: multi_step<TF, 0>(acc, win, dny, gr, xr, tid, T); break;
-                case 1: multi_step<TF, 1 % TF>(acc, win, dny, gr, xr, tid, T); break;
-                case 2: multi_step<TF, 2 % TF>(acc, win, dny, gr, xr, tid, T); break;
-                case 3: multi_step<TF, 3 % TF>(acc, win, dny, gr, xr, tid, T); break;
-                case 4: multi_step<TF, 4 % TF>(acc, win, dny, gr, xr, tid, T); break;
-                case 5: multi_step<TF, 5 % TF>(acc, win, dny, gr, xr, tid, T); break;
-                case 6: multi_step<TF, 6 % TF>(acc, win, dny, gr, xr, tid, T); break;
-                default: multi_step<TF, 7 % TF>(acc, win, dny, gr, xr, tid, T); break;
+                case 0: multi_step<TF, 0>(acc, win, dny, gr, xr, tid); break;
+                case 1: multi_step<TF, 1 % TF>(acc, win, dny, gr, xr, tid); break;
+                case 2: multi_step<TF, 2 % TF>(acc, win, dny, gr, xr, tid); break;
+                case 3: multi_step<TF, 3 % TF>(acc, win, dny, gr, xr, tid); break;
+                case 4: multi_step<TF, 4 % TF>(acc, win, dny, gr, xr, tid); break;
+                case 5: multi_step<TF, 5 % TF>(acc, win, dny, gr, xr, tid); break;
+                case 6: multi_step<TF, 6 % TF>(acc, win, dny, gr, xr, tid); break;
+                default: multi_step<TF, 7 % TF>(acc, win, dny, gr, xr, tid); break;
             }
         }
 
-        __syncthreads();
-        if ((tid == 0) && (it + NS < n_iter))
-            issue(it + NS);
+        c_q            += QB;
+        if (++c_s == NS)    { c_s = 0; c_par ^= 1u; }
+
+        /* this warp is done with stage s */
+        __syncwarp();
+        if ((tid & 31) == 0)
+            mbar_arrive(&empty[s]);
     }
 
     #pragma unroll
@@ -920,14 +936,12 @@ k_mac_multi(const StepArgs a, const MacShape sh)
     {
         if ((tile == 0) && (tid == 0))
         {
-            acc[j][0].x    += dny[j];
-            acc[j][0].y     = dny[j];
+            acc[j].x       += dny[j];
+            acc[j].y        = dny[j];
         }
         float4 *yp      = reinterpret_cast<float4 *>(
             a.ypart + ((uint64_t(j) * a.n_active + jobi) * a.splits + split) * M + uint64_t(tile) * TB);
-        #pragma unroll
-        for (int v = 0; v < MAC_VPT; ++v)
-            yp[tid + v * T] = acc[j][v];
+        yp[tid]         = acc[j];
     }
 }
 
@@ -1003,21 +1017,36 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
     const float2 *Xt        = d.ring;
     const uint32_t row_bytes = M * uint32_t(sizeof(float2));
 
-    auto issue = [&](uint32_t it)
+    /* Stage-ring bookkeeping is incremental (next stage buffer, next position in the chunk, next
+     * ring slot): no integer division inside the streaming loop.  `issued` = stages fetched. */
+    const uint32_t slot_q0  = uint32_t((uint64_t(job.slot0) + q0) % d.S);
+    uint32_t issued = 0, f_s = 0, f_stg = shift;
+    uint32_t f_slot         = slot_q0 + shift * QB;
+    if (f_slot >= d.S)      f_slot -= d.S;
+    auto issue_next = [&]()
     {
-        uint32_t s      = it % NS;
-        uint32_t stg    = (it + shift) % n_iter;
-        uint32_t q      = q0 + stg * QB;
+        uint32_t q      = q0 + f_stg * QB;
         uint32_t rows   = min(QB, q1 - q);
-        float2 *g       = stages + size_t(s) * 2 * stage_elems;
+        float2 *g       = stages + size_t(f_s) * 2 * stage_elems;
         float2 *x       = g + stage_elems;
-        mbar_expect_tx(&full[s], 2u * rows * row_bytes);
-        bulk_g2s(g, Gt + uint64_t(q - d.q_lo) * M, rows * row_bytes, &full[s]);
-        uint32_t first  = uint32_t((uint64_t(job.slot0) + q) % d.S);
-        uint32_t n1     = min(rows, d.S - first);
-        bulk_g2s(x, Xt + uint64_t(first) * M, n1 * row_bytes, &full[s]);
+        mbar_expect_tx(&full[f_s], 2u * rows * row_bytes);
+        bulk_g2s(g, Gt + uint64_t(q - d.q_lo) * M, rows * row_bytes, &full[f_s]);
+        uint32_t n1     = min(rows, d.S - f_slot);
+        bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s]);
         if (n1 < rows)
-            bulk_g2s(x + size_t(n1) * M, Xt, (rows - n1) * row_bytes, &full[s]);
+            bulk_g2s(x + size_t(n1) * M, Xt, (rows - n1) * row_bytes, &full[f_s]);
+        ++issued;
+        if (++f_s == NS)    f_s = 0;
+        if (++f_stg == n_iter)
+        {
+            f_stg           = 0;            /* the rotated first stage comes last */
+            f_slot          = slot_q0;
+        }
+        else
+        {
+            f_slot         += QB;
+            if (f_slot >= d.S)  f_slot -= d.S;
+        }
     };
 
     /* prologue: the FFT CTA keeps the last SCR stage buffers as transform scratch (two work
@@ -1025,7 +1054,6 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
      * final stage yet -- that one reads the spectrum which is about to be written */
     const uint32_t SCR      = ((NS >= 3) && (2 * stage_elems >= N)) ? 2 : 1;
     uint32_t pre            = min(NS, n_iter);
-    uint32_t issued         = 0;            /* thread 0: stages fetched so far */
     if (fft_cta)
     {
         /* Its partitions q >= 1 need the spectra of frames <= t - 1.  In steady state they were
@@ -1039,8 +1067,8 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
             if (int32_t(have - job.tlo) >= 0)
             {
                 asm volatile("fence.proxy.async;" ::: "memory");
-                for ( ; issued < pre; ++issued)
-                    issue(issued);
+                while (issued < pre)
+                    issue_next();
             }
         }
     }
@@ -1062,8 +1090,8 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
             }
             asm volatile("fence.proxy.async;" ::: "memory");
         }
-        for ( ; issued < pre; ++issued)
-            issue(issued);
+        while (issued < pre)
+            issue_next();
     }
     if (fft_cta)
     {
@@ -1116,8 +1144,8 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
             const uint32_t head = job.tlo + 1u;
             asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(hp), "r"(head) : "memory");
             asm volatile("fence.proxy.async;" ::: "memory");
-            for ( ; (issued < NS) && (issued < n_iter); ++issued)
-                issue(issued);
+            while ((issued < NS) && (issued < n_iter))
+                issue_next();
         }
     }
 
@@ -1127,14 +1155,13 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
         acc[v]      = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float dny       = 0.0f;
 
+    uint32_t c_s = 0, c_par = 0, c_stg = shift;
     for (uint32_t it = 0; it < n_iter; ++it)
     {
-        uint32_t s      = it % NS;
-        uint32_t stg    = (it + shift) % n_iter;
-        uint32_t rows   = min(QB, q1 - (q0 + stg * QB));
-        mbar_wait(&full[s], (it / NS) & 1u);
+        uint32_t rows   = min(QB, q1 - (q0 + c_stg * QB));
+        mbar_wait(&full[c_s], c_par);
 
-        const float4 *g4 = reinterpret_cast<const float4 *>(stages + size_t(s) * 2 * stage_elems);
+        const float4 *g4 = reinterpret_cast<const float4 *>(stages + size_t(c_s) * 2 * stage_elems);
         const float4 *x4 = g4 + stage_elems / 2;
         for (uint32_t r = 0; r < rows; ++r)
         {
@@ -1155,10 +1182,12 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
                     dny         = fmaf(g.y, x.y, dny);
             }
         }
+        if (++c_stg == n_iter)  c_stg = 0;
+        if (++c_s == NS)        { c_s = 0; c_par ^= 1u; }
 
         __syncthreads();
-        if ((tid == 0) && (it + NS < n_iter))
-            issue(it + NS);
+        if ((tid == 0) && (issued < n_iter))
+            issue_next();
     }
 
     if (tid == 0)
