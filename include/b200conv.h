@@ -171,6 +171,20 @@ int     b200conv_fastconv_parse_apply(int device, float *dst, const float *c, co
 int     b200conv_fastconv_restore(int device, float *dst, const float *image, size_t rank,
                                   size_t count, void *stream);
 
+/* ---- offline linear convolution ("next" row f1 of the scope table) -------------------------- */
+
+/* Full linear convolution of `count` signals with ONE filter, host buffers:
+ *     dst[i][0 .. nx + nh - 1) = src[i][0 .. nx) (*) h[0 .. nh)
+ * The operation of SyncChirpProcessor::do_linear_convolution(s) (reference
+ * src/main/util/SyncChirpProcessor.cpp:1374-1508: O(P^2) partition pairs of fastconv_parse +
+ * fastconv_apply per channel), run as ONE batched multi-frame pass of the convolver engine:
+ * the filter is the impulse response, the signal zero-padded by nh - 1 is the input.
+ * `rank` as in b200conv_init (partition = 2^(rank-1) samples); rows are `*_stride` floats apart.
+ * Synchronous. */
+int     b200conv_linear_convolve(int device, float *dst, size_t dst_stride, const float *src,
+                                 size_t src_stride, size_t nx, size_t count, const float *h,
+                                 size_t nh, size_t rank);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 const char *b200conv_last_error(void);      /* thread-local text of the last failure */

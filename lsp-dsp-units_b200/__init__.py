@@ -88,6 +88,7 @@ _SIGNATURES = {
     "b200conv_fastconv_apply": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_fastconv_parse_apply": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_fastconv_restore": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _SZ, _SZ, _VP]),
+    "b200conv_linear_convolve": (ctypes.c_int, [ctypes.c_int, _VP, _SZ, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _SZ]),
     "b200conv_last_error": (ctypes.c_char_p, []),
     "b200conv_version": (ctypes.c_char_p, []),
 }
@@ -282,3 +283,18 @@ class Convolver:
 
     def state(self):
         return self._b.state(0) if self._b is not None else None
+
+
+def linear_convolve(src, h, rank=11, device=0):
+    """Full linear convolution of every row of ``src`` with ``h`` on the GPU
+    (``b200conv_linear_convolve``; SyncChirpProcessor::do_linear_convolution's operation)."""
+    src = np.ascontiguousarray(src, dtype=np.float32)
+    one = src.ndim == 1
+    if one:
+        src = src[None, :]
+    h = np.ascontiguousarray(h, dtype=np.float32)
+    count, nx = src.shape
+    out = np.empty((count, nx + h.size - 1), dtype=np.float32)
+    _check(lib().b200conv_linear_convolve(device, out.ctypes.data, out.shape[1], src.ctypes.data, nx, nx,
+                                          count, h.ctypes.data, h.size, rank))
+    return out[0] if one else out

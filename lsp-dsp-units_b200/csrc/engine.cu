@@ -1425,3 +1425,47 @@ extern "C" int b200conv_fastconv_parse_apply(int device, float *dst, const float
     CU(cudaGetLastError());
     return prim_inverse(c, dst, prod, rank, count, true, rows, st);
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* offline linear convolution                                                                   */
+
+extern "C" int b200conv_linear_convolve(int device, float *dst, size_t dst_stride, const float *src,
+                                        size_t src_stride, size_t nx, size_t count, const float *h,
+                                        size_t nh, size_t rank)
+{
+    if ((dst == nullptr) || (src == nullptr) || (h == nullptr) || (nx == 0) || (nh == 0) || (count == 0) ||
+        (src_stride < nx) || (dst_stride < nx + nh - 1))
+        return fail(B200CONV_ERR_ARG, "b200conv_linear_convolve: bad arguments");
+
+    b200conv_batch_t *b = nullptr;
+    TRY(b200conv_create(&b, device, count));
+    int rc = B200CONV_OK;
+    for (size_t i = 0; (i < count) && (rc == B200CONV_OK); ++i)
+        rc = b200conv_init(b, i, h, nh, rank, 0.0f);
+
+    float *in = nullptr, *out = nullptr;
+    if (rc == B200CONV_OK)
+    {
+        const size_t F      = size_t(1) << (b->rank - 1);
+        const size_t total  = ((nx + nh - 1 + F - 1) / F) * F;     /* whole frames: the fast path */
+        if ((cudaMallocHost(&in, count * total * sizeof(float)) != cudaSuccess) ||
+            (cudaMallocHost(&out, count * total * sizeof(float)) != cudaSuccess))
+            rc = fail(B200CONV_ERR_NOMEM, "b200conv_linear_convolve: out of page-locked host memory");
+        else
+        {
+            memset(in, 0, count * total * sizeof(float));
+            for (size_t i = 0; i < count; ++i)
+                memcpy(in + i * total, src + i * src_stride, nx * sizeof(float));
+            rc = b200conv_process_planar(b, out, in, total, total);
+            if (rc == B200CONV_OK)
+                for (size_t i = 0; i < count; ++i)
+                    memcpy(dst + i * dst_stride, out + i * total, (nx + nh - 1) * sizeof(float));
+        }
+    }
+    std::string keep = g_last_error;
+    if (in)  cudaFreeHost(in);
+    if (out) cudaFreeHost(out);
+    b200conv_free(b);
+    g_last_error = keep;
+    return rc;
+}

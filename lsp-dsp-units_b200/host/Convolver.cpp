@@ -72,8 +72,10 @@ namespace lsp
             if (count == 0)
                 return;
 
-            // the reference has no error channel here; a device failure yields silence
-            if (b200conv_process(pEngine, &dst, &src, count) != B200CONV_OK)
+            // a batch of one is a 1 x count planar matrix: page-locked buffers are read and
+            // written by the kernels directly, others are staged.  The reference has no error
+            // channel here; a device failure yields silence.
+            if (b200conv_process_planar(pEngine, dst, src, count, count) != B200CONV_OK)
                 ::memset(dst, 0, count * sizeof(float));
         }
 

@@ -78,3 +78,19 @@ def test_primitives_reject_bad_arguments(pkg):
     assert lib.b200conv_fastconv_parse(0, x.data_ptr(), x.data_ptr(), 7, 1, None) == pkg.ERR_ARG
     assert lib.b200conv_fastconv_parse(0, x.data_ptr(), x.data_ptr(), 17, 1, None) == pkg.ERR_ARG
     assert lib.b200conv_fastconv_restore(0, x.data_ptr(), x.data_ptr(), 9, 0, None) == pkg.ERR_ARG
+
+
+@pytest.mark.parametrize("nx,nh,rank,count", [(1000, 300, 8, 3), (48000, 20000, 11, 2), (5, 7, 9, 1),
+                                              (100000, 100000, 13, 1)])
+def test_linear_convolve_matches_float64(pkg, nx, nh, rank, count):
+    """Offline full linear convolution (scope-table row f1: SyncChirpProcessor::do_linear_convolution,
+    reference src/main/util/SyncChirpProcessor.cpp:1406-1508) as one batched multi-frame pass."""
+    from oracle.bindings import direct_convolve
+    rng = np.random.Generator(np.random.PCG64(nx + nh))
+    x = rng.uniform(-1, 1, (count, nx)).astype(np.float32)
+    h = rng.uniform(-1, 1, nh).astype(np.float32)
+    got = pkg.linear_convolve(x, h, rank=rank)
+    assert got.shape == (count, nx + nh - 1)
+    for i in range(count):
+        want = direct_convolve(x[i], h)
+        assert np.max(np.abs(got[i] - want)) <= 1e-5 * np.max(np.abs(want))
