@@ -841,12 +841,18 @@ static inline uint32_t slot_of(const Instance &in, uint64_t t)
     return uint32_t((tm == 0) ? 0 : in.S - tm);
 }
 
-/* Any call size / any phase: explicit job lists, one segment per instance per step. */
+/* Any call size / any phase: explicit job lists.  One step =
+ *     k_store + k_partial (samples of frames in progress, answered from their pending block)
+ *  -> k_fwd               (frames that just completed, and whole frames taken from the input)
+ *  -> k_mac -> k_inv      (whole frames: every partition -> output;
+ *                          frames about to start: partitions q >= 1 -> their pending block)
+ * and each instance contributes at most one item per stage.  A frame that completes has its
+ * spectrum pushed and the next frame's pending block prepared in the same step, so the samples
+ * that follow -- in this call or the next -- are one launch pair away. */
 static int process_general(Batch *b, float *dst, const float *src, size_t stride, size_t count,
                            cudaStream_t st)
 {
     const size_t F      = size_t(1) << (b->rank - 1);
-    const size_t nact   = b->active.size();
     TRY(upload_tables(b, st));
     std::vector<size_t> pos(b->n, 0);
     std::vector<Job> fft, mac, part;
@@ -863,70 +869,89 @@ static int process_general(Batch *b, float *dst, const float *src, size_t stride
             float *cur  = in.aux, *pend = in.aux + F;
             Job j;
 
-            if (in.off == F)
+            auto push_frame_spectrum = [&](const float *samples)
             {
-                /* the frame delivered in pieces is complete: its spectrum enters the ring */
                 memset(&j, 0, sizeof(j));
                 j.inst      = i;
-                j.src       = cur;
+                j.src       = samples;
                 j.slot0     = slot_of(in, in.frames);
                 j.spec      = in.ring + size_t(j.slot0) * F;
                 fft.push_back(j);
+            };
+            auto push_pending_block = [&]()
+            {
+                /* what the complete frames contribute to the frame about to start: q >= 1 */
+                memset(&j, 0, sizeof(j));
+                j.inst      = i;
+                j.dst       = pend;
+                j.slot0     = slot_of(in, in.frames);
+                j.qa        = uint32_t((in.q_lo > 1) ? in.q_lo : 1);
+                j.qb        = uint32_t(in.q_lo + in.nq);
+                mac.push_back(j);
+                bytes      += algo_bytes(b, in, j.qa, j.qb);
+                in.pend_valid = true;
+                b->stats.frames += 1;
+            };
+
+            if (in.off == F)
+            {
+                /* a complete frame whose spectrum is still owed to the ring */
+                push_frame_spectrum(cur);
                 in.frames  += 1;
                 in.off      = 0;
                 in.pend_valid = false;
             }
 
-            size_t n    = count - pos[i];
-            if (n > F - in.off)
-                n           = F - in.off;
-            const float *s  = src + size_t(i) * stride + pos[i];
-            float *d        = dst + size_t(i) * stride + pos[i];
-
-            if ((in.off == 0) && (n == F))
-            {
-                /* a whole frame at once: FFT -> MAC over every partition -> IFFT -> out */
-                memset(&j, 0, sizeof(j));
-                j.inst      = i;
-                j.src       = s;
-                j.dst       = d;
-                j.slot0     = slot_of(in, in.frames);
-                j.spec      = in.ring + size_t(j.slot0) * F;
-                j.qa        = uint32_t(in.q_lo);
-                j.qb        = uint32_t(in.q_lo + in.nq);
-                fft.push_back(j);
-                mac.push_back(j);
-                bytes      += algo_bytes(b, in, j.qa, j.qb);
-                in.frames  += 1;
-                in.pend_valid = false;
-                b->stats.frames += 1;
-            }
-            else
+            size_t rem  = count - pos[i];
+            if (!((in.off == 0) && (rem >= F)))
             {
                 if (!in.pend_valid)
                 {
-                    /* what the complete frames contribute to the frame in progress: q >= 1 */
-                    memset(&j, 0, sizeof(j));
-                    j.inst      = i;
-                    j.dst       = pend;
-                    j.slot0     = slot_of(in, in.frames);
-                    j.qa        = uint32_t((in.q_lo > 1) ? in.q_lo : 1);
-                    j.qb        = uint32_t(in.q_lo + in.nq);
-                    mac.push_back(j);
-                    bytes      += algo_bytes(b, in, j.qa, j.qb);
-                    in.pend_valid = true;
-                    b->stats.frames += 1;
+                    /* the pending block first; the samples are answered in the next step */
+                    push_pending_block();
+                    continue;
                 }
+
+                /* the next samples of the frame in progress (zero latency for any call size) */
+                size_t n    = (rem < F - in.off) ? rem : F - in.off;
                 memset(&j, 0, sizeof(j));
                 j.inst      = i;
-                j.src       = s;
-                j.dst       = d;
+                j.src       = src + size_t(i) * stride + pos[i];
+                j.dst       = dst + size_t(i) * stride + pos[i];
                 j.off       = uint32_t(in.off);
                 j.n         = uint32_t(n);
                 part.push_back(j);
                 in.off     += n;
+                pos[i]     += n;
+                rem        -= n;
+                if (in.off < F)
+                    continue;                       /* frame still open: the call is exhausted */
+
+                /* the frame is complete: spectrum into the ring in this same step (k_store runs
+                 * before k_fwd), and straight on to what the next samples will need */
+                push_frame_spectrum(cur);
+                in.frames  += 1;
+                in.off      = 0;
+                in.pend_valid = false;
+                if (rem < F)
+                {
+                    push_pending_block();
+                    continue;
+                }
             }
-            pos[i]     += n;
+
+            /* a whole frame at once: FFT -> MAC over every partition -> IFFT -> out */
+            push_frame_spectrum(src + size_t(i) * stride + pos[i]);
+            j.dst       = dst + size_t(i) * stride + pos[i];
+            j.qa        = uint32_t(in.q_lo);
+            j.qb        = uint32_t(in.q_lo + in.nq);
+            fft.back()  = j;
+            mac.push_back(j);
+            bytes      += algo_bytes(b, in, j.qa, j.qb);
+            in.frames  += 1;
+            in.pend_valid = false;
+            b->stats.frames += 1;
+            pos[i]     += F;
         }
 
         size_t total = fft.size() + mac.size() + part.size();
@@ -936,15 +961,29 @@ static int process_general(Batch *b, float *dst, const float *src, size_t stride
         size_t at = 0;
         TRY(reserve_jobs(b, total, st, &at));
         Job *hj = b->h_jobs + at;
-        if (!fft.empty())   memcpy(hj, fft.data(), fft.size() * sizeof(Job));
-        if (!mac.empty())   memcpy(hj + fft.size(), mac.data(), mac.size() * sizeof(Job));
-        if (!part.empty())  memcpy(hj + fft.size() + mac.size(), part.data(), part.size() * sizeof(Job));
+        if (!part.empty())  memcpy(hj, part.data(), part.size() * sizeof(Job));
+        if (!fft.empty())   memcpy(hj + part.size(), fft.data(), fft.size() * sizeof(Job));
+        if (!mac.empty())   memcpy(hj + part.size() + fft.size(), mac.data(), mac.size() * sizeof(Job));
         TRY(push_jobs(b, at, total, st));
 
         StepArgs a  = base_args(b);
-        if (!fft.empty())
+        if (!part.empty())
         {
             a.jobs      = b->d_jobs + at;
+            a.n_jobs    = uint32_t(part.size());
+            size_t maxn = 0;
+            for (const Job &pj : part)
+                if (pj.n > maxn) maxn = pj.n;
+            dim3 grid(uint32_t((maxn + 127) / 128), a.n_jobs);
+            k_store<<<grid, 128, 0, st>>>(a);
+            CU(cudaGetLastError());
+            k_partial<<<grid, 128, 0, st>>>(a);
+            CU(cudaGetLastError());
+            b->stats.launches += 2;
+        }
+        if (!fft.empty())
+        {
+            a.jobs      = b->d_jobs + at + part.size();
             a.n_jobs    = uint32_t(fft.size());
             CU(launch_fwd(a, a.n_jobs, st));
             b->stats.launches++;
@@ -955,7 +994,7 @@ static int process_general(Batch *b, float *dst, const float *src, size_t stride
                                     b->sm_count, b->tune_splits, b->tune_stages);
             TRY(ensure_ypart(b, mac.size() * plan.splits * F * sizeof(float2), st));
             a.ypart     = b->ypart;
-            a.jobs      = b->d_jobs + at + fft.size();
+            a.jobs      = b->d_jobs + at + part.size() + fft.size();
             a.n_jobs    = uint32_t(mac.size());
             a.splits    = plan.splits;
             CU(launch_mac(b, a, plan, a.n_jobs, st));
@@ -964,23 +1003,8 @@ static int process_general(Batch *b, float *dst, const float *src, size_t stride
             b->stats.mac_launches   += 1;
             b->stats.mac_algo_bytes += bytes;
         }
-        if (!part.empty())
-        {
-            a.jobs      = b->d_jobs + at + fft.size() + mac.size();
-            a.n_jobs    = uint32_t(part.size());
-            size_t maxn = 0;
-            for (const Job &j : part)
-                if (j.n > maxn) maxn = j.n;
-            dim3 grid(uint32_t((maxn + 127) / 128), a.n_jobs);
-            k_store<<<grid, 128, 0, st>>>(a);
-            CU(cudaGetLastError());
-            k_partial<<<grid, 128, 0, st>>>(a);
-            CU(cudaGetLastError());
-            b->stats.launches += 2;
-        }
     }
 
-    (void)nact;
     b->desc_dirty = true;       /* per-instance frame counters moved independently of t_batch */
     return B200CONV_OK;
 }
