@@ -116,6 +116,10 @@ int     b200conv_process_planar(b200conv_batch_t *h, float *dst, const float *sr
 int     b200conv_process_device(b200conv_batch_t *h, float *dst, const float *src,
                                 size_t stride, size_t count, void *stream);
 
+/* Same with separate row strides for the two matrices. */
+int     b200conv_process_device2(b200conv_batch_t *h, float *dst, size_t dst_stride,
+                                 const float *src, size_t src_stride, size_t count, void *stream);
+
 /* Waits for everything enqueued on the batch's own stream. */
 int     b200conv_sync(b200conv_batch_t *h);
 

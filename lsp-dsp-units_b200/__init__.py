@@ -73,6 +73,7 @@ _SIGNATURES = {
     "b200conv_process": (ctypes.c_int, [_VP, ctypes.POINTER(_FP), ctypes.POINTER(_FP), _SZ]),
     "b200conv_process_planar": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ]),
     "b200conv_process_device": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ, _VP]),
+    "b200conv_process_device2": (ctypes.c_int, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _VP]),
     "b200conv_sync": (ctypes.c_int, [_VP]),
     "b200conv_data_size": (_SZ, [_VP, _SZ]),
     "b200conv_rank": (_SZ, [_VP, _SZ]),
@@ -176,9 +177,11 @@ class ConvolverBatch:
         dp = (_FP * self.instances)(*[_ptr(a) for a in dsts])
         _check(lib().b200conv_process(self._h, dp, sp, count))
 
-    def process_device(self, dst_ptr, src_ptr, stride, count, stream=None):
-        """Device pointers (ints), ``[instances][stride]`` floats; asynchronous."""
-        _check(lib().b200conv_process_device(self._h, dst_ptr, src_ptr, stride, count, stream))
+    def process_device(self, dst_ptr, src_ptr, stride, count, stream=None, dst_stride=None):
+        """Device pointers (ints), ``[instances][stride]`` floats; asynchronous.  ``dst_stride``
+        (default: ``stride``) lets the output matrix have its own row pitch."""
+        _check(lib().b200conv_process_device2(self._h, dst_ptr, stride if dst_stride is None else dst_stride,
+                                              src_ptr, stride, count, stream))
 
     def sync(self):
         _check(lib().b200conv_sync(self._h))

@@ -745,8 +745,8 @@ extern "C" int b200conv_init(b200conv_batch_t *b, size_t idx, const float *data,
 
 /* All active instances sit on a frame boundary and `frames` whole frames arrive: derive the
  * jobs on the device, three launches per frame for all instances x partitions. */
-static int process_uniform(Batch *b, float *dst, const float *src, size_t stride, size_t frames,
-                           cudaStream_t st)
+static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float *src, size_t stride,
+                           size_t frames, cudaStream_t st)
 {
     const uint32_t nact = uint32_t(b->active.size());
     TRY(upload_tables(b, st));
@@ -763,6 +763,7 @@ static int process_uniform(Batch *b, float *dst, const float *src, size_t stride
     a.src           = src;
     a.dst           = dst;
     a.stride        = stride;
+    a.stride_dst    = dst_stride;
     a.splits        = plan.splits;
     a.n_jobs        = nact;
     a.t_base        = b->t_batch;
@@ -849,8 +850,8 @@ static inline uint32_t slot_of(const Instance &in, uint64_t t)
  * and each instance contributes at most one item per stage.  A frame that completes has its
  * spectrum pushed and the next frame's pending block prepared in the same step, so the samples
  * that follow -- in this call or the next -- are one launch pair away. */
-static int process_general(Batch *b, float *dst, const float *src, size_t stride, size_t count,
-                           cudaStream_t st)
+static int process_general(Batch *b, float *dst, size_t dst_stride, const float *src, size_t stride,
+                           size_t count, cudaStream_t st)
 {
     const size_t F      = size_t(1) << (b->rank - 1);
     TRY(upload_tables(b, st));
@@ -917,7 +918,7 @@ static int process_general(Batch *b, float *dst, const float *src, size_t stride
                 memset(&j, 0, sizeof(j));
                 j.inst      = i;
                 j.src       = src + size_t(i) * stride + pos[i];
-                j.dst       = dst + size_t(i) * stride + pos[i];
+                j.dst       = dst + size_t(i) * dst_stride + pos[i];
                 j.off       = uint32_t(in.off);
                 j.n         = uint32_t(n);
                 part.push_back(j);
@@ -942,7 +943,7 @@ static int process_general(Batch *b, float *dst, const float *src, size_t stride
 
             /* a whole frame at once: FFT -> MAC over every partition -> IFFT -> out */
             push_frame_spectrum(src + size_t(i) * stride + pos[i]);
-            j.dst       = dst + size_t(i) * stride + pos[i];
+            j.dst       = dst + size_t(i) * dst_stride + pos[i];
             j.qa        = uint32_t(in.q_lo);
             j.qb        = uint32_t(in.q_lo + in.nq);
             fft.back()  = j;
@@ -1009,14 +1010,14 @@ static int process_general(Batch *b, float *dst, const float *src, size_t stride
     return B200CONV_OK;
 }
 
-extern "C" int b200conv_process_device(b200conv_batch_t *b, float *dst, const float *src,
-                                       size_t stride, size_t count, void *stream)
+extern "C" int b200conv_process_device2(b200conv_batch_t *b, float *dst, size_t dst_stride,
+                                        const float *src, size_t src_stride, size_t count, void *stream)
 {
     if (b == nullptr)
         return fail(B200CONV_ERR_ARG, "b200conv_process_device: NULL handle");
     if (count == 0)
         return B200CONV_OK;
-    if ((dst == nullptr) || (src == nullptr) || (stride < count))
+    if ((dst == nullptr) || (src == nullptr) || ((b->n > 1) && ((src_stride < count) || (dst_stride < count))))
         return fail(B200CONV_ERR_ARG, "b200conv_process_device: bad buffers");
     TRY(set_device(b));
     cudaStream_t st = (stream != nullptr) ? cudaStream_t(stream) : b->stream;
@@ -1028,7 +1029,10 @@ extern "C" int b200conv_process_device(b200conv_batch_t *b, float *dst, const fl
         size_t j = i;
         while ((j < b->n) && (!b->inst[j].active))
             ++j;
-        CU(cudaMemset2DAsync(dst + i * stride, stride * sizeof(float), 0, count * sizeof(float), j - i, st));
+        if ((j - i == 1) || (dst_stride == count))
+            CU(cudaMemsetAsync(dst + i * dst_stride, 0, ((j - i - 1) * dst_stride + count) * sizeof(float), st));
+        else
+            CU(cudaMemset2DAsync(dst + i * dst_stride, dst_stride * sizeof(float), 0, count * sizeof(float), j - i, st));
         i = j;
     }
     if (b->active.empty())
@@ -1041,8 +1045,14 @@ extern "C" int b200conv_process_device(b200conv_batch_t *b, float *dst, const fl
             uniform = false;
 
     if (uniform)
-        return process_uniform(b, dst, src, stride, count / F, st);
-    return process_general(b, dst, src, stride, count, st);
+        return process_uniform(b, dst, dst_stride, src, src_stride, count / F, st);
+    return process_general(b, dst, dst_stride, src, src_stride, count, st);
+}
+
+extern "C" int b200conv_process_device(b200conv_batch_t *b, float *dst, const float *src,
+                                       size_t stride, size_t count, void *stream)
+{
+    return b200conv_process_device2(b, dst, stride, src, stride, count, stream);
 }
 
 static int ensure_staging(Batch *b, size_t floats)

@@ -64,7 +64,8 @@ struct StepArgs                     /* by-value kernel argument */
     uint32_t        pad0;
     const float    *src;            /* uniform mode: [instances][stride]                            */
     float          *dst;
-    uint64_t        stride;
+    uint64_t        stride;         /* uniform mode: floats between instance rows of src            */
+    uint64_t        stride_dst;     /* ... of dst                                                   */
     uint64_t        t_base;         /* uniform mode: batch frame counter of frame 0 of this launch  */
     uint32_t        n_active;
     uint32_t        n_jobs;
@@ -94,7 +95,7 @@ __device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
     r.tlo               = uint32_t(t);
     r.pad               = 0;
     r.src               = a.src + uint64_t(r.inst) * a.stride + uint64_t(f) * F;
-    r.dst               = a.dst + uint64_t(r.inst) * a.stride + uint64_t(f) * F;
+    r.dst               = a.dst + uint64_t(r.inst) * a.stride_dst + uint64_t(f) * F;
     r.spec              = d.ring + uint64_t(r.slot0) * F;
     r.qa                = d.q_lo;
     r.qb                = d.q_lo + d.nq;

@@ -48,6 +48,10 @@ namespace b200conv
             bool process_device(float *dst, const float *src, size_t stride, size_t count, void *stream = NULL)
                 { return b200conv_process_device(pBatch, dst, src, stride, count, stream) == B200CONV_OK; }
 
+            /** Same with separate row pitches for the two matrices */
+            bool process_device(float *dst, size_t dst_stride, const float *src, size_t src_stride, size_t count, void *stream)
+                { return b200conv_process_device2(pBatch, dst, dst_stride, src, src_stride, count, stream) == B200CONV_OK; }
+
             bool sync()                             { return b200conv_sync(pBatch) == B200CONV_OK; }
             size_t data_size(size_t idx) const      { return b200conv_data_size(pBatch, idx); }
             size_t rank(size_t idx) const           { return b200conv_rank(pBatch, idx); }

@@ -435,3 +435,31 @@ def test_multi_frame_calls_share_one_pass_over_the_ir(pkg, rank, multi):
         else:
             assert rel_err(out[c], direct_convolve(src[c], ir, total)) <= TOL, (c, lens[c])
     b.close()
+
+
+@pytest.mark.parametrize("block", [1024, 700])
+def test_device_api_with_separate_row_strides(pkg, block):
+    """b200conv_process_device2: the input and output matrices have their own row pitch
+    (whole-frame path for 1024-sample calls, partial-frame path for 700)."""
+    torch = pytest.importorskip("torch")
+    n, L, rank, nblk = 5, 9000, 11, 9
+    b = pkg.ConvolverBatch(n, 0)
+    irs = [synth.decaying_ir(c, L) for c in range(n)]
+    for c in range(n):
+        assert b.init(c, irs[c], rank, 0.0)
+    src = np.stack([synth.noise(90 + c, nblk * block) for c in range(n)])
+    dsrc = torch.from_numpy(src).cuda()                     # row pitch nblk * block
+    guard = 64
+    ddst = torch.full((n, block + guard), 7.0, device="cuda")   # one block per row + a guard band
+    out = np.empty_like(src)
+    torch.cuda.synchronize()
+    for i in range(nblk):
+        b.process_device(ddst.data_ptr(), dsrc.data_ptr() + 4 * i * block, nblk * block, block,
+                         dst_stride=block + guard)
+        b.sync()
+        blk = ddst.cpu().numpy()
+        assert np.all(blk[:, block:] == 7.0)                # nothing written past the block
+        out[:, i * block:(i + 1) * block] = blk[:, :block]
+    for c in range(n):
+        assert rel_err(out[c], direct_convolve(src[c], irs[c], nblk * block)) <= TOL
+    b.close()

@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--channels", type=int, default=8)
     ap.add_argument("--blocks", type=int, default=2000)
     ap.add_argument("--depth", type=int, default=4)
+    ap.add_argument("--reduce-every", type=int, default=1,
+                    help="blocks per all-reduce: 1 = every 1024-sample block gets its own 32 KiB reduce "
+                         "(real-time use); K > 1 amortises the per-collective host cost (offline use)")
     ap.add_argument("--check", action="store_true")
     args = ap.parse_args()
 
@@ -57,27 +60,33 @@ def main():
     nblk = args.blocks
     g = torch.Generator(device="cuda").manual_seed(1234)           # same input on every rank
     src = torch.rand((C, 64 * F), generator=g, device="cuda") * 2 - 1
-    ring = [torch.empty((C, F), device="cuda") for _ in range(args.depth)]
+    K = max(1, args.reduce_every)
+    ring = [torch.empty((C, K * F), device="cuda") for _ in range(args.depth)]
     done = [None] * args.depth
     out_keep = torch.empty((C, 64 * F), device="cuda") if args.check else None
     compute, comm = torch.cuda.Stream(), torch.cuda.Stream()
 
     def run(blocks, keep):
-        for t in range(blocks):
-            k = t % args.depth
+        for g0 in range(0, blocks, K):
+            k = (g0 // K) % args.depth
             if done[k] is not None:
                 compute.wait_event(done[k])                       # the slot's previous reduce has finished
-            i = t % 64
             with torch.cuda.stream(compute):
-                b.process_device(ring[k].data_ptr(), src.data_ptr() + 4 * i * F, 64 * F, F, compute.cuda_stream)
+                for u in range(K):                                # K consecutive 1024-sample process calls
+                    i = (g0 + u) % 64
+                    b.process_device(ring[k].data_ptr() + 4 * u * F, src.data_ptr() + 4 * i * F,
+                                     64 * F, F, compute.cuda_stream, dst_stride=K * F)
                 ready = torch.cuda.Event()
                 ready.record(compute)
             with torch.cuda.stream(comm):
                 comm.wait_event(ready)
                 if world > 1:
                     dist.all_reduce(ring[k], op=dist.ReduceOp.SUM)
-                if keep and t < 64:
-                    out_keep[:, t * F:(t + 1) * F].copy_(ring[k])
+                if keep:
+                    for u in range(K):
+                        t = g0 + u
+                        if t < 64:
+                            out_keep[:, t * F:(t + 1) * F].copy_(ring[k][:, u * F:(u + 1) * F])
                 ev = torch.cuda.Event()
                 ev.record(comm)
                 done[k] = ev
@@ -111,7 +120,7 @@ def main():
                       "NCCL all-reduce of %d-byte partial blocks" % (C, args.taps, world, C * F * 4),
             "n_gpus": world, "partitions_total": bins, "partitions_per_gpu": p_hi - p_lo,
             "samples_per_s": rate, "us_per_block": float(ms.item()) * 1e3 / nblk,
-            "realtime_factor": rate / (C * 48000.0), "blocks_in_flight": args.depth,
+            "realtime_factor": rate / (C * 48000.0), "blocks_in_flight": args.depth * K, "blocks_per_allreduce": K,
             "max_err_vs_float64_of_peak": err}), flush=True)
     b.close()
     if world > 1:
