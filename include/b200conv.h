@@ -123,6 +123,27 @@ int     b200conv_process_device2(b200conv_batch_t *h, float *dst, size_t dst_str
 /* Waits for everything enqueued on the batch's own stream. */
 int     b200conv_sync(b200conv_batch_t *h);
 
+/* ---- partition-range sharding across GPUs: fused NVLink reduce ---------------------------- */
+
+/* One long IR split by partition range over `world` GPUs (one process per GPU, each with a batch
+ * of the same instances initialised through b200conv_init_range): instead of calling a
+ * collective after every block, the launch tails exchange the partial output blocks over NVLink
+ * peer memory themselves and rank 0 writes the SUMMED block to its dst (other ranks' dst is not
+ * written).  Protocol:
+ *   1. every rank: b200conv_reduce_prepare(h, grank, world, handle)  -> 64-byte CUDA IPC handle
+ *      of its exchange buffer (call after the instances are initialised);
+ *   2. exchange the handles between the processes (any transport; the tests use
+ *      torch.distributed.all_gather), then every rank: b200conv_reduce_connect(h, all_handles);
+ *   3. b200conv_process_device / _planar as usual, the same sequence of whole-frame calls on every
+ *      rank (ranks 8..11; anything else returns B200CONV_ERR_STATE while connected);
+ *   4. b200conv_reduce_disconnect(h).
+ * b200conv_reduce_status reports whether any in-kernel wait for a peer timed out (2 s). */
+#define B200CONV_IPC_HANDLE_BYTES   64
+int     b200conv_reduce_prepare(b200conv_batch_t *h, int grank, int world, unsigned char *handle_out);
+int     b200conv_reduce_connect(b200conv_batch_t *h, const unsigned char *all_handles);
+int     b200conv_reduce_disconnect(b200conv_batch_t *h);
+int     b200conv_reduce_status(b200conv_batch_t *h, int *timed_out);
+
 /* ---- queries (Convolver.h:101,107) ------------------------------------------------------ */
 
 size_t  b200conv_data_size(const b200conv_batch_t *h, size_t idx);

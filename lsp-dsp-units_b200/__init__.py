@@ -75,6 +75,10 @@ _SIGNATURES = {
     "b200conv_process_device": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_process_device2": (ctypes.c_int, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _VP]),
     "b200conv_sync": (ctypes.c_int, [_VP]),
+    "b200conv_reduce_prepare": (ctypes.c_int, [_VP, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]),
+    "b200conv_reduce_connect": (ctypes.c_int, [_VP, ctypes.c_char_p]),
+    "b200conv_reduce_disconnect": (ctypes.c_int, [_VP]),
+    "b200conv_reduce_status": (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_int)]),
     "b200conv_data_size": (_SZ, [_VP, _SZ]),
     "b200conv_rank": (_SZ, [_VP, _SZ]),
     "b200conv_instances": (_SZ, [_VP]),
@@ -185,6 +189,25 @@ class ConvolverBatch:
 
     def sync(self):
         _check(lib().b200conv_sync(self._h))
+
+    # -- partition-range sharding: fused NVLink reduce (see include/b200conv.h) -----------------
+    def reduce_prepare(self, grank, world):
+        """Allocates the exchange buffer; returns its 64-byte CUDA IPC handle."""
+        buf = ctypes.create_string_buffer(64)
+        _check(lib().b200conv_reduce_prepare(self._h, grank, world, buf))
+        return buf.raw
+
+    def reduce_connect(self, handles):
+        """``handles``: the IPC handles of all ranks, in rank order."""
+        _check(lib().b200conv_reduce_connect(self._h, b"".join(handles)))
+
+    def reduce_disconnect(self):
+        _check(lib().b200conv_reduce_disconnect(self._h))
+
+    def reduce_timed_out(self):
+        flag = ctypes.c_int(0)
+        _check(lib().b200conv_reduce_status(self._h, ctypes.byref(flag)))
+        return bool(flag.value)
 
     # -- queries ------------------------------------------------------------------------------
     def data_size(self, idx):

@@ -23,6 +23,8 @@
 
 using namespace b200conv;
 
+extern "C" int b200conv_reduce_disconnect(b200conv_batch_t *b);
+
 /* ------------------------------------------------------------------------------------------- */
 /* errors                                                                                       */
 
@@ -206,7 +208,7 @@ static cudaError_t launch_mac_multi(const StepArgs &a, const MacPlan &p, uint32_
 
 template <int RANK>
 static cudaError_t launch_frame_r(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
-                                  bool pdl, cudaStream_t st)
+                                  const ReduceArgs &ra, bool pdl, cudaStream_t st)
 {
     static size_t attr_smem[MAX_DEVICES] = { 0 };
     int dev = current_device();
@@ -228,18 +230,18 @@ static cudaError_t launch_frame_r(const StepArgs &a, const MacPlan &p, uint32_t 
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs               = attr;
     cfg.numAttrs            = 1;
-    return cudaLaunchKernelEx(&cfg, k_frame<RANK>, a, p.sh, tickets);
+    return cudaLaunchKernelEx(&cfg, k_frame<RANK>, a, p.sh, tickets, ra);
 }
 
 static cudaError_t launch_frame(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
-                                bool pdl, cudaStream_t st)
+                                const ReduceArgs &ra, bool pdl, cudaStream_t st)
 {
     switch (a.rank)
     {
-        case 8:  return launch_frame_r<8>(a, p, jobs, tickets, pdl, st);
-        case 9:  return launch_frame_r<9>(a, p, jobs, tickets, pdl, st);
-        case 10: return launch_frame_r<10>(a, p, jobs, tickets, pdl, st);
-        case 11: return launch_frame_r<11>(a, p, jobs, tickets, pdl, st);
+        case 8:  return launch_frame_r<8>(a, p, jobs, tickets, ra, pdl, st);
+        case 9:  return launch_frame_r<9>(a, p, jobs, tickets, ra, pdl, st);
+        case 10: return launch_frame_r<10>(a, p, jobs, tickets, ra, pdl, st);
+        case 11: return launch_frame_r<11>(a, p, jobs, tickets, ra, pdl, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -331,6 +333,12 @@ struct b200conv_batch
     uint32_t                done_prev2  = 0;        /* ... through the launch before that */
     std::vector<uint32_t>   h_ring_head;
 
+    /* fused cross-GPU reduce (partition-range sharding) */
+    ReduceArgs              reduce      = {};
+    unsigned char          *xchg        = nullptr;              /* local exchange buffer (IPC shared) */
+    void                   *xchg_peer[REDUCE_MAX_WORLD] = { nullptr };  /* peers' buffers, opened */
+    size_t                  xchg_slots_bytes = 0, xchg_arrived_off = 0, xchg_consumed_off = 0, xchg_error_off = 0;
+
     bool                    profiling   = false;
     std::vector<cudaEvent_t> prof_events;           /* pairs: before / after each k_mac */
     size_t                  prof_used   = 0;
@@ -344,7 +352,7 @@ static cudaError_t launch_mac(Batch *b, const StepArgs &a, const MacPlan &p, uin
     auto go = [&]() -> cudaError_t
     {
         if (fused)
-            return launch_frame(a, p, jobs, b->d_tickets, (b->opt_pdl != 0) && (!b->profiling), st);
+            return launch_frame(a, p, jobs, b->d_tickets, b->reduce, (b->opt_pdl != 0) && (!b->profiling), st);
         return launch_mac_raw(a, p, jobs, st);
     };
     if (!b->profiling)
@@ -581,6 +589,7 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     if (b->h_out)       cudaFreeHost(b->h_out);
     if (b->d_in)        cudaFree(b->d_in);
     if (b->d_out)       cudaFree(b->d_out);
+    b200conv_reduce_disconnect(b);
     for (cudaEvent_t ev : b->prof_events)
         cudaEventDestroy(ev);
     if (b->stream)      cudaStreamDestroy(b->stream);
@@ -768,6 +777,8 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
     a.n_jobs        = nact;
     a.t_base        = b->t_batch;
     const bool fused = (b->opt_fused != 0) && (b->rank <= 11);
+    if ((b->reduce.mode != 0) && (!fused))
+        return fail(B200CONV_ERR_STATE, "the fused cross-GPU reduce needs the one-launch-per-block path (ranks 8..11, fused = 1)");
     plan.sh.bias    = fused ? uint32_t(b->opt_bias) : 0;
     bool used_multi = false;
     for (size_t f = 0; f < frames; )
@@ -777,7 +788,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
         /* several whole frames in one call: transform them all, then ONE pass over the IR
          * spectra serves tf frames (k_mac_multi), then all inverse transforms */
         uint32_t tf     = 0;
-        for (uint32_t c = uint32_t(b->opt_multi); c >= 2; c >>= 1)
+        for (uint32_t c = (b->reduce.mode != 0) ? 0u : uint32_t(b->opt_multi); c >= 2; c >>= 1)
             if (frames - f >= c) { tf = c; break; }
         if (tf >= 2)
         {
@@ -1046,6 +1057,8 @@ extern "C" int b200conv_process_device2(b200conv_batch_t *b, float *dst, size_t 
 
     if (uniform)
         return process_uniform(b, dst, dst_stride, src, src_stride, count / F, st);
+    if (b->reduce.mode != 0)
+        return fail(B200CONV_ERR_STATE, "the fused cross-GPU reduce handles whole-frame calls only");
     return process_general(b, dst, dst_stride, src, src_stride, count, st);
 }
 
@@ -1291,6 +1304,126 @@ extern "C" const char *b200conv_last_error(void)
 extern "C" const char *b200conv_version(void)
 {
     return "b200conv 0.1 (sm_100a)";
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* fused cross-GPU reduce (partition-range sharding)                                            */
+
+extern "C" int b200conv_reduce_prepare(b200conv_batch_t *b, int grank, int world, unsigned char *handle_out)
+{
+    if ((b == nullptr) || (handle_out == nullptr) || (world < 1) || (world > REDUCE_MAX_WORLD) ||
+        (grank < 0) || (grank >= world))
+        return fail(B200CONV_ERR_ARG, "b200conv_reduce_prepare: bad arguments");
+    if ((b->rank == 0) || (b->rank > 11))
+        return fail(B200CONV_ERR_STATE, "b200conv_reduce_prepare: initialise the instances first (ranks 8..11)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200CONV_IPC_HANDLE_BYTES, "IPC handle size");
+    TRY(set_device(b));
+    TRY(b200conv_reduce_disconnect(b));
+
+    const size_t F          = size_t(1) << (b->rank - 1);
+    const size_t C          = b->n;
+    b->xchg_slots_bytes     = size_t(2) * world * C * F * sizeof(float);
+    b->xchg_arrived_off     = b->xchg_slots_bytes;
+    b->xchg_consumed_off    = b->xchg_arrived_off + 2 * C * sizeof(uint32_t);
+    b->xchg_error_off       = b->xchg_consumed_off + C * sizeof(uint32_t);
+    b->xchg_error_off       = (b->xchg_error_off + 63) & ~size_t(63);
+    size_t total            = b->xchg_error_off + 64 + REDUCE_MAX_WORLD * sizeof(uint32_t *);
+    CU(cudaMalloc(&b->xchg, total));
+    CU(cudaMemset(b->xchg, 0, total));
+    cudaIpcMemHandle_t hnd;
+    CU(cudaIpcGetMemHandle(&hnd, b->xchg));
+    memcpy(handle_out, &hnd, sizeof(hnd));
+
+    memset(&b->reduce, 0, sizeof(b->reduce));
+    b->reduce.world         = uint32_t(world);
+    b->reduce.grank         = uint32_t(grank);
+    b->reduce.channels      = uint32_t(C);
+    b->reduce.frame         = uint32_t(F);
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_reduce_connect(b200conv_batch_t *b, const unsigned char *all_handles)
+{
+    if ((b == nullptr) || (all_handles == nullptr) || (b->xchg == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_reduce_connect: call b200conv_reduce_prepare first");
+    TRY(set_device(b));
+    CU(cudaStreamSynchronize(b->stream));
+    ReduceArgs &r = b->reduce;
+
+    /* every active instance must sit at the same whole-frame count */
+    uint64_t frames = 0;
+    bool first = true;
+    for (uint32_t i : b->active)
+    {
+        const Instance &in = b->inst[i];
+        if ((in.off != 0) || ((!first) && (in.frames != frames)))
+            return fail(B200CONV_ERR_STATE, "b200conv_reduce_connect: instances are not frame-aligned");
+        frames  = in.frames;
+        first   = false;
+    }
+
+    for (uint32_t g = 0; g < r.world; ++g)
+    {
+        b->xchg_peer[g] = nullptr;
+        bool need = (g != r.grank) && ((r.grank == 0) || (g == 0));     /* root opens all, others open root */
+        if (!need)
+            continue;
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, all_handles + size_t(g) * B200CONV_IPC_HANDLE_BYTES, sizeof(hnd));
+        CU(cudaIpcOpenMemHandle(&b->xchg_peer[g], hnd, cudaIpcMemLazyEnablePeerAccess));
+    }
+    unsigned char *root     = (r.grank == 0) ? b->xchg : static_cast<unsigned char *>(b->xchg_peer[0]);
+    r.slots_root            = reinterpret_cast<float *>(root);
+    r.arrived_root          = reinterpret_cast<uint32_t *>(root + b->xchg_arrived_off);
+    r.consumed_local        = reinterpret_cast<uint32_t *>(b->xchg + b->xchg_consumed_off);
+    r.error                 = reinterpret_cast<uint32_t *>(b->xchg + b->xchg_error_off);
+    uint32_t *table[REDUCE_MAX_WORLD] = { nullptr };
+    for (uint32_t g = 0; g < r.world; ++g)
+    {
+        unsigned char *base = (g == r.grank) ? b->xchg : static_cast<unsigned char *>(b->xchg_peer[g]);
+        table[g]            = (base != nullptr) ? reinterpret_cast<uint32_t *>(base + b->xchg_consumed_off) : nullptr;
+    }
+    r.consumed_peer         = reinterpret_cast<uint32_t **>(b->xchg + b->xchg_error_off + 64);
+    CU(cudaMemcpy(r.consumed_peer, table, sizeof(table), cudaMemcpyHostToDevice));
+    r.t0                    = uint32_t(frames);
+    r.mode                  = (r.world > 1) ? 1u : 0u;
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_reduce_disconnect(b200conv_batch_t *b)
+{
+    if (b == nullptr)
+        return fail(B200CONV_ERR_ARG, "b200conv_reduce_disconnect: NULL handle");
+    if (b->xchg == nullptr)
+        return B200CONV_OK;
+    cudaSetDevice(b->device);
+    if (b->stream)
+        cudaStreamSynchronize(b->stream);
+    cudaDeviceSynchronize();
+    for (int g = 0; g < REDUCE_MAX_WORLD; ++g)
+    {
+        if (b->xchg_peer[g] != nullptr)
+            cudaIpcCloseMemHandle(b->xchg_peer[g]);
+        b->xchg_peer[g] = nullptr;
+    }
+    cudaFree(b->xchg);
+    b->xchg = nullptr;
+    memset(&b->reduce, 0, sizeof(b->reduce));
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_reduce_status(b200conv_batch_t *b, int *timed_out)
+{
+    if ((b == nullptr) || (timed_out == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_reduce_status: bad arguments");
+    *timed_out = 0;
+    if (b->xchg == nullptr)
+        return B200CONV_OK;
+    TRY(set_device(b));
+    uint32_t flag = 0;
+    CU(cudaMemcpy(&flag, b->xchg + b->xchg_error_off, sizeof(flag), cudaMemcpyDeviceToHost));
+    *timed_out = int(flag);
+    return B200CONV_OK;
 }
 
 /* ------------------------------------------------------------------------------------------- */

@@ -77,6 +77,45 @@ struct StepArgs                     /* by-value kernel argument */
 
 enum { INV_FULL = 1 };
 
+/* Partition-range sharding across GPUs (one long IR): every rank's k_frame produces a
+ * PARTIAL output block; the sum is formed inside the launch tails over NVLink peer memory --
+ * no collective library call, no host in the loop.
+ *   rank g != 0 : its inverse transform stores the block straight into slot g of the exchange
+ *                 buffer in ROOT's memory (peer stores), fences at system scope and bumps root's
+ *                 arrival counter;
+ *   rank 0      : waits for world-1 arrivals, adds the slots to its own block, writes the output,
+ *                 and tells every peer (stores into THEIR memory) that the slot pair is free.
+ * Slots are double-buffered by block parity; all waits are bounded (a peer that never shows up
+ * raises *error instead of hanging the GPU). */
+constexpr int REDUCE_MAX_WORLD = 8;
+struct ReduceArgs
+{
+    uint32_t    mode;                               /* 0 = off */
+    uint32_t    world, grank;
+    uint32_t    t0;                                 /* frame counter (low 32 bits) at connect time */
+    uint32_t    channels;                           /* instances per rank */
+    uint32_t    frame;                              /* F */
+    float      *slots_root;                         /* [2][world][channels][F] in root's memory */
+    uint32_t   *arrived_root;                       /* [2][channels]           in root's memory */
+    uint32_t   *consumed_local;                     /* [channels]              in this rank's memory */
+    uint32_t  **consumed_peer;                      /* root only: [world] every rank's consumed array (table in root's memory) */
+    uint32_t   *error;                              /* local: set when a wait timed out */
+};
+
+__device__ __forceinline__ uint64_t global_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
 {
     if (a.jobs != nullptr)
@@ -963,7 +1002,7 @@ k_mac_multi(const StepArgs a, const MacShape sh)
 
 template <int RANK>
 __global__ void __launch_bounds__(FftCfg<RANK>::T, (FftCfg<RANK>::T >= 256) ? 4 : 8)
-k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
+k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs ra)
 {
     using C = FftCfg<RANK>;
     constexpr uint32_t M = C::M, T = C::T, N = C::N;
@@ -1240,7 +1279,74 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets)
             tws[i]          = a.tw[i];
         tw              = tws;                  /* visible after inv_body's first barrier */
     }
-    inv_body<RANK, true, 4>(wa, wb, yrow, a.splits, job.dst, a.tw, tw, false, int(tid));
+    if (ra.mode == 0)
+    {
+        inv_body<RANK, true, 4>(wa, wb, yrow, a.splits, job.dst, a.tw, tw, false, int(tid));
+        return;
+    }
+
+    /* ---- partition-range shard: sum the partial blocks of all ranks over NVLink ---- */
+    const uint32_t F        = ra.frame;
+    const uint32_t ch       = job.inst;
+    const uint32_t blk      = job.tlo - ra.t0;          /* block number since the ranks connected */
+    const uint32_t par      = blk & 1u;
+    float *slot             = ra.slots_root + ((size_t(par) * ra.world + ra.grank) * ra.channels + ch) * F;
+    uint32_t *arrived       = ra.arrived_root + par * ra.channels + ch;
+    const uint64_t deadline = global_ns() + 2000000000ull;
+
+    if (ra.grank != 0)
+    {
+        /* the slot pair of this parity is free once root has consumed block blk - 2 */
+        if (tid == 0)
+        {
+            while (int32_t(ld_acquire_sys(ra.consumed_local + ch) + 1u - blk) < 0)
+            {
+                if (global_ns() > deadline) { atomicExch(ra.error, 1u); break; }
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+        inv_body<RANK, true, 4>(wa, wb, yrow, a.splits, slot, a.tw, tw, false, int(tid));
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0)
+            asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(arrived), "r"(1u) : "memory");
+        return;
+    }
+
+    /* root: own block into slot 0, then gather */
+    inv_body<RANK, true, 4>(wa, wb, yrow, a.splits, slot, a.tw, tw, false, int(tid));
+    if (tid == 0)
+    {
+        while (ld_acquire_sys(arrived) < ra.world - 1u)
+        {
+            if (global_ns() > deadline) { atomicExch(ra.error, 1u); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    {
+        const float *base   = ra.slots_root + (size_t(par) * ra.world * ra.channels + ch) * F;
+        const size_t gstep  = size_t(ra.channels) * F;
+        for (uint32_t i = tid; i < F; i += T)
+        {
+            float sum           = base[i];                          /* own block (written above by this CTA) */
+            for (uint32_t g = 1; g < ra.world; ++g)
+                sum                += __ldcg(base + g * gstep + i);     /* peers' blocks, landed in L2 */
+            job.dst[i]          = sum;
+        }
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        *arrived            = 0;                        /* peers touch it again only after the release below */
+        __threadfence_system();
+        for (uint32_t g = 1; g < ra.world; ++g)
+        {
+            uint32_t *cp        = ra.consumed_peer[g] + ch;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(cp), "r"(blk + 1u) : "memory");
+        }
+    }
 }
 
 /* ------------------------------------------------------------------------------------------- */

@@ -88,3 +88,74 @@ def test_two_gpu_channel_and_partition_sharding_nccl():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert err_a <= 1e-5 and err_b <= 1e-5
+
+
+def _fused_worker(rank, world, port, result):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import __graft_entry__ as ge
+    import synth
+    from oracle.bindings import direct_convolve
+    pkg = ge.load()
+    import lsp_dsp_units_b200.sharding as sharding
+
+    R, F, ch, blocks = 11, 1024, 4, 60
+    L = 300 * F - 17
+    irs = [synth.decaying_ir(c, L) for c in range(ch)]
+    x = np.stack([synth.noise(c, blocks * F) for c in range(ch)])
+    p_lo, p_hi, t_lo, t_hi = sharding.partition_shard(L, F, world, rank)
+    b = pkg.ConvolverBatch(ch, rank)
+    for c in range(ch):
+        assert b.init(c, irs[c][t_lo:t_hi], R, 0.0, part_offset=p_lo)
+
+    # exchange the IPC handles of the exchange buffers (any transport; here NCCL all_gather)
+    mine = torch.tensor(list(b.reduce_prepare(rank, world)), dtype=torch.uint8, device="cuda")
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    b.reduce_connect([bytes(t.cpu().tolist()) for t in every])
+    dist.barrier()
+
+    src = torch.from_numpy(x).cuda()
+    dst = torch.zeros_like(src)
+    torch.cuda.synchronize()
+    for i in range(blocks):                 # back to back: launches overlap, tails talk over NVLink
+        b.process_device(dst.data_ptr() + 4 * i * F, src.data_ptr() + 4 * i * F, blocks * F, F)
+    b.sync()
+    timed_out = b.reduce_timed_out()
+    dist.barrier()
+    err = 0.0
+    if rank == 0:
+        out = dst.cpu().numpy()
+        for c in range(ch):
+            want = direct_convolve(x[c], irs[c], blocks * F)
+            err = max(err, float(np.max(np.abs(out[c] - want)) / np.max(np.abs(want))))
+    untouched = bool((dst == 0).all().item()) if rank != 0 else True
+    flags = torch.tensor([float(timed_out), float(not untouched)], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+    b.reduce_disconnect()
+    b.close()
+    if rank == 0:
+        result.put((err, float(flags[0].item()), float(flags[1].item())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_fused_nvlink_reduce_of_partition_shards():
+    """BASELINE config 5 in miniature without a collective call: the launch tails sum the partial
+    output blocks over NVLink peer memory (b200conv_reduce_*); rank 0 receives the full result."""
+    ctx = mp.get_context("spawn")
+    result = ctx.Queue()
+    procs = [ctx.Process(target=_fused_worker, args=(r, 2, 29651, result)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, timed_out, touched = result.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert timed_out == 0.0 and touched == 0.0
+    assert err <= 1e-5

@@ -39,6 +39,9 @@ def main():
                     help="blocks per all-reduce: 1 = every 1024-sample block gets its own 32 KiB reduce "
                          "(real-time use); K > 1 amortises the per-collective host cost (offline use)")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--fused-reduce", action="store_true",
+                    help="sum the partial blocks inside the launch tails over NVLink peer memory "
+                         "(b200conv_reduce_*) instead of one NCCL all-reduce per block")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -91,19 +94,43 @@ def main():
                 ev.record(comm)
                 done[k] = ev
 
-    run(64, args.check)                                           # warm-up (and the checked prefix)
+    fused = args.fused_reduce and world > 1
+    if fused:
+        mine = torch.tensor(list(b.reduce_prepare(rank, world)), dtype=torch.uint8, device="cuda")
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        b.reduce_connect([bytes(t.cpu().tolist()) for t in every])
+        dist.barrier()
+        fdst = torch.zeros((C, 64 * F), device="cuda")
+
+        def run_fused(blocks, keep):
+            with torch.cuda.stream(compute):
+                for t in range(blocks):
+                    i = t % 64
+                    b.process_device(fdst.data_ptr() + 4 * i * F, src.data_ptr() + 4 * i * F, 64 * F, F,
+                                     compute.cuda_stream)
+                if keep:
+                    compute.synchronize()
+                    out_keep.copy_(fdst)
+        run_ = run_fused
+    else:
+        run_ = run
+
+    run_(64, args.check)                                          # warm-up (and the checked prefix)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(compute)
-    run(nblk, False)
-    comm.synchronize()
-    e1.record(comm)
+    run_(nblk, False)
+    last = compute if fused else comm
+    last.synchronize()
+    e1.record(last)
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    timed_out = b.reduce_timed_out() if fused else False
 
     err = None
     if args.check and rank == 0:
@@ -117,11 +144,16 @@ def main():
         rate = C * F * nblk / (float(ms.item()) * 1e-3)
         print(json.dumps({
             "config": "cfg5: %d ch x %d-tap IR, rank 11, 1024-sample blocks, partition range split over %d GPU(s), "
-                      "NCCL all-reduce of %d-byte partial blocks" % (C, args.taps, world, C * F * 4),
+                      "%d-byte partial output blocks summed per block" % (C, args.taps, world, C * F * 4),
             "n_gpus": world, "partitions_total": bins, "partitions_per_gpu": p_hi - p_lo,
             "samples_per_s": rate, "us_per_block": float(ms.item()) * 1e3 / nblk,
             "realtime_factor": rate / (C * 48000.0), "blocks_in_flight": args.depth * K, "blocks_per_allreduce": K,
-            "max_err_vs_float64_of_peak": err}), flush=True)
+            "max_err_vs_float64_of_peak": err,
+            "reduce": ("fused in the launch tails over NVLink peer memory" if fused else
+                       ("NCCL all-reduce from the host" if world > 1 else "none")),
+            "peer_wait_timed_out": bool(timed_out)}), flush=True)
+    if fused:
+        b.reduce_disconnect()
     b.close()
     if world > 1:
         dist.destroy_process_group()
