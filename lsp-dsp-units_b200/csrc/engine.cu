@@ -372,11 +372,36 @@ static cudaError_t launch_mac(Batch *b, const StepArgs &a, const MacPlan &p, uin
     return e;
 }
 
-static int set_device(const Batch *b)
+/* Makes the batch's device current for the duration of an API call and restores the caller's
+ * device afterwards (the library must not leave a different current device behind). */
+class DeviceScope
 {
-    CU(cudaSetDevice(b->device));
-    return B200CONV_OK;
-}
+    private:
+        int         nPrev;
+        cudaError_t nErr;
+
+    public:
+        explicit DeviceScope(int device): nPrev(-1), nErr(cudaSuccess)
+        {
+            nErr = cudaGetDevice(&nPrev);
+            if ((nErr == cudaSuccess) && (nPrev != device))
+                nErr = cudaSetDevice(device);
+            else
+                nPrev = -1;                 /* nothing to restore */
+        }
+        ~DeviceScope()
+        {
+            if (nPrev >= 0)
+                cudaSetDevice(nPrev);
+        }
+        cudaError_t error() const           { return nErr; }
+};
+
+#define ENTER_DEVICE(b)                                                                     \
+    DeviceScope device_scope_((b)->device);                                                 \
+    if (device_scope_.error() != cudaSuccess)                                               \
+        return fail(B200CONV_ERR_CUDA, "cannot select device %d: %s", (b)->device,          \
+                    cudaGetErrorString(device_scope_.error()))
 
 static void free_instance_buffers(Instance &in)
 {
@@ -532,10 +557,10 @@ extern "C" int b200conv_create(b200conv_batch_t **out, int device, size_t instan
     b->h_ring_head.assign(instances, 0);
     memset(b->h_desc.data(), 0, instances * sizeof(InstDesc));
 
+    ENTER_DEVICE(b);
     int rc = B200CONV_OK;
     do
     {
-        if ((rc = set_device(b)) != B200CONV_OK) break;
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
             b->sm_count = prop.multiProcessorCount;
@@ -570,7 +595,7 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
 {
     if (b == nullptr)
         return;
-    cudaSetDevice(b->device);
+    DeviceScope device_scope_(b->device);
     if (b->stream)
         cudaStreamSynchronize(b->stream);
     for (Instance &in : b->inst)
@@ -606,7 +631,7 @@ extern "C" int b200conv_destroy(b200conv_batch_t *b, size_t idx)
     Instance &in = b->inst[idx];
     if (!in.active)
         return B200CONV_OK;
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
     CU(cudaStreamSynchronize(b->stream));
     free_instance_buffers(in);
     in = Instance();
@@ -635,7 +660,7 @@ extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float 
             return fail(B200CONV_ERR_ARG, "all instances of a batch share one rank (%zu active, %zu requested)",
                         b->inst[i].rank, rank);
 
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
     cudaStream_t st = b->stream;
 
     const size_t F      = size_t(1) << (rank - 1);
@@ -1030,7 +1055,7 @@ extern "C" int b200conv_process_device2(b200conv_batch_t *b, float *dst, size_t 
         return B200CONV_OK;
     if ((dst == nullptr) || (src == nullptr) || ((b->n > 1) && ((src_stride < count) || (dst_stride < count))))
         return fail(B200CONV_ERR_ARG, "b200conv_process_device: bad buffers");
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
     cudaStream_t st = (stream != nullptr) ? cudaStream_t(stream) : b->stream;
 
     /* not initialised -> zeros (Convolver.cpp:219-223) */
@@ -1099,7 +1124,7 @@ extern "C" int b200conv_process(b200conv_batch_t *b, float *const *dst, const fl
     for (size_t i = 0; i < b->n; ++i)
         if ((dst[i] == nullptr) || (src[i] == nullptr))
             return fail(B200CONV_ERR_ARG, "b200conv_process: NULL buffer for instance %zu", i);
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
 
     /* samples per instance per pass: bounded staging, at least one frame */
     size_t cap = (size_t(1) << 24) / b->n;
@@ -1139,7 +1164,7 @@ extern "C" int b200conv_process_planar(b200conv_batch_t *b, float *dst, const fl
         return B200CONV_OK;
     if ((dst == nullptr) || (src == nullptr) || (stride < count))
         return fail(B200CONV_ERR_ARG, "b200conv_process_planar: bad buffers");
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
 
     /* Page-locked host matrices are mapped into the device address space (UVA): the kernels
      * read the input block and write the output block across PCIe themselves -- the input fetch
@@ -1191,7 +1216,7 @@ extern "C" int b200conv_sync(b200conv_batch_t *b)
 {
     if (b == nullptr)
         return fail(B200CONV_ERR_ARG, "b200conv_sync: NULL handle");
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
     CU(cudaStreamSynchronize(b->stream));
     return B200CONV_OK;
 }
@@ -1258,7 +1283,7 @@ extern "C" int b200conv_get_profile(b200conv_batch_t *b, double *mac_ms, uint64_
 {
     if (b == nullptr)
         return fail(B200CONV_ERR_ARG, "b200conv_get_profile: NULL handle");
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
     double total = 0.0;
     for (size_t i = 0; i + 1 < b->prof_used; i += 2)
     {
@@ -1317,7 +1342,7 @@ extern "C" int b200conv_reduce_prepare(b200conv_batch_t *b, int grank, int world
     if ((b->rank == 0) || (b->rank > 11))
         return fail(B200CONV_ERR_STATE, "b200conv_reduce_prepare: initialise the instances first (ranks 8..11)");
     static_assert(sizeof(cudaIpcMemHandle_t) == B200CONV_IPC_HANDLE_BYTES, "IPC handle size");
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
     TRY(b200conv_reduce_disconnect(b));
 
     const size_t F          = size_t(1) << (b->rank - 1);
@@ -1346,7 +1371,7 @@ extern "C" int b200conv_reduce_connect(b200conv_batch_t *b, const unsigned char 
 {
     if ((b == nullptr) || (all_handles == nullptr) || (b->xchg == nullptr))
         return fail(B200CONV_ERR_ARG, "b200conv_reduce_connect: call b200conv_reduce_prepare first");
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
     CU(cudaStreamSynchronize(b->stream));
     ReduceArgs &r = b->reduce;
 
@@ -1396,7 +1421,7 @@ extern "C" int b200conv_reduce_disconnect(b200conv_batch_t *b)
         return fail(B200CONV_ERR_ARG, "b200conv_reduce_disconnect: NULL handle");
     if (b->xchg == nullptr)
         return B200CONV_OK;
-    cudaSetDevice(b->device);
+    ENTER_DEVICE(b);
     if (b->stream)
         cudaStreamSynchronize(b->stream);
     cudaDeviceSynchronize();
@@ -1419,7 +1444,7 @@ extern "C" int b200conv_reduce_status(b200conv_batch_t *b, int *timed_out)
     *timed_out = 0;
     if (b->xchg == nullptr)
         return B200CONV_OK;
-    TRY(set_device(b));
+    ENTER_DEVICE(b);
     uint32_t flag = 0;
     CU(cudaMemcpy(&flag, b->xchg + b->xchg_error_off, sizeof(flag), cudaMemcpyDeviceToHost));
     *timed_out = int(flag);
@@ -1450,11 +1475,8 @@ namespace
         cudaError_t e = cudaGetDeviceCount(&n);
         if ((e != cudaSuccess) || (n == 0))
             return fail(B200CONV_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
-        if (device < 0)
-            CU(cudaGetDevice(&device));
-        if ((device >= n) || (device >= 64))
+        if ((device < 0) || (device >= n) || (device >= 64))
             return fail(B200CONV_ERR_ARG, "device %d out of range", device);
-        CU(cudaSetDevice(device));
         PrimCtx &c = g_prim[device];
         if (c.tw[rank] == nullptr)
             TRY(make_twiddles(uint32_t(rank), &c.tw[rank]));
@@ -1508,9 +1530,19 @@ namespace
     }
 }
 
+/* device < 0 = the calling thread's current device */
+#define ENTER_PRIM_DEVICE(device)                                                           \
+    if ((device) < 0)                                                                       \
+        cudaGetDevice(&(device));                                                           \
+    DeviceScope device_scope_(device);                                                      \
+    if (device_scope_.error() != cudaSuccess)                                               \
+        return fail(B200CONV_ERR_CUDA, "cannot select device %d: %s", (device),             \
+                    cudaGetErrorString(device_scope_.error()))
+
 extern "C" int b200conv_fastconv_parse(int device, float *image, const float *src, size_t rank,
                                        size_t count, void *stream)
 {
+    ENTER_PRIM_DEVICE(device);
     std::lock_guard<std::mutex> lock(g_prim_lock);
     PrimCtx *c = nullptr;
     TRY(prim_prepare(device, rank, count, 0, &c));
@@ -1547,6 +1579,7 @@ static int prim_inverse(PrimCtx *c, float *dst, const float2 *images, size_t ran
 extern "C" int b200conv_fastconv_restore(int device, float *dst, const float *image, size_t rank,
                                          size_t count, void *stream)
 {
+    ENTER_PRIM_DEVICE(device);
     std::lock_guard<std::mutex> lock(g_prim_lock);
     PrimCtx *c = nullptr;
     TRY(prim_prepare(device, rank, count, 0, &c));
@@ -1557,6 +1590,7 @@ extern "C" int b200conv_fastconv_restore(int device, float *dst, const float *im
 extern "C" int b200conv_fastconv_apply(int device, float *dst, const float *c1, const float *c2,
                                        size_t rank, size_t count, void *stream)
 {
+    ENTER_PRIM_DEVICE(device);
     std::lock_guard<std::mutex> lock(g_prim_lock);
     size_t N = size_t(1) << rank, M = N / 2;
     PrimCtx *c = nullptr;
@@ -1576,6 +1610,7 @@ extern "C" int b200conv_fastconv_apply(int device, float *dst, const float *c1, 
 extern "C" int b200conv_fastconv_parse_apply(int device, float *dst, const float *cimg, const float *src,
                                              size_t rank, size_t count, void *stream)
 {
+    ENTER_PRIM_DEVICE(device);
     std::lock_guard<std::mutex> lock(g_prim_lock);
     size_t N = size_t(1) << rank, M = N / 2;
     PrimCtx *c = nullptr;

@@ -463,3 +463,21 @@ def test_device_api_with_separate_row_strides(pkg, block):
     for c in range(n):
         assert rel_err(out[c], direct_convolve(src[c], irs[c], nblk * block)) <= TOL
     b.close()
+
+
+def test_failed_init_keeps_the_previous_state(pkg):
+    """Convolver.cpp:103-108: init returns false on allocation failure and the old convolver keeps
+    working (the new slab is allocated before the old one is released)."""
+    import ctypes
+    ir, x = synth.decaying_ir(1, 5000), synth.noise(1, 8 * 1024)
+    b = pkg.ConvolverBatch(1, 0)
+    assert b.init(0, ir, 11, 0.0)
+    out = np.empty_like(x)
+    out[:4096] = b.process(x[None, :4096])[0]
+    # 2^40 taps cannot be allocated: the call must fail before it touches the (tiny) buffer
+    rc = pkg.lib().b200conv_init(b._h, 0, ir.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), 1 << 40, 11, 0.0)
+    assert rc == pkg.ERR_NOMEM
+    assert b.data_size(0) == 5000 and b.rank(0) == 11 and b.state(0)["frames"] == 4
+    out[4096:] = b.process(x[None, 4096:])[0]
+    assert rel_err(out, direct_convolve(x, ir, x.size)) <= TOL
+    b.close()
