@@ -806,7 +806,7 @@ k_mac(const StepArgs a, const MacShape sh)
 
 template <int TF, int PH>
 __device__ __forceinline__ void multi_step(float4 (&acc)[TF], float4 (&win)[TF], float (&dny)[TF],
-                                           const float4 *g4, const float4 *x4, uint32_t col)
+                                           const float4 *g4, const float4 *x4, uint32_t col, bool fix0)
 {
     /* the row that enters the window at this step is frame 0's operand */
     constexpr int NEW = (TF - PH) % TF;
@@ -824,7 +824,13 @@ __device__ __forceinline__ void multi_step(float4 (&acc)[TF], float4 (&win)[TF],
         acc[j].y        = fmaf(g.y, x.x, acc[j].y);
         acc[j].z        = fmaf(-g.w, x.w, acc[j].z);
         acc[j].w        = fmaf(g.w, x.z, acc[j].w);
-        dny[j]          = fmaf(g.y, x.y, dny[j]);
+    }
+    /* Nyquist fix-up of packed bin 0: only the warp that owns column 0 needs it */
+    if (fix0)
+    {
+        #pragma unroll
+        for (int j = 0; j < TF; ++j)
+            dny[j]          = fmaf(g.y, win[(j + TF - PH) % TF].y, dny[j]);
     }
 }
 
@@ -937,6 +943,7 @@ k_mac_multi(const StepArgs a, const MacShape sh)
         }
     }
 
+    const bool fix0 = (tile == 0) && (tid < 32);        /* warp-uniform */
     uint32_t step = 0, c_s = 0, c_par = 0, c_q = q0;
     for (uint32_t it = 0; it < n_iter; ++it)
     {
@@ -951,14 +958,14 @@ k_mac_multi(const StepArgs a, const MacShape sh)
             const float4 *gr = g4 + r * (TB / 2), *xr = x4 + r * (TB / 2);
             switch (step & (TF - 1))
             {
-                case 0: multi_step<TF, 0>(acc, win, dny, gr, xr, tid); break;
-                case 1: multi_step<TF, 1 % TF>(acc, win, dny, gr, xr, tid); break;
-                case 2: multi_step<TF, 2 % TF>(acc, win, dny, gr, xr, tid); break;
-                case 3: multi_step<TF, 3 % TF>(acc, win, dny, gr, xr, tid); break;
-                case 4: multi_step<TF, 4 % TF>(acc, win, dny, gr, xr, tid); break;
-                case 5: multi_step<TF, 5 % TF>(acc, win, dny, gr, xr, tid); break;
-                case 6: multi_step<TF, 6 % TF>(acc, win, dny, gr, xr, tid); break;
-                default: multi_step<TF, 7 % TF>(acc, win, dny, gr, xr, tid); break;
+                case 0: multi_step<TF, 0>(acc, win, dny, gr, xr, tid, fix0); break;
+                case 1: multi_step<TF, 1 % TF>(acc, win, dny, gr, xr, tid, fix0); break;
+                case 2: multi_step<TF, 2 % TF>(acc, win, dny, gr, xr, tid, fix0); break;
+                case 3: multi_step<TF, 3 % TF>(acc, win, dny, gr, xr, tid, fix0); break;
+                case 4: multi_step<TF, 4 % TF>(acc, win, dny, gr, xr, tid, fix0); break;
+                case 5: multi_step<TF, 5 % TF>(acc, win, dny, gr, xr, tid, fix0); break;
+                case 6: multi_step<TF, 6 % TF>(acc, win, dny, gr, xr, tid, fix0); break;
+                default: multi_step<TF, 7 % TF>(acc, win, dny, gr, xr, tid, fix0); break;
             }
         }
 
