@@ -302,6 +302,7 @@ struct b200conv_batch
     std::vector<Instance>   inst;
     size_t                  rank        = 0;        /* shared clamped rank, 0 = none active */
     cudaStream_t            stream      = nullptr;
+    cudaStream_t            last_stream = nullptr;  /* caller's stream of the latest process_device call, if any */
 
     std::vector<InstDesc>   h_desc;
     InstDesc               *d_desc      = nullptr;
@@ -402,6 +403,23 @@ class DeviceScope
     if (device_scope_.error() != cudaSuccess)                                               \
         return fail(B200CONV_ERR_CUDA, "cannot select device %d: %s", (b)->device,          \
                     cudaGetErrorString(device_scope_.error()))
+
+/* Waits for everything this batch has enqueued: on its own stream and on the caller's stream of
+ * the latest process_device call. */
+static cudaError_t quiesce(Batch *b)
+{
+    cudaError_t e = cudaSuccess;
+    if (b->stream)
+        e = cudaStreamSynchronize(b->stream);
+    if ((e == cudaSuccess) && (b->last_stream != nullptr) && (b->last_stream != b->stream))
+    {
+        /* the caller may have destroyed that stream since (then its work is complete anyway) */
+        if (cudaStreamSynchronize(b->last_stream) != cudaSuccess)
+            cudaGetLastError();
+    }
+    b->last_stream = nullptr;
+    return e;
+}
 
 static void free_instance_buffers(Instance &in)
 {
@@ -596,8 +614,7 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     if (b == nullptr)
         return;
     DeviceScope device_scope_(b->device);
-    if (b->stream)
-        cudaStreamSynchronize(b->stream);
+    quiesce(b);
     for (Instance &in : b->inst)
         free_instance_buffers(in);
     for (float2 *t : b->tw)
@@ -632,7 +649,7 @@ extern "C" int b200conv_destroy(b200conv_batch_t *b, size_t idx)
     if (!in.active)
         return B200CONV_OK;
     ENTER_DEVICE(b);
-    CU(cudaStreamSynchronize(b->stream));
+    CU(quiesce(b));
     free_instance_buffers(in);
     in = Instance();
     rebuild_tables(b);
@@ -661,6 +678,7 @@ extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float 
                         b->inst[i].rank, rank);
 
     ENTER_DEVICE(b);
+    CU(quiesce(b));                 /* the tables and buffers below may be in use by queued launches */
     cudaStream_t st = b->stream;
 
     const size_t F      = size_t(1) << (rank - 1);
@@ -1057,6 +1075,7 @@ extern "C" int b200conv_process_device2(b200conv_batch_t *b, float *dst, size_t 
         return fail(B200CONV_ERR_ARG, "b200conv_process_device: bad buffers");
     ENTER_DEVICE(b);
     cudaStream_t st = (stream != nullptr) ? cudaStream_t(stream) : b->stream;
+    b->last_stream  = st;
 
     /* not initialised -> zeros (Convolver.cpp:219-223) */
     for (size_t i = 0; i < b->n; )
@@ -1372,7 +1391,7 @@ extern "C" int b200conv_reduce_connect(b200conv_batch_t *b, const unsigned char 
     if ((b == nullptr) || (all_handles == nullptr) || (b->xchg == nullptr))
         return fail(B200CONV_ERR_ARG, "b200conv_reduce_connect: call b200conv_reduce_prepare first");
     ENTER_DEVICE(b);
-    CU(cudaStreamSynchronize(b->stream));
+    CU(quiesce(b));
     ReduceArgs &r = b->reduce;
 
     /* every active instance must sit at the same whole-frame count */
