@@ -481,3 +481,58 @@ def test_failed_init_keeps_the_previous_state(pkg):
     out[4096:] = b.process(x[None, 4096:])[0]
     assert rel_err(out, direct_convolve(x, ir, x.size)) <= TOL
     b.close()
+
+
+def test_randomised_batches_against_direct_convolution(pkg):
+    """Seeded random sweep: rank, batch size, IR lengths (ragged, some instances never initialised),
+    phases, call sizes (whole frames, fragments, several frames), occasional re-init and destroy --
+    every output sample against float64 direct convolution of what that instance has been fed."""
+    rng = np.random.Generator(np.random.PCG64(2024))
+    for case in range(24):
+        rank = int(rng.integers(8, 12)) if case % 6 else int(rng.integers(12, 15))
+        F = 1 << (rank - 1)
+        n = int(rng.integers(1, 6))
+        b = pkg.ConvolverBatch(n, 0)
+        if case % 3 == 0:
+            b.set_option("multi_frame", int(rng.choice([1, 2, 4, 8])))
+        irs, fed, got = [None] * n, [[] for _ in range(n)], [[] for _ in range(n)]
+
+        def init(c):
+            L = int(rng.choice([1, F - 1, F, F + 1, 3 * F + 7, int(rng.integers(1, 40 * F))]))
+            irs[c] = synth.decaying_ir(int(rng.integers(0, 1000)), L)
+            phase = float(rng.choice([0.0, 0.0, 0.25, 0.5, 0.9]))
+            assert b.init(c, irs[c], rank, phase)
+            fed[c], got[c] = [], []
+
+        for c in range(n):
+            if rng.random() < 0.85:
+                init(c)
+        aligned = bool(rng.random() < 0.5)
+        for _ in range(int(rng.integers(3, 9))):
+            count = int(rng.choice([1, 2, 4, 9])) * F if aligned else int(rng.integers(1, 3 * F))
+            x = rng.uniform(-1, 1, (n, count)).astype(np.float32)
+            y = b.process(x)
+            for c in range(n):
+                if irs[c] is None:
+                    assert not y[c].any()
+                else:
+                    fed[c].append(x[c])
+                    got[c].append(y[c])
+            if rng.random() < 0.15:
+                c = int(rng.integers(0, n))
+                # verify what this instance produced so far, then replace its IR (history discarded)
+                if irs[c] is not None and fed[c]:
+                    xin, out = np.concatenate(fed[c]), np.concatenate(got[c])
+                    want = direct_convolve(xin, irs[c], xin.size)
+                    assert np.max(np.abs(out - want)) <= TOL * max(np.max(np.abs(want)), 1e-3), (case, c)
+                if rng.random() < 0.5:
+                    init(c)
+                else:
+                    b.destroy(c)
+                    irs[c] = None
+        for c in range(n):
+            if irs[c] is not None and fed[c]:
+                xin, out = np.concatenate(fed[c]), np.concatenate(got[c])
+                want = direct_convolve(xin, irs[c], xin.size)
+                assert np.max(np.abs(out - want)) <= TOL * max(np.max(np.abs(want)), 1e-3), (case, c, rank)
+        b.close()
