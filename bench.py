@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--bias", type=int, default=6)
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--zero-copy", type=int, default=1)
+    ap.add_argument("--eager", type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -205,6 +206,7 @@ def main():
     batch.set_option("fft_bias", args.bias)
     batch.set_option("pdl", args.pdl)
     batch.set_option("zero_copy", args.zero_copy)
+    batch.set_option("eager", args.eager)
 
     # ---- synthetic data: decaying-noise IRs, white-noise input --------------------
     # A handful of distinct seeded IRs/inputs are cycled over the 64 instances: timing does not

@@ -172,6 +172,9 @@ void   *b200conv_stream(b200conv_batch_t *h);
  *   "pdl"         1 (default) = programmatic dependent launch between consecutive blocks
  *   "multi_frame" frames served by one pass over the IR spectra when a call brings several whole
  *                 frames: 8 (default), 4, 2, or 1 = off (one launch per frame)
+ *   "eager"       1 (default) = after a synchronous host call has delivered block t, the partitions
+ *                 q >= 1 of block t+1 are summed while the host is away; the next call then only
+ *                 transforms its input, adds partition 0 and inverts (low call latency)
  *   "zero_copy"   1 (default) = b200conv_process_planar lets the kernels read / write page-locked
  *                 host matrices directly (no staging copies); 0 = always stage */
 int     b200conv_set_option(b200conv_batch_t *h, const char *name, int value);

@@ -334,6 +334,18 @@ struct b200conv_batch
     uint32_t                done_prev2  = 0;        /* ... through the launch before that */
     std::vector<uint32_t>   h_ring_head;
 
+    /* eager pending MAC for synchronous host callers: right after block t has been delivered the
+     * partitions q >= 1 of block t+1 (complete frames only) are summed while the host is away,
+     * so the next call only transforms its input, adds partition 0 and inverts */
+    int                     opt_eager   = 1;
+    bool                    eager_call  = false;    /* set by the synchronous entry points */
+    bool                    pend_ready  = false;
+    uint64_t                pend_t      = 0;        /* batch frame counter the pending rows belong to */
+    uint32_t                pend_splits = 0;
+    cudaEvent_t             ev_done     = nullptr;  /* output of the current block is complete */
+    cudaEvent_t             ev_pend     = nullptr;  /* the pending MAC launched after it is complete */
+    bool                    pend_inflight = false;
+
     /* fused cross-GPU reduce (partition-range sharding) */
     ReduceArgs              reduce      = {};
     unsigned char          *xchg        = nullptr;              /* local exchange buffer (IPC shared) */
@@ -418,6 +430,7 @@ static cudaError_t quiesce(Batch *b)
             cudaGetLastError();
     }
     b->last_stream = nullptr;
+    b->pend_inflight = false;
     return e;
 }
 
@@ -456,6 +469,7 @@ static void rebuild_tables(Batch *b)
         d.S         = uint32_t(in.S);
     }
     b->desc_dirty = true;
+    b->pend_ready = false;
 }
 
 static int upload_tables(Batch *b, cudaStream_t st)
@@ -584,6 +598,8 @@ extern "C" int b200conv_create(b200conv_batch_t **out, int device, size_t instan
             b->sm_count = prop.multiProcessorCount;
         #define CU_BRK(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(B200CONV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); break; } }
         CU_BRK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+        CU_BRK(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
+        CU_BRK(cudaEventCreateWithFlags(&b->ev_pend, cudaEventDisableTiming));
         CU_BRK(cudaMalloc(&b->d_desc, instances * sizeof(InstDesc)));
         CU_BRK(cudaMalloc(&b->d_active, instances * sizeof(uint32_t)));
         CU_BRK(cudaMallocHost(&b->h_jobs, JOB_RING * sizeof(Job)));
@@ -632,6 +648,8 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     if (b->d_in)        cudaFree(b->d_in);
     if (b->d_out)       cudaFree(b->d_out);
     b200conv_reduce_disconnect(b);
+    if (b->ev_done)     cudaEventDestroy(b->ev_done);
+    if (b->ev_pend)     cudaEventDestroy(b->ev_pend);
     for (cudaEvent_t ev : b->prof_events)
         cudaEventDestroy(ev);
     if (b->stream)      cudaStreamDestroy(b->stream);
@@ -797,15 +815,27 @@ extern "C" int b200conv_init(b200conv_batch_t *b, size_t idx, const float *data,
 
 /* All active instances sit on a frame boundary and `frames` whole frames arrive: derive the
  * jobs on the device, three launches per frame for all instances x partitions. */
+static bool eager_possible(const Batch *b)
+{
+    return (b->opt_eager != 0) && (b->opt_fused != 0) && (b->rank >= 8) && (b->rank <= 11) &&
+           (b->reduce.mode == 0) && (!b->profiling) && (!b->active.empty());
+}
+
 static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float *src, size_t stride,
                            size_t frames, cudaStream_t st)
 {
     const uint32_t nact = uint32_t(b->active.size());
+    const bool tables_changed = b->desc_dirty;
     TRY(upload_tables(b, st));
     MacPlan plan    = plan_mac(uint32_t(b->rank), nact, uint32_t(b->max_nq), b->sm_count,
                                b->tune_splits, b->tune_stages);
     const size_t F  = size_t(1) << (b->rank - 1);
-    TRY(ensure_ypart(b, size_t(nact) * plan.splits * F * sizeof(float2), st));
+    const bool eager = b->eager_call && (frames == 1) && eager_possible(b);
+    /* one extra row per job when the pending MAC runs ahead (it must not be re-allocated between
+     * the pending launch and the call that consumes it) */
+    TRY(ensure_ypart(b, size_t(nact) * (plan.splits + 1) * F * sizeof(float2), st));
+    if (tables_changed || (b->pend_splits != plan.splits))
+        b->pend_ready   = false;
 
     uint64_t per_frame_bytes = 0;
     for (uint32_t i : b->active)
@@ -852,6 +882,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             b->stats.mac_algo_bytes += per_frame_bytes * tf;
             b->stats.frames         += uint64_t(nact) * tf;
             used_multi      = true;
+            b->pend_ready   = false;
             f              += tf;
             continue;
         }
@@ -860,15 +891,36 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             /* one launch per block for all instances x partitions; the ring slot it overwrites
              * was last read by the launch before the previous one */
             a.need_done     = b->done_prev2;
-            CU(launch_mac(b, a, plan, nact, st, true));
-            b->done_prev2   = b->done_prev;
-            b->done_prev   += plan.splits;
+            if (eager && b->pend_ready && (b->pend_t == b->t_batch + f) && (!tables_changed))
+            {
+                /* partitions q >= 1 were summed ahead of time (launch_pending_mac): transform the
+                 * input, add partition 0, invert -- one CTA per instance */
+                MacPlan fp      = plan;
+                fp.splits       = 1;
+                fp.sh.bias      = 0;
+                StepArgs af     = a;
+                af.splits       = 1;
+                af.rows         = b->pend_splits + 1;
+                af.row0         = b->pend_splits;
+                af.flags       |= STEP_HEAD_ONLY;
+                CU(launch_mac(b, af, fp, nact, st, true));
+                b->done_prev2   = b->done_prev;
+                b->done_prev   += 1;
+            }
+            else
+            {
+                CU(launch_mac(b, a, plan, nact, st, true));
+                b->done_prev2   = b->done_prev;
+                b->done_prev   += plan.splits;
+            }
+            b->pend_ready   = false;
             b->stats.launches       += 1;
         }
         else
         {
             MacPlan sp      = plan;
             sp.sh.bias      = 0;
+            b->pend_ready   = false;
             CU(launch_fwd(a, nact, st));
             CU(launch_mac(b, a, sp, nact, st));
             CU(launch_inv(a, nact, st));
@@ -887,6 +939,45 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
         b->inst[i].frames      += frames;
         b->inst[i].pend_valid   = false;
     }
+    return B200CONV_OK;
+}
+
+/* Sums, ahead of time, the partitions q >= 1 of the block that the next whole-frame call will
+ * bring (they need complete frames only): rows 0 .. splits-1 of every job; row `splits` is left
+ * for that call's own partition 0.  Called by the synchronous host entry points after the
+ * output of the current block is on its way, so the work hides behind the host's round trip --
+ * the GPU analogue of the reference spreading its tail blocks over the frame
+ * (Convolver.cpp:199-210,275). */
+static int launch_pending_mac(Batch *b, cudaStream_t st)
+{
+    if (!eager_possible(b) || b->desc_dirty)
+        return B200CONV_OK;
+    for (uint32_t i : b->active)
+        if (b->inst[i].off != 0)
+            return B200CONV_OK;
+
+    const uint32_t nact = uint32_t(b->active.size());
+    MacPlan plan    = plan_mac(uint32_t(b->rank), nact, uint32_t(b->max_nq), b->sm_count,
+                               b->tune_splits, b->tune_stages);
+    const size_t F  = size_t(1) << (b->rank - 1);
+    if (size_t(nact) * (plan.splits + 1) * F * sizeof(float2) > b->ypart_bytes)
+        return B200CONV_OK;                 /* sized by the next process call */
+
+    StepArgs a      = base_args(b);
+    a.splits        = plan.splits;
+    a.rows          = plan.splits + 1;
+    a.row0          = 0;
+    a.flags         = STEP_FROM_Q1;
+    a.n_jobs        = nact;
+    a.t_base        = b->t_batch;           /* the block about to arrive */
+    a.frame0        = 0;
+    plan.sh.bias    = 0;
+    CU(launch_mac_raw(a, plan, nact, st));
+    b->stats.launches       += 1;
+    b->stats.mac_launches   += 1;
+    b->pend_ready   = true;
+    b->pend_t       = b->t_batch;
+    b->pend_splits  = plan.splits;
     return B200CONV_OK;
 }
 
@@ -1061,6 +1152,7 @@ static int process_general(Batch *b, float *dst, size_t dst_stride, const float 
     }
 
     b->desc_dirty = true;       /* per-instance frame counters moved independently of t_batch */
+    b->pend_ready = false;
     return B200CONV_OK;
 }
 
@@ -1076,6 +1168,8 @@ extern "C" int b200conv_process_device2(b200conv_batch_t *b, float *dst, size_t 
     ENTER_DEVICE(b);
     cudaStream_t st = (stream != nullptr) ? cudaStream_t(stream) : b->stream;
     b->last_stream  = st;
+    if (b->pend_inflight && (st != b->stream))
+        CU(cudaStreamWaitEvent(st, b->ev_pend, 0));     /* a pending MAC may still be running on the own stream */
 
     /* not initialised -> zeros (Convolver.cpp:219-223) */
     for (size_t i = 0; i < b->n; )
@@ -1110,6 +1204,21 @@ extern "C" int b200conv_process_device(b200conv_batch_t *b, float *dst, const fl
                                        size_t stride, size_t count, void *stream)
 {
     return b200conv_process_device2(b, dst, stride, src, stride, count, stream);
+}
+
+/* End of a synchronous host call: the output of this block is on its way on the own stream.
+ * Queue the next block's pending MAC behind it, but return as soon as the OUTPUT is complete. */
+static int finish_sync_call(Batch *b)
+{
+    CU(cudaEventRecord(b->ev_done, b->stream));
+    TRY(launch_pending_mac(b, b->stream));
+    if (b->pend_ready)
+    {
+        CU(cudaEventRecord(b->ev_pend, b->stream));
+        b->pend_inflight = true;
+    }
+    CU(cudaEventSynchronize(b->ev_done));
+    return B200CONV_OK;
 }
 
 static int ensure_staging(Batch *b, size_t floats)
@@ -1162,9 +1271,15 @@ extern "C" int b200conv_process(b200conv_batch_t *b, float *const *dst, const fl
             if (b->inst[i].active)
                 memcpy(b->h_in + i * c, src[i] + done, c * sizeof(float));
         CU(cudaMemcpyAsync(b->d_in, b->h_in, b->n * c * sizeof(float), cudaMemcpyHostToDevice, b->stream));
-        TRY(b200conv_process_device(b, b->d_out, b->d_in, c, c, b->stream));
+        b->eager_call = true;
+        int rc = b200conv_process_device(b, b->d_out, b->d_in, c, c, b->stream);
+        b->eager_call = false;
+        TRY(rc);
         CU(cudaMemcpyAsync(b->h_out, b->d_out, b->n * c * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
-        CU(cudaStreamSynchronize(b->stream));
+        if (done + c >= count)
+            TRY(finish_sync_call(b));
+        else
+            CU(cudaStreamSynchronize(b->stream));
         for (size_t i = 0; i < b->n; ++i)
             memcpy(dst[i] + done, b->h_out + i * c, c * sizeof(float));
         b->stats.h2d_bytes += b->n * c * sizeof(float);
@@ -1196,9 +1311,12 @@ extern "C" int b200conv_process_planar(b200conv_batch_t *b, float *dst, const fl
             (as.type == cudaMemoryTypeHost) && (ad.type == cudaMemoryTypeHost) &&
             (as.devicePointer != nullptr) && (ad.devicePointer != nullptr))
         {
-            TRY(b200conv_process_device(b, static_cast<float *>(ad.devicePointer),
-                                        static_cast<const float *>(as.devicePointer), stride, count, b->stream));
-            CU(cudaStreamSynchronize(b->stream));
+            b->eager_call = true;
+            int rc = b200conv_process_device(b, static_cast<float *>(ad.devicePointer),
+                                             static_cast<const float *>(as.devicePointer), stride, count, b->stream);
+            b->eager_call = false;
+            TRY(rc);
+            TRY(finish_sync_call(b));
             b->stats.h2d_bytes += b->n * count * sizeof(float);
             b->stats.d2h_bytes += b->n * count * sizeof(float);
             return B200CONV_OK;
@@ -1220,10 +1338,16 @@ extern "C" int b200conv_process_planar(b200conv_batch_t *b, float *dst, const fl
         TRY(ensure_staging(b, b->n * c));
         CU(cudaMemcpy2DAsync(b->d_in, c * sizeof(float), src + done, stride * sizeof(float),
                              c * sizeof(float), b->n, cudaMemcpyHostToDevice, b->stream));
-        TRY(b200conv_process_device(b, b->d_out, b->d_in, c, c, b->stream));
+        b->eager_call = true;
+        int rc = b200conv_process_device(b, b->d_out, b->d_in, c, c, b->stream);
+        b->eager_call = false;
+        TRY(rc);
         CU(cudaMemcpy2DAsync(dst + done, stride * sizeof(float), b->d_out, c * sizeof(float),
                              c * sizeof(float), b->n, cudaMemcpyDeviceToHost, b->stream));
-        CU(cudaStreamSynchronize(b->stream));
+        if (done + c >= count)
+            TRY(finish_sync_call(b));
+        else
+            CU(cudaStreamSynchronize(b->stream));
         b->stats.h2d_bytes += b->n * c * sizeof(float);
         b->stats.d2h_bytes += b->n * c * sizeof(float);
         done += c;
@@ -1237,6 +1361,7 @@ extern "C" int b200conv_sync(b200conv_batch_t *b)
         return fail(B200CONV_ERR_ARG, "b200conv_sync: NULL handle");
     ENTER_DEVICE(b);
     CU(cudaStreamSynchronize(b->stream));
+    b->pend_inflight = false;
     return B200CONV_OK;
 }
 
@@ -1332,11 +1457,13 @@ extern "C" int b200conv_set_option(b200conv_batch_t *b, const char *name, int va
     else if (!strcmp(name, "fft_bias") && (value >= 0) && (value <= 64))    b->opt_bias = value;
     else if (!strcmp(name, "pdl") && (value >= 0) && (value <= 1))          b->opt_pdl = value;
     else if (!strcmp(name, "zero_copy") && (value >= 0) && (value <= 1))    b->opt_zero_copy = value;
+    else if (!strcmp(name, "eager") && (value >= 0) && (value <= 1))        b->opt_eager = value;
     else if (!strcmp(name, "multi_frame") && ((value == 0) || (value == 1) || (value == 2) || (value == 4) || (value == 8)))
         b->opt_multi = (value == 1) ? 0 : value;
     else
         return fail(B200CONV_ERR_ARG, "b200conv_set_option: unknown option or bad value: %s = %d", name, value);
     b->desc_dirty   = true;     /* the hand-shake counters are re-seeded before the next launch */
+    b->pend_ready   = false;
     return B200CONV_OK;
 }
 

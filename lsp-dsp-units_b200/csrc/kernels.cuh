@@ -61,6 +61,9 @@ struct StepArgs                     /* by-value kernel argument */
     uint32_t       *ring_head;      /* [instance] frames whose spectrum is in the ring (low 32 bits) */
     uint32_t       *stream_done;    /* [instance] k_frame CTAs that finished reading the ring, cumulative */
     uint32_t        need_done;      /* k_frame: stream_done value after which ring slot (-t) mod S is free */
+    uint32_t        rows;           /* partial rows per job in ypart (0 = splits); a launch writes rows
+                                       row0 .. row0 + splits - 1, the inverse transform sums all `rows` */
+    uint32_t        row0;
     uint32_t        pad0;
     const float    *src;            /* uniform mode: [instances][stride]                            */
     float          *dst;
@@ -75,7 +78,7 @@ struct StepArgs                     /* by-value kernel argument */
     uint32_t        flags;
 };
 
-enum { INV_FULL = 1 };
+enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4 };
 
 /* Partition-range sharding across GPUs (one long IR): every rank's k_frame produces a
  * PARTIAL output block; the sum is formed inside the launch tails over NVLink peer memory --
@@ -116,6 +119,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
     return v;
 }
 
+__device__ __forceinline__ uint32_t rows_per_job(const StepArgs &a)
+{
+    return (a.rows != 0) ? a.rows : a.splits;
+}
+
 __device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
 {
     if (a.jobs != nullptr)
@@ -138,6 +146,10 @@ __device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
     r.spec              = d.ring + uint64_t(r.slot0) * F;
     r.qa                = d.q_lo;
     r.qb                = d.q_lo + d.nq;
+    if (a.flags & STEP_FROM_Q1)         /* complete frames only: what is pending for the frame about to arrive */
+        r.qa                = max(r.qa, 1u);
+    if (a.flags & STEP_HEAD_ONLY)       /* the arriving frame's own partition; the rest is already in ypart */
+        r.qb                = min(r.qb, 1u);
     r.off               = 0;
     r.n                 = F;
     return r;
@@ -567,7 +579,7 @@ k_inv(const StepArgs a)
         tw                  = tws;          /* visible after inv_body's first barrier */
     }
     const Job job           = fetch_job(a, blockIdx.x);
-    inv_body<RANK, C::PP>(A, B, a.ypart + uint64_t(blockIdx.x) * a.splits * C::M, a.splits, job.dst,
+    inv_body<RANK, C::PP>(A, B, a.ypart + uint64_t(blockIdx.x) * rows_per_job(a) * C::M, rows_per_job(a), job.dst,
                           a.tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
 }
 
@@ -783,7 +795,7 @@ k_mac(const StepArgs a, const MacShape sh)
         acc[0].y    = dny;
     }
 
-    float4 *yp      = reinterpret_cast<float4 *>(a.ypart + (uint64_t(jobi) * a.splits + split) * M
+    float4 *yp      = reinterpret_cast<float4 *>(a.ypart + (uint64_t(jobi) * rows_per_job(a) + a.row0 + split) * M
                                                  + uint64_t(tile) * TB);
     #pragma unroll
     for (int v = 0; v < MAC_VPT; ++v)
@@ -1253,8 +1265,9 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     if (tid == 0)
         asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(a.stream_done + job.inst), "r"(1u) : "memory");
 
-    float2 *yrow    = a.ypart + uint64_t(jobi) * a.splits * M;
-    float4 *yp      = reinterpret_cast<float4 *>(yrow + uint64_t(split) * M);
+    const uint32_t rows = rows_per_job(a);
+    float2 *yrow    = a.ypart + uint64_t(jobi) * rows * M;
+    float4 *yp      = reinterpret_cast<float4 *>(yrow + uint64_t(a.row0 + split) * M);
     #pragma unroll
     for (int v = 0; v < MAC_VPT; ++v)
         __stcg(&yp[tid + v * T], acc[v]);
@@ -1288,7 +1301,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     }
     if (ra.mode == 0)
     {
-        inv_body<RANK, true, 4>(wa, wb, yrow, a.splits, job.dst, a.tw, tw, false, int(tid));
+        inv_body<RANK, true, 4>(wa, wb, yrow, rows, job.dst, a.tw, tw, false, int(tid));
         return;
     }
 
@@ -1313,7 +1326,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
             }
         }
         __syncthreads();
-        inv_body<RANK, true, 4>(wa, wb, yrow, a.splits, slot, a.tw, tw, false, int(tid));
+        inv_body<RANK, true, 4>(wa, wb, yrow, rows, slot, a.tw, tw, false, int(tid));
         /* the barrier orders every thread's peer stores before thread 0, whose (cumulative)
          * system-scope release then publishes the whole block: one fence, not one per thread */
         __syncthreads();
@@ -1323,7 +1336,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     }
 
     /* root: own block into slot 0, then gather */
-    inv_body<RANK, true, 4>(wa, wb, yrow, a.splits, slot, a.tw, tw, false, int(tid));
+    inv_body<RANK, true, 4>(wa, wb, yrow, rows, slot, a.tw, tw, false, int(tid));
     if (tid == 0)
     {
         while (ld_acquire_sys(arrived) < ra.world - 1u)

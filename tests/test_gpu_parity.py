@@ -536,3 +536,40 @@ def test_randomised_batches_against_direct_convolution(pkg):
                 want = direct_convolve(xin, irs[c], xin.size)
                 assert np.max(np.abs(out - want)) <= TOL * max(np.max(np.abs(want)), 1e-3), (case, c, rank)
         b.close()
+
+
+@pytest.mark.parametrize("eager", [1, 0])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_eager_pending_mac_for_synchronous_calls(pkg, eager, pinned):
+    """Synchronous one-frame calls: after block t is delivered the partitions q >= 1 of block t+1
+    are summed while the host is away; the next call finishes with partition 0 only.  Mixed with
+    multi-frame calls, fragments, a re-init and a destroy (each must invalidate the pending rows)."""
+    torch = pytest.importorskip("torch")
+    n, rank, F = 3, 11, 1024
+    lens = [50 * F + 3, 7 * F, 200 * F - 1]
+    b = pkg.ConvolverBatch(n, 0)
+    b.set_option("eager", eager)
+    irs = [synth.decaying_ir(c, L) for c, L in enumerate(lens)]
+    for c in range(n):
+        assert b.init(c, irs[c], rank, 0.0)
+    calls = [F] * 6 + [3 * F] + [F] * 3 + [700, 324] + [F] * 4 + [8 * F] + [F] * 5
+    total = sum(calls)
+    src = np.stack([synth.noise(30 + c, total) for c in range(n)])
+    if pinned:
+        hsrc, hdst = torch.from_numpy(src.copy()).pin_memory(), torch.zeros((n, total)).pin_memory()
+        xin, out = hsrc.numpy(), hdst.numpy()
+    else:
+        xin, out = src, np.zeros_like(src)
+    i = 0
+    for k, cnt in enumerate(calls):
+        b.process(xin[:, i:i + cnt], out[:, i:i + cnt])
+        i += cnt
+        if k == 12:
+            cut = i                                     # instance 1 gets a new IR here
+            irs1_new = synth.decaying_ir(77, 9 * F + 5)
+            assert b.init(1, irs1_new, rank, 0.0)
+    for c in (0, 2):
+        assert rel_err(out[c], direct_convolve(src[c], irs[c], total)) <= TOL
+    assert rel_err(out[1][:cut], direct_convolve(src[1][:cut], irs[1], cut)) <= TOL
+    assert rel_err(out[1][cut:], direct_convolve(src[1][cut:], irs1_new, total - cut)) <= TOL
+    b.close()
