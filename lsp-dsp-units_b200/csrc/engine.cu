@@ -65,6 +65,25 @@ static int current_device()
     return ((dev >= 0) && (dev < MAX_DEVICES)) ? dev : 0;
 }
 
+/* k_fwd / k_inv loop over their jobs: never launch more CTAs than fit on the device at once */
+static uint32_t resident_grid(uint32_t jobs, int threads, size_t smem)
+{
+    static int sms[MAX_DEVICES] = { 0 };
+    int dev = current_device();
+    if (sms[dev] == 0)
+    {
+        cudaDeviceProp prop;
+        sms[dev] = (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) ? prop.multiProcessorCount : 148;
+    }
+    size_t by_smem      = (227u * 1024u) / (smem + 1024u);
+    size_t by_threads   = 2048u / size_t(threads);
+    size_t per_sm       = (by_smem < by_threads) ? by_smem : by_threads;
+    if (per_sm < 1)     per_sm = 1;
+    if (per_sm > 16)    per_sm = 16;
+    size_t cap          = per_sm * size_t(sms[dev]);
+    return (jobs < cap) ? jobs : uint32_t(cap);
+}
+
 template <int RANK>
 static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t st)
 {
@@ -78,7 +97,7 @@ static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t s
             return e;
     }
     attr_set[dev] = true;
-    k_fwd<RANK><<<grid, C::T, C::SMEM, st>>>(a);
+    k_fwd<RANK><<<resident_grid(grid, C::T, C::SMEM), C::T, C::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -95,7 +114,7 @@ static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t s
             return e;
     }
     attr_set[dev] = true;
-    k_inv<RANK><<<grid, C::T, C::SMEM, st>>>(a);
+    k_inv<RANK><<<resident_grid(grid, C::T, C::SMEM), C::T, C::SMEM, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -113,14 +132,19 @@ static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t s
         default: return cudaErrorInvalidValue;                          \
     }
 
-static cudaError_t launch_fwd(const StepArgs &a, uint32_t grid, cudaStream_t st)
+/* `jobs` frame transforms (the kernels loop over them with a resident grid) */
+static cudaError_t launch_fwd(const StepArgs &args, uint32_t jobs, cudaStream_t st)
 {
-    RANK_SWITCH(launch_fwd_r, a.rank, a, grid, st)
+    StepArgs a  = args;
+    a.n_jobs    = jobs;
+    RANK_SWITCH(launch_fwd_r, a.rank, a, jobs, st)
 }
 
-static cudaError_t launch_inv(const StepArgs &a, uint32_t grid, cudaStream_t st)
+static cudaError_t launch_inv(const StepArgs &args, uint32_t jobs, cudaStream_t st)
 {
-    RANK_SWITCH(launch_inv_r, a.rank, a, grid, st)
+    StepArgs a  = args;
+    a.n_jobs    = jobs;
+    RANK_SWITCH(launch_inv_r, a.rank, a, jobs, st)
 }
 
 struct MacPlan

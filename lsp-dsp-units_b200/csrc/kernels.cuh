@@ -382,8 +382,14 @@ k_fwd(const StepArgs a)
             tws[i]              = a.tw[i];
         tw                  = tws;          /* visible after fwd_body's first barrier */
     }
-    const Job job           = fetch_job(a, blockIdx.x);
-    fwd_body<RANK, C::PP>(A, B, job.src, job.spec, a.tw, tw, threadIdx.x);
+    /* grid-stride over the jobs: a launch over many frames (IR ingest, multi-frame calls) keeps
+     * one resident set of CTAs and stages the twiddle table once per CTA */
+    for (uint32_t j = blockIdx.x; j < a.n_jobs; j += gridDim.x)
+    {
+        const Job job           = fetch_job(a, j);
+        fwd_body<RANK, C::PP>(A, B, job.src, job.spec, a.tw, tw, threadIdx.x);
+        __syncthreads();            /* the work buffers are reused by the next job */
+    }
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -578,9 +584,13 @@ k_inv(const StepArgs a)
             tws[i]              = a.tw[i];
         tw                  = tws;          /* visible after inv_body's first barrier */
     }
-    const Job job           = fetch_job(a, blockIdx.x);
-    inv_body<RANK, C::PP>(A, B, a.ypart + uint64_t(blockIdx.x) * rows_per_job(a) * C::M, rows_per_job(a), job.dst,
-                          a.tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
+    for (uint32_t j = blockIdx.x; j < a.n_jobs; j += gridDim.x)
+    {
+        const Job job           = fetch_job(a, j);
+        inv_body<RANK, C::PP>(A, B, a.ypart + uint64_t(j) * rows_per_job(a) * C::M, rows_per_job(a), job.dst,
+                              a.tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
+        __syncthreads();
+    }
 }
 
 /* ------------------------------------------------------------------------------------------- */
