@@ -275,16 +275,28 @@ static cudaError_t launch_frame(const StepArgs &a, const MacPlan &p, uint32_t jo
 
 static int make_twiddles(uint32_t rank, float2 **out)
 {
-    size_t N = size_t(1) << rank;
-    std::vector<float2> h(N);
-    for (size_t j = 0; j < N; ++j)
+    /* layout: FftCfg<RANK> in kernels.cuh (radix-4 passes | w_M^m | w_N^k), all from double */
+    const size_t N = size_t(1) << rank, M = N / 2, P = M / 2;
+    const size_t ns0 = ((rank - 2) & 1) ? 2 : 1;
+    std::vector<float2> h;
+    h.reserve(3 * P + 2);
+    auto root = [](double num, double den)
     {
-        double ang  = -2.0 * M_PI * double(j) / double(N);
-        h[j]        = make_float2(float(cos(ang)), float(sin(ang)));
-    }
+        double ang = -2.0 * M_PI * num / den;
+        return make_float2(float(cos(ang)), float(sin(ang)));
+    };
+    for (size_t ns = ns0; ns < P; ns <<= 2)
+        for (size_t r = 1; r <= 3; ++r)
+            for (size_t k = 0; k < ns; ++k)
+                h.push_back(root(double(k * r), double(4 * ns)));
+    for (size_t m = 0; m < P; ++m)
+        h.push_back(root(double(m), double(M)));
+    for (size_t k = 0; k <= M / 2; ++k)
+        h.push_back(root(double(k), double(N)));
+
     float2 *d = nullptr;
-    CU(cudaMalloc(&d, N * sizeof(float2)));
-    cudaError_t e = cudaMemcpy(d, h.data(), N * sizeof(float2), cudaMemcpyHostToDevice);
+    CU(cudaMalloc(&d, h.size() * sizeof(float2)));
+    cudaError_t e = cudaMemcpy(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice);
     if (e != cudaSuccess)
     {
         cudaFree(d);

@@ -201,7 +201,18 @@ struct FftCfg
     static constexpr bool PP    = (RANK <= 12);                         /* ping-pong work buffers   */
     static constexpr bool TWS   = (RANK <= 12);                         /* twiddle table in smem    */
     static constexpr int WORK   = NH * P;                               /* float2 per work buffer   */
-    static constexpr size_t SMEM = (size_t(WORK) * (PP ? 2 : 1) + (TWS ? N : 0)) * sizeof(float2);
+
+    /* Twiddle table layout (float2 entries; built by make_twiddles on the host).  Every access a
+     * warp makes is unit-stride in its lane index, so the shared-memory copy is conflict-free:
+     *   [0, TW_PRE)            radix-4 passes in execution order (Ns = NS0, 4 NS0, ... < P), each
+     *                          3 * Ns entries: exp(-2 pi i k r / (4 Ns)), r = 1, 2, 3, k < Ns
+     *   [TW_PRE, TW_POST)      w_M^m = exp(-2 pi i m / M), m < P       (odd-half pre/post twiddle)
+     *   [TW_POST, TW_TOTAL)    w_N^k = exp(-2 pi i k / N), k <= M/2    (real-FFT split / merge)     */
+    static constexpr int NS0    = (LOGP & 1) ? 2 : 1;
+    static constexpr int TW_PRE = P - NS0;                              /* 3 * (NS0 + 4 NS0 + ... + P/4) */
+    static constexpr int TW_POST = TW_PRE + P;
+    static constexpr int TW_TOTAL = TW_POST + M / 2 + 1;
+    static constexpr size_t SMEM = (size_t(WORK) * (PP ? 2 : 1) + (TWS ? TW_TOTAL : 0)) * sizeof(float2);
 };
 
 /* Transforms the NH sequences held in A; returns the buffer that holds the result (A or B). */
@@ -209,7 +220,7 @@ template <int RANK, bool INV, bool PP>
 __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *tw, int tid)
 {
     using C = FftCfg<RANK>;
-    constexpr int P = C::P, T = C::T, BPT = C::BPT, NH = C::NH, N = C::N;
+    constexpr int P = C::P, T = C::T, BPT = C::BPT, NH = C::NH;
 
     float2 *in  = A;
     float2 *out = PP ? B : A;
@@ -265,7 +276,7 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
         if (!PP)
             __syncthreads();
 
-        const int step = N / (4 * Ns);          /* exp(-2 pi i k / (4 Ns)) = tw[k * step] */
+        const float2 *tws = tw + (Ns - C::NS0);     /* this pass: 3 * Ns entries, r-major (see FftCfg) */
         #pragma unroll
         for (int i = 0; i < BPT; ++i)
         {
@@ -277,9 +288,9 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
                 float2 x0 = v[i][0], x1 = v[i][1], x2 = v[i][2], x3 = v[i][3];
                 if (Ns > 1)
                 {
-                    float2 w1 = tw[k * step];
-                    float2 w2 = tw[2 * k * step];
-                    float2 w3 = tw[3 * k * step];
+                    float2 w1 = tws[k];
+                    float2 w2 = tws[Ns + k];
+                    float2 w3 = tws[2 * Ns + k];
                     if (INV)    { x1 = cmulc(x1, w1); x2 = cmulc(x2, w2); x3 = cmulc(x3, w3); }
                     else        { x1 = cmul(x1, w1);  x2 = cmul(x2, w2);  x3 = cmul(x3, w3);  }
                 }
@@ -324,7 +335,7 @@ __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src,
         {
             float2 z    = src8 ? reinterpret_cast<const float2 *>(src)[m]
                                : make_float2(src[2 * m], src[2 * m + 1]);
-            float2 zb   = cmul(z, twg[2 * m]);                  /* w_M^m = w_N^(2m) */
+            float2 zb   = cmul(z, twg[C::TW_PRE + m]);          /* w_M^m */
             if (NH == 2)    { A[m] = z; A[P + m] = zb; }
             else            { A[m] = (pass == 0) ? z : zb; }
         }
@@ -356,7 +367,7 @@ __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src,
             /* e = (zk + conj(zm))/2 ; o = (zk - conj(zm))/2 ; X[k] = e - i w^k o */
             float2 e    = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
             float2 o    = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
-            float2 wo   = cmul(tw[k], o);
+            float2 wo   = cmul(tw[C::TW_POST + k], o);
             out[k]      = make_float2(e.x + wo.y, e.y - wo.x);
             /* X[M-k] = conj(e) - i conj(w) conj(o) = conj(e) - i conj(wo) */
             out[M - k]  = make_float2(e.x - wo.y, -e.y - wo.x);
@@ -378,7 +389,7 @@ k_fwd(const StepArgs a)
     if (C::TWS)
     {
         float2 *tws         = sm + C::WORK * (C::PP ? 2 : 1);
-        for (int i = threadIdx.x; i < C::N; i += C::T)
+        for (int i = threadIdx.x; i < C::TW_TOTAL; i += C::T)
             tws[i]              = a.tw[i];
         tw                  = tws;          /* visible after fwd_body's first barrier */
     }
@@ -508,7 +519,7 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
                 /* e = yk + conj(ym) ; o = conj(w^k) (yk - conj(ym)) ; Z[k] = e + i o ; Z[M-k] = conj(e) + i conj(o) */
                 float2 e    = make_float2(yk[u].x + ym[u].x, yk[u].y - ym[u].y);
                 float2 df   = make_float2(yk[u].x - ym[u].x, yk[u].y + ym[u].y);
-                float2 o    = cmulc(df, twg[k[u]]);
+                float2 o    = cmulc(df, twg[C::TW_POST + k[u]]);
                 int ik      = k[u] >> 1;
                 int im      = par ? (P - 1 - ik) : (P - ik);
                 half[ik]    = make_float2(e.x - o.y, e.y + o.x);
@@ -526,14 +537,14 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
             if (NH == 2)
             {
                 float2 av   = R[m];
-                float2 bv   = cmulc(R[P + m], tw[2 * m]);
+                float2 bv   = cmulc(R[P + m], tw[C::TW_PRE + m]);
                 lo          = make_float2((av.x + bv.x) * scale, (av.y + bv.y) * scale);
                 hi          = make_float2((av.x - bv.x) * scale, (av.y - bv.y) * scale);
             }
             else if (pass == 0)
             {
                 /* park conj(w) B / N where the result will go; the same thread reads it back */
-                float2 bv   = cmulc(R[m], tw[2 * m]);
+                float2 bv   = cmulc(R[m], tw[C::TW_PRE + m]);
                 dst[2 * m]      = bv.x * scale;
                 dst[2 * m + 1]  = bv.y * scale;
                 continue;
@@ -580,7 +591,7 @@ k_inv(const StepArgs a)
     if (C::TWS)
     {
         float2 *tws         = sm + C::WORK * (C::PP ? 2 : 1);
-        for (int i = threadIdx.x; i < C::N; i += C::T)
+        for (int i = threadIdx.x; i < C::TW_TOTAL; i += C::T)
             tws[i]              = a.tw[i];
         tw                  = tws;          /* visible after inv_body's first barrier */
     }
@@ -1170,7 +1181,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
         if (SCR == 2)
         {
             float2 *tws         = scr + 2 * stage_elems;
-            for (uint32_t i = tid; i < N; i += T)
+            for (uint32_t i = tid; i < uint32_t(C::TW_TOTAL); i += T)
                 tws[i]              = a.tw[i];
             tw                  = tws;          /* visible after fwd_body's first barrier */
         }
@@ -1305,7 +1316,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     if ((NS >= 2) && (2 * stage_elems >= N))
     {
         float2 *tws     = stages + 2 * stage_elems;
-        for (uint32_t i = tid; i < N; i += T)
+        for (uint32_t i = tid; i < uint32_t(C::TW_TOTAL); i += T)
             tws[i]          = a.tw[i];
         tw              = tws;                  /* visible after inv_body's first barrier */
     }
