@@ -199,6 +199,15 @@ int     b200conv_fastconv_parse_apply(int device, float *dst, const float *c, co
 int     b200conv_fastconv_restore(int device, float *dst, const float *image, size_t rank,
                                   size_t count, void *stream);
 
+/* dsp::convolve (reference call site Convolver.cpp:295; same as the test helper
+ * src/test/utest/util/convolver.cpp:32-40), batched on the device:
+ *     dst[i][a + b] += src[i][a] * conv[i][b]    a < count, b < length
+ * for `batch` independent problems; rows are `*_stride` floats apart (DEVICE pointers; dst rows hold
+ * count + length - 1 valid samples and are accumulated into, like the reference's). */
+int     b200conv_convolve(int device, float *dst, size_t dst_stride, const float *src, size_t src_stride,
+                          const float *conv, size_t conv_stride, size_t length, size_t count,
+                          size_t batch, void *stream);
+
 /* ---- offline linear convolution ("next" row f1 of the scope table) -------------------------- */
 
 /* Full linear convolution of `count` signals with ONE filter, host buffers:

@@ -93,6 +93,7 @@ _SIGNATURES = {
     "b200conv_fastconv_apply": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_fastconv_parse_apply": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_fastconv_restore": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _SZ, _SZ, _VP]),
+    "b200conv_convolve": (ctypes.c_int, [ctypes.c_int, _VP, _SZ, _VP, _SZ, _VP, _SZ, _SZ, _SZ, _SZ, _VP]),
     "b200conv_linear_convolve": (ctypes.c_int, [ctypes.c_int, _VP, _SZ, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _SZ]),
     "b200conv_last_error": (ctypes.c_char_p, []),
     "b200conv_version": (ctypes.c_char_p, []),

@@ -1810,6 +1810,24 @@ extern "C" int b200conv_fastconv_parse_apply(int device, float *dst, const float
     return prim_inverse(c, dst, prod, rank, count, true, rows, st);
 }
 
+extern "C" int b200conv_convolve(int device, float *dst, size_t dst_stride, const float *src, size_t src_stride,
+                                 const float *conv, size_t conv_stride, size_t length, size_t count,
+                                 size_t batch, void *stream)
+{
+    if ((dst == nullptr) || (src == nullptr) || (conv == nullptr) || (batch > 65535) ||
+        (length >= (size_t(1) << 31)) || (count >= (size_t(1) << 31)))
+        return fail(B200CONV_ERR_ARG, "b200conv_convolve: bad arguments");
+    if ((length == 0) || (count == 0) || (batch == 0))
+        return B200CONV_OK;
+    ENTER_PRIM_DEVICE(device);
+    size_t n        = count + length - 1;
+    dim3 grid(uint32_t((n + 127) / 128 > 1024 ? 1024 : (n + 127) / 128), uint32_t(batch));
+    k_convolve<<<grid, 128, 0, cudaStream_t(stream)>>>(dst, dst_stride, src, src_stride, conv, conv_stride,
+                                                       uint32_t(length), uint32_t(count));
+    CU(cudaGetLastError());
+    return B200CONV_OK;
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* offline linear convolution                                                                   */
 

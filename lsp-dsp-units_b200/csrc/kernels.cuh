@@ -1455,6 +1455,26 @@ __global__ void k_accumulate(float *dst, const float *add, uint64_t total)
         dst[i]     += add[i];
 }
 
+/* dsp::convolve, batched: dst[a + b] += src[a] * conv[b].  One thread per output sample gathers
+ * its terms (no atomics, deterministic order). */
+__global__ void k_convolve(float *dst, uint64_t dst_stride, const float *src, uint64_t src_stride,
+                           const float *conv, uint64_t conv_stride, uint32_t length, uint32_t count)
+{
+    const float *x      = src + uint64_t(blockIdx.y) * src_stride;
+    const float *h      = conv + uint64_t(blockIdx.y) * conv_stride;
+    float *y            = dst + uint64_t(blockIdx.y) * dst_stride;
+    const uint32_t n    = count + length - 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        uint32_t a0     = (i >= length) ? i - length + 1 : 0;
+        uint32_t a1     = (i < count) ? i : count - 1;
+        float acc       = 0.0f;
+        for (uint32_t a = a0; a <= a1; ++a)
+            acc             = fmaf(x[a], h[i - a], acc);
+        y[i]           += acc;
+    }
+}
+
 /* packed spectrum product for the fastconv primitives: y = a * b, bin 0 component-wise */
 __global__ void k_cmul(float2 *y, const float2 *a, const float2 *b, uint32_t M, uint64_t total)
 {

@@ -94,3 +94,23 @@ def test_linear_convolve_matches_float64(pkg, nx, nh, rank, count):
     for i in range(count):
         want = direct_convolve(x[i], h)
         assert np.max(np.abs(got[i] - want)) <= 1e-5 * np.max(np.abs(want))
+
+
+def test_direct_convolve_accumulates(pkg):
+    """dsp::convolve on the device (scope row a16): dst[a+b] += src[a]*conv[b], batched."""
+    lib = pkg.lib()
+    rng = np.random.Generator(np.random.PCG64(16))
+    for length, count, batch in ((128, 127, 3), (31, 0x2000, 1), (5, 1, 2), (1, 9, 4)):
+        x = rng.uniform(-1, 1, (batch, count)).astype(np.float32)
+        h = rng.uniform(-1, 1, (batch, length)).astype(np.float32)
+        n = count + length - 1
+        base = rng.uniform(-1, 1, (batch, n + 3)).astype(np.float32)       # row pitch n + 3
+        dx, dh, dy = torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), torch.from_numpy(base).cuda()
+        _check(pkg, lib.b200conv_convolve(0, dy.data_ptr(), n + 3, dx.data_ptr(), count, dh.data_ptr(), length,
+                                          length, count, batch, None))
+        torch.cuda.synchronize()
+        got = dy.cpu().numpy()
+        for i in range(batch):
+            want = base[i].astype(np.float64)
+            want[:n] += np.convolve(x[i].astype(np.float64), h[i].astype(np.float64))
+            assert np.max(np.abs(got[i] - want)) <= 1e-5 * max(1.0, np.abs(want).max())
