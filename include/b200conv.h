@@ -166,7 +166,7 @@ void   *b200conv_stream(b200conv_batch_t *h);
 /* Tuning / A-B knobs (value 0 = automatic unless stated):
  *   "mac_splits"  partition splits per instance-frame (1..32)
  *   "mac_stages"  shared-memory pipeline stages of the MAC stream (2..12)
- *   "fused"       1 (default) = ranks 8..11 run FFT + MAC + IFFT as ONE launch per block
+ *   "fused"       1 (default) = ranks 8..13 run FFT + MAC + IFFT as ONE launch per block
  *                 (k_frame); 0 = always three launches (k_fwd, k_mac, k_inv)
  *   "fft_bias"    partitions taken off the split that also transforms the input (default 6)
  *   "pdl"         1 (default) = programmatic dependent launch between consecutive blocks

@@ -245,7 +245,7 @@ static cudaError_t launch_frame_r(const StepArgs &a, const MacPlan &p, uint32_t 
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim             = dim3(jobs * p.splits);
+    cfg.gridDim             = dim3(jobs * p.splits, p.tiles);
     cfg.blockDim            = dim3(p.threads);
     cfg.dynamicSmemBytes    = p.smem;
     cfg.stream              = st;
@@ -266,6 +266,8 @@ static cudaError_t launch_frame(const StepArgs &a, const MacPlan &p, uint32_t jo
         case 9:  return launch_frame_r<9>(a, p, jobs, tickets, ra, pdl, st);
         case 10: return launch_frame_r<10>(a, p, jobs, tickets, ra, pdl, st);
         case 11: return launch_frame_r<11>(a, p, jobs, tickets, ra, pdl, st);
+        case 12: return launch_frame_r<12>(a, p, jobs, tickets, ra, pdl, st);
+        case 13: return launch_frame_r<13>(a, p, jobs, tickets, ra, pdl, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -885,7 +887,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
     a.splits        = plan.splits;
     a.n_jobs        = nact;
     a.t_base        = b->t_batch;
-    const bool fused = (b->opt_fused != 0) && (b->rank <= 11);
+    const bool fused = (b->opt_fused != 0) && (b->rank <= 13);     /* k_frame: ranks 8..13 */
     if ((b->reduce.mode != 0) && (!fused))
         return fail(B200CONV_ERR_STATE, "the fused cross-GPU reduce needs the one-launch-per-block path (ranks 8..11, fused = 1)");
     plan.sh.bias    = fused ? uint32_t(b->opt_bias) : 0;

@@ -187,7 +187,7 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b)
 /* registers.  With a second buffer (PP) a pass is load A -> butterflies -> store B -> barrier;  */
 /* without it, load -> barrier -> store -> barrier in place.                                    */
 
-template <int RANK>
+template <int RANK, int TT = 0>                 /* TT: threads doing the transform (0 = natural count) */
 struct FftCfg
 {
     static constexpr int N      = 1 << RANK;
@@ -196,7 +196,7 @@ struct FftCfg
     static constexpr int LOGP   = RANK - 2;
     static constexpr int NH     = (RANK >= 16) ? 1 : 2;                 /* halves resident in smem */
     static constexpr int BF     = NH * P / 4;                           /* radix-4 butterflies/pass */
-    static constexpr int T      = (BF >= 512) ? 512 : ((BF < 32) ? 32 : BF);
+    static constexpr int T      = (TT > 0) ? TT : ((BF >= 512) ? 512 : ((BF < 32) ? 32 : BF));
     static constexpr int BPT    = (BF + T - 1) / T;                     /* butterflies per thread   */
     static constexpr bool PP    = (RANK <= 12);                         /* ping-pong work buffers   */
     static constexpr bool TWS   = (RANK <= 12);                         /* twiddle table in smem    */
@@ -216,10 +216,10 @@ struct FftCfg
 };
 
 /* Transforms the NH sequences held in A; returns the buffer that holds the result (A or B). */
-template <int RANK, bool INV, bool PP>
+template <int RANK, bool INV, bool PP, int TT = 0>
 __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *tw, int tid)
 {
-    using C = FftCfg<RANK>;
+    using C = FftCfg<RANK, TT>;
     constexpr int P = C::P, T = C::T, BPT = C::BPT, NH = C::NH;
 
     float2 *in  = A;
@@ -320,11 +320,11 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
 /* twg = twiddle table in global memory (used next to the global loads), tw = the table the      */
 /* transform passes read (shared-memory copy when the caller staged one, else twg).              */
 
-template <int RANK, bool PP>
+template <int RANK, bool PP, int TT = 0>
 __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src, float2 *out,
                                          const float2 *twg, const float2 *tw, int tid)
 {
-    using C = FftCfg<RANK>;
+    using C = FftCfg<RANK, TT>;
     constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH;
 
     #pragma unroll 1
@@ -341,7 +341,7 @@ __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src,
         }
         __syncthreads();
 
-        const float2 *R = fft_smem<RANK, false, PP>(A, B, tw, tid);
+        const float2 *R = fft_smem<RANK, false, PP, TT>(A, B, tw, tid);
 
         /* split post-pass over pairs (k, M-k), k = 0 .. M/2; thread 0 takes k = 0 and k = M/2 */
         for (int k = tid; k < M / 2; k += T)
@@ -409,11 +409,11 @@ k_fwd(const StepArgs a)
 /* samples (the second half is time-aliased garbage in the folded-overlap form).  `full` also    */
 /* emits samples [F, 2F) (used by the fastconv primitives).                                      */
 
-template <int RANK, bool PP, int RG = 8>     /* RG: partial rows loaded per round (registers) */
+template <int RANK, bool PP, int RG = 8, int TT = 0>     /* RG: partial rows loaded per round (registers) */
 __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp, uint32_t splits,
                                          float *dst, const float2 *twg, const float2 *tw, bool full, int tid)
 {
-    using C = FftCfg<RANK>;
+    using C = FftCfg<RANK, TT>;
     constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH, N = C::N;
     constexpr int ITER = (M / 2) / T;           /* bins k = tid + it*T handled by this thread; even */
     static_assert((ITER >= 2) && ((ITER & 1) == 0), "inv_body: two bins per round");
@@ -528,7 +528,7 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
         }
         __syncthreads();
 
-        const float2 *R = fft_smem<RANK, true, PP>(A, B, tw, tid);
+        const float2 *R = fft_smem<RANK, true, PP, TT>(A, B, tw, tid);
 
         /* z[m] = (A[m] + conj(w_M^m) B[m]) / N ; z[m + P] = (A[m] - conj(w_M^m) B[m]) / N */
         for (int m = tid; m < P; m += T)
@@ -1040,24 +1040,37 @@ k_mac_multi(const StepArgs a, const MacShape sh)
 /* Launched with programmatic stream serialisation: the prologue overlaps the previous frame's   */
 /* tail; nothing global is touched before griddepcontrol.wait.                                   */
 
+/* Ranks 12 and 13 have 2 / 4 bin tiles of 1024 per instance (grid.y): the CTA (split 0, tile 0)
+ * transforms the frame with its 256 threads, the other tiles of split 0 learn through ring_head
+ * that the spectrum has landed, and the last of the splits x tiles CTAs of a job inverts. */
 template <int RANK>
-__global__ void __launch_bounds__(FftCfg<RANK>::T, (FftCfg<RANK>::T >= 256) ? 4 : 8)
+struct FrameCfg
+{
+    static constexpr int M      = 1 << (RANK - 1);
+    static constexpr int TB     = (M < 1024) ? M : 1024;            /* bins per CTA tile       */
+    static constexpr int T      = TB / 4;                           /* threads per CTA         */
+    static constexpr int MINB   = (RANK >= 13) ? 2 : ((T >= 256) ? 4 : 8);  /* CTAs per SM (register cap) */
+};
+
+template <int RANK>
+__global__ void __launch_bounds__(FrameCfg<RANK>::T, FrameCfg<RANK>::MINB)
 k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs ra)
 {
-    using C = FftCfg<RANK>;
-    constexpr uint32_t M = C::M, T = C::T, N = C::N;
-    static_assert(C::T == C::M / 4, "k_frame: FFT and MAC thread counts must agree (ranks 8..11)");
+    using C = FftCfg<RANK, FrameCfg<RANK>::T>;
+    constexpr uint32_t M = C::M, T = C::T, TB = FrameCfg<RANK>::TB;
     static_assert(C::NH == 2, "k_frame: both FFT halves resident");
+    static_assert(RANK <= 13, "k_frame: the frame transform must fit the stage buffers");
 
     extern __shared__ __align__(128) unsigned char smraw[];
 
-    const uint32_t QB       = sh.QB, NS = sh.NS;                    /* TB == M */
+    const uint32_t QB       = sh.QB, NS = sh.NS;
     const uint32_t tid      = threadIdx.x;
     const uint32_t jobi     = blockIdx.x / a.splits;
     const uint32_t split    = blockIdx.x % a.splits;
+    const uint32_t tile     = blockIdx.y;
 
     /* stage s = [ G rows : stage_elems float2 | ring rows : stage_elems float2 ], back to back */
-    const uint32_t stage_elems = QB * M;                            /* 1024 float2 for ranks 8..11 */
+    const uint32_t stage_elems = QB * TB;                           /* 1024 float2 */
     float2 *stages          = reinterpret_cast<float2 *>(smraw);
     uint64_t *full          = reinterpret_cast<uint64_t *>(stages + size_t(NS) * 2 * stage_elems);
     uint32_t *flag          = reinterpret_cast<uint32_t *>(full + NS);
@@ -1089,13 +1102,13 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     chunk_range(nq, split, a.splits, sh.bias, c0, c1);
     const uint32_t q0       = qa + c0, q1 = qa + c1;
     const uint32_t n_iter   = (q1 - q0 + QB - 1) / QB;
-    const bool fft_cta      = (split == 0);
+    const bool fft_cta      = (split == 0) && (tile == 0);
     /* the stage holding partition qa goes last in the FFT CTA */
     const uint32_t shift    = (fft_cta && (n_iter > 1)) ? 1 : 0;
 
-    const float2 *Gt        = d.G;
-    const float2 *Xt        = d.ring;
-    const uint32_t row_bytes = M * uint32_t(sizeof(float2));
+    const float2 *Gt        = d.G + uint64_t(tile) * TB;            /* row r at Gt + r * M */
+    const float2 *Xt        = d.ring + uint64_t(tile) * TB;
+    const uint32_t row_bytes = TB * uint32_t(sizeof(float2));
 
     /* Stage-ring bookkeeping is incremental (next stage buffer, next position in the chunk, next
      * ring slot): no integer division inside the streaming loop.  `issued` = stages fetched. */
@@ -1114,7 +1127,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
         uint32_t n1     = min(rows, d.S - f_slot);
         bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s]);
         if (n1 < rows)
-            bulk_g2s(x + size_t(n1) * M, Xt, (rows - n1) * row_bytes, &full[f_s]);
+            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s]);
         ++issued;
         if (++f_s == NS)    f_s = 0;
         if (++f_stg == n_iter)
@@ -1132,14 +1145,19 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     /* prologue: the FFT CTA keeps the last SCR stage buffers as transform scratch (two work
      * buffers, and the twiddle table when a second buffer can be spared) and must not fetch its
      * final stage yet -- that one reads the spectrum which is about to be written */
-    const uint32_t SCR      = ((NS >= 3) && (2 * stage_elems >= N)) ? 2 : 1;
+    /* transform scratch: FFT_STAGES stage buffers for the work buffer(s) (ping-pong when two fit
+     * into one stage buffer), plus one more for the twiddle table when the ring is deep enough */
+    constexpr bool FFT_PP           = (2 * C::WORK <= 2048);                    /* ranks 8..11 */
+    constexpr uint32_t FFT_STAGES   = (C::WORK * (FFT_PP ? 2 : 1) + 2047) / 2048; /* 1, rank 13: 2 */
+    const bool fwd_table    = (NS >= FFT_STAGES + 2) && (uint32_t(C::TW_TOTAL) <= 2 * stage_elems);
+    const uint32_t SCR      = FFT_STAGES + (fwd_table ? 1u : 0u);
     uint32_t pre            = min(NS, n_iter);
     if (fft_cta)
     {
         /* Its partitions q >= 1 need the spectra of frames <= t - 1.  In steady state they were
          * published long ago and the first stages are fetched right away; if the previous
          * launch's split-0 CTA is still at work, fetching waits until after the transform. */
-        pre                 = (n_iter > 0) ? min(NS - SCR, n_iter - 1) : 0;
+        pre                 = ((n_iter > 0) && (NS > SCR)) ? min(NS - SCR, n_iter - 1) : 0;
         if (tid == 0)
         {
             uint32_t have;
@@ -1176,11 +1194,11 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     if (fft_cta)
     {
         float2 *scr         = stages + size_t(NS - SCR) * 2 * stage_elems;
-        float2 *wa          = scr, *wb = scr + stage_elems;
+        float2 *wa          = scr, *wb = FFT_PP ? scr + C::WORK : nullptr;
         const float2 *tw    = a.tw;
-        if (SCR == 2)
+        if (fwd_table)
         {
-            float2 *tws         = scr + 2 * stage_elems;
+            float2 *tws         = scr + size_t(FFT_STAGES) * 2 * stage_elems;
             for (uint32_t i = tid; i < uint32_t(C::TW_TOTAL); i += T)
                 tws[i]              = a.tw[i];
             tw                  = tws;          /* visible after fwd_body's first barrier */
@@ -1201,7 +1219,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
                 __nanosleep(100);
             }
         }
-        fwd_body<RANK, true>(wa, wb, job.src, job.spec, a.tw, tw, int(tid));
+        fwd_body<RANK, FFT_PP, int(T)>(wa, wb, job.src, job.spec, a.tw, tw, int(tid));
         /* generic-proxy global writes -> visible to the TMA (async proxy) reads issued below */
         __threadfence();
         asm volatile("fence.proxy.async;" ::: "memory");
@@ -1248,8 +1266,8 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
             #pragma unroll
             for (int v = 0; v < MAC_VPT; ++v)
             {
-                float4 g    = g4[r * (M / 2) + tid + v * T];
-                float4 x    = x4[r * (M / 2) + tid + v * T];
+                float4 g    = g4[r * (TB / 2) + tid + v * T];
+                float4 x    = x4[r * (TB / 2) + tid + v * T];
                 acc[v].x    = fmaf(g.x, x.x, acc[v].x);
                 acc[v].y    = fmaf(g.x, x.y, acc[v].y);
                 acc[v].z    = fmaf(g.z, x.z, acc[v].z);
@@ -1270,7 +1288,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
             issue_next();
     }
 
-    if (tid == 0)
+    if ((tile == 0) && (tid == 0))
     {
         acc[0].x   += dny;
         acc[0].y    = dny;
@@ -1288,7 +1306,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
 
     const uint32_t rows = rows_per_job(a);
     float2 *yrow    = a.ypart + uint64_t(jobi) * rows * M;
-    float4 *yp      = reinterpret_cast<float4 *>(yrow + uint64_t(a.row0 + split) * M);
+    float4 *yp      = reinterpret_cast<float4 *>(yrow + uint64_t(a.row0 + split) * M + uint64_t(tile) * TB);
     #pragma unroll
     for (int v = 0; v < MAC_VPT; ++v)
         __stcg(&yp[tid + v * T], acc[v]);
@@ -1299,7 +1317,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     if (tid == 0)
     {
         uint32_t old    = atomicAdd(&tickets[jobi], 1u);
-        uint32_t last   = (old == a.splits - 1) ? 1u : 0u;
+        uint32_t last   = (old == a.splits * gridDim.y - 1) ? 1u : 0u;
         if (last)
             tickets[jobi]   = 0;                /* ready for the next launch */
         *flag           = last;
@@ -1311,18 +1329,20 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
 
     /* The inverse transform is the exposed tail of the launch: twiddles go to shared memory
      * (the stage buffers are idle now) so that its dependent loads stay on chip. */
-    float2 *wa      = stages, *wb = stages + stage_elems;
+    constexpr bool TAIL_PP = (RANK <= 12);      /* two work buffers fit the (>= 2) stage buffers */
+    constexpr uint32_t TAIL_WORK = C::WORK * (TAIL_PP ? 2 : 1);
+    float2 *wa      = stages, *wb = TAIL_PP ? stages + C::WORK : nullptr;
     const float2 *tw = a.tw;
-    if ((NS >= 2) && (2 * stage_elems >= N))
+    if (TAIL_WORK + uint32_t(C::TW_TOTAL) <= NS * 2 * stage_elems)
     {
-        float2 *tws     = stages + 2 * stage_elems;
+        float2 *tws     = stages + TAIL_WORK;
         for (uint32_t i = tid; i < uint32_t(C::TW_TOTAL); i += T)
             tws[i]          = a.tw[i];
         tw              = tws;                  /* visible after inv_body's first barrier */
     }
     if (ra.mode == 0)
     {
-        inv_body<RANK, true, 4>(wa, wb, yrow, rows, job.dst, a.tw, tw, false, int(tid));
+        inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, job.dst, a.tw, tw, false, int(tid));
         return;
     }
 
@@ -1347,7 +1367,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
             }
         }
         __syncthreads();
-        inv_body<RANK, true, 4>(wa, wb, yrow, rows, slot, a.tw, tw, false, int(tid));
+        inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, slot, a.tw, tw, false, int(tid));
         /* the barrier orders every thread's peer stores before thread 0, whose (cumulative)
          * system-scope release then publishes the whole block: one fence, not one per thread */
         __syncthreads();
@@ -1357,7 +1377,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     }
 
     /* root: own block into slot 0, then gather */
-    inv_body<RANK, true, 4>(wa, wb, yrow, rows, slot, a.tw, tw, false, int(tid));
+    inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, slot, a.tw, tw, false, int(tid));
     if (tid == 0)
     {
         while (ld_acquire_sys(arrived) < ra.world - 1u)

@@ -307,12 +307,12 @@ def test_device_pointer_api_and_stats(pkg, fused):
     b.close()
 
 
-@pytest.mark.parametrize("rank", [8, 9, 10, 11])
+@pytest.mark.parametrize("rank", [8, 9, 10, 11, 12, 13])
 @pytest.mark.parametrize("opts", [dict(fused=1), dict(fused=0), dict(fused=1, pdl=0, fft_bias=0),
                                   dict(fused=1, mac_splits=7, mac_stages=2),
                                   dict(fused=1, mac_splits=1, mac_stages=5)])
 def test_one_launch_per_block_matches_three_kernel_path(pkg, rank, opts):
-    """k_frame (FFT + MAC + IFFT in one launch, ranks 8..11) against direct convolution on a ragged
+    """k_frame (FFT + MAC + IFFT in one launch, ranks 8..13) against direct convolution on a ragged
     batch: IRs shorter than the number of partition splits, exactly one frame, many frames."""
     F = 1 << (rank - 1)
     lens = [1, F - 1, F, F + 1, 5 * F + 3, 40 * F + 7, 0, 200 * F]
@@ -353,13 +353,14 @@ def test_planar_host_api_strided_views(pkg):
     b.close()
 
 
-@pytest.mark.parametrize("n,taps,frames", [(8, 100 * 1024 + 3, 600), (64, 480000, 150)])
-def test_overlapped_launches_are_bit_identical_to_serialised(pkg, n, taps, frames):
+@pytest.mark.parametrize("n,taps,frames,rank", [(8, 100 * 1024 + 3, 600, 11), (64, 480000, 150, 11),
+                                                (6, 300000, 200, 12), (5, 300000, 120, 13), (7, 50000, 400, 9)])
+def test_overlapped_launches_are_bit_identical_to_serialised(pkg, n, taps, frames, rank):
     """Back-to-back blocks overlap on the GPU (programmatic dependent launch, ring_head /
     stream_done hand-shakes).  Any ordering bug would change bits: the overlapped run must equal
     the fully serialised one exactly, block for block."""
     torch = pytest.importorskip("torch")
-    rank, F = 11, 1024
+    F = 1 << (rank - 1)
     irs = [synth.decaying_ir(c, taps) for c in range(min(n, 4))]
     g = torch.Generator(device="cuda").manual_seed(7)
     src = torch.rand((n, frames * F), generator=g, device="cuda") * 2 - 1
