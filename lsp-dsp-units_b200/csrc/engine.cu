@@ -803,7 +803,7 @@ extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float 
         }
         if (rc != B200CONV_OK) break;
 
-        dim3 grid(uint32_t((F + 255) / 256), uint32_t(nq));
+        dim3 grid(uint32_t((F + 255) / 256), uint32_t((nq < 65535) ? nq : 65535));
         k_fold<<<grid, 256, 0, st>>>(fresh.G, H, uint32_t(bins), uint32_t(F));
         CU_BRK(cudaGetLastError());
         b->stats.launches++;
@@ -1158,7 +1158,7 @@ static int process_general(Batch *b, float *dst, size_t dst_stride, const float 
             size_t maxn = 0;
             for (const Job &pj : part)
                 if (pj.n > maxn) maxn = pj.n;
-            dim3 grid(uint32_t((maxn + 127) / 128), a.n_jobs);
+            dim3 grid(uint32_t((maxn + 127) / 128), (a.n_jobs < 65535u) ? a.n_jobs : 65535u);
             k_store<<<grid, 128, 0, st>>>(a);
             CU(cudaGetLastError());
             k_partial<<<grid, 128, 0, st>>>(a);

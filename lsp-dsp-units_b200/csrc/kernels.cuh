@@ -1419,10 +1419,13 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
 /* cur[off .. off+n) = src[0 .. n) */
 __global__ void k_store(const StepArgs a)
 {
-    const Job job       = a.jobs[blockIdx.y];
-    float *cur          = a.inst[job.inst].cur;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x)
-        cur[job.off + i]    = job.src[i];
+    for (uint32_t jb = blockIdx.y; jb < a.n_jobs; jb += gridDim.y)
+    {
+        const Job job       = a.jobs[jb];
+        float *cur          = a.inst[job.inst].cur;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x)
+            cur[job.off + i]    = job.src[i];
+    }
 }
 
 /* dst[m - off] = pend[m] + sum_{j <= m} cur[j] * head[m - j],  m in [off, off+n):
@@ -1430,23 +1433,26 @@ __global__ void k_store(const StepArgs a)
  * in direct form (reference: dsp::convolve and the raising levels, Convolver.cpp:251-262,295). */
 __global__ void k_partial(const StepArgs a)
 {
-    const Job job       = a.jobs[blockIdx.y];
-    const InstDesc &d   = a.inst[job.inst];
-    const float *cur    = d.cur;
-    const float *head   = d.head;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x)
+    for (uint32_t jb = blockIdx.y; jb < a.n_jobs; jb += gridDim.y)
     {
-        uint32_t m      = job.off + i;
-        double total    = 0.0;
-        for (uint32_t j0 = 0; j0 <= m; j0 += 128)
+        const Job job       = a.jobs[jb];
+        const InstDesc &d   = a.inst[job.inst];
+        const float *cur    = d.cur;
+        const float *head   = d.head;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x)
         {
-            uint32_t j1     = min(j0 + 128, m + 1);
-            float part      = 0.0f;
-            for (uint32_t j = j0; j < j1; ++j)
-                part            = fmaf(cur[j], head[m - j], part);
-            total          += double(part);
+            uint32_t m      = job.off + i;
+            double total    = 0.0;
+            for (uint32_t j0 = 0; j0 <= m; j0 += 128)
+            {
+                uint32_t j1     = min(j0 + 128, m + 1);
+                float part      = 0.0f;
+                for (uint32_t j = j0; j < j1; ++j)
+                    part            = fmaf(cur[j], head[m - j], part);
+                total          += double(part);
+            }
+            job.dst[i]      = d.pend[m] + float(total);
         }
-        job.dst[i]      = d.pend[m] + float(total);
     }
 }
 
@@ -1457,7 +1463,8 @@ __global__ void k_partial(const StepArgs a)
  * (DC, Nyquist = bin M), both even, so it takes '+' like every even bin. */
 __global__ void k_fold(float2 *G, const float2 *H, uint32_t bins, uint32_t M)
 {
-    uint32_t q          = blockIdx.y;
+    /* grid.y strides over the rows: IRs with more than 65535 partitions exist (rank 8, minutes) */
+    for (uint32_t q = blockIdx.y; q <= bins; q += gridDim.y)
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < M; k += gridDim.x * blockDim.x)
     {
         float2 cur      = (q < bins) ? H[uint64_t(q) * M + k] : make_float2(0.0f, 0.0f);

@@ -574,3 +574,19 @@ def test_eager_pending_mac_for_synchronous_calls(pkg, eager, pinned):
     assert rel_err(out[1][:cut], direct_convolve(src[1][:cut], irs[1], cut)) <= TOL
     assert rel_err(out[1][cut:], direct_convolve(src[1][cut:], irs1_new, total - cut)) <= TOL
     b.close()
+
+
+def test_ir_with_more_than_65535_partitions(pkg):
+    """Maximum-size edge: a 3-minute IR at the smallest rank has 70 000 partitions of 128 taps
+    (beyond the 65 535 grid-y limit and the 32 768-entry job ring of the IR ingest)."""
+    rank, F = 8, 128
+    L = 70000 * F - 5
+    ir = synth.decaying_ir(4, L)
+    n = 40 * F
+    x = synth.noise(4, n)
+    b = pkg.ConvolverBatch(1, 0)
+    assert b.init(0, ir, rank, 0.0)
+    assert b.state(0)["bins"] == 70000 and b.state(0)["partitions"] == 70001
+    out = np.concatenate([b.process(x[None, i:i + 5 * F])[0] for i in range(0, n, 5 * F)])
+    assert rel_err(out, direct_convolve(x, ir, n)) <= TOL
+    b.close()
