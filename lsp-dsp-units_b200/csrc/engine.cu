@@ -1873,3 +1873,13 @@ extern "C" int b200conv_linear_convolve(int device, float *dst, size_t dst_strid
     g_last_error = keep;
     return rc;
 }
+
+#ifdef B200CONV_TIMING
+/* developer instrumentation: copies the per-CTA timestamps of the last k_frame launch */
+extern "C" int b200conv_debug_frame_times(unsigned long long *out, size_t count)
+{
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out, g_frame_times, count * sizeof(unsigned long long)));
+    return B200CONV_OK;
+}
+#endif

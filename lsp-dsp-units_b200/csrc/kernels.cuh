@@ -1043,6 +1043,14 @@ k_mac_multi(const StepArgs a, const MacShape sh)
 /* Ranks 12 and 13 have 2 / 4 bin tiles of 1024 per instance (grid.y): the CTA (split 0, tile 0)
  * transforms the frame with its 256 threads, the other tiles of split 0 learn through ring_head
  * that the spectrum has landed, and the last of the splits x tiles CTAs of a job inverts. */
+#ifdef B200CONV_TIMING
+/* developer instrumentation (tools/frame_timeline.py): per-CTA timestamps of the last k_frame launch */
+__device__ unsigned long long g_frame_times[8192 * 4];
+#define FRAME_STAMP(slot)   do { if ((threadIdx.x == 0) && (blockIdx.x < 8192)) g_frame_times[blockIdx.x * 4 + (slot)] = global_ns(); } while (0)
+#else
+#define FRAME_STAMP(slot)   do { } while (0)
+#endif
+
 template <int RANK>
 struct FrameCfg
 {
@@ -1082,6 +1090,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
      *   - its split-0 CTAs (input block, ring write) and every CTA's partial-row / ticket /
      *     output writes sit behind griddepcontrol.wait, i.e. after this launch has completed. */
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    FRAME_STAMP(0);
     if (tid == 0)
     {
         for (uint32_t s = 0; s < NS; ++s)
@@ -1293,6 +1302,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
         acc[0].x   += dny;
         acc[0].y    = dny;
     }
+    FRAME_STAMP(1);
 
     /* partial rows, tickets and the output block are shared with the previous launch's tail */
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1323,6 +1333,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
         *flag           = last;
     }
     __syncthreads();
+    FRAME_STAMP(2);
     if (*flag == 0)
         return;
     __threadfence();
@@ -1343,6 +1354,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     if (ra.mode == 0)
     {
         inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, job.dst, a.tw, tw, false, int(tid));
+        FRAME_STAMP(3);
         return;
     }
 
