@@ -13,9 +13,13 @@ rank owns its own 64 instances -- independent channels, no collective on the dat
 ("scaling": "weak"); `value` = samples of all ranks / max-over-ranks device time.
 
 One JSON line on rank 0; see the task contract for the keys.  `roofline` is for the dominant
-kernel k_mac: algorithmic bytes per launch (64 x (16*F*bins + 24*F)) / its average
-launch duration measured with CUDA events on the launching stream in an extra pass right after
-the timed steps; peak = MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s).
+kernel -- k_frame<11>, the one launch per block: algorithmic bytes per launch
+(64 x (16*F*bins + 24*F)) / its average launch duration.  The timed region consists of
+nothing but those launches, back to back on one stream (CUDA events on that stream), so its
+duration / launches is the kernel's launch duration as deployed; `isolated_*` repeats the
+measurement with every launch bracketed by its own event pair (no overlap between blocks) in an
+extra pass right after the timed steps.  peak = MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s);
+`e2e` = synchronous b200conv_process_planar calls on pinned host buffers.
 """
 import argparse
 import json

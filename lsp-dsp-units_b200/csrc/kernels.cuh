@@ -5,8 +5,14 @@
  *   dsp::fastconv_parse  (Convolver.cpp:159,174,191,270)  -> k_fwd   : F reals -> M packed bins
  *   dsp::fastconv_apply  (Convolver.cpp:280-285, the hot   -> k_mac   : sum_q G_q * X_{t-q}
  *        loop: nBlocks x (spectrum multiply + IFFT + add)     k_inv   : ONE inverse FFT per frame
+ *   the three above for one audio block, all instances     -> k_frame : one launch per block
+ *        x partitions (ranks 8..13), blocks overlapped        (+ fused NVLink reduce of
+ *        on the device                                         partition-range shards)
+ *   ... for several frames of one call                     -> k_mac_multi : one pass over the IR
+ *                                                             spectra serves up to 8 frames
  *   dsp::fastconv_parse_apply head (Convolver.cpp:256,293) -> folded into partition q = 0
- *   dsp::convolve        (Convolver.cpp:295)               -> k_partial (unaligned call sizes)
+ *   dsp::convolve        (Convolver.cpp:295)               -> k_partial (unaligned call sizes),
+ *                                                             k_convolve (exported primitive)
  *   dsp::copy/move/fill_zero (Convolver.cpp:291,296,308-310) -> ring indices, nothing moves
  *
  * Notation: rank R, N = 2^R, F = M = N/2 (frame length = packed complex bins), P = M/2.
