@@ -17,7 +17,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libb200conv.so")
+LIB_PATH = os.environ.get("B200CONV_LIB", os.path.join(_HERE, "libb200conv.so"))     # override: A/B builds
 
 RANK_MIN, RANK_MAX = 8, 16
 OK, ERR_ARG, ERR_NOMEM, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4

@@ -653,11 +653,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 /* global -> shared bulk copy (TMA, 1-D); bytes % 16 == 0, both addresses 16-byte aligned */
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+/* IR spectra and ring rows are read once per block and the working set is several times the L2:
+ * they are fetched with an evict-first L2 policy so that they do not push out what IS reused
+ * (partial rows, the freshly written spectrum, the tables).  Measured on config 3: 67.2 us per
+ * block with the hint, 70.0 us without (profiles/README.md). */
+__device__ __forceinline__ uint64_t stream_policy()
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy)
 {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
 struct MacShape
@@ -733,6 +745,7 @@ k_mac(const StepArgs a, const MacShape sh)
     const float2 *Gt        = d.G + uint64_t(tile) * TB;            /* row r at Gt + r * M */
     const float2 *Xt        = d.ring + uint64_t(tile) * TB;
     const uint32_t row_bytes = TB * uint32_t(sizeof(float2));
+    const uint64_t l2_stream = stream_policy();
 
     if (tid == 0)
     {
@@ -754,12 +767,12 @@ k_mac(const StepArgs a, const MacShape sh)
         float2 *x       = sX + size_t(f_s) * stage_elems;
         mbar_expect_tx(&full[f_s], 2u * rows * row_bytes);
         /* IR rows q .. q+rows-1 are contiguous when TB == M (QB > 1 only then) */
-        bulk_g2s(g, Gt + uint64_t(f_q - d.q_lo) * M, rows * row_bytes, &full[f_s]);
+        bulk_g2s(g, Gt + uint64_t(f_q - d.q_lo) * M, rows * row_bytes, &full[f_s], l2_stream);
         /* ring slots (slot0 + q) mod S ascend with q: one copy, or two around the wrap */
         uint32_t n1     = min(rows, d.S - f_slot);
-        bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s]);
+        bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s], l2_stream);
         if (n1 < rows)
-            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s]);
+            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s], l2_stream);
         ++f_it;
         f_q            += QB;
         f_slot         += QB;
@@ -918,6 +931,7 @@ k_mac_multi(const StepArgs a, const MacShape sh)
     const float2 *Gt        = d.G + uint64_t(tile) * TB;
     const float2 *Xt        = d.ring + uint64_t(tile) * TB;
     const uint32_t row_bytes = TB * uint32_t(sizeof(float2));
+    const uint64_t l2_stream = stream_policy();
 
     if (tid == 0)
     {
@@ -946,11 +960,11 @@ k_mac_multi(const StepArgs a, const MacShape sh)
                 float2 *g       = sG + size_t(f_s) * stage_elems;
                 float2 *x       = sX + size_t(f_s) * stage_elems;
                 mbar_expect_tx(&full[f_s], 2u * rows * row_bytes);
-                bulk_g2s(g, Gt + uint64_t(f_q - d.q_lo) * M, rows * row_bytes, &full[f_s]);
+                bulk_g2s(g, Gt + uint64_t(f_q - d.q_lo) * M, rows * row_bytes, &full[f_s], l2_stream);
                 uint32_t n1     = min(rows, d.S - f_slot);
-                bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s]);
+                bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s], l2_stream);
                 if (n1 < rows)
-                    bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s]);
+                    bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s], l2_stream);
                 f_q            += QB;
                 f_slot         += QB;
                 if (f_slot >= d.S)  f_slot -= d.S;
@@ -1124,6 +1138,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     const float2 *Gt        = d.G + uint64_t(tile) * TB;            /* row r at Gt + r * M */
     const float2 *Xt        = d.ring + uint64_t(tile) * TB;
     const uint32_t row_bytes = TB * uint32_t(sizeof(float2));
+    const uint64_t l2_stream = stream_policy();
 
     /* Stage-ring bookkeeping is incremental (next stage buffer, next position in the chunk, next
      * ring slot): no integer division inside the streaming loop.  `issued` = stages fetched. */
@@ -1138,11 +1153,11 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
         float2 *g       = stages + size_t(f_s) * 2 * stage_elems;
         float2 *x       = g + stage_elems;
         mbar_expect_tx(&full[f_s], 2u * rows * row_bytes);
-        bulk_g2s(g, Gt + uint64_t(q - d.q_lo) * M, rows * row_bytes, &full[f_s]);
+        bulk_g2s(g, Gt + uint64_t(q - d.q_lo) * M, rows * row_bytes, &full[f_s], l2_stream);
         uint32_t n1     = min(rows, d.S - f_slot);
-        bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s]);
+        bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s], l2_stream);
         if (n1 < rows)
-            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s]);
+            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s], l2_stream);
         ++issued;
         if (++f_s == NS)    f_s = 0;
         if (++f_stg == n_iter)
