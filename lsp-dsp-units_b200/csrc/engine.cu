@@ -25,6 +25,9 @@ using namespace b200conv;
 
 extern "C" int b200conv_reduce_disconnect(b200conv_batch_t *b);
 
+/* The C ABI must not leak C++ exceptions: the entry points that allocate host containers run
+ * their body through a guarded shim (end of file). */
+
 /* ------------------------------------------------------------------------------------------- */
 /* errors                                                                                       */
 
@@ -601,7 +604,7 @@ static uint64_t algo_bytes(const Batch *b, const Instance &in, size_t qa, size_t
 /* ------------------------------------------------------------------------------------------- */
 /* create / free                                                                                */
 
-extern "C" int b200conv_create(b200conv_batch_t **out, int device, size_t instances)
+static int create_impl(b200conv_batch_t **out, int device, size_t instances)
 {
     if ((out == nullptr) || (instances == 0) || (instances > (size_t(1) << 20)))
         return fail(B200CONV_ERR_ARG, "b200conv_create: bad arguments");
@@ -712,7 +715,7 @@ extern "C" int b200conv_destroy(b200conv_batch_t *b, size_t idx)
     return B200CONV_OK;
 }
 
-extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float *data, size_t count,
+static int init_range_impl(b200conv_batch_t *b, size_t idx, const float *data, size_t count,
                                    size_t rank, float phase, size_t part_offset)
 {
     if ((b == nullptr) || (idx >= b->n))
@@ -1194,7 +1197,7 @@ static int process_general(Batch *b, float *dst, size_t dst_stride, const float 
     return B200CONV_OK;
 }
 
-extern "C" int b200conv_process_device2(b200conv_batch_t *b, float *dst, size_t dst_stride,
+static int process_device2_impl(b200conv_batch_t *b, float *dst, size_t dst_stride,
                                         const float *src, size_t src_stride, size_t count, void *stream)
 {
     if (b == nullptr)
@@ -1883,3 +1886,27 @@ extern "C" int b200conv_debug_frame_times(unsigned long long *out, size_t count)
     return B200CONV_OK;
 }
 #endif
+
+/* ------------------------------------------------------------------------------------------- */
+/* exception guards for the entry points that allocate host containers                          */
+
+extern "C" int b200conv_create(b200conv_batch_t **out, int device, size_t instances)
+{
+    try { return create_impl(out, device, instances); }
+    catch (const std::bad_alloc &) { return fail(B200CONV_ERR_NOMEM, "out of host memory"); }
+}
+
+extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float *data, size_t count,
+                                   size_t rank, float phase, size_t part_offset)
+{
+    try { return init_range_impl(b, idx, data, count, rank, phase, part_offset); }
+    catch (const std::bad_alloc &) { return fail(B200CONV_ERR_NOMEM, "out of host memory"); }
+}
+
+extern "C" int b200conv_process_device2(b200conv_batch_t *b, float *dst, size_t dst_stride,
+                                        const float *src, size_t src_stride, size_t count, void *stream)
+{
+    try { return process_device2_impl(b, dst, dst_stride, src, src_stride, count, stream); }
+    catch (const std::bad_alloc &) { return fail(B200CONV_ERR_NOMEM, "out of host memory"); }
+}
+
