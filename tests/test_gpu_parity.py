@@ -354,7 +354,9 @@ def test_planar_host_api_strided_views(pkg):
 
 
 @pytest.mark.parametrize("n,taps,frames,rank", [(8, 100 * 1024 + 3, 600, 11), (64, 480000, 150, 11),
-                                                (6, 300000, 200, 12), (5, 300000, 120, 13), (7, 50000, 400, 9)])
+                                                (6, 300000, 200, 12), (5, 300000, 120, 13), (7, 50000, 400, 9),
+                                                (1500, 6000, 60, 11),      # more CTAs than the device holds at once
+                                                (700, 40000, 40, 10)])
 def test_overlapped_launches_are_bit_identical_to_serialised(pkg, n, taps, frames, rank):
     """Back-to-back blocks overlap on the GPU (programmatic dependent launch, ring_head /
     stream_done hand-shakes).  Any ordering bug would change bits: the overlapped run must equal
@@ -590,3 +592,29 @@ def test_ir_with_more_than_65535_partitions(pkg):
     out = np.concatenate([b.process(x[None, i:i + 5 * F])[0] for i in range(0, n, 5 * F)])
     assert rel_err(out, direct_convolve(x, ir, n)) <= TOL
     b.close()
+
+
+def test_overlapped_launch_soak(pkg):
+    """20 000 back-to-back blocks (cycling over a 512-block buffer): the overlapped pipeline
+    stays bit-identical to the serialised one over a long run (wrap-around of the ring, the job
+    counters and the hand-shake epochs)."""
+    torch = pytest.importorskip("torch")
+    n, rank, F, taps, frames, window = 6, 11, 1024, 37 * 1024 + 9, 20000, 512
+    irs = [synth.decaying_ir(c, taps) for c in range(n)]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    src = torch.rand((n, window * F), generator=g, device="cuda") * 2 - 1
+    outs = []
+    for pdl in (1, 0):
+        b = pkg.ConvolverBatch(n, 0)
+        b.set_option("pdl", pdl)
+        for c in range(n):
+            assert b.init(c, irs[c], rank, 0.0)
+        dst = torch.zeros_like(src)
+        for i in range(frames):
+            k = i % window
+            b.process_device(dst.data_ptr() + 4 * k * F, src.data_ptr() + 4 * k * F, window * F, F)
+        b.sync()
+        assert b.state(0)["frames"] == frames
+        outs.append(dst.cpu().numpy())
+        b.close()
+    assert np.array_equal(outs[0], outs[1])
