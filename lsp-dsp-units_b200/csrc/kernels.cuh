@@ -294,9 +294,11 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
                 float2 x0 = v[i][0], x1 = v[i][1], x2 = v[i][2], x3 = v[i][3];
                 if (Ns > 1)
                 {
+                    /* ranks >= 12 read the table from global memory / L2: one load instead of
+                     * three, the other two factors by multiplication (a few 1e-8 of error) */
                     float2 w1 = tws[k];
-                    float2 w2 = tws[Ns + k];
-                    float2 w3 = tws[2 * Ns + k];
+                    float2 w2 = (RANK >= 12) ? cmul(w1, w1) : tws[Ns + k];
+                    float2 w3 = (RANK >= 12) ? cmul(w2, w1) : tws[2 * Ns + k];
                     if (INV)    { x1 = cmulc(x1, w1); x2 = cmulc(x2, w2); x3 = cmulc(x3, w3); }
                     else        { x1 = cmul(x1, w1);  x2 = cmul(x2, w2);  x3 = cmul(x3, w3);  }
                 }
