@@ -222,6 +222,45 @@ int     b200conv_linear_convolve(int device, float *dst, size_t dst_stride, cons
                                  size_t src_stride, size_t nx, size_t count, const float *h,
                                  size_t nh, size_t rank);
 
+/* ---- Equalizer, FIR / FFT modes ("next" row f2 of the scope table) --------------------------- */
+
+/* The DATA PATH of lsp::dspu::Equalizer in its EQM_FIR / EQM_FFT modes for a batch of equalizers:
+ * one-partition overlap-add convolution with nFirSize = 2^fir_rank samples of latency and a
+ * cross-fade when a kernel is handed over smoothly.  The filter DESIGN (FilterBank,
+ * Filter::freq_chart, window) stays with the caller: the boundary is the point where the
+ * reference calls dsp::fastconv_parse on the finished impulse response.
+ *
+ *   b200conv_eq_create        buffers of Equalizer::init(filters, fir_rank)
+ *                             (reference src/main/filters/Equalizer.cpp:96-121); fir_rank in [7, 15]
+ *   b200conv_eq_set_kernel    Equalizer::reconfigure's hand-over (Equalizer.cpp:336-345): `ir` holds
+ *                             nFirSize taps (host); smooth = 0 replaces the kernel at once (vConv),
+ *                             smooth != 0 installs it as vNewConv and raises EF_XFADE, consumed by
+ *                             the next block boundary (:486-501)
+ *   b200conv_eq_clear         EF_CLEAR (Equalizer.cpp:273-278), all instances
+ *   b200conv_eq_process*      Equalizer::process, EQM_FIR / EQM_FFT case (Equalizer.cpp:474-518),
+ *                             for ALL instances in one call: host pointer per instance, one planar
+ *                             host matrix, or device matrices (stream-ordered, never synchronises;
+ *                             stream NULL = the batch's own stream)
+ *   b200conv_eq_latency       the data path's share of Equalizer::get_latency(): nFirSize (the
+ *                             other nFirSize / 2 of Equalizer.cpp:347 is the kernel's own delay)
+ */
+typedef struct b200conv_eq b200conv_eq_t;
+
+int     b200conv_eq_create(b200conv_eq_t **out, int device, size_t instances, size_t fir_rank);
+void    b200conv_eq_free(b200conv_eq_t *e);
+int     b200conv_eq_set_kernel(b200conv_eq_t *e, size_t idx, const float *ir, int smooth);
+int     b200conv_eq_clear(b200conv_eq_t *e);
+int     b200conv_eq_process(b200conv_eq_t *e, float *const *dst, const float *const *src, size_t samples);
+int     b200conv_eq_process_planar(b200conv_eq_t *e, float *dst, const float *src, size_t stride,
+                                   size_t samples);
+int     b200conv_eq_process_device(b200conv_eq_t *e, float *dst, size_t dst_stride, const float *src,
+                                   size_t src_stride, size_t samples, void *stream);
+int     b200conv_eq_sync(b200conv_eq_t *e);
+void   *b200conv_eq_stream(b200conv_eq_t *e);
+size_t  b200conv_eq_fir_size(const b200conv_eq_t *e);
+size_t  b200conv_eq_latency(const b200conv_eq_t *e);
+size_t  b200conv_eq_instances(const b200conv_eq_t *e);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 const char *b200conv_last_error(void);      /* thread-local text of the last failure */

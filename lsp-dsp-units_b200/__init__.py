@@ -50,7 +50,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def build(verbose=False):
     """Compile csrc/engine.cu for sm_100a into libb200conv.so (in-tree)."""
     src = os.path.join(_HERE, "csrc", "engine.cu")
-    deps = [src, os.path.join(_HERE, "csrc", "kernels.cuh"), os.path.join(_ROOT, "include", "b200conv.h")]
+    deps = [src, os.path.join(_HERE, "csrc", "kernels.cuh"), os.path.join(_HERE, "csrc", "equalizer.cuh"),
+            os.path.join(_ROOT, "include", "b200conv.h")]
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
     cmd = ["nvcc"] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", LIB_PATH, src]
@@ -95,6 +96,18 @@ _SIGNATURES = {
     "b200conv_fastconv_restore": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_convolve": (ctypes.c_int, [ctypes.c_int, _VP, _SZ, _VP, _SZ, _VP, _SZ, _SZ, _SZ, _SZ, _VP]),
     "b200conv_linear_convolve": (ctypes.c_int, [ctypes.c_int, _VP, _SZ, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _SZ]),
+    "b200conv_eq_create": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_int, _SZ, _SZ]),
+    "b200conv_eq_free": (None, [_VP]),
+    "b200conv_eq_set_kernel": (ctypes.c_int, [_VP, _SZ, _FP, ctypes.c_int]),
+    "b200conv_eq_clear": (ctypes.c_int, [_VP]),
+    "b200conv_eq_process": (ctypes.c_int, [_VP, ctypes.POINTER(_FP), ctypes.POINTER(_FP), _SZ]),
+    "b200conv_eq_process_planar": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ]),
+    "b200conv_eq_process_device": (ctypes.c_int, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _VP]),
+    "b200conv_eq_sync": (ctypes.c_int, [_VP]),
+    "b200conv_eq_stream": (_VP, [_VP]),
+    "b200conv_eq_fir_size": (_SZ, [_VP]),
+    "b200conv_eq_latency": (_SZ, [_VP]),
+    "b200conv_eq_instances": (_SZ, [_VP]),
     "b200conv_last_error": (ctypes.c_char_p, []),
     "b200conv_version": (ctypes.c_char_p, []),
 }
@@ -325,3 +338,64 @@ def linear_convolve(src, h, rank=11, device=0):
     _check(lib().b200conv_linear_convolve(device, out.ctypes.data, out.shape[1], src.ctypes.data, nx, nx,
                                           count, h.ctypes.data, h.size, rank))
     return out[0] if one else out
+
+
+class EqualizerBatch:
+    """Data path of ``dspu::Equalizer`` (EQM_FIR / EQM_FFT) for ``instances`` equalizers on one GPU
+    (``b200conv_eq_*``): ``set_kernel`` takes the finished ``2**fir_rank``-tap impulse response,
+    ``process`` has ``fir_size`` samples of latency (reference Equalizer.cpp:474-518)."""
+
+    def __init__(self, instances, fir_rank, device=-1):
+        self._h = _VP()
+        _check(lib().b200conv_eq_create(ctypes.byref(self._h), device, instances, fir_rank))
+        self.instances = instances
+        self.fir_size = lib().b200conv_eq_fir_size(self._h)
+
+    def close(self):
+        if self._h:
+            lib().b200conv_eq_free(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def latency(self):
+        return lib().b200conv_eq_latency(self._h)
+
+    def set_kernel(self, idx, ir, smooth=False):
+        ir = np.ascontiguousarray(ir, dtype=np.float32)
+        if ir.size != self.fir_size:
+            raise ValueError("kernel must hold fir_size = %d taps" % self.fir_size)
+        _check(lib().b200conv_eq_set_kernel(self._h, idx, _ptr(ir), int(bool(smooth))))
+
+    def clear(self):
+        _check(lib().b200conv_eq_clear(self._h))
+
+    def process(self, src):
+        """src: [instances][samples] float32 (host) -> same shape."""
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        if src.ndim != 2 or src.shape[0] != self.instances:
+            raise ValueError("expected [instances][samples]")
+        out = np.empty_like(src)
+        _check(lib().b200conv_eq_process_planar(self._h, out.ctypes.data, src.ctypes.data, src.shape[1],
+                                                src.shape[1]))
+        return out
+
+    def process_pointers(self, dsts, srcs, samples):
+        n = self.instances
+        d = (_FP * n)(*[_ptr(a) for a in dsts])
+        s = (_FP * n)(*[_ptr(a) for a in srcs])
+        _check(lib().b200conv_eq_process(self._h, d, s, samples))
+
+    def process_device(self, dst_ptr, dst_stride, src_ptr, src_stride, samples, stream=None):
+        _check(lib().b200conv_eq_process_device(self._h, dst_ptr, dst_stride, src_ptr, src_stride, samples,
+                                                stream))
+
+    def sync(self):
+        _check(lib().b200conv_eq_sync(self._h))
+
+    def stream(self):
+        return lib().b200conv_eq_stream(self._h)

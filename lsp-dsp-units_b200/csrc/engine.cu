@@ -1877,6 +1877,8 @@ extern "C" int b200conv_linear_convolve(int device, float *dst, size_t dst_strid
     return rc;
 }
 
+#include "equalizer.cuh"
+
 #ifdef B200CONV_TIMING
 /* developer instrumentation: copies the per-CTA timestamps of the last k_frame launch */
 extern "C" int b200conv_debug_frame_times(unsigned long long *out, size_t count)

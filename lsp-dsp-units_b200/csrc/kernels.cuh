@@ -328,10 +328,14 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
 /* twg = twiddle table in global memory (used next to the global loads), tw = the table the      */
 /* transform passes read (shared-memory copy when the caller staged one, else twg).              */
 
-template <int RANK, bool PP, int TT = 0>
+template <int RANK, bool PP, int TT = 0, bool SMEM_OUT = false>
 __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src, float2 *out,
-                                         const float2 *twg, const float2 *tw, int tid)
+                                         const float2 *twg, const float2 *tw, int tid,
+                                         float2 **smem_out = nullptr)
 {
+    /* SMEM_OUT (ping-pong ranks only): the bins go to whichever work buffer the transform did
+     * not end in, reported through *smem_out; `out` is ignored */
+    static_assert((!SMEM_OUT) || (PP && (FftCfg<RANK, TT>::NH == 2)), "fwd_body: SMEM_OUT needs two work buffers");
     using C = FftCfg<RANK, TT>;
     constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH;
 
@@ -350,6 +354,11 @@ __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src,
         __syncthreads();
 
         const float2 *R = fft_smem<RANK, false, PP, TT>(A, B, tw, tid);
+        if (SMEM_OUT)
+        {
+            out         = (R == A) ? B : A;
+            *smem_out   = out;
+        }
 
         /* split post-pass over pairs (k, M-k), k = 0 .. M/2; thread 0 takes k = 0 and k = M/2 */
         for (int k = tid; k < M / 2; k += T)
@@ -417,10 +426,16 @@ k_fwd(const StepArgs a)
 /* samples (the second half is time-aliased garbage in the folded-overlap form).  `full` also    */
 /* emits samples [F, 2F) (used by the fastconv primitives).                                      */
 
-template <int RANK, bool PP, int RG = 8, int TT = 0>     /* RG: partial rows loaded per round (registers) */
+/* MODE bit 0 (INV_OLA, needs `full` and an 8-byte aligned dst of 2F floats): overlap-add with a
+ * shift, dst[j] = dst[j + F] + y[j], dst[j + F] = y[j + F] (Equalizer.cpp:482-484);
+ * MODE bit 1 (INV_PRESUMMED, ping-pong ranks): B already holds the spectrum, yp / splits unused. */
+enum { INV_OLA = 1, INV_PRESUMMED = 2 };
+
+template <int RANK, bool PP, int RG = 8, int TT = 0, int MODE = 0>     /* RG: partial rows loaded per round (registers) */
 __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp, uint32_t splits,
                                          float *dst, const float2 *twg, const float2 *tw, bool full, int tid)
 {
+    static_assert((!(MODE & INV_PRESUMMED)) || PP, "inv_body: INV_PRESUMMED needs the second work buffer");
     using C = FftCfg<RANK, TT>;
     constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH, N = C::N;
     constexpr int ITER = (M / 2) / T;           /* bins k = tid + it*T handled by this thread; even */
@@ -433,7 +448,7 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
         /* with one resident half the odd half goes first and is parked in dst */
         const int want = (NH == 1) ? (1 - pass) : 0;
 
-        if (PP)
+        if (PP && !(MODE & INV_PRESUMMED))
         {
             /* Reduce the partial rows first, as coalesced float4 columns, into the second work
              * buffer.  The loads are volatile asm so that a whole group is in flight before the
@@ -565,7 +580,13 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
                 hi          = make_float2(av.x * scale - pk.x, av.y * scale - pk.y);
             }
 
-            if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)
+            if (MODE & INV_OLA)
+            {
+                float2 tail = reinterpret_cast<const float2 *>(dst)[m + P];
+                reinterpret_cast<float2 *>(dst)[m]      = make_float2(tail.x + lo.x, tail.y + lo.y);
+                reinterpret_cast<float2 *>(dst)[m + P]  = hi;
+            }
+            else if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)
             {
                 reinterpret_cast<float2 *>(dst)[m]  = lo;
                 if (full)

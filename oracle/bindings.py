@@ -181,3 +181,56 @@ def direct_convolve(src, ir, count=None):
         from scipy.signal import fftconvolve
         y = fftconvolve(src, ir)
     return y if count is None else y[:count]
+
+
+class CpuEqualizer:
+    """Data path of ``dspu::Equalizer`` in EQM_FIR / EQM_FFT mode (oracle/equalizer_oracle.c):
+    ``set_kernel(ir, smooth)`` / ``clear()`` / ``process(x)`` with ``fir_size`` samples of latency."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            lib = ctypes.CDLL(os.path.join(_HERE, "liboracle.so"))
+            lib.orc_eq_create.restype = ctypes.c_void_p
+            lib.orc_eq_create.argtypes = [_SZ]
+            lib.orc_eq_free.argtypes = [ctypes.c_void_p]
+            lib.orc_eq_set_kernel.argtypes = [ctypes.c_void_p, _FP, ctypes.c_int]
+            lib.orc_eq_clear.argtypes = [ctypes.c_void_p]
+            lib.orc_eq_process.argtypes = [ctypes.c_void_p, _FP, _FP, _SZ]
+            lib.orc_eq_fir_size.argtypes = [ctypes.c_void_p]
+            lib.orc_eq_fir_size.restype = _SZ
+            cls._lib = lib
+        return cls._lib
+
+    def __init__(self, fir_rank):
+        self._h = self.lib().orc_eq_create(fir_rank)
+        if not self._h:
+            raise MemoryError("orc_eq_create")
+        self.fir_size = 1 << fir_rank
+
+    def set_kernel(self, ir, smooth=False):
+        ir = np.ascontiguousarray(ir, dtype=np.float32)
+        assert ir.size == self.fir_size
+        self.lib().orc_eq_set_kernel(self._h, _ptr(ir), int(bool(smooth)))
+
+    def clear(self):
+        self.lib().orc_eq_clear(self._h)
+
+    def process(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.empty_like(x)
+        self.lib().orc_eq_process(self._h, _ptr(y), _ptr(x), x.size)
+        return y
+
+    def run(self, x, step):
+        return np.concatenate([self.process(x[i:i + step]) for i in range(0, len(x), step)])
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.lib().orc_eq_free(self._h)
+                self._h = None
+        except Exception:
+            pass
