@@ -57,6 +57,99 @@ __device__ __forceinline__ float ld_cg_f1(const float *p)
     return v;
 }
 
+/* The block of a ping-pong rank, without the packed spectrum ever being materialised:
+ *   eq_forward          z[m] = x[2m] + i x[2m+1] and z[m] w_M^m  ->  two P-point forward transforms
+ *   eq_middle_inverse   per bin pair (k, M-k): real-FFT split (fwd_body's post-pass), product with
+ *                       the kernel spectrum, real-FFT merge (inv_body's pre-pass) -- all in
+ *                       registers, from one work buffer into the other -- then two inverse
+ *                       transforms and the combine pass, which also shifts and overlap-adds
+ *                       vOutBuffer (Equalizer.cpp:482-484).
+ * Same arithmetic as fwd_body -> multiply -> inv_body, three shared-memory sweeps fewer. */
+template <int RANK>
+__device__ __forceinline__ void eq_forward(float2 *A, float2 *B, const float *x, const float2 *tw, int tid)
+{
+    using C = FftCfg<RANK>;
+    constexpr int P = C::P, T = C::T;
+    for (int m = tid; m < P; m += T)
+    {
+        float2 z    = reinterpret_cast<const float2 *>(x)[m];
+        A[m]        = z;
+        A[P + m]    = cmul(z, tw[C::TW_PRE + m]);
+    }
+    __syncthreads();
+}
+
+template <int RANK>
+__device__ __forceinline__ void eq_middle_inverse(float2 *A, float2 *B, float2 *H, float *ob, float *emit,
+                                                  uint64_t *bar_h, uint32_t &ph_h, const float2 *tw, int tid)
+{
+    using C = FftCfg<RANK>;
+    constexpr int P = C::P, M = C::M, N = C::N, T = C::T;
+    float2 *R   = fft_smem<RANK, false, true, 0, true, true>(A, B, tw, tid); /* Z even | Z odd */
+    float2 *D   = (R == A) ? B : A;
+
+    for (int k = tid; k < M / 2; k += T)
+    {
+        if (k == 0)
+        {
+            float2 z0   = R[0], h0 = H[0];                              /* bin 0 = (DC, Nyquist) */
+            float2 y0   = make_float2((z0.x + z0.y) * h0.x, (z0.x - z0.y) * h0.y);
+            D[0]        = make_float2(y0.x + y0.y, y0.x - y0.y);
+            float2 zh   = R[P / 2];                                     /* bin M/2 pairs with itself */
+            float2 yh   = cmul(make_float2(zh.x, -zh.y), H[M / 2]);
+            D[P / 2]    = make_float2(2.0f * yh.x, -2.0f * yh.y);
+            continue;
+        }
+        const int par   = k & 1, ik = k >> 1;
+        const int im    = par ? (P - 1 - ik) : (P - ik);
+        const float2 w  = tw[C::TW_POST + k];
+        float2 zk = R[par * P + ik], zm = R[par * P + im];
+        /* split: X[k] = e - i w o, X[M-k] = conj(e) - i conj(w o) */
+        float2 e    = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        float2 o    = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
+        float2 wo   = cmul(w, o);
+        float2 yk   = cmul(make_float2(e.x + wo.y, e.y - wo.x), H[k]);
+        float2 ym   = cmul(make_float2(e.x - wo.y, -e.y - wo.x), H[M - k]);
+        /* merge: Z[k] = e' + i o', Z[M-k] = conj(e') + i conj(o'), o' = conj(w) (yk - conj(ym)) */
+        float2 e2   = make_float2(yk.x + ym.x, yk.y - ym.y);
+        float2 o2   = cmulc(make_float2(yk.x - ym.x, yk.y + ym.y), w);
+        D[par * P + ik] = make_float2(e2.x - o2.y, e2.y + o2.x);
+        D[par * P + im] = make_float2(e2.x + o2.y, o2.x - e2.y);
+    }
+    __syncthreads();
+
+    /* the kernel spectrum has been consumed: its buffer now receives the overlap tail
+     * vOutBuffer[F, 2F) while the inverse transforms run */
+    const float2 *tail_s = reinterpret_cast<const float2 *>(H);
+    if (tid == 0)
+    {
+        mbar_expect_tx(bar_h, M * sizeof(float));
+        bulk_g2s_plain(H, ob + M, M * sizeof(float), bar_h);
+    }
+
+    float2 *Q   = fft_smem<RANK, true, true, 0, true, true>(D, R, tw, tid);
+
+    mbar_wait(bar_h, ph_h);
+    ph_h ^= 1u;
+
+    /* y[2m], y[2m+1] = (Qe[m] + conj(w_M^m) Qo[m]) / N ; the same with a minus sign F samples later.
+     * emit != NULL: the call takes the whole block, so the first half goes straight to the
+     * caller (vOutBuffer[0, F) would be dead: the next block boundary overwrites it unread). */
+    const float scale = 1.0f / float(N);
+    for (int m = tid; m < P; m += T)
+    {
+        float2 av   = Q[m];
+        float2 bv   = cmulc(Q[P + m], tw[C::TW_PRE + m]);
+        float2 tail = tail_s[m];
+        float2 lo   = make_float2(tail.x + (av.x + bv.x) * scale, tail.y + (av.y + bv.y) * scale);
+        if (emit != nullptr)
+            reinterpret_cast<float2 *>(emit)[m]    = lo;
+        else
+            reinterpret_cast<float2 *>(ob)[m]      = lo;
+        reinterpret_cast<float2 *>(ob)[m + P]  = make_float2((av.x - bv.x) * scale, (av.y - bv.y) * scale);
+    }
+}
+
 /* A CTA walks through load -> transform -> load -> transform phases separated by barriers, so
  * every global load it waits for is exposed.  On the ping-pong ranks the two block-sized operands
  * therefore arrive through TMA bulk copies issued a phase ahead by one elected thread:
@@ -73,10 +166,11 @@ struct EqCfg
     static constexpr size_t OFF_BAR = OFF_IB + (PIPE ? C::M * sizeof(float) : 0);
     static constexpr size_t SMEM    = PIPE ? OFF_BAR + 2 * sizeof(uint64_t) : C::SMEM;
     static constexpr int    XPT     = PIPE ? C::M / C::T : 1;           /* input samples per thread */
+    static constexpr int    MINB    = (RANK == 11) ? 5 : 1;             /* rank 11: five CTAs fit in shared memory */
 };
 
 template <int RANK>
-__global__ void __launch_bounds__(FftCfg<RANK>::T)
+__global__ void __launch_bounds__(FftCfg<RANK>::T, EqCfg<RANK>::MINB)
 k_eq(const EqArgs a)
 {
     using C = FftCfg<RANK>;
@@ -113,6 +207,7 @@ k_eq(const EqArgs a)
     }
     __syncthreads();
     uint32_t ph_ib = 0, ph_h = 0;
+    uint32_t st_next        = (a.do_block && (blockIdx.x < a.n_inst)) ? a.state[blockIdx.x] : 0u;
 
     for (uint32_t inst = blockIdx.x; inst < a.n_inst; inst += gridDim.x)
     {
@@ -132,17 +227,20 @@ k_eq(const EqArgs a)
             }
         }
 
+        bool emitted            = false;
         if (a.do_block)
         {
             float2 *xs              = a.spec + uint64_t(inst) * 2 * M;
             float2 *ys              = xs + M;
             float *c0               = a.conv + uint64_t(inst) * 2 * N;
             float *c1               = c0 + N;
-            const uint32_t st       = a.state[inst];
+            const uint32_t st       = st_next;
             const uint32_t cur      = st & 1u;
             const bool xfade        = (st & 2u) != 0;
             const float2 *H         = a.kern + (uint64_t(inst) * 2 + cur) * M;
             const bool more         = (inst + gridDim.x < a.n_inst);
+            if (more)
+                st_next                 = a.state[inst + gridDim.x];
 
             if (E::PIPE)
             {
@@ -151,7 +249,6 @@ k_eq(const EqArgs a)
                     mbar_expect_tx(&bars[1], M * sizeof(float2));
                     bulk_g2s_plain(Hs, H, M * sizeof(float2), &bars[1]);
                 }
-                prefetch_span(ob + F, F * sizeof(float), tid, T);
                 mbar_wait(&bars[0], ph_ib);
                 ph_ib ^= 1u;
             }
@@ -163,23 +260,18 @@ k_eq(const EqArgs a)
                  * (:482-484) on its way out */
                 if constexpr (E::PIPE)
                 {
-                    float2 *S   = nullptr;
-                    fwd_body<RANK, true, 0, true>(A, B, ibs, nullptr, twg, tw, tid, &S);
-                    __syncthreads();
-                    if ((tid == 0) && more)         /* ibs has been consumed: fetch the next block */
+                    eq_forward<RANK>(A, B, ibs, tw, tid);       /* ends with a barrier: ibs is free */
+                    if ((tid == 0) && more)                     /* fetch the next instance's block */
                     {
                         mbar_expect_tx(&bars[0], F * sizeof(float));
                         bulk_g2s_plain(ibs, ib + uint64_t(gridDim.x) * F, F * sizeof(float), &bars[0]);
                     }
                     mbar_wait(&bars[1], ph_h);
                     ph_h ^= 1u;
-                    for (int k = tid; k < M; k += T)
-                    {
-                        float2 x    = S[k], h = Hs[k];
-                        B[k]        = (k == 0) ? make_float2(x.x * h.x, x.y * h.y) : cmul(x, h);     /* in place when S == B */
-                    }
-                    __syncthreads();
-                    inv_body<RANK, true, 8, 0, INV_OLA | INV_PRESUMMED>(A, B, nullptr, 0, ob, twg, tw, true, tid);
+                    /* whole-block call on an 8-byte aligned row: the result goes straight out */
+                    emitted                 = (a.off == 0) && (a.n == uint32_t(F)) &&
+                                              ((reinterpret_cast<uintptr_t>(d) & 7) == 0);
+                    eq_middle_inverse<RANK>(A, B, Hs, ob, emitted ? d : nullptr, &bars[1], ph_h, tw, tid);
                 }
                 else
                 {
@@ -250,9 +342,12 @@ k_eq(const EqArgs a)
                 uint32_t i      = uint32_t(tid + j * T);
                 if (i < a.n)
                 {
-                    float y         = ob[a.off + i];
+                    if (!emitted)
+                    {
+                        float y         = ob[a.off + i];
+                        d[i]            = y;
+                    }
                     ib[a.off + i]   = xr[j];
-                    d[i]            = y;
                 }
             }
         }

@@ -222,7 +222,22 @@ struct FftCfg
 };
 
 /* Transforms the NH sequences held in A; returns the buffer that holds the result (A or B). */
-template <int RANK, bool INV, bool PP, int TT = 0>
+/* WMUL: one twiddle load per butterfly, w^2 and w^3 by multiplication (a few 1e-8 of error).
+ * Always on where the table is read from global memory / L2 (ranks >= 12); throughput-bound
+ * callers turn it on for the shared-memory table too, where it saves two of three LDS. */
+/* FAST1: the first, twiddle-free pass (stride 1) is a radix-8 pass when log2(P) is odd (it
+ * replaces the radix-2 pass and the first radix-4 pass) and a radix-4 pass otherwise, and its
+ * outputs -- 64 / 32 contiguous bytes per thread -- leave as 16-byte stores whose order is
+ * rotated per lane so that every quarter-warp covers all 32 banks.  (The plain passes store
+ * 8 bytes at a 16 .. 64 byte lane stride: 2- to 4-way bank conflicts, the largest share of the
+ * shared-memory wavefronts of a throughput-bound caller.) */
+template <bool INV>
+__device__ __forceinline__ float2 rot90(float2 z)       /* forward: -i z ; inverse: +i z */
+{
+    return INV ? make_float2(-z.y, z.x) : make_float2(z.y, -z.x);
+}
+
+template <int RANK, bool INV, bool PP, int TT = 0, bool WMUL = (RANK >= 12), bool FAST1 = true>
 __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *tw, int tid)
 {
     using C = FftCfg<RANK, TT>;
@@ -231,7 +246,104 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
     float2 *in  = A;
     float2 *out = PP ? B : A;
     int Ns = 1;
-    if (C::LOGP & 1)
+    if (FAST1 && (C::LOGP & 1))
+    {
+        constexpr int B8    = NH * P / 8;                       /* radix-8 butterflies */
+        constexpr int IT8   = (B8 + T - 1) / T;
+        float2 v[IT8][8];
+        #pragma unroll
+        for (int i = 0; i < IT8; ++i)
+        {
+            int idx = tid + i * T;
+            if (idx < B8)
+            {
+                int h   = idx / (P / 8), j = idx % (P / 8);
+                #pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    v[i][r] = in[h * P + j + r * (P / 8)];
+            }
+        }
+        if (!PP)
+            __syncthreads();
+        const int sw = (tid >> 1) & 3;                          /* per-lane rotation of the four 16-byte chunks */
+        #pragma unroll
+        for (int i = 0; i < IT8; ++i)
+        {
+            int idx = tid + i * T;
+            if (idx < B8)
+            {
+                int h   = idx / (P / 8), j = idx % (P / 8);
+                const float r2 = 0.70710678118654752f;
+                float2 a0 = cadd(v[i][0], v[i][4]), a1 = csub(v[i][0], v[i][4]);
+                float2 a2 = cadd(v[i][2], v[i][6]), a3 = rot90<INV>(csub(v[i][2], v[i][6]));
+                float2 a4 = cadd(v[i][1], v[i][5]), a5 = csub(v[i][1], v[i][5]);
+                float2 a6 = cadd(v[i][3], v[i][7]), a7 = rot90<INV>(csub(v[i][3], v[i][7]));
+                float2 b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = csub(a1, a3);
+                float2 b4 = cadd(a4, a6), b6 = rot90<INV>(csub(a4, a6));
+                float2 t5 = cadd(a5, a7), t7 = csub(a5, a7);
+                /* w8 = (1 -+ i) / sqrt 2 ; w8^3 = (-1 -+ i) / sqrt 2  (forward / inverse) */
+                float2 b5 = INV ? make_float2((t5.x - t5.y) * r2, (t5.x + t5.y) * r2)
+                                : make_float2((t5.x + t5.y) * r2, (t5.y - t5.x) * r2);
+                float2 b7 = INV ? make_float2((-t7.x - t7.y) * r2, (t7.x - t7.y) * r2)
+                                : make_float2((t7.y - t7.x) * r2, (-t7.x - t7.y) * r2);
+                float2 V0 = cadd(b0, b4), V1 = cadd(b1, b5), V2 = cadd(b2, b6), V3 = cadd(b3, b7);
+                float2 V4 = csub(b0, b4), V5 = csub(b1, b5), V6 = csub(b2, b6), V7 = csub(b3, b7);
+                float4 c0 = make_float4(V0.x, V0.y, V1.x, V1.y), c1 = make_float4(V2.x, V2.y, V3.x, V3.y);
+                float4 c2 = make_float4(V4.x, V4.y, V5.x, V5.y), c3 = make_float4(V6.x, V6.y, V7.x, V7.y);
+                /* e_n = chunk (n + sw) & 3, by a two-stage barrel rotation */
+                float4 d0 = (sw & 1) ? c1 : c0, d1 = (sw & 1) ? c2 : c1, d2 = (sw & 1) ? c3 : c2, d3 = (sw & 1) ? c0 : c3;
+                float4 e0 = (sw & 2) ? d2 : d0, e1 = (sw & 2) ? d3 : d1, e2 = (sw & 2) ? d0 : d2, e3 = (sw & 2) ? d1 : d3;
+                float4 *row = reinterpret_cast<float4 *>(out + h * P + 8 * j);
+                row[(0 + sw) & 3]   = e0;
+                row[(1 + sw) & 3]   = e1;
+                row[(2 + sw) & 3]   = e2;
+                row[(3 + sw) & 3]   = e3;
+            }
+        }
+        __syncthreads();
+        if (PP) { float2 *t = in; in = out; out = t; }
+        Ns = 8;
+    }
+    else if (FAST1)
+    {
+        /* radix-4, Ns = 1: no twiddles, outputs 4 j .. 4 j + 3 are contiguous */
+        float2 v[BPT][4];
+        #pragma unroll
+        for (int i = 0; i < BPT; ++i)
+        {
+            int idx = tid + i * T;
+            if (idx < NH * P / 4)
+            {
+                int h   = idx / (P / 4), j = idx % (P / 4);
+                #pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    v[i][r] = in[h * P + j + r * (P / 4)];
+            }
+        }
+        if (!PP)
+            __syncthreads();
+        const int sw = (tid >> 2) & 1;
+        #pragma unroll
+        for (int i = 0; i < BPT; ++i)
+        {
+            int idx = tid + i * T;
+            if (idx < NH * P / 4)
+            {
+                int h   = idx / (P / 4), j = idx % (P / 4);
+                float2 s0 = cadd(v[i][0], v[i][2]), s1 = csub(v[i][0], v[i][2]);
+                float2 s2 = cadd(v[i][1], v[i][3]), rot = rot90<INV>(csub(v[i][1], v[i][3]));
+                float2 V0 = cadd(s0, s2), V1 = cadd(s1, rot), V2 = csub(s0, s2), V3 = csub(s1, rot);
+                float4 c0 = make_float4(V0.x, V0.y, V1.x, V1.y), c1 = make_float4(V2.x, V2.y, V3.x, V3.y);
+                float4 *row = reinterpret_cast<float4 *>(out + h * P + 4 * j);
+                row[sw]     = sw ? c1 : c0;
+                row[sw ^ 1] = sw ? c0 : c1;
+            }
+        }
+        __syncthreads();
+        if (PP) { float2 *t = in; in = out; out = t; }
+        Ns = 4;
+    }
+    else if (C::LOGP & 1)
     {
         /* radix-2, Ns = 1: twiddles are all 1.  NH*P/2 butterflies = 2*BPT per thread. */
         float2 a[2 * BPT], b[2 * BPT];
@@ -294,11 +406,9 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
                 float2 x0 = v[i][0], x1 = v[i][1], x2 = v[i][2], x3 = v[i][3];
                 if (Ns > 1)
                 {
-                    /* ranks >= 12 read the table from global memory / L2: one load instead of
-                     * three, the other two factors by multiplication (a few 1e-8 of error) */
                     float2 w1 = tws[k];
-                    float2 w2 = (RANK >= 12) ? cmul(w1, w1) : tws[Ns + k];
-                    float2 w3 = (RANK >= 12) ? cmul(w2, w1) : tws[2 * Ns + k];
+                    float2 w2 = WMUL ? cmul(w1, w1) : tws[Ns + k];
+                    float2 w3 = WMUL ? cmul(w2, w1) : tws[2 * Ns + k];
                     if (INV)    { x1 = cmulc(x1, w1); x2 = cmulc(x2, w2); x3 = cmulc(x3, w3); }
                     else        { x1 = cmul(x1, w1);  x2 = cmul(x2, w2);  x3 = cmul(x3, w3);  }
                 }

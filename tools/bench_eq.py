@@ -2,9 +2,9 @@
 """Throughput of the Equalizer FIR / FFT data path (b200conv_eq_*, scope-table row f2) on ONE GPU.
 
 Per (instances, fir_rank): device-resident output samples/s of block-aligned process_device calls
-(CUDA events on the batch's stream), the share of the HBM roofline at 40 algorithmic bytes per
-sample per instance (4 in + 4 out + 8 kernel spectrum + 8 vInBuffer write/read + 16 vOutBuffer
-tail read / store / emit), and the CPU oracle (one thread, one instance) beside it.
+(CUDA events on the batch's stream), the share of the HBM roofline at 32 algorithmic bytes per
+sample per instance (4 in + 4 out + 8 kernel spectrum + 8 vInBuffer store / load + 8 vOutBuffer
+overlap tail load / store), and the CPU oracle (one thread, one instance) beside it.
 
     python tools/bench_eq.py > profiles/rN_equalizer.jsonl
 """
@@ -25,7 +25,7 @@ import __graft_entry__ as ge
 import synth
 from equalizer_model import band_kernel
 
-BYTES_PER_SAMPLE = 40.0
+BYTES_PER_SAMPLE = 32.0
 
 
 def main():
