@@ -87,6 +87,11 @@ static uint32_t resident_grid(uint32_t jobs, int threads, size_t smem)
     return (jobs < cap) ? jobs : uint32_t(cap);
 }
 
+static uint32_t rows_per_job_host(const StepArgs &a)
+{
+    return (a.rows != 0) ? a.rows : a.splits;
+}
+
 template <int RANK>
 static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t st)
 {
@@ -104,21 +109,30 @@ static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t s
     return cudaGetLastError();
 }
 
-template <int RANK>
-static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t st)
+template <int RANK, int RG>
+static cudaError_t launch_inv_rg(const StepArgs &a, uint32_t grid, cudaStream_t st)
 {
     using C = FftCfg<RANK>;
     static bool attr_set[MAX_DEVICES] = { false };
     int dev = current_device();
     if ((!attr_set[dev]) && (C::SMEM > 48 * 1024))
     {
-        cudaError_t e = cudaFuncSetAttribute(k_inv<RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM));
+        cudaError_t e = cudaFuncSetAttribute(k_inv<RANK, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM));
         if (e != cudaSuccess)
             return e;
     }
     attr_set[dev] = true;
-    k_inv<RANK><<<resident_grid(grid, C::T, C::SMEM), C::T, C::SMEM, st>>>(a);
+    k_inv<RANK, RG><<<resident_grid(grid, C::T, C::SMEM), C::T, C::SMEM, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int RANK>
+static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t st)
+{
+    /* the row-group size only matters on the ping-pong ranks (FftCfg::PP) */
+    if (FftCfg<RANK>::PP && (rows_per_job_host(a) <= 2))
+        return launch_inv_rg<RANK, 2>(a, grid, st);
+    return launch_inv_rg<RANK, 8>(a, grid, st);
 }
 
 #define RANK_SWITCH(fn, rank, ...)                                      \

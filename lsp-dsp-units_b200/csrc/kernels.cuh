@@ -438,7 +438,7 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
 /* twg = twiddle table in global memory (used next to the global loads), tw = the table the      */
 /* transform passes read (shared-memory copy when the caller staged one, else twg).              */
 
-template <int RANK, bool PP, int TT = 0, bool SMEM_OUT = false>
+template <int RANK, bool PP, int TT = 0, bool SMEM_OUT = false, bool WM = (RANK >= 12)>
 __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src, float2 *out,
                                          const float2 *twg, const float2 *tw, int tid,
                                          float2 **smem_out = nullptr)
@@ -463,7 +463,7 @@ __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src,
         }
         __syncthreads();
 
-        const float2 *R = fft_smem<RANK, false, PP, TT>(A, B, tw, tid);
+        const float2 *R = fft_smem<RANK, false, PP, TT, WM>(A, B, tw, tid);
         if (SMEM_OUT)
         {
             out         = (R == A) ? B : A;
@@ -518,14 +518,16 @@ k_fwd(const StepArgs a)
         float2 *tws         = sm + C::WORK * (C::PP ? 2 : 1);
         for (int i = threadIdx.x; i < C::TW_TOTAL; i += C::T)
             tws[i]              = a.tw[i];
-        tw                  = tws;          /* visible after fwd_body's first barrier */
+        tw                  = tws;
+        __syncthreads();
     }
     /* grid-stride over the jobs: a launch over many frames (IR ingest, multi-frame calls) keeps
-     * one resident set of CTAs and stages the twiddle table once per CTA */
+     * one resident set of CTAs and stages the twiddle table once per CTA; these launches are
+     * throughput-bound, so every twiddle comes from the shared-memory copy (one load per butterfly) */
     for (uint32_t j = blockIdx.x; j < a.n_jobs; j += gridDim.x)
     {
         const Job job           = fetch_job(a, j);
-        fwd_body<RANK, C::PP>(A, B, job.src, job.spec, a.tw, tw, threadIdx.x);
+        fwd_body<RANK, C::PP, 0, false, true>(A, B, job.src, job.spec, tw, tw, threadIdx.x);
         __syncthreads();            /* the work buffers are reused by the next job */
     }
 }
@@ -541,7 +543,7 @@ k_fwd(const StepArgs a)
  * MODE bit 1 (INV_PRESUMMED, ping-pong ranks): B already holds the spectrum, yp / splits unused. */
 enum { INV_OLA = 1, INV_PRESUMMED = 2 };
 
-template <int RANK, bool PP, int RG = 8, int TT = 0, int MODE = 0>     /* RG: partial rows loaded per round (registers) */
+template <int RANK, bool PP, int RG = 8, int TT = 0, int MODE = 0, bool WM = (RANK >= 12)>     /* RG: partial rows loaded per round (registers) */
 __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp, uint32_t splits,
                                          float *dst, const float2 *twg, const float2 *tw, bool full, int tid)
 {
@@ -661,7 +663,7 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
         }
         __syncthreads();
 
-        const float2 *R = fft_smem<RANK, true, PP, TT>(A, B, tw, tid);
+        const float2 *R = fft_smem<RANK, true, PP, TT, WM>(A, B, tw, tid);
 
         /* z[m] = (A[m] + conj(w_M^m) B[m]) / N ; z[m + P] = (A[m] - conj(w_M^m) B[m]) / N */
         for (int m = tid; m < P; m += T)
@@ -718,8 +720,16 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
     }
 }
 
-template <int RANK>
-__global__ void __launch_bounds__(FftCfg<RANK>::T)
+/* RG = 2 serves launches with one or two partial rows per job (multi-frame calls, the fastconv
+ * primitives): few registers, so that as many CTAs as shared memory allows are resident. */
+template <int RANK, int RG>
+struct InvCfg
+{
+    static constexpr int MINB = (RG > 2) ? 0 : (RANK == 11) ? 5 : (RANK == 12) ? 2 : 0;     /* 0: left to the compiler */
+};
+
+template <int RANK, int RG = 8>
+__global__ void __launch_bounds__(FftCfg<RANK>::T, InvCfg<RANK, RG>::MINB)
 k_inv(const StepArgs a)
 {
     using C = FftCfg<RANK>;
@@ -732,13 +742,14 @@ k_inv(const StepArgs a)
         float2 *tws         = sm + C::WORK * (C::PP ? 2 : 1);
         for (int i = threadIdx.x; i < C::TW_TOTAL; i += C::T)
             tws[i]              = a.tw[i];
-        tw                  = tws;          /* visible after inv_body's first barrier */
+        tw                  = tws;
+        __syncthreads();
     }
     for (uint32_t j = blockIdx.x; j < a.n_jobs; j += gridDim.x)
     {
         const Job job           = fetch_job(a, j);
-        inv_body<RANK, C::PP>(A, B, a.ypart + uint64_t(j) * rows_per_job(a) * C::M, rows_per_job(a), job.dst,
-                              a.tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
+        inv_body<RANK, C::PP, RG, 0, 0, true>(A, B, a.ypart + uint64_t(j) * rows_per_job(a) * C::M, rows_per_job(a),
+                                              job.dst, tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
         __syncthreads();
     }
 }

@@ -34,6 +34,7 @@ CONFIGS = {
     8: ("64 ch x 10 s IR, rank 9, 256 blocks",        64,  480000,  9,  256,  (0.0,),        "low-latency rank, one k_frame<9> launch per block"),
     9: ("64 ch x 10 s IR, rank 13, 4096 blocks",      64,  480000,  13, 4096, (0.0,),        "ranks 12..16: k_fwd -> k_mac -> k_inv per block (not fused yet)"),
     10: ("64 ch x 10 s IR, rank 16, 32768 blocks",    64,  480000,  16, 32768, (0.0,),       "largest rank"),
+    11: ("4096 mono x 1024-tap IR, 8192-sample calls",  4096, 1024,    11, 8192, (0.0,),        "one partition: the transforms alone (k_fwd + k_inv over 32768 frames per call)"),
     5: ("cfg5 8 ch x 120 s IR on ONE GPU",            8,   5760000, 11, 1024, (0.0,),        "all 5625 partitions on one GPU; the 8-way split is 1/8 of this per GPU + a 32 KiB all-reduce"),
 }
 
