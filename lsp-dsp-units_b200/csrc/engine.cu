@@ -105,6 +105,25 @@ static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t s
             return e;
     }
     attr_set[dev] = true;
+    if constexpr (C::PP)
+    {
+        /* many jobs per CTA and device-resident input: prefetch the next job's input (k_fwd_staged) */
+        constexpr size_t SS = StageCfg<RANK>::FWD_SMEM;
+        const uint32_t cap  = resident_grid(grid, C::T, SS);
+        if ((grid >= 2 * cap) && !(a.flags & STEP_HOST_IO))
+        {
+            static bool attr_staged[MAX_DEVICES] = { false };
+            if ((!attr_staged[dev]) && (SS > 48 * 1024))
+            {
+                cudaError_t e = cudaFuncSetAttribute(k_fwd_staged<RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SS));
+                if (e != cudaSuccess)
+                    return e;
+            }
+            attr_staged[dev] = true;
+            k_fwd_staged<RANK><<<cap, C::T, SS, st>>>(a);
+            return cudaGetLastError();
+        }
+    }
     k_fwd<RANK><<<resident_grid(grid, C::T, C::SMEM), C::T, C::SMEM, st>>>(a);
     return cudaGetLastError();
 }
@@ -129,6 +148,27 @@ static cudaError_t launch_inv_rg(const StepArgs &a, uint32_t grid, cudaStream_t 
 template <int RANK>
 static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t st)
 {
+    using C = FftCfg<RANK>;
+    if constexpr (C::PP)
+    {
+        /* one partial row per job and many jobs per CTA: prefetch the next row (k_inv_staged) */
+        constexpr size_t SS = StageCfg<RANK>::INV_SMEM;
+        const uint32_t cap  = resident_grid(grid, C::T, SS);
+        if ((rows_per_job_host(a) == 1) && (grid >= 2 * cap) && ((reinterpret_cast<uintptr_t>(a.ypart) & 15) == 0))
+        {
+            static bool attr_staged[MAX_DEVICES] = { false };
+            int dev = current_device();
+            if ((!attr_staged[dev]) && (SS > 48 * 1024))
+            {
+                cudaError_t e = cudaFuncSetAttribute(k_inv_staged<RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SS));
+                if (e != cudaSuccess)
+                    return e;
+            }
+            attr_staged[dev] = true;
+            k_inv_staged<RANK><<<cap, C::T, SS, st>>>(a);
+            return cudaGetLastError();
+        }
+    }
     /* the row-group size only matters on the ping-pong ranks (FftCfg::PP) */
     if (FftCfg<RANK>::PP && (rows_per_job_host(a) <= 2))
         return launch_inv_rg<RANK, 2>(a, grid, st);
@@ -381,6 +421,7 @@ struct b200conv_batch
 
     b200conv_stats_t        stats       = {};
     int                     tune_splits = 0, tune_stages = 0;
+    bool                    host_io     = false;    /* the running call reads / writes page-locked host matrices */
     int                     opt_fused   = 1, opt_bias = 6, opt_pdl = 1, opt_zero_copy = 1, opt_multi = 8;
     uint32_t               *d_tickets   = nullptr;  /* k_frame: one arrival counter per job */
     uint32_t               *d_ring_head = nullptr;  /* k_frame: frames published per instance */
@@ -595,6 +636,7 @@ static StepArgs base_args(const Batch *b)
     a.inst      = b->d_desc;
     a.active    = b->d_active;
     a.tw        = b->tw[b->rank];
+    a.flags     = b->host_io ? uint32_t(STEP_HOST_IO) : 0u;
     a.ypart     = b->ypart;
     a.ring_head = b->d_ring_head;
     a.stream_done = b->d_stream_done;
@@ -1022,7 +1064,7 @@ static int launch_pending_mac(Batch *b, cudaStream_t st)
     a.splits        = plan.splits;
     a.rows          = plan.splits + 1;
     a.row0          = 0;
-    a.flags         = STEP_FROM_Q1;
+    a.flags        |= STEP_FROM_Q1;
     a.n_jobs        = nact;
     a.t_base        = b->t_batch;           /* the block about to arrive */
     a.frame0        = 0;
@@ -1367,9 +1409,11 @@ extern "C" int b200conv_process_planar(b200conv_batch_t *b, float *dst, const fl
             (as.devicePointer != nullptr) && (ad.devicePointer != nullptr))
         {
             b->eager_call = true;
+            b->host_io    = true;
             int rc = b200conv_process_device(b, static_cast<float *>(ad.devicePointer),
                                              static_cast<const float *>(as.devicePointer), stride, count, b->stream);
             b->eager_call = false;
+            b->host_io    = false;
             TRY(rc);
             TRY(finish_sync_call(b));
             b->stats.h2d_bytes += b->n * count * sizeof(float);

@@ -43,13 +43,6 @@ __device__ __forceinline__ void prefetch_span(const void *p, uint32_t bytes, int
         asm volatile("prefetch.global.L1 [%0];" :: "l"(c + o));
 }
 
-__device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 __device__ __forceinline__ float ld_cg_f1(const float *p)
 {
     float v;

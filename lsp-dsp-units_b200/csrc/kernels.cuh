@@ -84,7 +84,8 @@ struct StepArgs                     /* by-value kernel argument */
     uint32_t        flags;
 };
 
-enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4 };
+enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
+       STEP_HOST_IO = 8 /* src / dst are page-locked HOST matrices: no bulk-copy staging */ };
 
 /* Partition-range sharding across GPUs (one long IR): every rank's k_frame produces a
  * PARTIAL output block; the sum is formed inside the launch tails over NVLink peer memory --
@@ -540,8 +541,9 @@ k_fwd(const StepArgs a)
 
 /* MODE bit 0 (INV_OLA, needs `full` and an 8-byte aligned dst of 2F floats): overlap-add with a
  * shift, dst[j] = dst[j + F] + y[j], dst[j + F] = y[j + F] (Equalizer.cpp:482-484);
- * MODE bit 1 (INV_PRESUMMED, ping-pong ranks): B already holds the spectrum, yp / splits unused. */
-enum { INV_OLA = 1, INV_PRESUMMED = 2 };
+ * MODE bit 1 (INV_PRESUMMED, ping-pong ranks): B already holds the spectrum, yp / splits unused;
+ * MODE bit 2 (INV_STAGED, ping-pong ranks): yp is ONE spectrum row in shared memory. */
+enum { INV_OLA = 1, INV_PRESUMMED = 2, INV_STAGED = 4 };
 
 template <int RANK, bool PP, int RG = 8, int TT = 0, int MODE = 0, bool WM = (RANK >= 12)>     /* RG: partial rows loaded per round (registers) */
 __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp, uint32_t splits,
@@ -560,7 +562,7 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
         /* with one resident half the odd half goes first and is parked in dst */
         const int want = (NH == 1) ? (1 - pass) : 0;
 
-        if (PP && !(MODE & INV_PRESUMMED))
+        if (PP && !(MODE & (INV_PRESUMMED | INV_STAGED)))
         {
             /* Reduce the partial rows first, as coalesced float4 columns, into the second work
              * buffer.  The loads are volatile asm so that a whole group is in flight before the
@@ -613,11 +615,12 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
             float2 yk[2], ym[2];
             if (PP)
             {
+                const float2 *Y = (MODE & INV_STAGED) ? yp : B;
                 #pragma unroll
                 for (int u = 0; u < 2; ++u)
                 {
-                    yk[u]       = B[k[u]];
-                    ym[u]       = B[km[u]];
+                    yk[u]       = Y[k[u]];
+                    ym[u]       = Y[km[u]];
                 }
             }
             else
@@ -814,6 +817,152 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* k_fwd_staged / k_inv_staged : the transforms of launches that loop over MANY jobs per CTA     */
+/* (multi-frame calls, IR ingest, the fastconv primitives) on the ping-pong ranks.  A CTA's      */
+/* phases are separated by barriers, so a plain global load at the start of a job is fully       */
+/* exposed; here one elected thread fetches the NEXT job's input -- F samples, or one spectrum   */
+/* row -- with a TMA bulk copy into a two-slot shared-memory ring while the current job is       */
+/* transformed.  Inputs that are not 16-byte aligned are read directly, as in k_fwd / k_inv.     */
+
+template <int RANK>
+struct StageCfg
+{
+    using C = FftCfg<RANK>;
+    static constexpr size_t OFF         = (C::SMEM + 127) & ~size_t(127);
+    static constexpr size_t FWD_SLOT    = C::M * sizeof(float);
+    static constexpr size_t INV_SLOT    = C::M * sizeof(float2);
+    static constexpr size_t FWD_SMEM    = OFF + 2 * FWD_SLOT + 2 * sizeof(uint64_t);
+    static constexpr size_t INV_SMEM    = OFF + 2 * INV_SLOT + 2 * sizeof(uint64_t);
+    static constexpr int    INV_MINB    = (RANK == 11) ? 5 : (RANK == 12) ? 2 : 0;
+};
+
+__device__ __forceinline__ bool tma_aligned(const void *p)
+{
+    return (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+
+template <int RANK>
+__global__ void __launch_bounds__(FftCfg<RANK>::T)
+k_fwd_staged(const StepArgs a)
+{
+    using C = FftCfg<RANK>;
+    using S = StageCfg<RANK>;
+    static_assert(C::PP && C::TWS, "k_fwd_staged: ping-pong ranks only");
+    extern __shared__ __align__(128) unsigned char st_sm[];
+    float2 *A               = reinterpret_cast<float2 *>(st_sm);
+    float2 *B               = A + C::WORK;
+    float2 *tws             = A + 2 * C::WORK;
+    float *slots            = reinterpret_cast<float *>(st_sm + S::OFF);
+    uint64_t *bars          = reinterpret_cast<uint64_t *>(st_sm + S::OFF + 2 * S::FWD_SLOT);
+    const int tid           = threadIdx.x;
+
+    for (int i = tid; i < C::TW_TOTAL; i += C::T)
+        tws[i]                  = a.tw[i];
+    uint32_t j              = blockIdx.x;
+    Job job;
+    memset(&job, 0, sizeof(job));
+    if (j < a.n_jobs)
+        job                     = fetch_job(a, j);
+    if (tid == 0)
+    {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if ((j < a.n_jobs) && tma_aligned(job.src))
+        {
+            mbar_expect_tx(&bars[0], uint32_t(S::FWD_SLOT));
+            bulk_g2s_plain(slots, job.src, uint32_t(S::FWD_SLOT), &bars[0]);
+        }
+    }
+    __syncthreads();
+
+    uint32_t ph0 = 0, ph1 = 0;
+    for (uint32_t it = 0; j < a.n_jobs; ++it, j += gridDim.x)
+    {
+        const uint32_t s        = it & 1u;
+        Job next                = job;
+        const bool more         = (j + gridDim.x < a.n_jobs);
+        if (more)
+            next                    = fetch_job(a, j + gridDim.x);
+        if ((tid == 0) && more && tma_aligned(next.src))
+        {
+            /* slot s ^ 1 was last read by the job before this one; a barrier lies in between */
+            mbar_expect_tx(&bars[s ^ 1u], uint32_t(S::FWD_SLOT));
+            bulk_g2s_plain(slots + (s ^ 1u) * C::M, next.src, uint32_t(S::FWD_SLOT), &bars[s ^ 1u]);
+        }
+        const float *src        = job.src;
+        if (tma_aligned(job.src))
+        {
+            if (s)  { mbar_wait(&bars[1], ph1); ph1 ^= 1u; }
+            else    { mbar_wait(&bars[0], ph0); ph0 ^= 1u; }
+            src                     = slots + s * C::M;
+        }
+        fwd_body<RANK, true, 0, false, true>(A, B, src, job.spec, tws, tws, tid);
+        __syncthreads();            /* work buffers and the slot are reused */
+        job                     = next;
+    }
+}
+
+template <int RANK>
+__global__ void __launch_bounds__(FftCfg<RANK>::T, StageCfg<RANK>::INV_MINB)
+k_inv_staged(const StepArgs a)     /* one partial row per job */
+{
+    using C = FftCfg<RANK>;
+    using S = StageCfg<RANK>;
+    static_assert(C::PP && C::TWS, "k_inv_staged: ping-pong ranks only");
+    extern __shared__ __align__(128) unsigned char st_sm[];
+    float2 *A               = reinterpret_cast<float2 *>(st_sm);
+    float2 *B               = A + C::WORK;
+    float2 *tws             = A + 2 * C::WORK;
+    float2 *slots           = reinterpret_cast<float2 *>(st_sm + S::OFF);
+    uint64_t *bars          = reinterpret_cast<uint64_t *>(st_sm + S::OFF + 2 * S::INV_SLOT);
+    const int tid           = threadIdx.x;
+    const bool full         = (a.flags & INV_FULL) != 0;
+
+    for (int i = tid; i < C::TW_TOTAL; i += C::T)
+        tws[i]                  = a.tw[i];
+    uint32_t j              = blockIdx.x;
+    if (tid == 0)
+    {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (j < a.n_jobs)
+        {
+            mbar_expect_tx(&bars[0], uint32_t(S::INV_SLOT));
+            bulk_g2s_plain(slots, a.ypart + uint64_t(j) * C::M, uint32_t(S::INV_SLOT), &bars[0]);
+        }
+    }
+    __syncthreads();
+
+    uint32_t ph0 = 0, ph1 = 0;
+    for (uint32_t it = 0; j < a.n_jobs; ++it, j += gridDim.x)
+    {
+        const uint32_t s        = it & 1u;
+        const Job job           = fetch_job(a, j);
+        if ((tid == 0) && (j + gridDim.x < a.n_jobs))
+        {
+            mbar_expect_tx(&bars[s ^ 1u], uint32_t(S::INV_SLOT));
+            bulk_g2s_plain(slots + (s ^ 1u) * C::M, a.ypart + uint64_t(j + gridDim.x) * C::M, uint32_t(S::INV_SLOT),
+                           &bars[s ^ 1u]);
+        }
+        if (s)  { mbar_wait(&bars[1], ph1); ph1 ^= 1u; }
+        else    { mbar_wait(&bars[0], ph0); ph0 ^= 1u; }
+        inv_body<RANK, true, 2, 0, INV_STAGED, true>(A, B, slots + s * C::M, 1, job.dst, tws, tws, full, tid);
+        __syncthreads();
+    }
 }
 
 struct MacShape
