@@ -159,7 +159,7 @@ struct EqCfg
     static constexpr size_t OFF_BAR = OFF_IB + (PIPE ? C::M * sizeof(float) : 0);
     static constexpr size_t SMEM    = PIPE ? OFF_BAR + 2 * sizeof(uint64_t) : C::SMEM;
     static constexpr int    XPT     = PIPE ? C::M / C::T : 1;           /* input samples per thread */
-    static constexpr int    MINB    = (RANK == 11) ? 5 : 1;             /* rank 11: five CTAs fit in shared memory */
+    static constexpr int    MINB    = (RANK == 11) ? 5 : (RANK == 12) ? 2 : (RANK == 10) ? 1 : 0;     /* measured (profiles/r1_equalizer.jsonl); 0: left to the compiler */
 };
 
 template <int RANK>
