@@ -175,6 +175,12 @@ void   *b200conv_stream(b200conv_batch_t *h);
  *   "eager"       1 (default) = after a synchronous host call has delivered block t, the partitions
  *                 q >= 1 of block t+1 are summed while the host is away; the next call then only
  *                 transforms its input, adds partition 0 and inverts (low call latency)
+ *   "early_pend"  2 = that ahead-of-time sum starts while the launch that delivers block t is still
+ *                 in its tail (back-to-back synchronous calls then run at the device rate);
+ *                 0 = it starts after that launch has completed (lowest latency for a caller that
+ *                 comes back once per audio block: nothing competes with the delivering launch);
+ *                 1 (default) = automatic: early only while the caller keeps the GPU busy, i.e. the
+ *                 previous ahead-of-time sum was still running when the call arrived
  *   "zero_copy"   1 (default) = b200conv_process_planar lets the kernels read / write page-locked
  *                 host matrices directly (no staging copies); 0 = always stage */
 int     b200conv_set_option(b200conv_batch_t *h, const char *name, int value);

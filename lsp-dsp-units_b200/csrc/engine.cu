@@ -242,7 +242,8 @@ static MacPlan plan_mac(uint32_t rank, uint32_t jobs, uint32_t max_nq, int sm_co
     return p;
 }
 
-static cudaError_t launch_mac_raw(const StepArgs &a, const MacPlan &p, uint32_t jobs, cudaStream_t st)
+static cudaError_t launch_mac_raw(const StepArgs &a, const MacPlan &p, uint32_t jobs, cudaStream_t st,
+                                  bool pdl = false)
 {
     static size_t attr_smem[MAX_DEVICES] = { 0 };
     int dev = current_device();
@@ -254,6 +255,22 @@ static cudaError_t launch_mac_raw(const StepArgs &a, const MacPlan &p, uint32_t 
         attr_smem[dev] = p.smem;
     }
     dim3 grid(jobs * p.splits, p.tiles);
+    if (pdl)
+    {
+        /* may start while the preceding k_frame launch is in its tail (STEP_WAIT_HEAD) */
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim             = grid;
+        cfg.blockDim            = dim3(p.threads);
+        cfg.dynamicSmemBytes    = p.smem;
+        cfg.stream              = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id              = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs               = attr;
+        cfg.numAttrs            = 1;
+        return cudaLaunchKernelEx(&cfg, k_mac, a, p.sh);
+    }
     k_mac<<<grid, p.threads, p.smem, st>>>(a, p.sh);
     return cudaGetLastError();
 }
@@ -421,6 +438,7 @@ struct b200conv_batch
 
     b200conv_stats_t        stats       = {};
     int                     tune_splits = 0, tune_stages = 0;
+    bool                    last_was_frame = false; /* the last launch on the stream was a k_frame of this batch */
     bool                    host_io     = false;    /* the running call reads / writes page-locked host matrices */
     int                     opt_fused   = 1, opt_bias = 6, opt_pdl = 1, opt_zero_copy = 1, opt_multi = 8;
     uint32_t               *d_tickets   = nullptr;  /* k_frame: one arrival counter per job */
@@ -434,6 +452,8 @@ struct b200conv_batch
      * partitions q >= 1 of block t+1 (complete frames only) are summed while the host is away,
      * so the next call only transforms its input, adds partition 0 and inverts */
     int                     opt_eager   = 1;
+    int                     opt_early_pend = 1;     /* the pending MAC may start under the tail of the launch before it: 0 never, 1 auto, 2 always */
+    bool                    caller_busy = false;    /* the previous pending MAC was still running when the current call arrived */
     bool                    eager_call  = false;    /* set by the synchronous entry points */
     bool                    pend_ready  = false;
     uint64_t                pend_t      = 0;        /* batch frame counter the pending rows belong to */
@@ -1011,6 +1031,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
                 b->done_prev   += plan.splits;
             }
             b->pend_ready   = false;
+            b->last_was_frame = (st == b->stream) && (!b->profiling);
             b->stats.launches       += 1;
         }
         else
@@ -1069,7 +1090,17 @@ static int launch_pending_mac(Batch *b, cudaStream_t st)
     a.t_base        = b->t_batch;           /* the block about to arrive */
     a.frame0        = 0;
     plan.sh.bias    = 0;
-    CU(launch_mac_raw(a, plan, nact, st));
+    /* Behind a k_frame launch of this batch the MAC may start early: it polls ring_head for the
+     * spectrum that launch publishes and holds its rows back until that launch has completed. */
+    /* auto: early only while the caller keeps the GPU busy (the previous pending MAC was still
+     * running when this call arrived); a caller that comes back once per audio block gets the
+     * delivering launch to itself */
+    const bool early = (b->opt_pdl != 0) && b->last_was_frame &&
+                       ((b->opt_early_pend == 2) || ((b->opt_early_pend == 1) && b->caller_busy));
+    if (early)
+        a.flags        |= STEP_WAIT_HEAD;
+    CU(launch_mac_raw(a, plan, nact, st, early));
+    b->last_was_frame = false;
     b->stats.launches       += 1;
     b->stats.mac_launches   += 1;
     b->pend_ready   = true;
@@ -1265,6 +1296,9 @@ static int process_device2_impl(b200conv_batch_t *b, float *dst, size_t dst_stri
     ENTER_DEVICE(b);
     cudaStream_t st = (stream != nullptr) ? cudaStream_t(stream) : b->stream;
     b->last_stream  = st;
+    b->last_was_frame = false;
+    if (b->eager_call)
+        b->caller_busy  = b->pend_inflight && (cudaEventQuery(b->ev_pend) == cudaErrorNotReady);
     if (b->pend_inflight && (st != b->stream))
         CU(cudaStreamWaitEvent(st, b->ev_pend, 0));     /* a pending MAC may still be running on the own stream */
 
@@ -1557,6 +1591,7 @@ extern "C" int b200conv_set_option(b200conv_batch_t *b, const char *name, int va
     else if (!strcmp(name, "pdl") && (value >= 0) && (value <= 1))          b->opt_pdl = value;
     else if (!strcmp(name, "zero_copy") && (value >= 0) && (value <= 1))    b->opt_zero_copy = value;
     else if (!strcmp(name, "eager") && (value >= 0) && (value <= 1))        b->opt_eager = value;
+    else if (!strcmp(name, "early_pend") && (value >= 0) && (value <= 2))   b->opt_early_pend = value;
     else if (!strcmp(name, "multi_frame") && ((value == 0) || (value == 1) || (value == 2) || (value == 4) || (value == 8)))
         b->opt_multi = (value == 1) ? 0 : value;
     else

@@ -85,7 +85,9 @@ struct StepArgs                     /* by-value kernel argument */
 };
 
 enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
-       STEP_HOST_IO = 8 /* src / dst are page-locked HOST matrices: no bulk-copy staging */ };
+       STEP_HOST_IO = 8 /* src / dst are page-locked HOST matrices: no bulk-copy staging */,
+       STEP_WAIT_HEAD = 16 /* k_mac launched early (programmatic serialization) behind a k_frame:
+                              poll ring_head before touching the newest spectra */ };
 
 /* Partition-range sharding across GPUs (one long IR): every rank's k_frame produces a
  * PARTIAL output block; the sum is formed inside the launch tails over NVLink peer memory --
@@ -1010,6 +1012,12 @@ k_mac(const StepArgs a, const MacShape sh)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
 
+    /* A k_frame launch that follows with the programmatic-serialization attribute (the head-only
+     * launch of a synchronous host call after the eager pending MAC) may become resident now: it
+     * fetches and transforms its input block, which this launch never touches, and reads these
+     * partial rows only after its griddepcontrol.wait.  A no-op for any other successor. */
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     const uint32_t M        = 1u << (a.rank - 1);
     const uint32_t TB       = sh.TB, QB = sh.QB, NS = sh.NS;
     const uint32_t T        = blockDim.x;
@@ -1075,6 +1083,23 @@ k_mac(const StepArgs a, const MacShape sh)
 
     if (tid == 0)
     {
+        if ((a.flags & STEP_WAIT_HEAD) && (n_iter > 0))
+        {
+            /* The eager pending MAC of a synchronous caller starts while the k_frame launch that
+             * delivers the previous block is still running: partitions q >= q0 >= 1 of block t need
+             * the spectra of frames <= t - q0, the newest of which that launch is publishing. */
+            const uint32_t need = job.tlo - q0 + 1u;
+            const uint32_t *hp  = a.ring_head + job.inst;
+            uint32_t have;
+            for (;;)
+            {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(hp) : "memory");
+                if (int32_t(have - need) >= 0)
+                    break;
+                __nanosleep(100);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
         while ((f_it < NS) && (f_it < n_iter))
             issue_next();
     }
@@ -1127,6 +1152,9 @@ k_mac(const StepArgs a, const MacShape sh)
         acc[0].x   += dny;
         acc[0].y    = dny;
     }
+
+    /* launched early: the previous launch may still be reading the rows this one replaces */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     float4 *yp      = reinterpret_cast<float4 *>(a.ypart + (uint64_t(jobi) * rows_per_job(a) + a.row0 + split) * M
                                                  + uint64_t(tile) * TB);

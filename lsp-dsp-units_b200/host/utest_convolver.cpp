@@ -7,6 +7,7 @@
  */
 #include <lsp-plug.in/dsp-units/util/Convolver.h>
 #include "ConvolverBatch.h"
+#include "EqualizerBatch.h"
 
 #include <math.h>
 #include <stdint.h>
@@ -123,6 +124,41 @@ int main()
         }
         failures += check("batch ch0 (phase 0)", y0, direct(x0, h0), 1e-5);
         failures += check("batch ch1 (phase 0.5)", y1, direct(x1, h1), 1e-5);
+    }
+
+    {   // Equalizer FIR data path, in the spirit of src/test/utest/filters/equalizer.cpp:34-84:
+        // impulse in, the peak of the response sits at latency + (kernel peak = nFirSize / 2);
+        // plus the delayed-direct-convolution identity on a second instance
+        const size_t fir_rank = 10, F = size_t(1) << fir_rank, n = 6 * F;
+        uint64_t seed = 5;
+        std::vector<float> k0(F), k1(F), x0(n, 0.0f), x1(n), y0(n), y1(n);
+        for (size_t i = 0; i < F; ++i)
+        {
+            double t = (double(i) - double(F / 2)) * 0.35, w = 0.5 - 0.5 * cos(2.0 * M_PI * double(i) / double(F - 1));
+            k0[i] = float(((t == 0.0) ? 1.0 : sin(t) / t) * w);      // windowed sinc, peak at F / 2
+            k1[i] = urand(seed) * 0.05f;
+        }
+        x0[0] = 1.0f;
+        for (float &v : x1) v = urand(seed);
+        b200conv::EqualizerBatch e(2, fir_rank);
+        if (!e.valid() || !e.set_kernel(0, k0.data()) || !e.set_kernel(1, k1.data()))
+            { printf("equalizer setup failed: %s\n", e.error()); return 2; }
+        for (size_t i = 0; i < n; i += 300)
+        {
+            size_t m = (n - i < 300) ? n - i : 300;
+            const float *src[2] = { &x0[i], &x1[i] };
+            float *dst[2]       = { &y0[i], &y1[i] };
+            if (!e.process(dst, src, m)) { printf("equalizer process failed: %s\n", e.error()); return 2; }
+        }
+        size_t peak = 0;
+        for (size_t i = 0; i < n; ++i)
+            if (fabsf(y0[i]) > fabsf(y0[peak])) peak = i;
+        int ok = (peak == e.latency() + F / 2) && (e.latency() == F);
+        printf("%-28s peak at %zu, latency %zu + %zu  %s\n", "equalizer latency", peak, e.latency(), F / 2, ok ? "ok" : "FAILED");
+        failures += !ok;
+        std::vector<double> want(n, 0.0), full = direct(x1, k1);
+        for (size_t i = F; i < n; ++i) want[i] = full[i - F];
+        failures += check("equalizer = delayed direct", y1, want, 1e-5);
     }
 
     printf("%s\n", failures ? "FAILED" : "ALL PASSED");

@@ -578,6 +578,35 @@ def test_eager_pending_mac_for_synchronous_calls(pkg, eager, pinned):
     b.close()
 
 
+@pytest.mark.parametrize("n,taps,rank", [(64, 480000, 11), (5, 40000, 9), (150, 9000, 8)])
+def test_early_pending_mac_is_bit_identical_to_the_serialised_one(pkg, n, taps, rank):
+    """Back-to-back synchronous one-frame calls on page-locked matrices: the pending MAC of block
+    t+1 starts under the tail of the launch that delivers block t (programmatic serialization,
+    ring_head poll, rows held back by griddepcontrol.wait).  Same arithmetic in the same order as
+    with early_pend = 0 (2 = always early, 1 = automatic), so the outputs must be bit-identical;
+    instance 0 is also checked against float64 truth."""
+    torch = pytest.importorskip("torch")
+    F = 1 << (rank - 1)
+    blocks = 200 if n >= 64 else 400
+    irs = [synth.decaying_ir(c, taps - 13 * c) for c in range(min(n, 4))]
+    src = np.stack([synth.noise(300 + c, blocks * F) for c in range(n)])
+    hsrc = torch.from_numpy(src.copy()).pin_memory()
+    outs = []
+    for early in (2, 0):
+        b = pkg.ConvolverBatch(n, 0)
+        b.set_option("early_pend", early)
+        for c in range(n):
+            assert b.init(c, irs[c % len(irs)], rank, 0.0)
+        hdst = torch.zeros((n, blocks * F)).pin_memory()
+        xin, out = hsrc.numpy(), hdst.numpy()
+        for k in range(blocks):
+            b.process(xin[:, k * F:(k + 1) * F], out[:, k * F:(k + 1) * F])
+        outs.append(out.copy())
+        b.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert rel_err(outs[0][0], direct_convolve(src[0], irs[0], blocks * F)) <= TOL
+
+
 def test_ir_with_more_than_65535_partitions(pkg):
     """Maximum-size edge: a 3-minute IR at the smallest rank has 70 000 partitions of 128 taps
     (beyond the 65 535 grid-y limit and the 32 768-entry job ring of the IR ingest)."""

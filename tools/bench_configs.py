@@ -118,6 +118,21 @@ def main():
                 b.process(a, o)
                 paced.append(time.perf_counter() - t0)
         paced = np.sort(np.array(paced if paced else [0.0])) * 1e6
+        # ... and with the pending MAC forced to start under the delivering launch (early_pend = 2;
+        # the default, 1, does that only for a caller that keeps the GPU busy): it competes with
+        # the latency-critical launch
+        paced_lat = []
+        if not args.no_host:
+            b.set_option("early_pend", 2)
+            for _ in range(60):
+                t_wait = time.perf_counter() + 1e-3
+                while time.perf_counter() < t_wait:
+                    pass
+                t0 = time.perf_counter()
+                b.process(a, o)
+                paced_lat.append(time.perf_counter() - t0)
+            b.set_option("early_pend", 1)
+        paced_lat = np.sort(np.array(paced_lat if paced_lat else [0.0])) * 1e6
         line = {
             "config": name, "instances": n, "taps": taps, "rank": rank, "block": block, "partitions": bins,
             "device_samples_per_s": rate, "device_us_per_call": us_per_call,
@@ -127,6 +142,7 @@ def main():
             "host_call_us_median": float(lat[len(lat) // 2]), "host_call_us_p99": float(lat[int(len(lat) * 0.99)]),
             "host_samples_per_s": n * block / (float(lat[len(lat) // 2]) * 1e-6),
             "host_call_us_paced_median": float(paced[len(paced) // 2]),
+            "host_call_us_paced_median_early_pend_2": float(paced_lat[len(paced_lat) // 2]),
             "block_duration_us_at_48k": block / 48000.0 * 1e6, "note": note,
         }
         print(json.dumps(line), flush=True)
