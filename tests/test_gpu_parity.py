@@ -607,6 +607,30 @@ def test_early_pending_mac_is_bit_identical_to_the_serialised_one(pkg, n, taps, 
     assert rel_err(outs[0][0], direct_convolve(src[0], irs[0], blocks * F)) <= TOL
 
 
+@pytest.mark.parametrize("n,rank,taps,frames", [(300, 11, 3000, 8), (700, 9, 1500, 8), (120, 12, 5000, 16)])
+def test_multi_frame_calls_on_many_instances(pkg, n, rank, taps, frames):
+    """Enough (instance, frame) jobs per call that the transforms run as k_fwd_staged /
+    k_inv_staged (several jobs per CTA, next input prefetched by TMA); every instance is checked
+    against float64 FFT convolution, two calls so that ring history is exercised."""
+    from scipy.signal import fftconvolve
+    F = 1 << (rank - 1)
+    total = 2 * frames * F
+    irs = [synth.decaying_ir(c, taps - c) for c in range(4)]
+    src = np.stack([synth.noise(500 + c, total) for c in range(n)])
+    b = pkg.ConvolverBatch(n, 0)
+    for c in range(n):
+        assert b.init(c, irs[c % 4], rank, 0.0)
+    out = np.empty_like(src)
+    half = frames * F
+    out[:, :half] = b.process(src[:, :half])
+    out[:, half:] = b.process(src[:, half:])
+    b.close()
+    for k in range(4):
+        idx = np.arange(k, n, 4)
+        want = fftconvolve(src[idx].astype(np.float64), irs[k].astype(np.float64)[None, :], axes=1)[:, :total]
+        assert np.max(np.abs(out[idx] - want)) <= TOL * np.max(np.abs(want))
+
+
 def test_ir_with_more_than_65535_partitions(pkg):
     """Maximum-size edge: a 3-minute IR at the smallest rank has 70 000 partitions of 128 taps
     (beyond the 65 535 grid-y limit and the 32 768-entry job ring of the IR ingest)."""

@@ -114,3 +114,35 @@ def test_direct_convolve_accumulates(pkg):
             want = base[i].astype(np.float64)
             want[:n] += np.convolve(x[i].astype(np.float64), h[i].astype(np.float64))
             assert np.max(np.abs(got[i] - want)) <= 1e-5 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("rank,count", [(9, 5000), (11, 2000), (12, 1000), (8, 6000)])
+def test_large_batches_take_the_staged_transforms(pkg, rank, count):
+    """Launches that loop over several jobs per CTA on the ping-pong ranks run k_fwd_staged /
+    k_inv_staged (next job's input through TMA into a two-slot ring): parse -> restore round trip
+    and parse_apply against float64 FFT convolution, every row checked."""
+    lib = pkg.lib()
+    n, F = 1 << rank, 1 << (rank - 1)
+    rng = np.random.Generator(np.random.PCG64(100 + rank))
+    a = rng.uniform(-1, 1, (count, F)).astype(np.float32)
+    h = rng.uniform(-1, 1, F).astype(np.float32)
+    da = torch.from_numpy(a).cuda()
+    dh = torch.from_numpy(np.tile(h, (count, 1))).cuda()
+    ia = torch.empty((count, n), device="cuda", dtype=torch.float32)
+    ih = torch.empty_like(ia)
+    _check(pkg, lib.b200conv_fastconv_parse(0, ia.data_ptr(), da.data_ptr(), rank, count, None))
+    _check(pkg, lib.b200conv_fastconv_parse(0, ih.data_ptr(), dh.data_ptr(), rank, count, None))
+
+    back = torch.full((count, n), 3.0, device="cuda", dtype=torch.float32)
+    _check(pkg, lib.b200conv_fastconv_restore(0, back.data_ptr(), ia.data_ptr(), rank, count, None))
+    torch.cuda.synchronize()
+    got = back.cpu().numpy()
+    assert np.max(np.abs(got[:, :F] - a)) <= 1e-5
+    assert np.max(np.abs(got[:, F:])) <= 1e-5
+
+    dst = torch.zeros((count, n), device="cuda", dtype=torch.float32)
+    _check(pkg, lib.b200conv_fastconv_parse_apply(0, dst.data_ptr(), ih.data_ptr(), da.data_ptr(), rank, count, None))
+    torch.cuda.synchronize()
+    want = np.fft.irfft(np.fft.rfft(a.astype(np.float64), n, axis=1) * np.fft.rfft(h.astype(np.float64), n)[None, :],
+                        n, axis=1)
+    assert np.max(np.abs(dst.cpu().numpy() - want)) <= 1e-5 * np.abs(want).max()
