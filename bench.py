@@ -243,12 +243,17 @@ def main():
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps - 1)]
         ev0.record(stream)
-        for _ in range(args.steps):
+        for s_i in range(args.steps):
             step()
+            if s_i < args.steps - 1:
+                marks[s_i].record(stream)        # per-step durations (min / median), SURVEY 8d
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
+        edges = [ev0] + marks + [ev1]
+        step_ms = sorted(edges[i].elapsed_time(edges[i + 1]) for i in range(args.steps))
         clocks = sampler.stop() if rank == 0 else None
         stats = batch.stats()
 
@@ -321,9 +326,12 @@ def main():
                 "value_share_of_hbm_roofline": value / world * (16 * BINS + 24) / (peak * 1e9),
             },
             "clocks": clocks,
+            "step_ms": {"min": step_ms[0], "median": step_ms[len(step_ms) // 2], "max": step_ms[-1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": io_bytes,
                     "d2h_bytes_per_step": io_bytes,
-                    "api": "b200conv_process_planar (pinned host buffers, synchronous per 1024-sample call; %s)" % ("kernels read/write the pinned buffers over PCIe" if args.zero_copy else "staged H2D/D2H copies")},
+                    "api": "b200conv_process_planar (pinned host buffers, synchronous per 1024-sample call; %s; "
+                           "the next block's partitions q >= 1 are summed while the host is away)"
+                           % ("kernels read/write the pinned buffers over PCIe" if args.zero_copy else "staged H2D/D2H copies")},
             "gpu_launches": stats["launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
@@ -336,8 +344,9 @@ def main():
         if (world == 1) and (not args.no_cpu_baseline):
             cores = min(os.cpu_count() or 1, INSTANCES)
             rate, sec, kind = cpu_reference_rate(cores, 192)
+            one_rate, _, _ = cpu_reference_rate(1, 96)
             line["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                "value": rate, "unit": UNIT, "cores": cores, "kind": kind, "one_core_value": one_rate,
                 "sample": "%d of the 64 instances (one per host thread), 480000-tap IR, rank 11, 192 "
                           "process() calls of 1024 samples each after 4 warm calls (%.1f s); reference "
                           "Convolver.cpp compiled verbatim over restated scalar dsp:: kernels "
