@@ -420,10 +420,28 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
                 /* forward: rot = -i * s3 ; inverse: rot = +i * s3 */
                 float2 rot = INV ? make_float2(-s3.y, s3.x) : make_float2(s3.y, -s3.x);
                 float2 *o  = out + h * P + ((j - k) << 2) + k;
-                o[0]        = cadd(s0, s2);
-                o[Ns]       = cadd(s1, rot);
-                o[2 * Ns]   = csub(s0, s2);
-                o[3 * Ns]   = csub(s1, rot);
+                float2 V0 = cadd(s0, s2), V1 = cadd(s1, rot), V2 = csub(s0, s2), V3 = csub(s1, rot);
+                if (FAST1 && (Ns < 16))
+                {
+                    /* Strides 4 and 8: a half-warp holds 4 / 2 groups of Ns consecutive lanes whose
+                     * outputs for one r fall into the same banks.  Group g stores its outputs in the
+                     * order r = g, g+1, ... instead (a barrel rotation of four registers), which
+                     * spreads the groups over all 32 banks. */
+                    const int rn = (Ns == 4) ? ((tid >> 2) & 3) : ((tid >> 3) & 1);
+                    float2 d0 = (rn & 1) ? V1 : V0, d1 = (rn & 1) ? V2 : V1, d2 = (rn & 1) ? V3 : V2, d3 = (rn & 1) ? V0 : V3;
+                    float2 e0 = (rn & 2) ? d2 : d0, e1 = (rn & 2) ? d3 : d1, e2 = (rn & 2) ? d0 : d2, e3 = (rn & 2) ? d1 : d3;
+                    o[((0 + rn) & 3) * Ns]  = e0;
+                    o[((1 + rn) & 3) * Ns]  = e1;
+                    o[((2 + rn) & 3) * Ns]  = e2;
+                    o[((3 + rn) & 3) * Ns]  = e3;
+                }
+                else
+                {
+                    o[0]        = V0;
+                    o[Ns]       = V1;
+                    o[2 * Ns]   = V2;
+                    o[3 * Ns]   = V3;
+                }
             }
         }
         __syncthreads();
