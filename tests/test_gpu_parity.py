@@ -631,6 +631,37 @@ def test_multi_frame_calls_on_many_instances(pkg, n, rank, taps, frames):
         assert np.max(np.abs(out[idx] - want)) <= TOL * np.max(np.abs(want))
 
 
+def test_multi_frame_device_call_with_unaligned_rows(pkg):
+    """Device matrices whose rows start 4 bytes off a 16-byte boundary (and an odd row pitch): the
+    staged forward transform must fall back to direct loads for those jobs (TMA bulk copies need
+    16-byte aligned sources); results identical to the aligned call."""
+    torch = pytest.importorskip("torch")
+    from scipy.signal import fftconvolve
+    n, rank, taps, frames = 300, 11, 2500, 8
+    F = 1 << (rank - 1)
+    total = frames * F
+    irs = [synth.decaying_ir(c, taps) for c in range(2)]
+    src = np.stack([synth.noise(900 + c, total) for c in range(n)])
+    outs = []
+    for shift, pitch in ((0, total), (1, total + 3)):
+        b = pkg.ConvolverBatch(n, 0)
+        for c in range(n):
+            assert b.init(c, irs[c % 2], rank, 0.0)
+        dsrc = torch.zeros((n * pitch + 8,), device="cuda", dtype=torch.float32)
+        ddst = torch.zeros_like(dsrc)
+        view = dsrc[shift:shift + n * pitch].view(n, pitch)
+        view[:, :total] = torch.from_numpy(src).cuda()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        b.process_device(ddst.data_ptr() + 4 * shift, dsrc.data_ptr() + 4 * shift, pitch, total, s.cuda_stream)
+        s.synchronize()
+        outs.append(ddst[shift:shift + n * pitch].view(n, pitch)[:, :total].cpu().numpy())
+        b.close()
+    assert np.array_equal(outs[0], outs[1])
+    want = fftconvolve(src[::2].astype(np.float64), irs[0].astype(np.float64)[None, :], axes=1)[:, :total]
+    assert np.max(np.abs(outs[0][::2] - want)) <= TOL * np.max(np.abs(want))
+
+
 def test_ir_with_more_than_65535_partitions(pkg):
     """Maximum-size edge: a 3-minute IR at the smallest rank has 70 000 partitions of 128 taps
     (beyond the 65 535 grid-y limit and the 32 768-entry job ring of the IR ingest)."""
