@@ -9,11 +9,16 @@
  * (:486-501).  Samples leave the output buffer while the next block is collected, hence a block
  * of latency.
  *
- * Here: one launch per block boundary for the whole batch.  A CTA owns one instance: forward
- * transform of the finished block (fwd_body), product with the kernel spectrum, full-length
- * inverse transform (inv_body, `full`), overlap-add / cross-fade, and the sample exchange
- * (input segment -> vInBuffer, vOutBuffer -> output segment) of the call that triggered it.
+ * Here: one launch per block boundary for the whole batch (k_eq).  A CTA iteration owns one
+ * instance: forward transform of the finished block, product with the kernel spectrum,
+ * full-length inverse transform, overlap-add / cross-fade, and the sample exchange (input
+ * segment -> vInBuffer, vOutBuffer -> output segment) of the call that triggered it.  On the
+ * ping-pong ranks (transform rank <= 12) the real-FFT split, the product and the merge are fused
+ * in registers, the operands arrive through TMA bulk copies a phase ahead, and a call that takes
+ * the whole block gets its outputs straight from the last inverse pass; the other ranks and the
+ * (rare) hand-over blocks go through fwd_body / inv_body and global scratch.
  * The kernel spectra use the engine's packed half-spectrum layout (bin 0 = (DC, Nyquist)).
+ * Measured progression and ncu summary: profiles/README.md; design notes: DESIGN.md 4.3.
  */
 #ifndef B200CONV_EQUALIZER_CUH_
 #define B200CONV_EQUALIZER_CUH_
@@ -34,14 +39,6 @@ struct EqArgs
     uint32_t        off, n;         /* segment: n samples at offset off of the block (nBufSize)     */
     uint32_t        do_block;       /* a block boundary precedes the segment                        */
 };
-
-/* L1 prefetch of `bytes` bytes at p, one 128-byte line per thread */
-__device__ __forceinline__ void prefetch_span(const void *p, uint32_t bytes, int tid, int threads)
-{
-    const char *c = static_cast<const char *>(p);
-    for (uint32_t o = uint32_t(tid) * 128u; o < bytes; o += uint32_t(threads) * 128u)
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(c + o));
-}
 
 __device__ __forceinline__ float ld_cg_f1(const float *p)
 {
