@@ -1298,7 +1298,11 @@ static int process_device2_impl(b200conv_batch_t *b, float *dst, size_t dst_stri
     b->last_stream  = st;
     b->last_was_frame = false;
     if (b->eager_call)
+    {
         b->caller_busy  = b->pend_inflight && (cudaEventQuery(b->ev_pend) == cudaErrorNotReady);
+        cudaGetLastError();         /* "not ready" is an answer, not an error: do not leave it behind
+                                       for the cudaGetLastError() after the next <<< >>> launch */
+    }
     if (b->pend_inflight && (st != b->stream))
         CU(cudaStreamWaitEvent(st, b->ev_pend, 0));     /* a pending MAC may still be running on the own stream */
 

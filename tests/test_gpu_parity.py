@@ -578,6 +578,28 @@ def test_eager_pending_mac_for_synchronous_calls(pkg, eager, pinned):
     b.close()
 
 
+def test_back_to_back_synchronous_calls_without_programmatic_launch(pkg):
+    """pdl = 0 with the eager pending MAC: the engine asks whether the previous pending MAC is
+    still running (cudaEventQuery -> "not ready") and then launches with <<< >>>; the query's
+    answer must not surface as a launch error."""
+    torch = pytest.importorskip("torch")
+    n, rank, F, blocks = 16, 11, 1024, 60
+    irs = [synth.decaying_ir(c, 300000) for c in range(2)]
+    src = np.stack([synth.noise(700 + c, blocks * F) for c in range(n)])
+    hsrc = torch.from_numpy(src.copy()).pin_memory()
+    hdst = torch.zeros((n, blocks * F)).pin_memory()
+    b = pkg.ConvolverBatch(n, 0)
+    b.set_option("pdl", 0)
+    for c in range(n):
+        assert b.init(c, irs[c % 2], rank, 0.0)
+    xin, out = hsrc.numpy(), hdst.numpy()
+    for k in range(blocks):
+        b.process(xin[:, k * F:(k + 1) * F], out[:, k * F:(k + 1) * F])
+    b.close()
+    for c in (0, 1):
+        assert rel_err(out[c], direct_convolve(src[c], irs[c], blocks * F)) <= TOL
+
+
 @pytest.mark.parametrize("n,taps,rank", [(64, 480000, 11), (5, 40000, 9), (150, 9000, 8)])
 def test_early_pending_mac_is_bit_identical_to_the_serialised_one(pkg, n, taps, rank):
     """Back-to-back synchronous one-frame calls on page-locked matrices: the pending MAC of block
