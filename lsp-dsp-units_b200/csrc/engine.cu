@@ -59,6 +59,7 @@ static int fail(int code, const char *fmt, ...)
 /* per-rank kernel dispatch                                                                     */
 
 static const int MAX_DEVICES = 64;
+static const uint32_t MAX_FEW_JOBS = 148;     /* up to this many frames per launch count as "few" (one per SM) */
 
 /* function attributes are per device; the caller has made the batch's device current */
 static int current_device()
@@ -121,6 +122,25 @@ static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t s
             }
             attr_staged[dev] = true;
             k_fwd_staged<RANK><<<cap, C::T, SS, st>>>(a);
+            return cudaGetLastError();
+        }
+    }
+    if constexpr (!C::PP)
+    {
+        /* few frames at a big rank: one CTA per half frame (k_fwd_half); rank 16 always, its two
+         * halves would otherwise run one after the other in the same CTA */
+        using H = FftCfg<RANK, 0, 1>;
+        if ((RANK >= 16) || (grid <= 2 * MAX_FEW_JOBS))
+        {
+            static bool attr_half[MAX_DEVICES] = { false };
+            if ((!attr_half[dev]) && (H::SMEM > 48 * 1024))
+            {
+                cudaError_t e = cudaFuncSetAttribute(k_fwd_half<RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H::SMEM));
+                if (e != cudaSuccess)
+                    return e;
+            }
+            attr_half[dev] = true;
+            k_fwd_half<RANK><<<resident_grid(2 * grid, H::T, H::SMEM), H::T, H::SMEM, st>>>(a);
             return cudaGetLastError();
         }
     }

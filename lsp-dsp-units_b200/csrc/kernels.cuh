@@ -196,14 +196,14 @@ __device__ __forceinline__ float2 cmulc(float2 a, float2 b)
 /* registers.  With a second buffer (PP) a pass is load A -> butterflies -> store B -> barrier;  */
 /* without it, load -> barrier -> store -> barrier in place.                                    */
 
-template <int RANK, int TT = 0>                 /* TT: threads doing the transform (0 = natural count) */
+template <int RANK, int TT = 0, int NHO = 0>    /* TT: threads doing the transform (0 = natural count); NHO: override of NH */
 struct FftCfg
 {
     static constexpr int N      = 1 << RANK;
     static constexpr int M      = N / 2;
     static constexpr int P      = M / 2;
     static constexpr int LOGP   = RANK - 2;
-    static constexpr int NH     = (RANK >= 16) ? 1 : 2;                 /* halves resident in smem */
+    static constexpr int NH     = (NHO > 0) ? NHO : (RANK >= 16) ? 1 : 2;  /* halves resident in smem */
     static constexpr int BF     = NH * P / 4;                           /* radix-4 butterflies/pass */
     static constexpr int T      = (TT > 0) ? TT : ((BF >= 512) ? 512 : ((BF < 32) ? 32 : BF));
     static constexpr int BPT    = (BF + T - 1) / T;                     /* butterflies per thread   */
@@ -240,10 +240,10 @@ __device__ __forceinline__ float2 rot90(float2 z)       /* forward: -i z ; inver
     return INV ? make_float2(-z.y, z.x) : make_float2(z.y, -z.x);
 }
 
-template <int RANK, bool INV, bool PP, int TT = 0, bool WMUL = (RANK >= 12), bool FAST1 = true>
+template <int RANK, bool INV, bool PP, int TT = 0, bool WMUL = (RANK >= 12), bool FAST1 = true, int NHO = 0>
 __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *tw, int tid)
 {
-    using C = FftCfg<RANK, TT>;
+    using C = FftCfg<RANK, TT, NHO>;
     constexpr int P = C::P, T = C::T, BPT = C::BPT, NH = C::NH;
 
     float2 *in  = A;
@@ -459,20 +459,24 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
 /* twg = twiddle table in global memory (used next to the global loads), tw = the table the      */
 /* transform passes read (shared-memory copy when the caller staged one, else twg).              */
 
-template <int RANK, bool PP, int TT = 0, bool SMEM_OUT = false, bool WM = (RANK >= 12)>
+template <int RANK, bool PP, int TT = 0, bool SMEM_OUT = false, bool WM = (RANK >= 12), int NHO = 0>
 __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src, float2 *out,
                                          const float2 *twg, const float2 *tw, int tid,
-                                         float2 **smem_out = nullptr)
+                                         float2 **smem_out = nullptr, int only_pass = -1)
 {
+    /* only_pass (one resident half, NH == 1): 0 = even bins only, 1 = odd bins only -- the two
+     * halves of a frame are independent all the way to the output row (k_fwd_half) */
     /* SMEM_OUT (ping-pong ranks only): the bins go to whichever work buffer the transform did
      * not end in, reported through *smem_out; `out` is ignored */
-    static_assert((!SMEM_OUT) || (PP && (FftCfg<RANK, TT>::NH == 2)), "fwd_body: SMEM_OUT needs two work buffers");
-    using C = FftCfg<RANK, TT>;
+    static_assert((!SMEM_OUT) || (PP && (FftCfg<RANK, TT, NHO>::NH == 2)), "fwd_body: SMEM_OUT needs two work buffers");
+    using C = FftCfg<RANK, TT, NHO>;
     constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH;
 
     #pragma unroll 1
     for (int pass = 0; pass < 2 / NH; ++pass)
     {
+        if ((only_pass >= 0) && (pass != only_pass))
+            continue;
         const bool src8 = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
         for (int m = tid; m < P; m += T)
         {
@@ -484,7 +488,7 @@ __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src,
         }
         __syncthreads();
 
-        const float2 *R = fft_smem<RANK, false, PP, TT, WM>(A, B, tw, tid);
+        const float2 *R = fft_smem<RANK, false, PP, TT, WM, true, NHO>(A, B, tw, tid);
         if (SMEM_OUT)
         {
             out         = (R == A) ? B : A;
@@ -550,6 +554,26 @@ k_fwd(const StepArgs a)
         const Job job           = fetch_job(a, j);
         fwd_body<RANK, C::PP, 0, false, true>(A, B, job.src, job.spec, tw, tw, threadIdx.x);
         __syncthreads();            /* the work buffers are reused by the next job */
+    }
+}
+
+/* k_fwd_half : ranks 13..16 with few frames per launch.  One CTA transforms a whole frame in k_fwd,
+ * so 64 instances keep 64 of 148 SMs busy (and at rank 16, where only one half fits in shared
+ * memory, run the two halves one after the other).  The even and odd bins are independent all the
+ * way to the output row, so here work item w = (job w / 2, half w % 2) gets a CTA of its own. */
+template <int RANK>
+__global__ void __launch_bounds__(FftCfg<RANK, 0, 1>::T)
+k_fwd_half(const StepArgs a)
+{
+    using C = FftCfg<RANK, 0, 1>;
+    static_assert(!C::PP && !C::TWS, "k_fwd_half: ranks 13..16");
+    extern __shared__ float2 sm[];
+    for (uint32_t w = blockIdx.x; w < 2 * a.n_jobs; w += gridDim.x)
+    {
+        const Job job           = fetch_job(a, w >> 1);
+        fwd_body<RANK, false, 0, false, true, 1>(sm, nullptr, job.src, job.spec, a.tw, a.tw, threadIdx.x,
+                                                 nullptr, int(w & 1u));
+        __syncthreads();
     }
 }
 
