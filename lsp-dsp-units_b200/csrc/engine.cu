@@ -189,6 +189,31 @@ static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t s
             return cudaGetLastError();
         }
     }
+    if constexpr (!C::PP)
+    {
+        /* few frames at a big rank: one CTA per half frame, then an element-wise combine */
+        using H = FftCfg<RANK, 0, 1>;
+        if ((a.park != nullptr) && ((RANK >= 16) || (grid <= 2 * MAX_FEW_JOBS)))
+        {
+            static bool attr_half[MAX_DEVICES] = { false };
+            int dev = current_device();
+            if ((!attr_half[dev]) && (H::SMEM > 48 * 1024))
+            {
+                cudaError_t e = cudaFuncSetAttribute(k_inv_half<RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H::SMEM));
+                if (e != cudaSuccess)
+                    return e;
+            }
+            attr_half[dev] = true;
+            k_inv_half<RANK><<<resident_grid(2 * grid, H::T, H::SMEM), H::T, H::SMEM, st>>>(a);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess)
+                return e;
+            const uint32_t F = 1u << (RANK - 1);
+            dim3 cg((F / 256 < 32) ? F / 256 : 32, (grid < 4096) ? grid : 4096);
+            k_inv_combine<<<cg, 256, 0, st>>>(a);
+            return cudaGetLastError();
+        }
+    }
     /* the row-group size only matters on the ping-pong ranks (FftCfg::PP) */
     if (FftCfg<RANK>::PP && (rows_per_job_host(a) <= 2))
         return launch_inv_rg<RANK, 2>(a, grid, st);
@@ -458,6 +483,8 @@ struct b200conv_batch
 
     b200conv_stats_t        stats       = {};
     int                     tune_splits = 0, tune_stages = 0;
+    float                  *park        = nullptr;  /* k_inv_half scratch */
+    size_t                  park_bytes  = 0;
     bool                    last_was_frame = false; /* the last launch on the stream was a k_frame of this batch */
     bool                    host_io     = false;    /* the running call reads / writes page-locked host matrices */
     int                     opt_fused   = 1, opt_bias = 6, opt_pdl = 1, opt_zero_copy = 1, opt_multi = 8;
@@ -646,6 +673,34 @@ static int ensure_ypart(Batch *b, size_t bytes, cudaStream_t st)
     return B200CONV_OK;
 }
 
+/* Ranks 13..16 with few frames per launch: scratch for the half-frame inverse transform
+ * (k_inv_half, [job][2][F] floats).  Leaves a.park NULL when the launch does not qualify. */
+static int attach_park(Batch *b, StepArgs &a, size_t jobs, cudaStream_t st)
+{
+    a.park          = nullptr;
+    if ((b->rank < 13) || (jobs == 0) || ((b->rank < 16) && (jobs > 2 * MAX_FEW_JOBS)))
+        return B200CONV_OK;
+    const size_t bytes = jobs * (size_t(2) << (b->rank - 1)) * sizeof(float);
+    if (bytes > (size_t(1) << 30))
+        return B200CONV_OK;
+    if (bytes > b->park_bytes)
+    {
+        CU(cudaStreamSynchronize(st));
+        if (b->park)
+            cudaFree(b->park);
+        b->park         = nullptr;
+        b->park_bytes   = 0;
+        if (cudaMalloc(&b->park, bytes) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return B200CONV_OK;             /* no scratch: the one-CTA-per-frame kernel still works */
+        }
+        b->park_bytes   = bytes;
+    }
+    a.park          = b->park;
+    return B200CONV_OK;
+}
+
 /* Reserves `count` consecutive slots of the job upload ring and returns their index. */
 static int reserve_jobs(Batch *b, size_t count, cudaStream_t st, size_t *pos)
 {
@@ -773,6 +828,7 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     for (float2 *t : b->tw)
         if (t) cudaFree(t);
     if (b->ypart)       cudaFree(b->ypart);
+    if (b->park)        cudaFree(b->park);
     if (b->d_desc)      cudaFree(b->d_desc);
     if (b->d_active)    cudaFree(b->d_active);
     if (b->d_tickets)   cudaFree(b->d_tickets);
@@ -1013,6 +1069,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             a.n_jobs        = nact * tf;
             CU(launch_fwd(a, nact * tf, st));
             CU(launch_mac_multi(a, mp, nact, tf, st));
+            TRY(attach_park(b, a, size_t(nact) * tf, st));
             CU(launch_inv(a, nact * tf, st));
             b->stats.launches       += 3;
             b->stats.mac_launches   += 1;
@@ -1061,6 +1118,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             b->pend_ready   = false;
             CU(launch_fwd(a, nact, st));
             CU(launch_mac(b, a, sp, nact, st));
+            TRY(attach_park(b, a, nact, st));
             CU(launch_inv(a, nact, st));
             b->stats.launches       += 3;
         }
@@ -1292,6 +1350,7 @@ static int process_general(Batch *b, float *dst, size_t dst_stride, const float 
             a.n_jobs    = uint32_t(mac.size());
             a.splits    = plan.splits;
             CU(launch_mac(b, a, plan, a.n_jobs, st));
+            TRY(attach_park(b, a, a.n_jobs, st));
             CU(launch_inv(a, a.n_jobs, st));
             b->stats.launches       += 2;
             b->stats.mac_launches   += 1;

@@ -64,6 +64,7 @@ struct StepArgs                     /* by-value kernel argument */
     const uint32_t *active;         /* uniform mode: instance ids                                   */
     const float2   *tw;             /* N-point twiddle table exp(-2 pi i j / N)                     */
     float2         *ypart;          /* [job][split][M] partial spectra                              */
+    float          *park;           /* k_inv_half: [job][2][F] half results (odd, even); NULL = not available */
     uint32_t       *ring_head;      /* [instance] frames whose spectrum is in the ring (low 32 bits) */
     uint32_t       *stream_done;    /* [instance] k_frame CTAs that finished reading the ring, cumulative */
     uint32_t        need_done;      /* k_frame: stream_done value after which ring slot (-t) mod S is free */
@@ -589,12 +590,15 @@ k_fwd_half(const StepArgs a)
  * MODE bit 2 (INV_STAGED, ping-pong ranks): yp is ONE spectrum row in shared memory. */
 enum { INV_OLA = 1, INV_PRESUMMED = 2, INV_STAGED = 4 };
 
-template <int RANK, bool PP, int RG = 8, int TT = 0, int MODE = 0, bool WM = (RANK >= 12)>     /* RG: partial rows loaded per round (registers) */
+template <int RANK, bool PP, int RG = 8, int TT = 0, int MODE = 0, bool WM = (RANK >= 12), int NHO = 0>     /* RG: partial rows loaded per round (registers) */
 __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp, uint32_t splits,
-                                         float *dst, const float2 *twg, const float2 *tw, bool full, int tid)
+                                         float *dst, const float2 *twg, const float2 *tw, bool full, int tid,
+                                         int only_pass = -1)
 {
+    /* only_pass (one resident half, NH == 1; k_inv_half): 0 = the odd bins' half, 1 = the even
+     * bins' half; either way dst receives that half's F scaled samples and nothing is combined */
     static_assert((!(MODE & INV_PRESUMMED)) || PP, "inv_body: INV_PRESUMMED needs the second work buffer");
-    using C = FftCfg<RANK, TT>;
+    using C = FftCfg<RANK, TT, NHO>;
     constexpr int P = C::P, M = C::M, T = C::T, NH = C::NH, N = C::N;
     constexpr int ITER = (M / 2) / T;           /* bins k = tid + it*T handled by this thread; even */
     static_assert((ITER >= 2) && ((ITER & 1) == 0), "inv_body: two bins per round");
@@ -603,6 +607,8 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
     #pragma unroll 1
     for (int pass = 0; pass < 2 / NH; ++pass)
     {
+        if ((only_pass >= 0) && (pass != only_pass))
+            continue;
         /* with one resident half the odd half goes first and is parked in dst */
         const int want = (NH == 1) ? (1 - pass) : 0;
 
@@ -710,7 +716,7 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
         }
         __syncthreads();
 
-        const float2 *R = fft_smem<RANK, true, PP, TT, WM>(A, B, tw, tid);
+        const float2 *R = fft_smem<RANK, true, PP, TT, WM, true, NHO>(A, B, tw, tid);
 
         /* z[m] = (A[m] + conj(w_M^m) B[m]) / N ; z[m + P] = (A[m] - conj(w_M^m) B[m]) / N */
         for (int m = tid; m < P; m += T)
@@ -729,6 +735,12 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
                 float2 bv   = cmulc(R[m], tw[C::TW_PRE + m]);
                 dst[2 * m]      = bv.x * scale;
                 dst[2 * m + 1]  = bv.y * scale;
+                continue;
+            }
+            else if (only_pass == 1)
+            {
+                dst[2 * m]      = R[m].x * scale;
+                dst[2 * m + 1]  = R[m].y * scale;
                 continue;
             }
             else
@@ -798,6 +810,47 @@ k_inv(const StepArgs a)
         inv_body<RANK, C::PP, RG, 0, 0, true>(A, B, a.ypart + uint64_t(j) * rows_per_job(a) * C::M, rows_per_job(a),
                                               job.dst, tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
         __syncthreads();
+    }
+}
+
+/* k_inv_half + k_inv_combine : the inverse transform of ranks 13..16 with few frames per launch,
+ * one CTA per HALF frame (see k_fwd_half).  The halves meet only in the last pass,
+ * y[j] = e[j] + o[j], y[j + F] = e[j] - o[j], so each CTA leaves its F scaled samples in
+ * park[job][half] and an element-wise launch combines them. */
+template <int RANK>
+__global__ void __launch_bounds__(FftCfg<RANK, 0, 1>::T)
+k_inv_half(const StepArgs a)
+{
+    using C = FftCfg<RANK, 0, 1>;
+    static_assert(!C::PP && !C::TWS, "k_inv_half: ranks 13..16");
+    extern __shared__ float2 sm[];
+    const uint32_t rows = rows_per_job(a);
+    for (uint32_t w = blockIdx.x; w < 2 * a.n_jobs; w += gridDim.x)
+    {
+        const uint32_t j = w >> 1, half = w & 1u;       /* half 0: odd bins, half 1: even bins */
+        inv_body<RANK, false, 8, 0, 0, true, 1>(sm, nullptr, a.ypart + uint64_t(j) * rows * C::M, rows,
+                                                a.park + (uint64_t(j) * 2 + half) * C::M, a.tw, a.tw, false,
+                                                threadIdx.x, int(half));
+        __syncthreads();
+    }
+}
+
+__global__ void k_inv_combine(const StepArgs a)
+{
+    const uint32_t F    = 1u << (a.rank - 1);
+    const bool full     = (a.flags & INV_FULL) != 0;
+    for (uint32_t j = blockIdx.y; j < a.n_jobs; j += gridDim.y)
+    {
+        const Job job       = fetch_job(a, j);
+        const float *o      = a.park + uint64_t(j) * 2 * F;
+        const float *e      = o + F;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F; i += gridDim.x * blockDim.x)
+        {
+            float ev = e[i], ov = o[i];
+            job.dst[i]          = ev + ov;
+            if (full)
+                job.dst[F + i]      = ev - ov;
+        }
     }
 }
 
