@@ -75,6 +75,44 @@ def _channel_worker(rank, world, port, result):
     dist.destroy_process_group()
 
 
+def _equalizer_worker(rank, world, port, result):
+    """Row f2: equalizers are independent instances -- contiguous ranges per rank, no collective on
+    the data path; one rank hands a kernel over smoothly mid-stream, the others must not notice."""
+    sharding = _setup(rank, world, port)
+    import synth
+    from equalizer_model import ModelEqualizer, band_kernel
+    fir_rank, instances, blocks = 7, 7, 6
+    F = 1 << fir_rank
+    lo, hi = sharding.channel_shard(instances, world, rank)
+    errs = []
+    for c in range(lo, hi):
+        k0, k1 = band_kernel(fir_rank, 0.0, 0.1 * (c + 1)), band_kernel(fir_rank, 0.3, 0.9)
+        x = synth.noise(c, blocks * F)
+        eq = ModelEqualizer(fir_rank)
+        eq.set_kernel(k0)
+        first = eq.process(x[:2 * F + 17])
+        swapped = (c == 0)
+        if swapped:
+            eq.set_kernel(k1, smooth=True)
+        out = np.concatenate([first, eq.process(x[2 * F + 17:])])
+        if not swapped:
+            want = np.concatenate([np.zeros(F), np.convolve(x.astype(np.float64), k0.astype(np.float64))])[:blocks * F]
+            errs.append(float(np.max(np.abs(out - want)) / np.max(np.abs(want))))
+        else:
+            # after the cross-fade block the output is the new kernel's delayed convolution
+            want = np.concatenate([np.zeros(F), np.convolve(x.astype(np.float64), k1.astype(np.float64))])[:blocks * F]
+            tail = slice(5 * F, blocks * F)
+            errs.append(float(np.max(np.abs(out[tail] - want[tail])) / np.max(np.abs(want))))
+    owned = torch.zeros(instances, dtype=torch.int32)
+    owned[lo:hi] = 1
+    dist.all_reduce(owned, op=dist.ReduceOp.SUM)
+    worst = torch.tensor([max(errs) if errs else 0.0], dtype=torch.float64)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        result.put(("equalizer", bool((owned == 1).all()), float(worst.item())))
+    dist.destroy_process_group()
+
+
 def _run(worker, port):
     ctx = mp.get_context("spawn")
     result = ctx.Queue()
@@ -96,6 +134,11 @@ def test_partition_range_shards_allreduce_gloo_world2():
 def test_channel_shards_no_collective_gloo_world2():
     tag, complete, err = _run(_channel_worker, 29612)
     assert tag == "channel" and complete and err <= 1e-5
+
+
+def test_equalizer_instances_shard_by_instance_gloo_world2():
+    tag, complete, err = _run(_equalizer_worker, 29613)
+    assert tag == "equalizer" and complete and err <= 1e-9
 
 
 def test_shard_plans_cover_everything():
