@@ -156,6 +156,158 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def timed_blocks(batch_call, blocks, stream, barrier):
+    """Device time (ms, CUDA events on `stream`) of `blocks` back-to-back one-frame process calls."""
+    import torch
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(blocks):
+        batch_call(t)
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def max_over_ranks(x, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_strong_cfg3(pkg, args, rank, local_rank, world, barrier, peak):
+    """BASELINE configs[2] read literally: the 64-channel batch sharded by channel over the ranks
+    (64 / N channels per GPU, fixed total work), no collective."""
+    import torch
+    import synth
+    from lsp_dsp_units_b200 import sharding
+    lo, hi = sharding.channel_shard(INSTANCES, world, rank)
+    n = hi - lo
+    b = pkg.ConvolverBatch(n, device=local_rank)
+    irs = [synth.decaying_ir(c, TAPS) for c in range(4)]
+    for c in range(n):
+        assert b.init(c, irs[(lo + c) % 4], RANK, 0.0)
+    frames = BINS
+    g = torch.Generator(device="cuda").manual_seed(0x5EED1000 + rank)
+    src = torch.rand((n, 64 * BLOCK), generator=g, device="cuda") * 2.0 - 1.0
+    dst = torch.empty_like(src)
+    stream = torch.cuda.Stream()
+    sp, dp = src.data_ptr(), dst.data_ptr()
+
+    def call(t):
+        o = 4 * (t % 64) * BLOCK
+        b.process_device(dp + o, sp + o, 64 * BLOCK, BLOCK, stream.cuda_stream)
+
+    with torch.cuda.stream(stream):
+        for t in range(frames):                 # fill the ring
+            call(t)
+        reps = 4
+        ms = timed_blocks(call, reps * frames, stream, barrier)
+    ms = max_over_ranks(ms, world)
+    b.close()
+    us = ms * 1e3 / (reps * frames)
+    rate = INSTANCES * BLOCK / (us * 1e-6)
+    per_gpu_bytes = n * BYTES_PER_INSTANCE_FRAME
+    return {
+        "workload": "cfg3 strong: 64 ch x 480000 taps TOTAL, %d ch per GPU, rank 11, 1024-sample calls" % n,
+        "n_gpus": world, "channels_per_gpu": n, "samples_per_s": rate, "us_per_block": us,
+        "algorithmic_bytes_per_block_per_gpu": per_gpu_bytes,
+        "share_of_hbm_roofline_per_gpu": per_gpu_bytes / (us * 1e-6) / 1e9 / peak,
+        "working_set_mb_per_gpu": 2 * n * (BINS + 1) * F * 8 / 1e6,
+        "note": "working set per GPU (IR spectra + ring) below ~126 MB sits in L2: a share > 1 of the HBM "
+                "roofline is then L2 traffic, not DRAM (see profiles/ for the ncu dram__bytes of this shape)",
+        "collective": "none (independent channels)",
+    }
+
+
+def run_cfg5(pkg, args, rank, local_rank, world, barrier, peak):
+    """BASELINE configs[4]: ONE 8-channel convolver with a 120 s IR (5.76 M taps, 5625 partitions of
+    1024 taps) split by partition range over the ranks; the partial output blocks are summed inside
+    the kernel tails, all-to-all over NVLink peer memory (no collective call per block).  Parity:
+    channel 0 against float64 FFT convolution over the WHOLE impulse-response length."""
+    import numpy as np
+    import torch
+    import synth
+    from lsp_dsp_units_b200 import sharding
+    C5, TAPS5 = 8, 5760000
+    bins5 = (TAPS5 + F - 1) // F
+    irs = [synth.decaying_ir(100 + c, TAPS5) for c in range(C5)]
+    conv = sharding.PartitionShardedConvolver(pkg, C5, RANK, local_rank, reduce="fused")
+    assert conv.init(irs), "device allocation failed"
+    p_lo, p_hi, _, _ = sharding.partition_shard(TAPS5, F, world, rank)
+    stream = torch.cuda.Stream()
+
+    # ---- parity over the whole IR length: 16 blocks of noise, then silence --------------------
+    nz = 16
+    total = bins5 + nz
+    g = torch.Generator(device="cuda").manual_seed(0x5EED5000)     # the same input on every rank
+    head = torch.rand((C5, nz * BLOCK), generator=g, device="cuda") * 2.0 - 1.0
+    zeros = torch.zeros((C5, BLOCK), device="cuda")
+    out = torch.empty((C5, total * BLOCK), device="cuda")
+    with torch.cuda.stream(stream):
+        for t in range(total):
+            src = head[:, t * BLOCK:(t + 1) * BLOCK] if t < nz else zeros
+            conv.process_device(out[:, t * BLOCK:(t + 1) * BLOCK], src, BLOCK, stream)
+        stream.synchronize()
+    err = None
+    if rank == 0:
+        from scipy.signal import fftconvolve
+        x = head[0].cpu().numpy().astype(np.float64)
+        full = fftconvolve(x, irs[0].astype(np.float64))
+        want = np.zeros(total * BLOCK)
+        want[:min(full.size, want.size)] = full[:want.size]
+        got = out[0].cpu().numpy().astype(np.float64)
+        err = float(np.max(np.abs(got - want)) / np.max(np.abs(want)))
+    same = True
+    if world > 1:
+        import torch.distributed as dist
+        ref0 = out[:, -64 * BLOCK:].clone()
+        dist.broadcast(ref0, src=0)
+        same = bool(torch.equal(ref0, out[:, -64 * BLOCK:]))
+    del out
+
+    # ---- throughput: back-to-back 1024-sample blocks ------------------------------------------
+    g = torch.Generator(device="cuda").manual_seed(0x5EED5001)
+    src = torch.rand((C5, 64 * BLOCK), generator=g, device="cuda") * 2.0 - 1.0
+    dst = torch.empty_like(src)
+
+    sp, dp, raw = src.data_ptr(), dst.data_ptr(), conv.batch
+
+    def call(t):                                # lean host path: the block period is ~15 us at 8 GPUs
+        o = 4 * (t % 64) * BLOCK
+        raw.process_device(dp + o, sp + o, 64 * BLOCK, BLOCK, stream.cuda_stream)
+
+    blocks = 2000
+    with torch.cuda.stream(stream):
+        for t in range(256):
+            call(t)
+        ms = timed_blocks(call, blocks, stream, barrier)
+    ms = max_over_ranks(ms, world)
+    timed_out = conv.timed_out()
+    flags = max_over_ranks(float(timed_out) + 2.0 * float(not same), world)
+    conv.close()
+    us = ms * 1e3 / blocks
+    per_gpu_bytes = C5 * (16 * F * (p_hi - p_lo) + 24 * F)
+    return {
+        "workload": "cfg5: ONE 8-ch convolver, 5760000-tap IR (120 s), rank 11, 1024-sample blocks, "
+                    "partition range split over %d GPU(s)" % world,
+        "n_gpus": world, "partitions_total": bins5, "partitions_this_gpu": p_hi - p_lo,
+        "samples_per_s": C5 * BLOCK / (us * 1e-6), "us_per_block": us, "blocks_timed": blocks,
+        "realtime_factor": C5 * BLOCK / (us * 1e-6) / (C5 * 48000.0),
+        "algorithmic_bytes_per_block_per_gpu": per_gpu_bytes,
+        "share_of_hbm_roofline_per_gpu": per_gpu_bytes / (us * 1e-6) / 1e9 / peak,
+        "max_err_vs_float64_of_peak": err,
+        "parity_span": "%d blocks = the whole IR length + %d (every partition of every rank contributes)" % (total, nz),
+        "all_ranks_bit_identical": bool(int(flags) & 2 == 0),
+        "peer_wait_timed_out": bool(int(flags) & 1),
+        "reduce": ("fused into the k_frame tails: all-to-all over NVLink peer memory, every rank ends with "
+                   "the sum, %d blocks in flight" % 4) if world > 1 else "none (one GPU holds every partition)",
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -173,6 +325,9 @@ def main():
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--zero-copy", type=int, default=1)
     ap.add_argument("--eager", type=int, default=1)
+    ap.add_argument("--extras-timeout", type=int, default=420)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra multi-GPU shapes (cfg3 strong scaling, cfg5 partition split)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -293,8 +448,35 @@ def main():
     e2e_value = world * args.steps * e2e_frames * BLOCK * INSTANCES / float(t.item())
     io_bytes = e2e_frames * INSTANCES * BLOCK * 4
 
+    peak, peak_src = hbm_peak()
+    extras = {}
+    batch.close()
+    del src, dst
+    torch.cuda.empty_cache()
+    extras_hung = False
+    if not args.no_extras:
+        # the multi-GPU shapes that CAN fail: fixed total work, and the one real exchange step.
+        # They run on a worker thread with a deadline: whatever happens to them (an exception on
+        # one rank, a peer that never answers), the headline line above is still printed.
+        import threading
+
+        def run_extras():
+            torch.cuda.set_device(local_rank)
+            for name, fn in (("strong_cfg3", run_strong_cfg3), ("cfg5_split", run_cfg5)):
+                try:
+                    extras[name] = fn(pkg, args, rank, local_rank, world, barrier, peak)
+                except Exception as exc:
+                    extras[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                    break                               # the ranks may be out of step now
+
+        th = threading.Thread(target=run_extras, daemon=True)
+        th.start()
+        th.join(timeout=args.extras_timeout)
+        extras_hung = th.is_alive()
+        if extras_hung:
+            extras.setdefault("error", "extra shapes did not finish within %d s" % args.extras_timeout)
+
     if rank == 0:
-        peak, peak_src = hbm_peak()
         bytes_per_launch = INSTANCES * BYTES_PER_INSTANCE_FRAME
         iso_ms = mac_ms / max(1, mac_n)             # event-bracketed launches (no overlap between them)
         if args.fused:
@@ -341,6 +523,7 @@ def main():
                          "isolated_frac": bytes_per_launch / (iso_ms * 1e-3) / 1e9 / peak if iso_ms > 0 else None,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src},
         }
+        line.update(extras)
         if (world == 1) and (not args.no_cpu_baseline):
             cores = min(os.cpu_count() or 1, INSTANCES)
             rate, sec, kind = cpu_reference_rate(cores, 192)
@@ -353,7 +536,9 @@ def main():
                           "(lsp-dsp-lib AVX/SSE is not available offline)" % (cores, sec)}
         print(json.dumps(line), flush=True)
 
-    batch.close()
+    if extras_hung:
+        sys.stdout.flush()
+        os._exit(0)                 # a stuck collective cannot be unwound; the line is out
     if world > 1:
         dist.destroy_process_group()
 

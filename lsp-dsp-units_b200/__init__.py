@@ -172,6 +172,10 @@ class ConvolverBatch:
         assert src.shape[0] == self.instances
         if out is None:
             out = np.empty(src.shape, dtype=np.float32)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.float32 or out.shape != src.shape
+              or not out.flags.writeable):
+            # the C ABI reinterprets the buffer as float*: anything else would be silent garbage
+            raise ValueError("out must be a writeable float32 array of shape %r" % (src.shape,))
         n = src.shape[1]
         planar = (src.strides[1] == 4 and out.strides[1] == 4 and out.shape == src.shape
                   and (self.instances == 1 or (src.strides[0] == out.strides[0] and src.strides[0] % 4 == 0
@@ -300,6 +304,9 @@ class Convolver:
         src = np.ascontiguousarray(src, dtype=np.float32)
         if out is None:
             out = np.empty_like(src)
+        elif (not isinstance(out, np.ndarray) or out.dtype != np.float32 or out.shape != src.shape
+              or not out.flags.writeable):
+            raise ValueError("out must be a writeable float32 array of shape %r" % (src.shape,))
         if self._b is None:                     # Convolver.cpp:219-223
             out[...] = 0.0
             return out

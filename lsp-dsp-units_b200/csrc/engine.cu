@@ -459,7 +459,8 @@ struct b200conv_batch
     std::vector<Instance>   inst;
     size_t                  rank        = 0;        /* shared clamped rank, 0 = none active */
     cudaStream_t            stream      = nullptr;
-    cudaStream_t            last_stream = nullptr;  /* caller's stream of the latest process_device call, if any */
+    cudaEvent_t             ev_last     = nullptr;  /* end of the latest process_device call on a CALLER's stream */
+    bool                    last_foreign = false;   /* ... and whether there was one since the last quiesce      */
 
     std::vector<InstDesc>   h_desc;
     InstDesc               *d_desc      = nullptr;
@@ -490,9 +491,7 @@ struct b200conv_batch
     int                     opt_fused   = 1, opt_bias = 6, opt_pdl = 1, opt_zero_copy = 1, opt_multi = 8;
     uint32_t               *d_tickets   = nullptr;  /* k_frame: one arrival counter per job */
     uint32_t               *d_ring_head = nullptr;  /* k_frame: frames published per instance */
-    uint32_t               *d_stream_done = nullptr; /* k_frame: CTAs done reading the ring, cumulative */
-    uint32_t                done_prev   = 0;        /* cumulative CTAs per instance through the previous launch */
-    uint32_t                done_prev2  = 0;        /* ... through the launch before that */
+    uint32_t               *h_error     = nullptr;  /* page-locked, device-mapped: a bounded in-kernel wait gave up */
     std::vector<uint32_t>   h_ring_head;
 
     /* eager pending MAC for synchronous host callers: right after block t has been delivered the
@@ -513,7 +512,7 @@ struct b200conv_batch
     ReduceArgs              reduce      = {};
     unsigned char          *xchg        = nullptr;              /* local exchange buffer (IPC shared) */
     void                   *xchg_peer[REDUCE_MAX_WORLD] = { nullptr };  /* peers' buffers, opened */
-    size_t                  xchg_slots_bytes = 0, xchg_arrived_off = 0, xchg_consumed_off = 0, xchg_error_off = 0;
+    size_t                  xchg_slots_bytes = 0, xchg_flags_off = 0, xchg_consumed_off = 0;
 
     bool                    profiling   = false;
     std::vector<cudaEvent_t> prof_events;           /* pairs: before / after each k_mac */
@@ -579,22 +578,31 @@ class DeviceScope
         return fail(B200CONV_ERR_CUDA, "cannot select device %d: %s", (b)->device,          \
                     cudaGetErrorString(device_scope_.error()))
 
-/* Waits for everything this batch has enqueued: on its own stream and on the caller's stream of
- * the latest process_device call. */
+/* Waits for everything this batch has enqueued: on its own stream and on a caller's stream.  The
+ * caller's stream handle is never kept past the call that received it (the caller may destroy it);
+ * an event recorded on it at the end of that call stands in for it. */
 static cudaError_t quiesce(Batch *b)
 {
     cudaError_t e = cudaSuccess;
     if (b->stream)
         e = cudaStreamSynchronize(b->stream);
-    if ((e == cudaSuccess) && (b->last_stream != nullptr) && (b->last_stream != b->stream))
-    {
-        /* the caller may have destroyed that stream since (then its work is complete anyway) */
-        if (cudaStreamSynchronize(b->last_stream) != cudaSuccess)
-            cudaGetLastError();
-    }
-    b->last_stream = nullptr;
+    if ((e == cudaSuccess) && b->last_foreign && (b->ev_last != nullptr))
+        e = cudaEventSynchronize(b->ev_last);
+    b->last_foreign = false;
     b->pend_inflight = false;
     return e;
+}
+
+/* A bounded in-kernel wait gave up (kernels.cuh, wait_ge): the results since then are garbage. */
+static int check_device_error(Batch *b)
+{
+    const uint32_t code = (b->h_error != nullptr) ? *reinterpret_cast<volatile uint32_t *>(b->h_error) : 0u;
+    if (code == 0)
+        return B200CONV_OK;
+    return fail(B200CONV_ERR_STATE, "an in-kernel wait timed out (%s); results since then are invalid -- "
+                "re-create the batch%s", (code == SPIN_ERR_PEER) ? "a peer GPU of the fused reduce did not answer"
+                                                                 : "a predecessor launch did not publish its spectrum",
+                (code == SPIN_ERR_PEER) ? " and reconnect the reduce" : "");
 }
 
 static void free_instance_buffers(Instance &in)
@@ -646,9 +654,6 @@ static int upload_tables(Batch *b, cudaStream_t st)
             b->h_desc[i].t_delta = int64_t(b->inst[i].frames) - int64_t(b->t_batch);
     }
     CU(cudaMemcpyAsync(b->d_ring_head, b->h_ring_head.data(), b->n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    /* the memset is a full stream dependency: every earlier launch has completed when it runs */
-    CU(cudaMemsetAsync(b->d_stream_done, 0, b->n * sizeof(uint32_t), st));
-    b->done_prev = b->done_prev2 = 0;
     /* pageable sources: cudaMemcpyAsync stages them before returning */
     CU(cudaMemcpyAsync(b->d_desc, b->h_desc.data(), b->n * sizeof(InstDesc), cudaMemcpyHostToDevice, st));
     if (!b->active.empty())
@@ -734,7 +739,7 @@ static StepArgs base_args(const Batch *b)
     a.flags     = b->host_io ? uint32_t(STEP_HOST_IO) : 0u;
     a.ypart     = b->ypart;
     a.ring_head = b->d_ring_head;
-    a.stream_done = b->d_stream_done;
+    a.error     = b->h_error;       /* UVA: the mapped host word is addressable from the device */
     a.rank      = uint32_t(b->rank);
     a.n_active  = uint32_t(b->active.size());
     a.splits    = 1;
@@ -792,6 +797,7 @@ static int create_impl(b200conv_batch_t **out, int device, size_t instances)
         CU_BRK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
         CU_BRK(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
         CU_BRK(cudaEventCreateWithFlags(&b->ev_pend, cudaEventDisableTiming));
+        CU_BRK(cudaEventCreateWithFlags(&b->ev_last, cudaEventDisableTiming));
         CU_BRK(cudaMalloc(&b->d_desc, instances * sizeof(InstDesc)));
         CU_BRK(cudaMalloc(&b->d_active, instances * sizeof(uint32_t)));
         CU_BRK(cudaMallocHost(&b->h_jobs, JOB_RING * sizeof(Job)));
@@ -799,8 +805,8 @@ static int create_impl(b200conv_batch_t **out, int device, size_t instances)
         CU_BRK(cudaMemset(b->d_desc, 0, instances * sizeof(InstDesc)));
         CU_BRK(cudaMalloc(&b->d_tickets, instances * sizeof(uint32_t)));
         CU_BRK(cudaMemset(b->d_tickets, 0, instances * sizeof(uint32_t)));
-        CU_BRK(cudaMalloc(&b->d_stream_done, instances * sizeof(uint32_t)));
-        CU_BRK(cudaMemset(b->d_stream_done, 0, instances * sizeof(uint32_t)));
+        CU_BRK(cudaHostAlloc(&b->h_error, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        *b->h_error = 0;
         CU_BRK(cudaMalloc(&b->d_ring_head, instances * sizeof(uint32_t)));
         CU_BRK(cudaMemset(b->d_ring_head, 0, instances * sizeof(uint32_t)));
         #undef CU_BRK
@@ -833,7 +839,7 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     if (b->d_active)    cudaFree(b->d_active);
     if (b->d_tickets)   cudaFree(b->d_tickets);
     if (b->d_ring_head) cudaFree(b->d_ring_head);
-    if (b->d_stream_done) cudaFree(b->d_stream_done);
+    if (b->h_error)     cudaFreeHost(b->h_error);
     if (b->d_jobs)      cudaFree(b->d_jobs);
     if (b->h_jobs)      cudaFreeHost(b->h_jobs);
     if (b->h_in)        cudaFreeHost(b->h_in);
@@ -843,6 +849,7 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     b200conv_reduce_disconnect(b);
     if (b->ev_done)     cudaEventDestroy(b->ev_done);
     if (b->ev_pend)     cudaEventDestroy(b->ev_pend);
+    if (b->ev_last)     cudaEventDestroy(b->ev_last);
     for (cudaEvent_t ev : b->prof_events)
         cudaEventDestroy(ev);
     if (b->stream)      cudaStreamDestroy(b->stream);
@@ -1044,7 +1051,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
     a.t_base        = b->t_batch;
     const bool fused = (b->opt_fused != 0) && (b->rank <= 13);     /* k_frame: ranks 8..13 */
     if ((b->reduce.mode != 0) && (!fused))
-        return fail(B200CONV_ERR_STATE, "the fused cross-GPU reduce needs the one-launch-per-block path (ranks 8..11, fused = 1)");
+        return fail(B200CONV_ERR_STATE, "the fused cross-GPU reduce needs the one-launch-per-block path (ranks 8..13, fused = 1)");
     plan.sh.bias    = fused ? uint32_t(b->opt_bias) : 0;
     bool used_multi = false;
     for (size_t f = 0; f < frames; )
@@ -1082,9 +1089,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
         }
         if (fused && (!used_multi))
         {
-            /* one launch per block for all instances x partitions; the ring slot it overwrites
-             * was last read by the launch before the previous one */
-            a.need_done     = b->done_prev2;
+            /* one launch per block for all instances x partitions */
             if (eager && b->pend_ready && (b->pend_t == b->t_batch + f) && (!tables_changed))
             {
                 /* partitions q >= 1 were summed ahead of time (launch_pending_mac): transform the
@@ -1097,16 +1102,14 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
                 af.rows         = b->pend_splits + 1;
                 af.row0         = b->pend_splits;
                 af.flags       |= STEP_HEAD_ONLY;
+                /* the predecessor on the own stream is this batch's pending MAC, which never
+                 * touches the caller's input block: fetch and transform it under that MAC */
+                if (st == b->stream)
+                    af.flags       |= STEP_EARLY_SRC;
                 CU(launch_mac(b, af, fp, nact, st, true));
-                b->done_prev2   = b->done_prev;
-                b->done_prev   += 1;
             }
             else
-            {
                 CU(launch_mac(b, a, plan, nact, st, true));
-                b->done_prev2   = b->done_prev;
-                b->done_prev   += plan.splits;
-            }
             b->pend_ready   = false;
             b->last_was_frame = (st == b->stream) && (!b->profiling);
             b->stats.launches       += 1;
@@ -1128,7 +1131,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
         f              += 1;
     }
     if (used_multi)
-        b->desc_dirty   = true;     /* ring_head / stream_done were bypassed: re-seed before the next k_frame */
+        b->desc_dirty   = true;     /* ring_head was bypassed: re-seed before the next k_frame */
     b->t_batch     += frames;
     for (uint32_t i : b->active)
     {
@@ -1374,7 +1377,7 @@ static int process_device2_impl(b200conv_batch_t *b, float *dst, size_t dst_stri
         return fail(B200CONV_ERR_ARG, "b200conv_process_device: bad buffers");
     ENTER_DEVICE(b);
     cudaStream_t st = (stream != nullptr) ? cudaStream_t(stream) : b->stream;
-    b->last_stream  = st;
+    TRY(check_device_error(b));
     b->last_was_frame = false;
     if (b->eager_call)
     {
@@ -1407,11 +1410,19 @@ static int process_device2_impl(b200conv_batch_t *b, float *dst, size_t dst_stri
         if (b->inst[i].off != 0)
             uniform = false;
 
+    int rc;
     if (uniform)
-        return process_uniform(b, dst, dst_stride, src, src_stride, count / F, st);
-    if (b->reduce.mode != 0)
+        rc = process_uniform(b, dst, dst_stride, src, src_stride, count / F, st);
+    else if (b->reduce.mode != 0)
         return fail(B200CONV_ERR_STATE, "the fused cross-GPU reduce handles whole-frame calls only");
-    return process_general(b, dst, dst_stride, src, src_stride, count, st);
+    else
+        rc = process_general(b, dst, dst_stride, src, src_stride, count, st);
+    if ((rc == B200CONV_OK) && (st != b->stream))
+    {
+        CU(cudaEventRecord(b->ev_last, st));
+        b->last_foreign = true;
+    }
+    return rc;
 }
 
 extern "C" int b200conv_process_device(b200conv_batch_t *b, float *dst, const float *src,
@@ -1432,7 +1443,7 @@ static int finish_sync_call(Batch *b)
         b->pend_inflight = true;
     }
     CU(cudaEventSynchronize(b->ev_done));
-    return B200CONV_OK;
+    return check_device_error(b);
 }
 
 static int ensure_staging(Batch *b, size_t floats)
@@ -1576,9 +1587,8 @@ extern "C" int b200conv_sync(b200conv_batch_t *b)
     if (b == nullptr)
         return fail(B200CONV_ERR_ARG, "b200conv_sync: NULL handle");
     ENTER_DEVICE(b);
-    CU(cudaStreamSynchronize(b->stream));
-    b->pend_inflight = false;
-    return B200CONV_OK;
+    CU(quiesce(b));
+    return check_device_error(b);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -1702,20 +1712,22 @@ extern "C" int b200conv_reduce_prepare(b200conv_batch_t *b, int grank, int world
     if ((b == nullptr) || (handle_out == nullptr) || (world < 1) || (world > REDUCE_MAX_WORLD) ||
         (grank < 0) || (grank >= world))
         return fail(B200CONV_ERR_ARG, "b200conv_reduce_prepare: bad arguments");
-    if ((b->rank == 0) || (b->rank > 11))
-        return fail(B200CONV_ERR_STATE, "b200conv_reduce_prepare: initialise the instances first (ranks 8..11)");
+    if ((b->rank == 0) || (b->rank > 13))
+        return fail(B200CONV_ERR_STATE, "b200conv_reduce_prepare: initialise the instances first (ranks 8..13)");
     static_assert(sizeof(cudaIpcMemHandle_t) == B200CONV_IPC_HANDLE_BYTES, "IPC handle size");
     ENTER_DEVICE(b);
     TRY(b200conv_reduce_disconnect(b));
 
+    /* exchange buffer (identical layout on every rank):
+     *   slots    [DEPTH][world][channels][F] floats
+     *   flags    [DEPTH][world][channels]    sequence numbers (block + 1)
+     *   consumed [world][channels]           blocks consumed, written by the consuming rank      */
     const size_t F          = size_t(1) << (b->rank - 1);
     const size_t C          = b->n;
-    b->xchg_slots_bytes     = size_t(2) * world * C * F * sizeof(float);
-    b->xchg_arrived_off     = b->xchg_slots_bytes;
-    b->xchg_consumed_off    = b->xchg_arrived_off + 2 * C * sizeof(uint32_t);
-    b->xchg_error_off       = b->xchg_consumed_off + C * sizeof(uint32_t);
-    b->xchg_error_off       = (b->xchg_error_off + 63) & ~size_t(63);
-    size_t total            = b->xchg_error_off + 64 + REDUCE_MAX_WORLD * sizeof(uint32_t *);
+    b->xchg_slots_bytes     = size_t(REDUCE_DEPTH) * world * C * F * sizeof(float);
+    b->xchg_flags_off       = (b->xchg_slots_bytes + 127) & ~size_t(127);
+    b->xchg_consumed_off    = (b->xchg_flags_off + size_t(REDUCE_DEPTH) * world * C * sizeof(uint32_t) + 127) & ~size_t(127);
+    size_t total            = b->xchg_consumed_off + size_t(world) * C * sizeof(uint32_t);
     CU(cudaMalloc(&b->xchg, total));
     CU(cudaMemset(b->xchg, 0, total));
     cudaIpcMemHandle_t hnd;
@@ -1750,31 +1762,26 @@ extern "C" int b200conv_reduce_connect(b200conv_batch_t *b, const unsigned char 
         first   = false;
     }
 
+    /* all-to-all: every rank opens every peer's exchange buffer */
     for (uint32_t g = 0; g < r.world; ++g)
     {
         b->xchg_peer[g] = nullptr;
-        bool need = (g != r.grank) && ((r.grank == 0) || (g == 0));     /* root opens all, others open root */
-        if (!need)
+        if (g == r.grank)
             continue;
         cudaIpcMemHandle_t hnd;
         memcpy(&hnd, all_handles + size_t(g) * B200CONV_IPC_HANDLE_BYTES, sizeof(hnd));
         CU(cudaIpcOpenMemHandle(&b->xchg_peer[g], hnd, cudaIpcMemLazyEnablePeerAccess));
     }
-    unsigned char *root     = (r.grank == 0) ? b->xchg : static_cast<unsigned char *>(b->xchg_peer[0]);
-    r.slots_root            = reinterpret_cast<float *>(root);
-    r.arrived_root          = reinterpret_cast<uint32_t *>(root + b->xchg_arrived_off);
-    r.consumed_local        = reinterpret_cast<uint32_t *>(b->xchg + b->xchg_consumed_off);
-    r.error                 = reinterpret_cast<uint32_t *>(b->xchg + b->xchg_error_off);
-    uint32_t *table[REDUCE_MAX_WORLD] = { nullptr };
     for (uint32_t g = 0; g < r.world; ++g)
     {
         unsigned char *base = (g == r.grank) ? b->xchg : static_cast<unsigned char *>(b->xchg_peer[g]);
-        table[g]            = (base != nullptr) ? reinterpret_cast<uint32_t *>(base + b->xchg_consumed_off) : nullptr;
+        r.slots[g]          = reinterpret_cast<float *>(base);
+        r.flags[g]          = reinterpret_cast<uint32_t *>(base + b->xchg_flags_off);
+        r.consumed[g]       = reinterpret_cast<uint32_t *>(base + b->xchg_consumed_off);
     }
-    r.consumed_peer         = reinterpret_cast<uint32_t **>(b->xchg + b->xchg_error_off + 64);
-    CU(cudaMemcpy(r.consumed_peer, table, sizeof(table), cudaMemcpyHostToDevice));
     r.t0                    = uint32_t(frames);
     r.mode                  = (r.world > 1) ? 1u : 0u;
+    *b->h_error             = 0;
     return B200CONV_OK;
 }
 
@@ -1804,13 +1811,7 @@ extern "C" int b200conv_reduce_status(b200conv_batch_t *b, int *timed_out)
 {
     if ((b == nullptr) || (timed_out == nullptr))
         return fail(B200CONV_ERR_ARG, "b200conv_reduce_status: bad arguments");
-    *timed_out = 0;
-    if (b->xchg == nullptr)
-        return B200CONV_OK;
-    ENTER_DEVICE(b);
-    uint32_t flag = 0;
-    CU(cudaMemcpy(&flag, b->xchg + b->xchg_error_off, sizeof(flag), cudaMemcpyDeviceToHost));
-    *timed_out = int(flag);
+    *timed_out = (b->h_error != nullptr) ? int(*reinterpret_cast<volatile uint32_t *>(b->h_error)) : 0;
     return B200CONV_OK;
 }
 

@@ -66,12 +66,10 @@ struct StepArgs                     /* by-value kernel argument */
     float2         *ypart;          /* [job][split][M] partial spectra                              */
     float          *park;           /* k_inv_half: [job][2][F] half results (odd, even); NULL = not available */
     uint32_t       *ring_head;      /* [instance] frames whose spectrum is in the ring (low 32 bits) */
-    uint32_t       *stream_done;    /* [instance] k_frame CTAs that finished reading the ring, cumulative */
-    uint32_t        need_done;      /* k_frame: stream_done value after which ring slot (-t) mod S is free */
+    uint32_t       *error;          /* host-mapped word: set when a bounded in-kernel wait gave up    */
     uint32_t        rows;           /* partial rows per job in ypart (0 = splits); a launch writes rows
                                        row0 .. row0 + splits - 1, the inverse transform sums all `rows` */
     uint32_t        row0;
-    uint32_t        pad0;
     const float    *src;            /* uniform mode: [instances][stride]                            */
     float          *dst;
     uint64_t        stride;         /* uniform mode: floats between instance rows of src            */
@@ -88,19 +86,27 @@ struct StepArgs                     /* by-value kernel argument */
 enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
        STEP_HOST_IO = 8 /* src / dst are page-locked HOST matrices: no bulk-copy staging */,
        STEP_WAIT_HEAD = 16 /* k_mac launched early (programmatic serialization) behind a k_frame:
-                              poll ring_head before touching the newest spectra */ };
+                              poll ring_head before touching the newest spectra */,
+       STEP_EARLY_SRC = 32 /* k_frame: the input block may be read before griddepcontrol.wait -- set by
+                              the host only when the predecessor on the stream is this batch's own pending
+                              k_mac and the input is a caller-owned HOST block no kernel writes */ };
 
 /* Partition-range sharding across GPUs (one long IR): every rank's k_frame produces a
  * PARTIAL output block; the sum is formed inside the launch tails over NVLink peer memory --
- * no collective library call, no host in the loop.
- *   rank g != 0 : its inverse transform stores the block straight into slot g of the exchange
- *                 buffer in ROOT's memory (peer stores), fences at system scope and bumps root's
- *                 arrival counter;
- *   rank 0      : waits for world-1 arrivals, adds the slots to its own block, writes the output,
- *                 and tells every peer (stores into THEIR memory) that the slot pair is free.
- * Slots are double-buffered by block parity; all waits are bounded (a peer that never shows up
- * raises *error instead of hanging the GPU). */
+ * no collective library call, no host in the loop, no root: an ALL-TO-ALL exchange after which
+ * every rank holds the summed block (added in rank order, hence bit-identical on all ranks).
+ *   every rank g : the CTA that finishes channel c of block b inverse-transforms its partial
+ *                  spectrum, stores the block into slot [b % depth][g][c] of EVERY rank's exchange
+ *                  buffer (posted peer stores), fences once at system scope and stores the sequence
+ *                  number b + 1 into flag [b % depth][g][c] of every rank;
+ *                  then waits until its own flags [b % depth][p][c] read b + 1 for all p, adds the
+ *                  world slots, writes the output block, and tells every rank that it has consumed
+ *                  block b of channel c (the slot is reused by block b + depth).
+ * Sequence numbers, not resettable counters: a late peer can never be mistaken for the next
+ * block.  All waits are bounded (a peer that never shows up raises *error instead of hanging the
+ * GPU; the host then fails the next call). */
 constexpr int REDUCE_MAX_WORLD = 8;
+constexpr int REDUCE_DEPTH     = 4;
 struct ReduceArgs
 {
     uint32_t    mode;                               /* 0 = off */
@@ -108,11 +114,9 @@ struct ReduceArgs
     uint32_t    t0;                                 /* frame counter (low 32 bits) at connect time */
     uint32_t    channels;                           /* instances per rank */
     uint32_t    frame;                              /* F */
-    float      *slots_root;                         /* [2][world][channels][F] in root's memory */
-    uint32_t   *arrived_root;                       /* [2][channels]           in root's memory */
-    uint32_t   *consumed_local;                     /* [channels]              in this rank's memory */
-    uint32_t  **consumed_peer;                      /* root only: [world] every rank's consumed array (table in root's memory) */
-    uint32_t   *error;                              /* local: set when a wait timed out */
+    float      *slots[REDUCE_MAX_WORLD];            /* rank p's [depth][world][channels][F]  (p == grank: local) */
+    uint32_t   *flags[REDUCE_MAX_WORLD];            /* rank p's [depth][world][channels] arrival sequence numbers */
+    uint32_t   *consumed[REDUCE_MAX_WORLD];         /* rank p's [world][channels]: blocks rank g has consumed, written by g */
 };
 
 __device__ __forceinline__ uint64_t global_ns()
@@ -127,6 +131,48 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+/* Bounded in-kernel waits.  Every spin in this file has a deadline: a predecessor that faulted
+ * (or a peer GPU that never shows up) must not hang the device.  A waiter that gives up stores a
+ * code into *err -- a host-mapped word the host checks at its next synchronisation point, which
+ * then fails with B200CONV_ERR_STATE -- and carries on (its output is garbage, the GPU is alive). */
+constexpr uint64_t SPIN_LIMIT_NS = 2000000000ull;
+enum { SPIN_ERR_RING = 1, SPIN_ERR_PEER = 2 };
+
+__device__ __forceinline__ void spin_fail(uint32_t *err, uint32_t code)
+{
+    if (err != nullptr)
+        *reinterpret_cast<volatile uint32_t *>(err) = code;
+}
+
+/* waits until int32(*p - need) >= 0; SYS: the word is written by another GPU */
+template <bool SYS>
+__device__ __forceinline__ void wait_ge(const uint32_t *p, uint32_t need, uint32_t *err, uint32_t code)
+{
+    uint32_t have   = SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p);
+    if (int32_t(have - need) >= 0)
+        return;
+    const uint64_t deadline = global_ns() + SPIN_LIMIT_NS;
+    for (uint32_t n = 1; ; ++n)
+    {
+        __nanosleep(SYS ? 200 : 100);
+        have            = SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p);
+        if (int32_t(have - need) >= 0)
+            return;
+        if (((n & 31u) == 0) && (global_ns() > deadline))
+        {
+            spin_fail(err, code);
+            return;
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t rows_per_job(const StepArgs &a)
@@ -1183,16 +1229,7 @@ k_mac(const StepArgs a, const MacShape sh)
             /* The eager pending MAC of a synchronous caller starts while the k_frame launch that
              * delivers the previous block is still running: partitions q >= q0 >= 1 of block t need
              * the spectra of frames <= t - q0, the newest of which that launch is publishing. */
-            const uint32_t need = job.tlo - q0 + 1u;
-            const uint32_t *hp  = a.ring_head + job.inst;
-            uint32_t have;
-            for (;;)
-            {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(hp) : "memory");
-                if (int32_t(have - need) >= 0)
-                    break;
-                __nanosleep(100);
-            }
+            wait_ge<false>(a.ring_head + job.inst, job.tlo - q0 + 1u, a.error, SPIN_ERR_RING);
             asm volatile("fence.proxy.async;" ::: "memory");
         }
         while ((f_it < NS) && (f_it < n_iter))
@@ -1462,23 +1499,25 @@ k_mac_multi(const StepArgs a, const MacShape sh)
 }
 
 /* ------------------------------------------------------------------------------------------- */
-/* k_frame : ranks 8..11 (one bin tile per instance), whole frames for every instance -- the     */
-/* block scheduler's "one launch per block".  grid = jobs * splits, M/4 threads.                 */
+/* k_frame : ranks 8..13, whole frames for every instance -- the block scheduler's "one launch    */
+/* per block".  grid = (jobs * splits, M / TB), TB / 4 threads.                                   */
 /*                                                                                             */
-/*   split 0 of each job  : transforms the input frame (fwd_body) into the ring while its first  */
-/*                          TMA stages are in flight, and handles partition q = qa (which needs   */
-/*                          that spectrum) LAST;                                                 */
-/*   every split          : streams its partition chunk exactly like k_mac and writes one        */
-/*                          partial row;                                                        */
-/*   the last split to    : (atomic ticket per job) sums the partial rows out of L2 and runs the  */
-/*   finish a job           inverse transform (inv_body) -> output block.                        */
+/*   every CTA            : streams its partition chunk exactly like k_mac and writes one        */
+/*                          partial row; the CTAs of split 0 take the stage with partition q = 0  */
+/*                          (the only one that needs the arriving frame's own spectrum) LAST;     */
+/*   (split 0, tile 0)    : before that last stage it transforms the input frame (fwd_body) into  */
+/*                          the ring and publishes it through ring_head;                         */
+/*   the last CTA to      : (atomic ticket per job) sums the partial rows out of L2 and runs the  */
+/*   finish a job           inverse transform (inv_body) -> output block (or the cross-GPU sum).  */
 /*                                                                                             */
-/* Launched with programmatic stream serialisation: the prologue overlaps the previous frame's   */
-/* tail; nothing global is touched before griddepcontrol.wait.                                   */
-
-/* Ranks 12 and 13 have 2 / 4 bin tiles of 1024 per instance (grid.y): the CTA (split 0, tile 0)
- * transforms the frame with its 256 threads, the other tiles of split 0 learn through ring_head
- * that the spectrum has landed, and the last of the splits x tiles CTAs of a job inverts. */
+/* Launched with programmatic stream serialisation: the partition stream of block t+1 overlaps   */
+/* the inverse-transform tail of block t.  Before griddepcontrol.wait a CTA touches only the IR   */
+/* spectra (immutable between inits), ring rows announced through ring_head (acquire / release)   */
+/* and tables written by stream-ordered copies.  The caller's INPUT block, the ring slot of the   */
+/* arriving frame, the partial rows, the tickets and the output block are all touched AFTER       */
+/* griddepcontrol.wait, i.e. when every earlier launch in the stream has completed and flushed -- */
+/* so a src that an earlier launch produced (two batches cascaded on one stream, or a batch fed   */
+/* its own dst) is final when it is read, whoever that producer was.                             */
 #ifdef B200CONV_TIMING
 /* developer instrumentation (tools/frame_timeline.py): per-CTA timestamps of the last k_frame launch */
 __device__ unsigned long long g_frame_times[8192 * 4];
@@ -1519,12 +1558,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     uint64_t *full          = reinterpret_cast<uint64_t *>(stages + size_t(NS) * 2 * stage_elems);
     uint32_t *flag          = reinterpret_cast<uint32_t *>(full + NS);
 
-    /* Let the next block's launch become resident as soon as this one frees SM slots.  What the
-     * next launch may touch before this one has completed is ordered explicitly below:
-     *   - its MAC chunks read only IR spectra and ring slots of frames already published through
-     *     ring_head (release/acquire), so they stream while this launch's inverse-FFT tail runs;
-     *   - its split-0 CTAs (input block, ring write) and every CTA's partial-row / ticket /
-     *     output writes sit behind griddepcontrol.wait, i.e. after this launch has completed. */
+    /* let the next block's launch become resident as soon as this one frees SM slots */
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     FRAME_STAMP(0);
     if (tid == 0)
@@ -1547,24 +1581,53 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     chunk_range(nq, split, a.splits, sh.bias, c0, c1);
     const uint32_t q0       = qa + c0, q1 = qa + c1;
     const uint32_t n_iter   = (q1 - q0 + QB - 1) / QB;
-    const bool fft_cta      = (split == 0) && (tile == 0);
-    /* the stage holding partition qa goes last in the FFT CTA */
-    const uint32_t shift    = (fft_cta && (n_iter > 1)) ? 1 : 0;
+    const bool split0       = (split == 0);
+    const bool fft_cta      = split0 && (tile == 0);
+    /* Split 0 owns the partitions that need the NEWEST spectra: q = 0 the arriving frame's own
+     * (written by this launch), q = 1 the previous frame's (published near the END of the previous
+     * launch's partition stream, and CTAs of this launch may have become resident long before
+     * that).  The `late` stages holding them go last, newest last:
+     *     stage order  late, late + 1, ..., n_iter - 1, late - 1, ..., 0.                        */
+    const uint32_t late     = split0 ? min(n_iter, (QB == 1) ? 2u : 1u) : 0u;
+    const uint32_t n_main   = split0 ? ((n_iter > 0) ? n_iter - 1 : 0) : n_iter;   /* all but stage 0 */
 
     const float2 *Gt        = d.G + uint64_t(tile) * TB;            /* row r at Gt + r * M */
     const float2 *Xt        = d.ring + uint64_t(tile) * TB;
     const uint32_t row_bytes = TB * uint32_t(sizeof(float2));
     const uint64_t l2_stream = stream_policy();
 
-    /* Stage-ring bookkeeping is incremental (next stage buffer, next position in the chunk, next
-     * ring slot): no integer division inside the streaming loop.  `issued` = stages fetched. */
+    /* Stage-ring bookkeeping is incremental (next stage buffer, next ring slot): no integer
+     * division inside the streaming loop.  `issued` = stages fetched so far. */
     const uint32_t slot_q0  = uint32_t((uint64_t(job.slot0) + q0) % d.S);
-    uint32_t issued = 0, f_s = 0, f_stg = shift;
-    uint32_t f_slot         = slot_q0 + shift * QB;
+    uint32_t issued = 0, f_s = 0;
+    uint32_t f_slot         = slot_q0 + late * QB;
     if (f_slot >= d.S)      f_slot -= d.S;
-    auto issue_next = [&]()
+    auto issue_next = [&]()                     /* thread 0 only */
     {
-        uint32_t q      = q0 + f_stg * QB;
+        uint32_t stg;
+        if (issued < n_iter - late)
+        {
+            stg             = late + issued;
+            if (issued == 0)
+            {
+                /* partitions q >= q0 + late * QB need frames <= t - (q0 + late * QB) */
+                wait_ge<false>(a.ring_head + job.inst, job.tlo - (q0 + late * QB) + 1u, a.error, SPIN_ERR_RING);
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+        }
+        else
+        {
+            stg             = n_iter - 1 - issued;
+            f_slot          = slot_q0 + stg * QB;
+            if (f_slot >= d.S)  f_slot -= d.S;
+            if (stg != 0)
+            {
+                /* the previous frame's spectrum: the previous launch publishes it late */
+                wait_ge<false>(a.ring_head + job.inst, job.tlo - (q0 + stg * QB) + 1u, a.error, SPIN_ERR_RING);
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+        }
+        uint32_t q      = q0 + stg * QB;
         uint32_t rows   = min(QB, q1 - q);
         float2 *g       = stages + size_t(f_s) * 2 * stage_elems;
         float2 *x       = g + stage_elems;
@@ -1576,122 +1639,13 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
             bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s], l2_stream);
         ++issued;
         if (++f_s == NS)    f_s = 0;
-        if (++f_stg == n_iter)
-        {
-            f_stg           = 0;            /* the rotated first stage comes last */
-            f_slot          = slot_q0;
-        }
-        else
-        {
-            f_slot         += QB;
-            if (f_slot >= d.S)  f_slot -= d.S;
-        }
+        f_slot         += QB;
+        if (f_slot >= d.S)  f_slot -= d.S;
     };
 
-    /* prologue: the FFT CTA keeps the last SCR stage buffers as transform scratch (two work
-     * buffers, and the twiddle table when a second buffer can be spared) and must not fetch its
-     * final stage yet -- that one reads the spectrum which is about to be written */
-    /* transform scratch: FFT_STAGES stage buffers for the work buffer(s) (ping-pong when two fit
-     * into one stage buffer), plus one more for the twiddle table when the ring is deep enough */
-    constexpr bool FFT_PP           = (2 * C::WORK <= 2048);                    /* ranks 8..11 */
-    constexpr uint32_t FFT_STAGES   = (C::WORK * (FFT_PP ? 2 : 1) + 2047) / 2048; /* 1, rank 13: 2 */
-    const bool fwd_table    = (NS >= FFT_STAGES + 2) && (uint32_t(C::TW_TOTAL) <= 2 * stage_elems);
-    const uint32_t SCR      = FFT_STAGES + (fwd_table ? 1u : 0u);
-    uint32_t pre            = min(NS, n_iter);
-    if (fft_cta)
-    {
-        /* Its partitions q >= 1 need the spectra of frames <= t - 1.  In steady state they were
-         * published long ago and the first stages are fetched right away; if the previous
-         * launch's split-0 CTA is still at work, fetching waits until after the transform. */
-        pre                 = ((n_iter > 0) && (NS > SCR)) ? min(NS - SCR, n_iter - 1) : 0;
-        if (tid == 0)
-        {
-            uint32_t have;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(a.ring_head + job.inst) : "memory");
-            if (int32_t(have - job.tlo) >= 0)
-            {
-                asm volatile("fence.proxy.async;" ::: "memory");
-                while (issued < pre)
-                    issue_next();
-            }
-        }
-    }
-    else if (tid == 0)
-    {
-        if (n_iter > 0)
-        {
-            /* partitions q >= q0 >= 1 need the spectra of frames <= t - q0; the newest of them may
-             * still be in flight in the previous launch's split-0 CTA */
-            const uint32_t need = job.tlo - q0 + 1u;
-            const uint32_t *hp  = a.ring_head + job.inst;
-            uint32_t have;
-            for (;;)
-            {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(hp) : "memory");
-                if (int32_t(have - need) >= 0)
-                    break;
-                __nanosleep(100);
-            }
-            asm volatile("fence.proxy.async;" ::: "memory");
-        }
-        while (issued < pre)
+    if (tid == 0)
+        while ((issued < NS) && (issued < n_main))
             issue_next();
-    }
-    if (fft_cta)
-    {
-        float2 *scr         = stages + size_t(NS - SCR) * 2 * stage_elems;
-        float2 *wa          = scr, *wb = FFT_PP ? scr + C::WORK : nullptr;
-        const float2 *tw    = a.tw;
-        if (fwd_table)
-        {
-            float2 *tws         = scr + size_t(FFT_STAGES) * 2 * stage_elems;
-            for (uint32_t i = tid; i < uint32_t(C::TW_TOTAL); i += T)
-                tws[i]              = a.tw[i];
-            tw                  = tws;          /* visible after fwd_body's first barrier */
-        }
-        /* The ring keeps one spare slot: slot (-t) mod S was last read two launches ago.  Those
-         * reads are over once every CTA of that launch has bumped stream_done (they may not be
-         * when only the PREVIOUS launch is known to have started).  The input block is the
-         * caller's and final: an early (programmatic) start only ever follows a k_frame. */
-        if (tid == 0)
-        {
-            const uint32_t *dp  = a.stream_done + job.inst;
-            uint32_t have;
-            for (;;)
-            {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(dp) : "memory");
-                if (int32_t(have - a.need_done) >= 0)
-                    break;
-                __nanosleep(100);
-            }
-        }
-        fwd_body<RANK, FFT_PP, int(T)>(wa, wb, job.src, job.spec, a.tw, tw, int(tid));
-        /* generic-proxy global writes -> visible to the TMA (async proxy) reads issued below */
-        __threadfence();
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __syncthreads();
-        if (tid == 0)
-        {
-            /* Publish "frames 0 .. t are in the ring" -- strictly in frame order: the split-0
-             * CTAs of consecutive launches run independently, and a later frame must not be
-             * announced before an earlier one has landed.  (The acquire/release chain also makes
-             * every older spectrum formally visible to whoever acquires the new value.) */
-            uint32_t *hp    = a.ring_head + job.inst;
-            uint32_t have;
-            for (;;)
-            {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(hp) : "memory");
-                if (int32_t(have - job.tlo) >= 0)
-                    break;
-                __nanosleep(100);
-            }
-            const uint32_t head = job.tlo + 1u;
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(hp), "r"(head) : "memory");
-            asm volatile("fence.proxy.async;" ::: "memory");
-            while ((issued < NS) && (issued < n_iter))
-                issue_next();
-        }
-    }
 
     float4 acc[MAC_VPT];
     #pragma unroll
@@ -1699,10 +1653,11 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
         acc[v]      = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float dny       = 0.0f;
 
-    uint32_t c_s = 0, c_par = 0, c_stg = shift;
-    for (uint32_t it = 0; it < n_iter; ++it)
+    uint32_t c_s = 0, c_par = 0, c_n = 0;
+    auto consume = [&]()
     {
-        uint32_t rows   = min(QB, q1 - (q0 + c_stg * QB));
+        const uint32_t stg = (c_n < n_iter - late) ? (late + c_n) : (n_iter - 1 - c_n);
+        uint32_t rows   = min(QB, q1 - (q0 + stg * QB));
         mbar_wait(&full[c_s], c_par);
 
         const float4 *g4 = reinterpret_cast<const float4 *>(stages + size_t(c_s) * 2 * stage_elems);
@@ -1726,12 +1681,72 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
                     dny         = fmaf(g.y, x.y, dny);
             }
         }
-        if (++c_stg == n_iter)  c_stg = 0;
+        ++c_n;
         if (++c_s == NS)        { c_s = 0; c_par ^= 1u; }
+    };
 
+    for (uint32_t it = 0; it < n_main; ++it)
+    {
+        consume();
         __syncthreads();
-        if ((tid == 0) && (issued < n_iter))
+        if ((tid == 0) && (issued < n_main))
             issue_next();
+    }
+
+    if (split0)
+    {
+        if (fft_cta)
+        {
+            /* The input block is the caller's: an earlier launch in the stream may have produced
+             * it (and that launch may still be in its tail while this one streams), so it is read
+             * only once every earlier launch has completed.  That also retires every reader of
+             * ring slot (-t) mod S.  Exception: the host knows the predecessor (STEP_EARLY_SRC). */
+            if (!(a.flags & STEP_EARLY_SRC))
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+            /* every stage buffer is idle here: two work buffers (one at rank 13) + the twiddle table */
+            constexpr bool FFT_PP       = (RANK <= 12);
+            constexpr uint32_t FFT_WORK = C::WORK * (FFT_PP ? 2 : 1);
+            float2 *wa          = stages, *wb = FFT_PP ? stages + C::WORK : nullptr;
+            const float2 *tw    = a.tw;
+            if (FFT_WORK + uint32_t(C::TW_TOTAL) <= NS * 2 * stage_elems)
+            {
+                float2 *tws         = stages + FFT_WORK;
+                for (uint32_t i = tid; i < uint32_t(C::TW_TOTAL); i += T)
+                    tws[i]              = a.tw[i];
+                tw                  = tws;          /* visible after fwd_body's first barrier */
+            }
+            fwd_body<RANK, FFT_PP, int(T)>(wa, wb, job.src, job.spec, a.tw, tw, int(tid));
+            /* generic-proxy global writes -> visible to the TMA (async proxy) reads issued below;
+             * the same fence orders the scratch use of the stage buffers before their refill */
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncthreads();
+            if (tid == 0)
+            {
+                /* Publish "frames 0 .. t are in the ring" -- strictly in frame order (the
+                 * acquire / release chain makes every older spectrum visible to whoever acquires
+                 * the new value). */
+                uint32_t *hp    = a.ring_head + job.inst;
+                wait_ge<false>(hp, job.tlo, a.error, SPIN_ERR_RING);
+                const uint32_t head = job.tlo + 1u;
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(hp), "r"(head) : "memory");
+            }
+        }
+        else if ((tid == 0) && (n_iter > 0))
+        {
+            /* the other bin tiles of split 0 (ranks 12 / 13) learn through ring_head that the
+             * arriving frame's spectrum has landed */
+            wait_ge<false>(a.ring_head + job.inst, job.tlo - q0 + 1u, a.error, SPIN_ERR_RING);
+        }
+        if (n_iter > 0)
+        {
+            if (tid == 0)
+            {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                issue_next();
+            }
+            consume();
+        }
     }
 
     if ((tile == 0) && (tid == 0))
@@ -1744,13 +1759,6 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     /* partial rows, tickets and the output block are shared with the previous launch's tail */
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    /* This CTA is done reading the ring.  Counted only now, after every earlier launch has
-     * completed, so that the counter advances in launch order: stream_done >= (CTAs of launches
-     * 0..L) holds exactly when all of them have finished streaming, however the CTAs of the
-     * launches in flight interleave. */
-    if (tid == 0)
-        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(a.stream_done + job.inst), "r"(1u) : "memory");
-
     const uint32_t rows = rows_per_job(a);
     float2 *yrow    = a.ypart + uint64_t(jobi) * rows * M;
     float4 *yp      = reinterpret_cast<float4 *>(yrow + uint64_t(a.row0 + split) * M + uint64_t(tile) * TB);
@@ -1758,7 +1766,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     for (int v = 0; v < MAC_VPT; ++v)
         __stcg(&yp[tid + v * T], acc[v]);
 
-    /* ticket: the last split of this job to get here finishes the frame */
+    /* ticket: the last CTA of this job to get here finishes the frame */
     __threadfence();
     __syncthreads();
     if (tid == 0)
@@ -1795,71 +1803,72 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
         return;
     }
 
-    /* ---- partition-range shard: sum the partial blocks of all ranks over NVLink ---- */
+    /* ---- partition-range shard: all-to-all sum of the partial blocks over NVLink ---- */
     const uint32_t F        = ra.frame;
+    const uint32_t W        = ra.world, g = ra.grank;
     const uint32_t ch       = job.inst;
     const uint32_t blk      = job.tlo - ra.t0;          /* block number since the ranks connected */
-    const uint32_t par      = blk & 1u;
-    float *slot             = ra.slots_root + ((size_t(par) * ra.world + ra.grank) * ra.channels + ch) * F;
-    uint32_t *arrived       = ra.arrived_root + par * ra.channels + ch;
-    const uint64_t deadline = global_ns() + 2000000000ull;
+    const uint32_t s        = blk % uint32_t(REDUCE_DEPTH);
+    const size_t   slot_of_g = ((size_t(s) * W + g) * ra.channels + ch) * F;    /* same offset in every rank's buffer */
+    const size_t   flag_of_g = (size_t(s) * W + g) * ra.channels + ch;
 
-    if (ra.grank != 0)
+    /* slot s is free on rank p once p has consumed block blk - DEPTH of this channel */
+    if ((tid < W) && (tid != g) && (blk >= uint32_t(REDUCE_DEPTH)))
+        wait_ge<true>(ra.consumed[g] + size_t(tid) * ra.channels + ch, blk - uint32_t(REDUCE_DEPTH) + 1u,
+                      a.error, SPIN_ERR_PEER);
+    __syncthreads();
+
+    float *mine             = ra.slots[g] + slot_of_g;
+    inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, mine, a.tw, tw, false, int(tid));
+    __syncthreads();
+    for (uint32_t i = tid; i < F / 4; i += T)
     {
-        /* the slot pair of this parity is free once root has consumed block blk - 2 */
-        if (tid == 0)
+        const float4 v      = reinterpret_cast<const float4 *>(mine)[i];
+        for (uint32_t p = 0; p < W; ++p)
+            if (p != g)
+                reinterpret_cast<float4 *>(ra.slots[p] + slot_of_g)[i] = v;     /* posted peer stores */
+    }
+    /* the barrier orders every thread's peer stores before thread 0, whose (cumulative)
+     * system-scope fence then publishes the whole block: one fence, then plain flag stores */
+    __syncthreads();
+    if (tid == 0)
+    {
+        __threadfence_system();
+        for (uint32_t p = 0; p < W; ++p)
+            if (p != g)
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(ra.flags[p] + flag_of_g), "r"(blk + 1u) : "memory");
+    }
+    if ((tid < W) && (tid != g))
+    {
+        /* equality on a sequence number: a late block of an earlier round can never satisfy it */
+        const uint32_t *fp  = ra.flags[g] + (size_t(s) * W + tid) * ra.channels + ch;
+        wait_ge<true>(fp, blk + 1u, a.error, SPIN_ERR_PEER);
+    }
+    __syncthreads();
+    {
+        const float *base   = ra.slots[g] + (size_t(s) * W * ra.channels + ch) * F;
+        const size_t gstep  = size_t(ra.channels) * F;
+        for (uint32_t i = tid; i < F / 4; i += T)
         {
-            while (int32_t(ld_acquire_sys(ra.consumed_local + ch) + 1u - blk) < 0)
+            float4 sum          = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (uint32_t p = 0; p < W; ++p)                        /* rank order: bit-identical on every rank */
             {
-                if (global_ns() > deadline) { atomicExch(ra.error, 1u); break; }
-                __nanosleep(200);
+                const float4 v      = __ldcg(reinterpret_cast<const float4 *>(base + p * gstep) + i);
+                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+            if ((reinterpret_cast<uintptr_t>(job.dst) & 15) == 0)
+                reinterpret_cast<float4 *>(job.dst)[i] = sum;
+            else
+            {
+                job.dst[4 * i] = sum.x; job.dst[4 * i + 1] = sum.y; job.dst[4 * i + 2] = sum.z; job.dst[4 * i + 3] = sum.w;
             }
         }
-        __syncthreads();
-        inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, slot, a.tw, tw, false, int(tid));
-        /* the barrier orders every thread's peer stores before thread 0, whose (cumulative)
-         * system-scope release then publishes the whole block: one fence, not one per thread */
-        __syncthreads();
-        if (tid == 0)
-            asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(arrived), "r"(1u) : "memory");
-        return;
-    }
-
-    /* root: own block into slot 0, then gather */
-    inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, slot, a.tw, tw, false, int(tid));
-    if (tid == 0)
-    {
-        while (ld_acquire_sys(arrived) < ra.world - 1u)
-        {
-            if (global_ns() > deadline) { atomicExch(ra.error, 1u); break; }
-            __nanosleep(200);
-        }
     }
     __syncthreads();
-    {
-        const float *base   = ra.slots_root + (size_t(par) * ra.world * ra.channels + ch) * F;
-        const size_t gstep  = size_t(ra.channels) * F;
-        for (uint32_t i = tid; i < F; i += T)
-        {
-            float sum           = base[i];                          /* own block (written above by this CTA) */
-            for (uint32_t g = 1; g < ra.world; ++g)
-                sum                += __ldcg(base + g * gstep + i);     /* peers' blocks, landed in L2 */
-            job.dst[i]          = sum;
-        }
-    }
-    __syncthreads();
-    if (tid == 0)
-    {
-        *arrived            = 0;                        /* peers touch it again only after the stores below */
-        /* ONE system-scope fence, then plain posted stores into every peer's memory: a release
-         * store per peer would pay a full fence each (measured: ~6 us x (world - 1) per block) */
-        __threadfence_system();
-        for (uint32_t g = 1; g < ra.world; ++g)
-        {
-            uint32_t *cp        = ra.consumed_peer[g] + ch;
-            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(cp), "r"(blk + 1u) : "memory");
-        }
-    }
+    if ((tid < W) && (tid != g))
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;"
+                     :: "l"(ra.consumed[tid] + size_t(g) * ra.channels + ch), "r"(blk + 1u) : "memory");
+    FRAME_STAMP(3);
 }
 
 /* ------------------------------------------------------------------------------------------- */

@@ -108,17 +108,9 @@ def _fused_worker(rank, world, port, result):
     L = 300 * F - 17
     irs = [synth.decaying_ir(c, L) for c in range(ch)]
     x = np.stack([synth.noise(c, blocks * F) for c in range(ch)])
-    p_lo, p_hi, t_lo, t_hi = sharding.partition_shard(L, F, world, rank)
-    b = pkg.ConvolverBatch(ch, rank)
-    for c in range(ch):
-        assert b.init(c, irs[c][t_lo:t_hi], R, 0.0, part_offset=p_lo)
-
-    # exchange the IPC handles of the exchange buffers (any transport; here NCCL all_gather)
-    mine = torch.tensor(list(b.reduce_prepare(rank, world)), dtype=torch.uint8, device="cuda")
-    every = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(every, mine)
-    b.reduce_connect([bytes(t.cpu().tolist()) for t in every])
-    dist.barrier()
+    conv = sharding.PartitionShardedConvolver(pkg, ch, R, rank, reduce="fused")
+    assert conv.init(irs)               # slices the IRs, exchanges the IPC handles, connects
+    b = conv.batch
 
     src = torch.from_numpy(x).cuda()
     dst = torch.zeros_like(src)
@@ -128,34 +120,36 @@ def _fused_worker(rank, world, port, result):
     b.sync()
     timed_out = b.reduce_timed_out()
     dist.barrier()
+    # EVERY rank ends with the summed block (all-to-all), bit-identical across ranks
+    out = dst.cpu().numpy()
     err = 0.0
-    if rank == 0:
-        out = dst.cpu().numpy()
-        for c in range(ch):
-            want = direct_convolve(x[c], irs[c], blocks * F)
-            err = max(err, float(np.max(np.abs(out[c] - want)) / np.max(np.abs(want))))
-    untouched = bool((dst == 0).all().item()) if rank != 0 else True
-    flags = torch.tensor([float(timed_out), float(not untouched)], device="cuda")
+    for c in range(ch):
+        want = direct_convolve(x[c], irs[c], blocks * F)
+        err = max(err, float(np.max(np.abs(out[c] - want)) / np.max(np.abs(want))))
+    ref0 = dst.clone()
+    dist.broadcast(ref0, src=0)
+    differs = float(not torch.equal(ref0, dst))
+    flags = torch.tensor([float(timed_out), differs, err], device="cuda", dtype=torch.float64)
     dist.all_reduce(flags, op=dist.ReduceOp.MAX)
-    b.reduce_disconnect()
-    b.close()
+    conv.close()
     if rank == 0:
-        result.put((err, float(flags[0].item()), float(flags[1].item())))
+        result.put((float(flags[2].item()), float(flags[0].item()), float(flags[1].item())))
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_two_gpu_fused_nvlink_reduce_of_partition_shards():
-    """BASELINE config 5 in miniature without a collective call: the launch tails sum the partial
-    output blocks over NVLink peer memory (b200conv_reduce_*); rank 0 receives the full result."""
+    """BASELINE config 5 in miniature without a collective call: the launch tails exchange the partial
+    output blocks over NVLink peer memory (b200conv_reduce_*, all-to-all); every rank ends with the
+    same summed block."""
     ctx = mp.get_context("spawn")
     result = ctx.Queue()
     procs = [ctx.Process(target=_fused_worker, args=(r, 2, 29651, result)) for r in range(2)]
     for p in procs:
         p.start()
-    err, timed_out, touched = result.get(timeout=600)
+    err, timed_out, differs = result.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert timed_out == 0.0 and touched == 0.0
+    assert timed_out == 0.0 and differs == 0.0
     assert err <= 1e-5

@@ -358,9 +358,9 @@ def test_planar_host_api_strided_views(pkg):
                                                 (1500, 6000, 60, 11),      # more CTAs than the device holds at once
                                                 (700, 40000, 40, 10)])
 def test_overlapped_launches_are_bit_identical_to_serialised(pkg, n, taps, frames, rank):
-    """Back-to-back blocks overlap on the GPU (programmatic dependent launch, ring_head /
-    stream_done hand-shakes).  Any ordering bug would change bits: the overlapped run must equal
-    the fully serialised one exactly, block for block."""
+    """Back-to-back blocks overlap on the GPU (programmatic dependent launch, ring_head
+    hand-shake).  Any ordering bug would change bits: the overlapped run must equal the fully
+    serialised one exactly, block for block."""
     torch = pytest.importorskip("torch")
     F = 1 << (rank - 1)
     irs = [synth.decaying_ir(c, taps) for c in range(min(n, 4))]
@@ -724,3 +724,80 @@ def test_overlapped_launch_soak(pkg):
         outs.append(dst.cpu().numpy())
         b.close()
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("n,taps,rank", [(8, 30000, 11), (64, 200000, 11), (3, 50000, 13), (16, 9000, 9)])
+def test_cascaded_batches_on_one_stream(pkg, n, taps, rank):
+    """Two batches cascaded on ONE caller stream (B.src == A.dst), launched back to back: B's launch
+    may become resident while A's is still in its inverse-transform tail (programmatic dependent
+    launch), so B must not read its input before every earlier launch has completed.  The
+    overlapped run must equal the serialised one bit for bit, and be the right answer."""
+    torch = pytest.importorskip("torch")
+    F = 1 << (rank - 1)
+    frames = 48
+    ira = [synth.decaying_ir(c, taps) for c in range(2)]
+    irb = [synth.decaying_ir(10 + c, taps // 2 + 7) for c in range(2)]
+    g = torch.Generator(device="cuda").manual_seed(11)
+    src = torch.rand((n, frames * F), generator=g, device="cuda") * 2 - 1
+    st = torch.cuda.Stream()
+    outs = []
+    for pdl in (1, 0):
+        A, B = pkg.ConvolverBatch(n, 0), pkg.ConvolverBatch(n, 0)
+        for b, irs in ((A, ira), (B, irb)):
+            b.set_option("pdl", pdl)
+            for c in range(n):
+                assert b.init(c, irs[c % 2], rank, 0.0)
+        mid = torch.zeros((n, F), device="cuda")        # ONE block, rewritten every step
+        dst = torch.zeros_like(src)
+        torch.cuda.synchronize()
+        for i in range(frames):
+            A.process_device(mid.data_ptr(), src.data_ptr() + 4 * i * F, frames * F, F, st.cuda_stream,
+                             dst_stride=F)
+            B.process_device(dst.data_ptr() + 4 * i * F, mid.data_ptr(), F, F, st.cuda_stream,
+                             dst_stride=frames * F)
+        st.synchronize()
+        outs.append(dst.cpu().numpy())
+        A.close()
+        B.close()
+    assert np.array_equal(outs[0], outs[1])
+    x = src[0].cpu().numpy().astype(np.float64)
+    want = np.convolve(np.convolve(x, ira[0].astype(np.float64))[:frames * F], irb[0].astype(np.float64))[:frames * F]
+    assert rel_err(outs[0][0], want) <= TOL
+
+
+@pytest.mark.parametrize("n,taps,rank", [(8, 20000, 11), (64, 100000, 10)])
+def test_batch_fed_its_own_previous_output(pkg, n, taps, rank):
+    """Feedback: block t's input is block t-1's OUTPUT buffer (same stream, back to back).  The
+    launch of block t must see the finished output of block t-1."""
+    torch = pytest.importorskip("torch")
+    F = 1 << (rank - 1)
+    frames = 40
+    irs = [0.5 * synth.decaying_ir(c, taps) for c in range(2)]
+    g = torch.Generator(device="cuda").manual_seed(12)
+    first = torch.rand((n, F), generator=g, device="cuda") * 2 - 1
+    outs = []
+    for pdl in (1, 0):
+        b = pkg.ConvolverBatch(n, 0)
+        b.set_option("pdl", pdl)
+        for c in range(n):
+            assert b.init(c, irs[c % 2], rank, 0.0)
+        buf = torch.zeros((n, (frames + 1) * F), device="cuda")
+        buf[:, :F] = first
+        torch.cuda.synchronize()
+        for i in range(frames):
+            b.process_device(buf.data_ptr() + 4 * (i + 1) * F, buf.data_ptr() + 4 * i * F, (frames + 1) * F, F)
+        b.sync()
+        outs.append(buf.cpu().numpy())
+        b.close()
+    assert np.array_equal(outs[0], outs[1])
+    # float64 model of the recursion for channel 0
+    h = irs[0].astype(np.float64)
+    x = np.zeros(frames * F)
+    cur = first[0].cpu().numpy().astype(np.float64)
+    got = outs[0][0]
+    hist = np.zeros(0)
+    for i in range(3):                                  # three blocks are enough to pin the data flow
+        hist = np.concatenate([hist, cur])
+        y = np.convolve(hist, h)[i * F:(i + 1) * F]
+        assert rel_err(got[(i + 1) * F:(i + 2) * F], y) <= 10 * TOL
+        cur = got[(i + 1) * F:(i + 2) * F].astype(np.float64)
