@@ -50,6 +50,28 @@ typedef struct b200conv_state
     uint64_t frames;        /* complete frames received since init                                   */
 } b200conv_state_t;
 
+/* The 18 fields lsp::dspu::Convolver::dump writes (reference src/main/util/Convolver.cpp:315-337),
+ * with the values the REFERENCE object would hold after the same init / process history:
+ *   scalars   nDataBufferSize = (bins + 1) F (:137), nDirectSize = min(count, 128) (:141), nFrameSize,
+ *             nFrameOff (:140, :298-311), nConvSize, nLevels (:165-181), nBlocks (:184-197),
+ *             nBlocksDone (:198, :268-285: reset at a frame start, raised to
+ *             min(nBlocks, size_t(nBlkInit + fBlkCoef * sub_id)) at every 128-sample boundary),
+ *             nRank, nBlkInit, fBlkCoef (:199-210) -- all reproduced arithmetically (the engine itself
+ *             has no raising levels and no load spreading);
+ *   pointers  the reference reports slices of its host slab; the engine reports the DEVICE buffer
+ *             that plays the same part: vDataBuffer -> pending block, vFrame -> frame in progress,
+ *             vConvBuffer -> partial-spectrum scratch, vTaskData -> input-spectrum ring,
+ *             vConvData -> folded IR spectra, vDirectData -> taps [0, F), vData -> the IR spectra
+ *             allocation.  All NULL / 0 when the instance is not initialised (construct(), :46-69). */
+typedef struct b200conv_dump
+{
+    const void *vDataBuffer, *vFrame, *vConvBuffer, *vTaskData, *vConvData, *vDirectData;
+    size_t      nDataBufferSize, nDirectSize, nFrameSize, nFrameOff, nConvSize;
+    size_t      nLevels, nBlocks, nBlocksDone, nRank, nBlkInit;
+    float       fBlkCoef;
+    const void *vData;
+} b200conv_dump_t;
+
 /* Counters since create (or the last b200conv_reset_stats). */
 typedef struct b200conv_stats
 {
@@ -91,6 +113,12 @@ int     b200conv_init(b200conv_batch_t *h, size_t idx, const float *data, size_t
 int     b200conv_init_range(b200conv_batch_t *h, size_t idx, const float *data, size_t count,
                             size_t rank, float phase, size_t part_offset);
 
+/* Convolver::init for instance `idx` with the SAME impulse response and rank as the initialised
+ * instance `src_idx` (many channels through one reverb): the device IR spectra are shared, only the
+ * input-spectrum ring and the frame buffers are new.  The lender cannot be destroyed or
+ * re-initialised while it is borrowed from (B200CONV_ERR_STATE). */
+int     b200conv_init_shared(b200conv_batch_t *h, size_t idx, size_t src_idx, float phase);
+
 /* Convolver::destroy for instance `idx` (Convolver.cpp:71-75); idempotent. */
 int     b200conv_destroy(b200conv_batch_t *h, size_t idx);
 
@@ -120,7 +148,8 @@ int     b200conv_process_device(b200conv_batch_t *h, float *dst, const float *sr
 int     b200conv_process_device2(b200conv_batch_t *h, float *dst, size_t dst_stride,
                                  const float *src, size_t src_stride, size_t count, void *stream);
 
-/* Waits for everything enqueued on the batch's own stream. */
+/* Waits for everything the batch has enqueued (own stream, and the latest call on a caller's stream).
+ * Returns B200CONV_ERR_STATE if a bounded in-kernel wait has given up since the batch was created. */
 int     b200conv_sync(b200conv_batch_t *h);
 
 /* ---- partition-range sharding across GPUs: fused NVLink reduce ---------------------------- */
@@ -150,6 +179,7 @@ size_t  b200conv_data_size(const b200conv_batch_t *h, size_t idx);
 size_t  b200conv_rank(const b200conv_batch_t *h, size_t idx);
 size_t  b200conv_instances(const b200conv_batch_t *h);
 int     b200conv_get_state(const b200conv_batch_t *h, size_t idx, b200conv_state_t *st);
+int     b200conv_get_dump(const b200conv_batch_t *h, size_t idx, b200conv_dump_t *out);
 int     b200conv_get_stats(const b200conv_batch_t *h, b200conv_stats_t *st);
 int     b200conv_reset_stats(b200conv_batch_t *h);
 
@@ -218,15 +248,56 @@ int     b200conv_convolve(int device, float *dst, size_t dst_stride, const float
 
 /* Full linear convolution of `count` signals with ONE filter, host buffers:
  *     dst[i][0 .. nx + nh - 1) = src[i][0 .. nx) (*) h[0 .. nh)
- * The operation of SyncChirpProcessor::do_linear_convolution(s) (reference
- * src/main/util/SyncChirpProcessor.cpp:1374-1508: O(P^2) partition pairs of fastconv_parse +
- * fastconv_apply per channel), run as ONE batched multi-frame pass of the convolver engine:
- * the filter is the impulse response, the signal zero-padded by nh - 1 is the input.
+ * The arithmetic core of SyncChirpProcessor::do_linear_convolution(s) without its padding / align
+ * layout (that is b200conv_chirp_linear_convolutions below), run as ONE batched multi-frame pass of
+ * the convolver engine: the filter is the impulse response (one set of spectra shared by all
+ * signals), the signal zero-padded by nh - 1 is the input.
  * `rank` as in b200conv_init (partition = 2^(rank-1) samples); rows are `*_stride` floats apart.
  * Synchronous. */
 int     b200conv_linear_convolve(int device, float *dst, size_t dst_stride, const float *src,
                                  size_t src_stride, size_t nx, size_t count, const float *h,
                                  size_t nh, size_t rank);
+
+/* SyncChirpProcessor::do_linear_convolutions(Sample **data, size_t *offset, size_t nchannels,
+ * size_t partSizeLimit) on plain arrays (reference src/main/util/SyncChirpProcessor.cpp:1374-1508):
+ * every channel's recording, from its offset on, is convolved with the processor's inverse filter
+ * in partitions of nPartitionSize samples.
+ *
+ *   b200conv_chirp_plan   calculateConvolutionPartitionSize (:1224-1250) and
+ *                         calculateConvolutionParameters (:1299-1331): partition size = the power of
+ *                         two >= min(part_size_limit, 32768) (0 means 32768), rank = log2 + 1; per
+ *                         channel vPartitions = max(in_len, inverse_len) / partition + 1,
+ *                         vPaddedLengths, vInversePrepends, vConvLengths = 2 * padded, vAlignOffsets;
+ *                         allocation_size = the largest vConvLengths = samples per result channel.
+ *                         The per-channel arrays (nchannels entries each) may be NULL.
+ *   b200conv_chirp_linear_convolutions
+ *                         inputs[ch] = data[ch]->channel(0, offset[ch]) (HOST), in_len[ch] =
+ *                         data[ch]->length() - offset[ch]; result = pConvResult, [nchannels] rows of
+ *                         result_stride >= allocation_size floats (HOST), zeroed here and then filled
+ *                         like the reference's: the convolution of the tail-padded input with the
+ *                         PREPEND-padded inverse filter lands at vAlignOffsets[ch] (:1499), and the
+ *                         first vConvLengths[ch] samples of the row are multiplied by `scale`
+ *                         (= fConvScale / fs^2; dsp::mul_k2 at :1508 starts at index 0).  Null
+ *                         partitions (:1457-1460, :1476-1479) contribute nothing either way.
+ *                         Runs as ONE batched multi-frame pass of the convolver engine; channels of
+ *                         equal padded length share one set of filter spectra.  Partition sizes
+ *                         below 128 (rank < 8) are not supported (B200CONV_ERR_ARG).  Synchronous. */
+typedef struct b200conv_chirp_plan
+{
+    size_t  partition_size;     /* sConvParams.nPartitionSize */
+    size_t  conv_rank;          /* sConvParams.nConvRank      */
+    size_t  image;              /* sConvParams.nImage (the reference's image size, informative) */
+    size_t  allocation_size;    /* sConvParams.nAllocationSize */
+} b200conv_chirp_plan_t;
+
+int     b200conv_chirp_plan(b200conv_chirp_plan_t *plan, size_t *partitions, size_t *padded,
+                            size_t *prepends, size_t *conv_lengths, size_t *align_offsets,
+                            const size_t *in_len, size_t nchannels, size_t inverse_len,
+                            size_t part_size_limit);
+int     b200conv_chirp_linear_convolutions(int device, float *result, size_t result_stride,
+                                           const float *const *inputs, const size_t *in_len,
+                                           size_t nchannels, const float *inverse, size_t inverse_len,
+                                           size_t part_size_limit, float scale);
 
 /* ---- Equalizer, FIR / FFT modes ("next" row f2 of the scope table) --------------------------- */
 

@@ -32,6 +32,14 @@ class State(ctypes.Structure):
                 ("bins", _SZ), ("partitions", _SZ), ("part_offset", _SZ), ("frames", ctypes.c_uint64)]
 
 
+class Dump(ctypes.Structure):
+    """b200conv_dump_t: the 18 fields of Convolver::dump (Convolver.cpp:315-337), in its order."""
+    _fields_ = ([(n, _VP) for n in ("vDataBuffer", "vFrame", "vConvBuffer", "vTaskData", "vConvData", "vDirectData")]
+                + [(n, _SZ) for n in ("nDataBufferSize", "nDirectSize", "nFrameSize", "nFrameOff", "nConvSize",
+                                      "nLevels", "nBlocks", "nBlocksDone", "nRank", "nBlkInit")]
+                + [("fBlkCoef", ctypes.c_float), ("vData", _VP)])
+
+
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("launches", "frames", "h2d_bytes", "d2h_bytes",
                                                "mac_launches", "mac_algo_bytes")]
@@ -70,6 +78,7 @@ _SIGNATURES = {
     "b200conv_free": (None, [_VP]),
     "b200conv_init": (ctypes.c_int, [_VP, _SZ, _FP, _SZ, _SZ, ctypes.c_float]),
     "b200conv_init_range": (ctypes.c_int, [_VP, _SZ, _FP, _SZ, _SZ, ctypes.c_float, _SZ]),
+    "b200conv_init_shared": (ctypes.c_int, [_VP, _SZ, _SZ, ctypes.c_float]),
     "b200conv_destroy": (ctypes.c_int, [_VP, _SZ]),
     "b200conv_process": (ctypes.c_int, [_VP, ctypes.POINTER(_FP), ctypes.POINTER(_FP), _SZ]),
     "b200conv_process_planar": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ]),
@@ -84,6 +93,7 @@ _SIGNATURES = {
     "b200conv_rank": (_SZ, [_VP, _SZ]),
     "b200conv_instances": (_SZ, [_VP]),
     "b200conv_get_state": (ctypes.c_int, [_VP, _SZ, ctypes.POINTER(State)]),
+    "b200conv_get_dump": (ctypes.c_int, [_VP, _SZ, ctypes.POINTER(Dump)]),
     "b200conv_get_stats": (ctypes.c_int, [_VP, ctypes.POINTER(Stats)]),
     "b200conv_reset_stats": (ctypes.c_int, [_VP]),
     "b200conv_set_profiling": (ctypes.c_int, [_VP, ctypes.c_int]),
@@ -96,6 +106,9 @@ _SIGNATURES = {
     "b200conv_fastconv_restore": (ctypes.c_int, [ctypes.c_int, _VP, _VP, _SZ, _SZ, _VP]),
     "b200conv_convolve": (ctypes.c_int, [ctypes.c_int, _VP, _SZ, _VP, _SZ, _VP, _SZ, _SZ, _SZ, _SZ, _VP]),
     "b200conv_linear_convolve": (ctypes.c_int, [ctypes.c_int, _VP, _SZ, _VP, _SZ, _SZ, _SZ, _VP, _SZ, _SZ]),
+    "b200conv_chirp_plan": (ctypes.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, ctypes.POINTER(_SZ), _SZ, _SZ, _SZ]),
+    "b200conv_chirp_linear_convolutions": (ctypes.c_int, [ctypes.c_int, _VP, _SZ, ctypes.POINTER(_FP),
+                                                            ctypes.POINTER(_SZ), _SZ, _FP, _SZ, _SZ, ctypes.c_float]),
     "b200conv_eq_create": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_int, _SZ, _SZ]),
     "b200conv_eq_free": (None, [_VP]),
     "b200conv_eq_set_kernel": (ctypes.c_int, [_VP, _SZ, _FP, ctypes.c_int]),
@@ -152,6 +165,14 @@ class ConvolverBatch:
         False only on allocation failure (previous state kept), like the reference."""
         data = np.ascontiguousarray(data, dtype=np.float32)
         rc = lib().b200conv_init_range(self._h, idx, _ptr(data), data.size, rank, phase, part_offset)
+        if rc == ERR_NOMEM:
+            return False
+        _check(rc)
+        return True
+
+    def init_shared(self, idx, src_idx, phase=0.0):
+        """Instance ``idx`` gets the same impulse response as ``src_idx`` and shares its device spectra."""
+        rc = lib().b200conv_init_shared(self._h, idx, src_idx, phase)
         if rc == ERR_NOMEM:
             return False
         _check(rc)
@@ -238,6 +259,12 @@ class ConvolverBatch:
         st = State()
         _check(lib().b200conv_get_state(self._h, idx, ctypes.byref(st)))
         return {n: int(getattr(st, n)) for n, _ in State._fields_}
+
+    def dump(self, idx):
+        """The fields ``Convolver::dump`` writes, as a dict in the reference's order."""
+        d = Dump()
+        _check(lib().b200conv_get_dump(self._h, idx, ctypes.byref(d)))
+        return {n: getattr(d, n) for n, _ in Dump._fields_}
 
     def stats(self):
         st = Stats()
@@ -345,6 +372,39 @@ def linear_convolve(src, h, rank=11, device=0):
     _check(lib().b200conv_linear_convolve(device, out.ctypes.data, out.shape[1], src.ctypes.data, nx, nx,
                                           count, h.ctypes.data, h.size, rank))
     return out[0] if one else out
+
+
+class ChirpPlan(ctypes.Structure):
+    _fields_ = [(n, _SZ) for n in ("partition_size", "conv_rank", "image", "allocation_size")]
+
+
+def chirp_plan(in_len, inverse_len, part_size_limit):
+    """``calculateConvolutionPartitionSize`` + ``calculateConvolutionParameters``
+    (SyncChirpProcessor.cpp:1224-1250, 1299-1331); no device needed."""
+    n = len(in_len)
+    plan = ChirpPlan()
+    arrs = [(_SZ * n)() for _ in range(5)]
+    _check(lib().b200conv_chirp_plan(ctypes.byref(plan), *[ctypes.cast(a, _VP) for a in arrs],
+                                     (_SZ * n)(*in_len), n, inverse_len, part_size_limit))
+    out = {k: int(getattr(plan, k)) for k, _ in ChirpPlan._fields_}
+    for k, a in zip(("partitions", "padded", "prepends", "conv_lengths", "align_offsets"), arrs):
+        out[k] = list(a)
+    return out
+
+
+def chirp_linear_convolutions(inputs, inverse, part_size_limit=0, scale=1.0, device=0):
+    """``SyncChirpProcessor::do_linear_convolutions`` on plain arrays: ``inputs[ch]`` is channel
+    ``ch``'s recording from its offset on; returns ``[nchannels][allocation_size]`` float32."""
+    inputs = [np.ascontiguousarray(x, dtype=np.float32) for x in inputs]
+    inverse = np.ascontiguousarray(inverse, dtype=np.float32)
+    n = len(inputs)
+    lens = [x.size for x in inputs]
+    plan = chirp_plan(lens, inverse.size, part_size_limit)
+    res = np.empty((n, plan["allocation_size"]), dtype=np.float32)
+    _check(lib().b200conv_chirp_linear_convolutions(
+        device, res.ctypes.data, res.shape[1], (_FP * n)(*[_ptr(x) for x in inputs]), (_SZ * n)(*lens), n,
+        _ptr(inverse), inverse.size, part_size_limit, scale))
+    return res
 
 
 class EqualizerBatch:

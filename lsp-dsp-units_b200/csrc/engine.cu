@@ -24,6 +24,7 @@
 using namespace b200conv;
 
 extern "C" int b200conv_reduce_disconnect(b200conv_batch_t *b);
+extern "C" int b200conv_init_shared(b200conv_batch_t *b, size_t idx, size_t src_idx, float phase);
 
 /* The C ABI must not leak C++ exceptions: the entry points that allocate host containers run
  * their body through a guarded shim (end of file). */
@@ -376,6 +377,41 @@ static cudaError_t launch_frame_r(const StepArgs &a, const MacPlan &p, uint32_t 
     return cudaLaunchKernelEx(&cfg, k_frame<RANK>, a, p.sh, tickets, ra);
 }
 
+/* the job-list form (general path): no programmatic serialisation, no cross-GPU reduce */
+template <int RANK>
+static cudaError_t launch_frame_gen_r(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
+                                      cudaStream_t st)
+{
+    static size_t attr_smem[MAX_DEVICES] = { 0 };
+    int dev = current_device();
+    if (p.smem > attr_smem[dev])
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_frame<RANK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem));
+        if (e != cudaSuccess)
+            return e;
+        attr_smem[dev] = p.smem;
+    }
+    ReduceArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    k_frame<RANK, true><<<dim3(jobs * p.splits, p.tiles), p.threads, p.smem, st>>>(a, p.sh, tickets, ra);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_frame_gen(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
+                                    cudaStream_t st)
+{
+    switch (a.rank)
+    {
+        case 8:  return launch_frame_gen_r<8>(a, p, jobs, tickets, st);
+        case 9:  return launch_frame_gen_r<9>(a, p, jobs, tickets, st);
+        case 10: return launch_frame_gen_r<10>(a, p, jobs, tickets, st);
+        case 11: return launch_frame_gen_r<11>(a, p, jobs, tickets, st);
+        case 12: return launch_frame_gen_r<12>(a, p, jobs, tickets, st);
+        case 13: return launch_frame_gen_r<13>(a, p, jobs, tickets, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 static cudaError_t launch_frame(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
                                 const ReduceArgs &ra, bool pdl, cudaStream_t st)
 {
@@ -441,15 +477,22 @@ struct Instance
     size_t      q_lo        = 0;
     size_t      S           = 0;
     size_t      off         = 0;        /* nFrameOff */
+    size_t      off0        = 0;        /* nFrameOff right after init (from phase) */
     uint64_t    frames      = 0;
     bool        pend_valid  = false;
     float2     *G           = nullptr;
     float2     *ring        = nullptr;
     float      *aux         = nullptr;  /* cur | pend | head, F floats each */
+    long        g_owner     = -1;       /* >= 0: G belongs to that instance (b200conv_init_shared) */
+    size_t      g_sharers   = 0;        /* instances borrowing this one's G */
 };
 
-static const size_t JOB_RING = size_t(1) << 15;
+static const size_t JOB_RING_MAX = size_t(1) << 15;    /* job upload ring: 64 entries per instance, within these bounds */
+static const size_t JOB_RING_MIN = size_t(1) << 10;
+static const size_t JOB_DIRECT   = 64;                  /* up to this many jobs a step the kernels read the
+                                                           page-locked list in place (no upload copy)        */
 static const size_t RING_SPARE = 8;
+static const size_t PART_MAX   = 1024;                  /* samples one P1 / P2 segment of a fused step answers */
 
 struct b200conv_batch
 {
@@ -474,9 +517,15 @@ struct b200conv_batch
     float2                 *ypart       = nullptr;
     size_t                  ypart_bytes = 0;
 
-    Job                    *h_jobs      = nullptr;  /* pinned */
+    Job                    *h_jobs      = nullptr;  /* page-locked, device-mapped */
+    Job                    *h_jobs_dev  = nullptr;  /* ... its device alias */
     Job                    *d_jobs      = nullptr;
+    size_t                  job_cap     = 0;
     size_t                  job_pos     = 0;
+    /* general-path scratch, sized once at create: process() never allocates */
+    std::vector<size_t>     g_pos;
+    std::vector<Job>        g_jobs, g_fft, g_mac, g_part;
+    bool                    uniform_stale = false;  /* instances advanced one by one: t_delta must be refreshed */
 
     float                  *h_in = nullptr, *h_out = nullptr;   /* pinned staging */
     float                  *d_in = nullptr, *d_out = nullptr;
@@ -607,7 +656,7 @@ static int check_device_error(Batch *b)
 
 static void free_instance_buffers(Instance &in)
 {
-    if (in.G)       cudaFree(in.G);
+    if (in.G && (in.g_owner < 0))   cudaFree(in.G);
     if (in.ring)    cudaFree(in.ring);
     if (in.aux)     cudaFree(in.aux);
     in.G = nullptr; in.ring = nullptr; in.aux = nullptr;
@@ -709,9 +758,9 @@ static int attach_park(Batch *b, StepArgs &a, size_t jobs, cudaStream_t st)
 /* Reserves `count` consecutive slots of the job upload ring and returns their index. */
 static int reserve_jobs(Batch *b, size_t count, cudaStream_t st, size_t *pos)
 {
-    if (count > JOB_RING)
+    if (count > b->job_cap)
         return fail(B200CONV_ERR_ARG, "job list too long (%zu)", count);
-    if (b->job_pos + count > JOB_RING)
+    if (b->job_pos + count > b->job_cap)
     {
         CU(cudaStreamSynchronize(st));      /* everything queued from the ring has been consumed */
         b->job_pos  = 0;
@@ -784,6 +833,11 @@ static int create_impl(b200conv_batch_t **out, int device, size_t instances)
     b->inst.resize(instances);
     b->h_desc.resize(instances);
     b->h_ring_head.assign(instances, 0);
+    b->g_pos.assign(instances, 0);
+    b->g_jobs.reserve(instances);
+    b->g_fft.reserve(instances);
+    b->g_mac.reserve(instances);
+    b->g_part.reserve(instances);
     memset(b->h_desc.data(), 0, instances * sizeof(InstDesc));
 
     ENTER_DEVICE(b);
@@ -800,8 +854,13 @@ static int create_impl(b200conv_batch_t **out, int device, size_t instances)
         CU_BRK(cudaEventCreateWithFlags(&b->ev_last, cudaEventDisableTiming));
         CU_BRK(cudaMalloc(&b->d_desc, instances * sizeof(InstDesc)));
         CU_BRK(cudaMalloc(&b->d_active, instances * sizeof(uint32_t)));
-        CU_BRK(cudaMallocHost(&b->h_jobs, JOB_RING * sizeof(Job)));
-        CU_BRK(cudaMalloc(&b->d_jobs, JOB_RING * sizeof(Job)));
+        b->job_cap = 64 * instances;
+        if (b->job_cap < JOB_RING_MIN)  b->job_cap = JOB_RING_MIN;
+        if (b->job_cap > JOB_RING_MAX)  b->job_cap = JOB_RING_MAX;
+        if (b->job_cap < 3 * instances) b->job_cap = 3 * instances;    /* one unfused step: three lists */
+        CU_BRK(cudaHostAlloc(&b->h_jobs, b->job_cap * sizeof(Job), cudaHostAllocMapped | cudaHostAllocPortable));
+        CU_BRK(cudaHostGetDevicePointer(&b->h_jobs_dev, b->h_jobs, 0));
+        CU_BRK(cudaMalloc(&b->d_jobs, b->job_cap * sizeof(Job)));
         CU_BRK(cudaMemset(b->d_desc, 0, instances * sizeof(InstDesc)));
         CU_BRK(cudaMalloc(&b->d_tickets, instances * sizeof(uint32_t)));
         CU_BRK(cudaMemset(b->d_tickets, 0, instances * sizeof(uint32_t)));
@@ -866,8 +925,13 @@ extern "C" int b200conv_destroy(b200conv_batch_t *b, size_t idx)
     Instance &in = b->inst[idx];
     if (!in.active)
         return B200CONV_OK;
+    if (in.g_sharers > 0)
+        return fail(B200CONV_ERR_STATE, "instance %zu lends its IR spectra to %zu other instance(s): destroy those first",
+                    idx, in.g_sharers);
     ENTER_DEVICE(b);
     CU(quiesce(b));
+    if (in.g_owner >= 0)
+        b->inst[size_t(in.g_owner)].g_sharers -= 1;
     free_instance_buffers(in);
     in = Instance();
     rebuild_tables(b);
@@ -894,6 +958,10 @@ static int init_range_impl(b200conv_batch_t *b, size_t idx, const float *data, s
         if ((i != idx) && b->inst[i].active && (b->inst[i].rank != rank))
             return fail(B200CONV_ERR_ARG, "all instances of a batch share one rank (%zu active, %zu requested)",
                         b->inst[i].rank, rank);
+
+    if (b->inst[idx].g_sharers > 0)
+        return fail(B200CONV_ERR_STATE, "instance %zu lends its IR spectra to %zu other instance(s): destroy those first",
+                    idx, b->inst[idx].g_sharers);
 
     ENTER_DEVICE(b);
     CU(quiesce(b));                 /* the tables and buffers below may be in use by queued launches */
@@ -945,9 +1013,9 @@ static int init_range_impl(b200conv_batch_t *b, size_t idx, const float *data, s
         StepArgs a  = base_args(b);
         a.rank      = uint32_t(rank);
         a.tw        = b->tw[rank];
-        for (size_t p0 = 0; p0 < bins; p0 += JOB_RING)
+        for (size_t p0 = 0; p0 < bins; p0 += b->job_cap)
         {
-            size_t cnt  = (bins - p0 < JOB_RING) ? bins - p0 : JOB_RING;
+            size_t cnt  = (bins - p0 < b->job_cap) ? bins - p0 : b->job_cap;
             size_t pos  = 0;
             if ((rc = reserve_jobs(b, cnt, st, &pos)) != B200CONV_OK) break;
             for (size_t p = 0; p < cnt; ++p)
@@ -986,6 +1054,8 @@ static int init_range_impl(b200conv_batch_t *b, size_t idx, const float *data, s
 
     /* swap in (Convolver.cpp:108-142) */
     Instance &in    = b->inst[idx];
+    if (in.g_owner >= 0)
+        b->inst[size_t(in.g_owner)].g_sharers -= 1;
     free_instance_buffers(in);
     in              = fresh;
     in.active       = true;
@@ -998,6 +1068,7 @@ static int init_range_impl(b200conv_batch_t *b, size_t idx, const float *data, s
     in.S            = S;
     float fo        = phase * float(F);                     /* Convolver.cpp:140, fp32 */
     in.off          = ((fo > 0.0f) && (fo < 1.8e19f)) ? (size_t(fo) % F) : 0;
+    in.off0         = in.off;
     in.frames       = 0;
     in.pend_valid   = false;
     rebuild_tables(b);
@@ -1008,6 +1079,71 @@ extern "C" int b200conv_init(b200conv_batch_t *b, size_t idx, const float *data,
                              size_t rank, float phase)
 {
     return b200conv_init_range(b, idx, data, count, rank, phase, 0);
+}
+
+/* Convolver::init for instance `idx` with the SAME impulse response (and rank) as the initialised
+ * instance `src_idx`: the device spectra are shared, only the input-spectrum ring and the frame
+ * buffers are new.  Many channels through one reverb pay for one set of IR spectra. */
+static int init_shared_impl(b200conv_batch_t *b, size_t idx, size_t src_idx, float phase)
+{
+    if ((b == nullptr) || (idx >= b->n) || (src_idx >= b->n) || (idx == src_idx))
+        return fail(B200CONV_ERR_ARG, "b200conv_init_shared: bad handle or index");
+    const Instance &from = b->inst[(b->inst[src_idx].g_owner >= 0) ? size_t(b->inst[src_idx].g_owner) : src_idx];
+    const size_t owner = size_t(&from - b->inst.data());
+    if ((!from.active) || (owner == idx))
+        return fail(B200CONV_ERR_STATE, "b200conv_init_shared: instance %zu is not initialised", src_idx);
+    if (b->inst[idx].g_sharers > 0)
+        return fail(B200CONV_ERR_STATE, "instance %zu lends its IR spectra to other instances: destroy those first", idx);
+
+    ENTER_DEVICE(b);
+    CU(quiesce(b));
+    cudaStream_t st = b->stream;
+    const size_t F  = from.F;
+
+    Instance fresh;
+    cudaError_t e   = cudaMalloc(&fresh.ring, from.S * F * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&fresh.aux, 3 * F * sizeof(float));
+    if (e != cudaSuccess)
+    {
+        if (fresh.ring) cudaFree(fresh.ring);
+        cudaGetLastError();
+        return fail(B200CONV_ERR_NOMEM, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    e = cudaMemsetAsync(fresh.ring, 0, from.S * F * sizeof(float2), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fresh.aux, 0, 2 * F * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(fresh.aux + 2 * F, from.aux + 2 * F, F * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+    {
+        cudaFree(fresh.ring);
+        cudaFree(fresh.aux);
+        return fail(B200CONV_ERR_CUDA, "b200conv_init_shared: %s", cudaGetErrorString(e));
+    }
+
+    Instance &in    = b->inst[idx];
+    if (in.g_owner >= 0)
+        b->inst[size_t(in.g_owner)].g_sharers -= 1;
+    free_instance_buffers(in);
+    in              = fresh;
+    in.G            = from.G;
+    in.g_owner      = long(owner);
+    in.g_sharers    = 0;
+    b->inst[owner].g_sharers += 1;
+    in.active       = true;
+    in.conv_size    = from.conv_size;
+    in.rank         = from.rank;
+    in.F            = F;
+    in.bins         = from.bins;
+    in.nq           = from.nq;
+    in.q_lo         = from.q_lo;
+    in.S            = from.S;
+    float fo        = phase * float(F);                     /* Convolver.cpp:140, fp32 */
+    in.off          = ((fo > 0.0f) && (fo < 1.8e19f)) ? (size_t(fo) % F) : 0;
+    in.off0         = in.off;
+    in.frames       = 0;
+    in.pend_valid   = false;
+    rebuild_tables(b);
+    return B200CONV_OK;
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -1025,6 +1161,9 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
                            size_t frames, cudaStream_t st)
 {
     const uint32_t nact = uint32_t(b->active.size());
+    if (b->uniform_stale)
+        b->desc_dirty   = true;         /* the general path moved the frame counters one by one */
+    b->uniform_stale = false;
     const bool tables_changed = b->desc_dirty;
     TRY(upload_tables(b, st));
     MacPlan plan    = plan_mac(uint32_t(b->rank), nact, uint32_t(b->max_nq), b->sm_count,
@@ -1196,21 +1335,208 @@ static inline uint32_t slot_of(const Instance &in, uint64_t t)
     return uint32_t((tm == 0) ? 0 : in.S - tm);
 }
 
-/* Any call size / any phase: explicit job lists.  One step =
+/* Where the kernels of one step find its job list: up to JOB_DIRECT jobs are read in place from
+ * the page-locked, device-mapped ring (no copy operation in the stream -- a real-time call is one
+ * kernel launch); longer lists are uploaded. */
+static int publish_jobs(Batch *b, size_t at, size_t count, cudaStream_t st, const Job **dev)
+{
+    if (count <= JOB_DIRECT)
+    {
+        *dev        = b->h_jobs_dev + at;
+        return B200CONV_OK;
+    }
+    TRY(push_jobs(b, at, count, st));
+    *dev        = b->d_jobs + at;
+    return B200CONV_OK;
+}
+
+/* Any call size / any phase, ranks 8..13: ONE launch per step.  Every instance contributes at most
+ * one job, and a job is whatever the instance needs next, in this order (kernels.cuh, Job):
+ *     P1   samples that continue the frame in progress, answered from its pending block
+ *     FFT  the frame is complete: its spectrum enters the ring
+ *     MAC  what the complete frames contribute to the frame about to start (q >= 1) -> the new
+ *          pending block; or, for a whole frame taken from the input on a frame boundary, every
+ *          partition -> the output block
+ *     P2   the first samples of that new frame, answered from the block just computed
+ * A 256-sample call of a phase-shifted instance (BASELINE config 2) is P1 + FFT + MAC + P2 in one
+ * k_frame<GEN> launch; a call inside a frame is one k_partial_fused launch. */
+static int process_general_fused(Batch *b, float *dst, size_t dst_stride, const float *src, size_t stride,
+                                 size_t count, cudaStream_t st)
+{
+    const size_t F      = size_t(1) << (b->rank - 1);
+    TRY(upload_tables(b, st));
+    std::vector<size_t> &pos = b->g_pos;
+    std::vector<Job> &jobs = b->g_jobs;
+    for (uint32_t i : b->active)
+        pos[i]          = 0;
+
+    for (;;)
+    {
+        jobs.clear();
+        uint64_t bytes  = 0;
+        size_t n_mac = 0, n_fft = 0, max_nq = 0;
+        for (uint32_t i : b->active)
+        {
+            Instance &in = b->inst[i];
+            if (pos[i] >= count)
+                continue;
+            float *cur  = in.aux, *pend = in.aux + F;
+            const float *x  = src + size_t(i) * stride;
+            float *y        = dst + size_t(i) * dst_stride;
+            size_t rem  = count - pos[i];
+            Job j;
+            memset(&j, 0, sizeof(j));
+            j.inst      = i;
+
+            auto pending_mac = [&]()
+            {
+                /* what the complete frames contribute to frame t = in.frames: partitions q >= 1 */
+                j.flags    |= JOB_MAC;
+                j.dst       = pend;
+                j.slot0     = slot_of(in, in.frames);
+                j.tlo       = uint32_t(in.frames);
+                j.qa        = uint32_t((in.q_lo > 1) ? in.q_lo : 1);
+                j.qb        = uint32_t(in.q_lo + in.nq);
+                bytes      += algo_bytes(b, in, j.qa, j.qb);
+                in.pend_valid = true;
+                b->stats.frames += 1;
+            };
+
+            if ((in.off == 0) && (rem >= F))
+            {
+                /* a whole frame on a frame boundary: FFT -> every partition -> IFFT -> out */
+                j.flags     = JOB_FFT | JOB_MAC;
+                j.src       = x + pos[i];
+                j.dst       = y + pos[i];
+                j.slot0     = slot_of(in, in.frames);
+                j.spec      = in.ring + size_t(j.slot0) * F;
+                j.tlo       = uint32_t(in.frames);
+                j.qa        = uint32_t(in.q_lo);
+                j.qb        = uint32_t(in.q_lo + in.nq);
+                bytes      += algo_bytes(b, in, j.qa, j.qb);
+                in.frames  += 1;
+                in.pend_valid = false;
+                b->stats.frames += 1;
+                pos[i]     += F;
+            }
+            else if (!in.pend_valid)
+            {
+                /* the pending block of the frame in progress first; its samples ride along (P2)
+                 * unless they would complete the frame -- that is the next step's P1 + FFT */
+                pending_mac();
+                if (rem < F - in.off)
+                {
+                    size_t n2   = (rem < PART_MAX) ? rem : PART_MAX;
+                    j.psrc2     = x + pos[i];
+                    j.pdst2     = y + pos[i];
+                    j.off2      = uint32_t(in.off);
+                    j.n2        = uint32_t(n2);
+                    in.off     += n2;
+                    pos[i]     += n2;
+                }
+            }
+            else
+            {
+                size_t n1   = (rem < F - in.off) ? rem : F - in.off;
+                if (n1 > PART_MAX)
+                    n1          = PART_MAX;
+                j.psrc      = x + pos[i];
+                j.pdst      = y + pos[i];
+                j.off       = uint32_t(in.off);
+                j.n         = uint32_t(n1);
+                in.off     += n1;
+                pos[i]     += n1;
+                rem        -= n1;
+                if (in.off == F)
+                {
+                    /* the frame is complete: its spectrum enters the ring in this same launch */
+                    j.flags    |= JOB_FFT | JOB_FFT_PREV;
+                    j.src       = cur;
+                    j.spec      = in.ring + size_t(slot_of(in, in.frames)) * F;
+                    in.frames  += 1;
+                    in.off      = 0;
+                    in.pend_valid = false;
+                    j.tlo       = uint32_t(in.frames);      /* = t of the frame about to start */
+                    if (rem < F)
+                    {
+                        /* ... and so does what the samples after it will need */
+                        pending_mac();
+                        size_t n2   = (rem < PART_MAX) ? rem : PART_MAX;
+                        if (n2 > 0)
+                        {
+                            j.psrc2     = x + pos[i];
+                            j.pdst2     = y + pos[i];
+                            j.off2      = 0;
+                            j.n2        = uint32_t(n2);
+                            in.off      = n2;
+                            pos[i]     += n2;
+                        }
+                    }
+                }
+            }
+            if (j.flags & JOB_MAC)
+            {
+                ++n_mac;
+                if (in.nq > max_nq)
+                    max_nq      = in.nq;
+            }
+            if (j.flags & JOB_FFT)
+                ++n_fft;
+            jobs.push_back(j);
+        }
+        if (jobs.empty())
+            break;
+
+        size_t at = 0;
+        TRY(reserve_jobs(b, jobs.size(), st, &at));
+        memcpy(b->h_jobs + at, jobs.data(), jobs.size() * sizeof(Job));
+        StepArgs a  = base_args(b);
+        TRY(publish_jobs(b, at, jobs.size(), st, &a.jobs));
+        a.n_jobs    = uint32_t(jobs.size());
+        if ((n_mac == 0) && (n_fft == 0))
+        {
+            /* every job sits inside a frame: store + answer, one CTA per job */
+            k_partial_fused<<<a.n_jobs, 256, 0, st>>>(a);
+            CU(cudaGetLastError());
+            b->stats.launches += 1;
+            continue;
+        }
+        MacPlan plan = plan_mac(uint32_t(b->rank), uint32_t(jobs.size()), uint32_t((max_nq > 0) ? max_nq : 2),
+                                b->sm_count, b->tune_splits, b->tune_stages);
+        plan.sh.bias = 0;
+        TRY(ensure_ypart(b, jobs.size() * plan.splits * F * sizeof(float2), st));
+        a.ypart     = b->ypart;
+        a.splits    = plan.splits;
+        CU(launch_frame_gen(a, plan, a.n_jobs, b->d_tickets, st));
+        b->stats.launches       += 1;
+        if (n_mac > 0)
+        {
+            b->stats.mac_launches   += 1;
+            b->stats.mac_algo_bytes += bytes;
+        }
+    }
+
+    b->uniform_stale = true;    /* per-instance frame counters moved independently of t_batch */
+    b->pend_ready = false;
+    return B200CONV_OK;
+}
+
+/* The same schedule with one kernel per stage (ranks 14..16, whose frame transform does not fit a
+ * k_frame CTA, and fused = 0):
  *     k_store + k_partial (samples of frames in progress, answered from their pending block)
  *  -> k_fwd               (frames that just completed, and whole frames taken from the input)
  *  -> k_mac -> k_inv      (whole frames: every partition -> output;
  *                          frames about to start: partitions q >= 1 -> their pending block)
- * and each instance contributes at most one item per stage.  A frame that completes has its
- * spectrum pushed and the next frame's pending block prepared in the same step, so the samples
- * that follow -- in this call or the next -- are one launch pair away. */
-static int process_general(Batch *b, float *dst, size_t dst_stride, const float *src, size_t stride,
-                           size_t count, cudaStream_t st)
+ * and each instance contributes at most one item per stage. */
+static int process_general_staged(Batch *b, float *dst, size_t dst_stride, const float *src, size_t stride,
+                                  size_t count, cudaStream_t st)
 {
     const size_t F      = size_t(1) << (b->rank - 1);
     TRY(upload_tables(b, st));
-    std::vector<size_t> pos(b->n, 0);
-    std::vector<Job> fft, mac, part;
+    std::vector<size_t> &pos = b->g_pos;
+    std::vector<Job> &fft = b->g_fft, &mac = b->g_mac, &part = b->g_part;
+    for (uint32_t i : b->active)
+        pos[i]          = 0;
 
     for (;;)
     {
@@ -1248,15 +1574,6 @@ static int process_general(Batch *b, float *dst, size_t dst_stride, const float 
                 b->stats.frames += 1;
             };
 
-            if (in.off == F)
-            {
-                /* a complete frame whose spectrum is still owed to the ring */
-                push_frame_spectrum(cur);
-                in.frames  += 1;
-                in.off      = 0;
-                in.pend_valid = false;
-            }
-
             size_t rem  = count - pos[i];
             if (!((in.off == 0) && (rem >= F)))
             {
@@ -1271,8 +1588,8 @@ static int process_general(Batch *b, float *dst, size_t dst_stride, const float 
                 size_t n    = (rem < F - in.off) ? rem : F - in.off;
                 memset(&j, 0, sizeof(j));
                 j.inst      = i;
-                j.src       = src + size_t(i) * stride + pos[i];
-                j.dst       = dst + size_t(i) * dst_stride + pos[i];
+                j.psrc      = src + size_t(i) * stride + pos[i];
+                j.pdst      = dst + size_t(i) * dst_stride + pos[i];
                 j.off       = uint32_t(in.off);
                 j.n         = uint32_t(n);
                 part.push_back(j);
@@ -1319,26 +1636,38 @@ static int process_general(Batch *b, float *dst, size_t dst_stride, const float 
         if (!part.empty())  memcpy(hj, part.data(), part.size() * sizeof(Job));
         if (!fft.empty())   memcpy(hj + part.size(), fft.data(), fft.size() * sizeof(Job));
         if (!mac.empty())   memcpy(hj + part.size() + fft.size(), mac.data(), mac.size() * sizeof(Job));
-        TRY(push_jobs(b, at, total, st));
+        const Job *dj = nullptr;
+        TRY(publish_jobs(b, at, total, st, &dj));
 
         StepArgs a  = base_args(b);
         if (!part.empty())
         {
-            a.jobs      = b->d_jobs + at;
+            a.jobs      = dj;
             a.n_jobs    = uint32_t(part.size());
             size_t maxn = 0;
             for (const Job &pj : part)
                 if (pj.n > maxn) maxn = pj.n;
-            dim3 grid(uint32_t((maxn + 127) / 128), (a.n_jobs < 65535u) ? a.n_jobs : 65535u);
-            k_store<<<grid, 128, 0, st>>>(a);
-            CU(cudaGetLastError());
-            k_partial<<<grid, 128, 0, st>>>(a);
-            CU(cudaGetLastError());
-            b->stats.launches += 2;
+            if (maxn <= 256)
+            {
+                k_partial_fused<<<a.n_jobs, 256, 0, st>>>(a);
+                CU(cudaGetLastError());
+                b->stats.launches += 1;
+            }
+            else
+            {
+                /* long segments: store, then share each job's outputs among several CTAs */
+                dim3 gs(uint32_t((maxn + 255) / 256), (a.n_jobs < 65535u) ? a.n_jobs : 65535u);
+                k_store<<<gs, 256, 0, st>>>(a);
+                CU(cudaGetLastError());
+                dim3 gp(uint32_t((maxn + 31) / 32 > 64 ? 64 : (maxn + 31) / 32), gs.y);
+                k_partial<<<gp, 256, 0, st>>>(a);
+                CU(cudaGetLastError());
+                b->stats.launches += 2;
+            }
         }
         if (!fft.empty())
         {
-            a.jobs      = b->d_jobs + at + part.size();
+            a.jobs      = dj + part.size();
             a.n_jobs    = uint32_t(fft.size());
             CU(launch_fwd(a, a.n_jobs, st));
             b->stats.launches++;
@@ -1349,7 +1678,7 @@ static int process_general(Batch *b, float *dst, size_t dst_stride, const float 
                                     b->sm_count, b->tune_splits, b->tune_stages);
             TRY(ensure_ypart(b, mac.size() * plan.splits * F * sizeof(float2), st));
             a.ypart     = b->ypart;
-            a.jobs      = b->d_jobs + at + part.size() + fft.size();
+            a.jobs      = dj + part.size() + fft.size();
             a.n_jobs    = uint32_t(mac.size());
             a.splits    = plan.splits;
             CU(launch_mac(b, a, plan, a.n_jobs, st));
@@ -1361,9 +1690,17 @@ static int process_general(Batch *b, float *dst, size_t dst_stride, const float 
         }
     }
 
-    b->desc_dirty = true;       /* per-instance frame counters moved independently of t_batch */
+    b->desc_dirty = true;       /* ring_head was bypassed; per-instance frame counters moved */
     b->pend_ready = false;
     return B200CONV_OK;
+}
+
+static int process_general(Batch *b, float *dst, size_t dst_stride, const float *src, size_t stride,
+                           size_t count, cudaStream_t st)
+{
+    if ((b->opt_fused != 0) && (b->rank <= 13))
+        return process_general_fused(b, dst, dst_stride, src, stride, count, st);
+    return process_general_staged(b, dst, dst_stride, src, stride, count, st);
 }
 
 static int process_device2_impl(b200conv_batch_t *b, float *dst, size_t dst_stride,
@@ -1622,6 +1959,74 @@ extern "C" int b200conv_get_state(const b200conv_batch_t *b, size_t idx, b200con
     st->partitions  = in.nq;
     st->part_offset = in.q_lo;
     st->frames      = in.frames + ((in.active && (in.off == in.F)) ? 1 : 0);
+    return B200CONV_OK;
+}
+
+extern "C" int b200conv_get_dump(const b200conv_batch_t *b, size_t idx, b200conv_dump_t *out)
+{
+    if ((b == nullptr) || (idx >= b->n) || (out == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_get_dump: bad arguments");
+    memset(out, 0, sizeof(*out));
+    const Instance &in = b->inst[idx];
+    if (!in.active)
+        return B200CONV_OK;                                 /* construct(): everything NULL / 0 */
+
+    const size_t F      = in.F, count = in.conv_size;
+    out->vDataBuffer    = in.aux + F;
+    out->vFrame         = in.aux;
+    out->vConvBuffer    = b->ypart;
+    out->vTaskData      = in.ring;
+    out->vConvData      = in.G;
+    out->vDirectData    = in.aux + 2 * F;
+    out->vData          = in.G;
+    out->nDataBufferSize = (in.bins + 1) * F;               /* Convolver.cpp:137 */
+    out->nFrameSize     = F;
+    out->nFrameOff      = (in.off == F) ? 0 : in.off;
+    out->nDirectSize    = (count < 128) ? count : 128;      /* :141 */
+    out->nConvSize      = count;
+    out->nRank          = in.rank;
+
+    /* the reference's partition map (:152-197): 128 direct taps, raising levels of 128, 256, ...
+     * taps up to F / 2, then blocks of F */
+    size_t left         = count - out->nDirectSize;
+    size_t levels       = 0;
+    for (size_t brank = 8; (left > 0) && (brank < in.rank); ++brank)
+    {
+        size_t n            = size_t(1) << (brank - 1);
+        left               -= (left < n) ? left : n;
+        ++levels;
+    }
+    out->nLevels        = levels;
+    out->nBlocks        = (left + F - 1) / F;
+
+    /* load spreading (:199-210), fp32 like the reference */
+    const long steps    = long(F >> 7);
+    if (steps <= 1)
+    {
+        out->nBlkInit       = out->nBlocks;
+        out->fBlkCoef       = 0.0f;
+    }
+    else
+    {
+        out->nBlkInit       = 1;
+        out->fBlkCoef       = (float(out->nBlocks) + 1e-3f) / (float(steps) - 1.0f);
+    }
+
+    /* nBlocksDone: nBlocks after init (:198); reset at the first sample of a frame (:268-272) and
+     * raised at every 128-sample boundary that has received a sample (:275-285) */
+    const size_t off    = out->nFrameOff;
+    const bool rolled   = (in.off == F);                    /* complete frame, not rolled over here yet */
+    const uint64_t done = in.frames + (rolled ? 1 : 0);     /* frames completed since init */
+    const bool reset_seen = (in.off0 == 0) ? ((done > 0) || (off > 0))
+                                           : ((done >= 2) || ((done == 1) && (off > 0)));
+    if ((out->nBlocks == 0) || (!reset_seen) || (off == 0))
+        out->nBlocksDone    = out->nBlocks;
+    else
+    {
+        const size_t sub_id = (off - 1) >> 7;
+        size_t target       = size_t(float(out->nBlkInit) + out->fBlkCoef * float(sub_id));
+        out->nBlocksDone    = (target < out->nBlocks) ? target : out->nBlocks;
+    }
     return B200CONV_OK;
 }
 
@@ -2024,8 +2429,9 @@ extern "C" int b200conv_linear_convolve(int device, float *dst, size_t dst_strid
     b200conv_batch_t *b = nullptr;
     TRY(b200conv_create(&b, device, count));
     int rc = B200CONV_OK;
-    for (size_t i = 0; (i < count) && (rc == B200CONV_OK); ++i)
-        rc = b200conv_init(b, i, h, nh, rank, 0.0f);
+    rc = b200conv_init(b, 0, h, nh, rank, 0.0f);                /* ONE set of filter spectra ... */
+    for (size_t i = 1; (i < count) && (rc == B200CONV_OK); ++i)
+        rc = b200conv_init_shared(b, i, 0, 0.0f);               /* ... borrowed by every other signal */
 
     float *in = nullptr, *out = nullptr;
     if (rc == B200CONV_OK)
@@ -2054,6 +2460,135 @@ extern "C" int b200conv_linear_convolve(int device, float *dst, size_t dst_strid
     return rc;
 }
 
+/* ------------------------------------------------------------------------------------------- */
+/* SyncChirpProcessor::do_linear_convolutions                                                   */
+
+static const size_t CHIRP_MAX_PART_SIZE = 32768;            /* MAX_PART_SIZE, SyncChirpProcessor.cpp:43 */
+
+extern "C" int b200conv_chirp_plan(b200conv_chirp_plan_t *plan, size_t *partitions, size_t *padded,
+                                   size_t *prepends, size_t *conv_lengths, size_t *align_offsets,
+                                   const size_t *in_len, size_t nchannels, size_t inverse_len,
+                                   size_t part_size_limit)
+{
+    if ((plan == nullptr) || (in_len == nullptr) || (nchannels == 0))
+        return fail(B200CONV_ERR_ARG, "b200conv_chirp_plan: bad arguments");       /* STATUS_NO_DATA, :1376 */
+    /* the partition: a power of two, at most MAX_PART_SIZE, 0 = MAX_PART_SIZE (:1226-1240) */
+    size_t limit        = (part_size_limit < CHIRP_MAX_PART_SIZE) ? part_size_limit : CHIRP_MAX_PART_SIZE;
+    if (limit == 0)
+        limit               = CHIRP_MAX_PART_SIZE;
+    size_t log2p        = 0;
+    while ((size_t(1) << log2p) < limit)
+        ++log2p;
+    const size_t P      = size_t(1) << log2p;
+    plan->partition_size    = P;
+    plan->conv_rank         = log2p + 1;
+    plan->image             = size_t(1) << (log2p + 2);
+    plan->allocation_size   = 0;
+    /* both sequences are thought of as padded to a whole number of partitions, the recording at
+     * its tail, the inverse filter at its head (:1313-1323) */
+    for (size_t ch = 0; ch < nchannels; ++ch)
+    {
+        const size_t longest    = (in_len[ch] > inverse_len) ? in_len[ch] : inverse_len;
+        const size_t np         = longest / P + 1;
+        if (partitions)     partitions[ch]      = np;
+        if (padded)         padded[ch]          = np * P;
+        if (prepends)       prepends[ch]        = np * P - inverse_len;
+        if (conv_lengths)   conv_lengths[ch]    = 2 * np * P;
+        if (2 * np * P > plan->allocation_size)
+            plan->allocation_size   = 2 * np * P;
+    }
+    /* rows are centred on the middle of the longest one (:1327-1330) */
+    if (align_offsets)
+        for (size_t ch = 0; ch < nchannels; ++ch)
+        {
+            const size_t longest    = (in_len[ch] > inverse_len) ? in_len[ch] : inverse_len;
+            align_offsets[ch]       = plan->allocation_size / 2 - (longest / P + 1) * P;
+        }
+    return B200CONV_OK;
+}
+
+static int chirp_impl(int device, float *result, size_t result_stride, const float *const *inputs,
+                      const size_t *in_len, size_t nchannels, const float *inverse, size_t inverse_len,
+                      size_t part_size_limit, float scale)
+{
+    if ((result == nullptr) || (inputs == nullptr) || (in_len == nullptr) || (nchannels == 0) ||
+        (inverse == nullptr) || (inverse_len == 0))
+        return fail(B200CONV_ERR_ARG, "b200conv_chirp_linear_convolutions: bad arguments");
+    for (size_t ch = 0; ch < nchannels; ++ch)
+        if ((inputs[ch] == nullptr) && (in_len[ch] > 0))
+            return fail(B200CONV_ERR_ARG, "b200conv_chirp_linear_convolutions: NULL input for channel %zu", ch);
+
+    std::vector<size_t> parts(nchannels), padded(nchannels), prepends(nchannels), clen(nchannels), align(nchannels);
+    b200conv_chirp_plan_t plan;
+    TRY(b200conv_chirp_plan(&plan, parts.data(), padded.data(), prepends.data(), clen.data(), align.data(),
+                            in_len, nchannels, inverse_len, part_size_limit));
+    if ((plan.conv_rank < B200CONV_RANK_MIN) || (plan.conv_rank > B200CONV_RANK_MAX))
+        return fail(B200CONV_ERR_ARG, "partition size %zu (rank %zu) is outside the engine's ranks 8..16",
+                    plan.partition_size, plan.conv_rank);
+    if (result_stride < plan.allocation_size)
+        return fail(B200CONV_ERR_ARG, "result rows must hold %zu samples", plan.allocation_size);
+
+    const size_t P      = plan.partition_size;
+    size_t frames       = 0;                            /* every channel: 2 * vPartitions frames of P samples */
+    for (size_t ch = 0; ch < nchannels; ++ch)
+        frames              = (2 * parts[ch] > frames) ? 2 * parts[ch] : frames;
+    const size_t total  = frames * P;
+
+    b200conv_batch_t *b = nullptr;
+    TRY(b200conv_create(&b, device, nchannels));
+    int rc = B200CONV_OK;
+    {
+        /* the prepend-padded inverse filter is the impulse response; channels of equal padded
+         * length see the same one and share its spectra */
+        std::vector<float> ir;
+        for (size_t ch = 0; (ch < nchannels) && (rc == B200CONV_OK); ++ch)
+        {
+            size_t same         = ch;
+            for (size_t k = 0; k < ch; ++k)
+                if (padded[k] == padded[ch]) { same = k; break; }
+            if (same != ch)
+            {
+                rc                  = b200conv_init_shared(b, ch, same, 0.0f);
+                continue;
+            }
+            ir.assign(padded[ch], 0.0f);
+            memcpy(ir.data() + prepends[ch], inverse, inverse_len * sizeof(float));
+            rc                  = b200conv_init(b, ch, ir.data(), ir.size(), plan.conv_rank, 0.0f);
+        }
+    }
+    if (rc == B200CONV_OK)
+    {
+        std::vector<float> in(nchannels * total, 0.0f), out(nchannels * total);
+        for (size_t ch = 0; ch < nchannels; ++ch)
+            if (in_len[ch] > 0)
+                memcpy(in.data() + ch * total, inputs[ch], in_len[ch] * sizeof(float));
+        rc = b200conv_process_planar(b, out.data(), in.data(), total, total);
+        if (rc == B200CONV_OK)
+            for (size_t ch = 0; ch < nchannels; ++ch)
+            {
+                float *row          = result + ch * result_stride;
+                memset(row, 0, plan.allocation_size * sizeof(float));       /* allocateConvolutionResult */
+                memcpy(row + align[ch], out.data() + ch * total, clen[ch] * sizeof(float));
+                for (size_t i = 0; i < clen[ch]; ++i)                      /* :1508, from index 0 */
+                    row[i]             *= scale;
+            }
+    }
+    std::string keep = g_last_error;
+    b200conv_free(b);
+    g_last_error = keep;
+    return rc;
+}
+
+extern "C" int b200conv_chirp_linear_convolutions(int device, float *result, size_t result_stride,
+                                                  const float *const *inputs, const size_t *in_len,
+                                                  size_t nchannels, const float *inverse, size_t inverse_len,
+                                                  size_t part_size_limit, float scale)
+{
+    try { return chirp_impl(device, result, result_stride, inputs, in_len, nchannels, inverse, inverse_len,
+                            part_size_limit, scale); }
+    catch (const std::bad_alloc &) { return fail(B200CONV_ERR_NOMEM, "out of host memory"); }
+}
+
 #include "equalizer.cuh"
 
 #ifdef B200CONV_TIMING
@@ -2079,6 +2614,12 @@ extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float 
                                    size_t rank, float phase, size_t part_offset)
 {
     try { return init_range_impl(b, idx, data, count, rank, phase, part_offset); }
+    catch (const std::bad_alloc &) { return fail(B200CONV_ERR_NOMEM, "out of host memory"); }
+}
+
+extern "C" int b200conv_init_shared(b200conv_batch_t *b, size_t idx, size_t src_idx, float phase)
+{
+    try { return init_shared_impl(b, idx, src_idx, phase); }
     catch (const std::bad_alloc &) { return fail(B200CONV_ERR_NOMEM, "out of host memory"); }
 }
 

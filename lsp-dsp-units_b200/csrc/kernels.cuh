@@ -44,18 +44,30 @@ struct InstDesc                     /* one per instance, device resident */
     uint32_t        pad;
 };
 
-struct Job                          /* explicit work item (general path and init) */
+struct Job                          /* explicit work item (general path, init, primitives) */
 {
-    const float    *src;            /* k_fwd: F input samples;  k_store/k_partial: call input       */
-    float          *dst;            /* k_inv / k_partial output                                     */
-    float2         *spec;           /* k_fwd output row                                             */
+    const float    *src;            /* transform input: F samples (caller's block, or the instance's `cur`) */
+    float          *dst;            /* inverse-transform output: F samples (caller's block, or `pend`)      */
+    float2         *spec;           /* ring row that receives the spectrum                                  */
+    const float    *psrc;           /* P1: n samples of the call -> cur[off ..), answered from the OLD pend  */
+    float          *pdst;
+    const float    *psrc2;          /* P2: n2 samples of the call -> cur[off2 ..), answered from the NEW pend */
+    float          *pdst2;
     uint32_t        inst;
     uint32_t        slot0;          /* ring slot of X_t for this job's frame index t                */
     uint32_t        qa, qb;         /* global partition range of the MAC                            */
-    uint32_t        off, n;         /* partial path: first sample index in the frame, sample count  */
+    uint32_t        off, n;         /* P1: first sample index in the frame, sample count            */
+    uint32_t        off2, n2;       /* P2                                                           */
     uint32_t        tlo;            /* low 32 bits of the job's frame index t                       */
-    uint32_t        pad;
+    uint32_t        flags;          /* JOB_*                                                        */
 };
+
+/* What one job of the general (any call size, any phase) path asks of its k_frame launch, in this
+ * order:  P1 (samples that continue the frame in progress)  ->  FFT (the frame is complete: its
+ * spectrum enters the ring)  ->  MAC over [qa, qb) + inverse transform into dst  ->  P2 (the first
+ * samples of the next frame, answered from the block just computed). */
+enum { JOB_FFT = 1, JOB_MAC = 2,
+       JOB_FFT_PREV = 4 /* the transformed frame is t - 1 (the MAC prepares frame t): publish t, not t + 1 */ };
 
 struct StepArgs                     /* by-value kernel argument */
 {
@@ -196,7 +208,10 @@ __device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
     uint32_t tm         = uint32_t(t % d.S);
     r.slot0             = (tm == 0) ? 0 : d.S - tm;
     r.tlo               = uint32_t(t);
-    r.pad               = 0;
+    r.flags             = JOB_FFT | JOB_MAC;
+    r.psrc = r.psrc2    = nullptr;
+    r.pdst = r.pdst2    = nullptr;
+    r.off2 = r.n2       = 0;
     r.src               = a.src + uint64_t(r.inst) * a.stride + uint64_t(f) * F;
     r.dst               = a.dst + uint64_t(r.inst) * a.stride_dst + uint64_t(f) * F;
     r.spec              = d.ring + uint64_t(r.slot0) * F;
@@ -207,7 +222,7 @@ __device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
     if (a.flags & STEP_HEAD_ONLY)       /* the arriving frame's own partition; the rest is already in ypart */
         r.qb                = min(r.qb, 1u);
     r.off               = 0;
-    r.n                 = F;
+    r.n                 = 0;
     return r;
 }
 
@@ -1499,6 +1514,60 @@ k_mac_multi(const StepArgs a, const MacShape sh)
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* partial_outputs : the samples of the frame in progress against taps [0, F) in direct form       */
+/* (reference: dsp::convolve and the raising levels, Convolver.cpp:251-262,295) -- zero latency    */
+/* for any call size:                                                                           */
+/*     dst[i] = pend[off + i] + sum_{j <= off + i} cur[j] * head[off + i - j],   i in [i0, i1)     */
+/* Parallel across outputs AND taps: a group of G lanes (a power of two, inside one warp) shares    */
+/* one output, lane l takes the taps j = l, l + G, ...; fp32 products in four independent chains,    */
+/* runs of <= 64 terms per lane, run totals in fp64, group totals by shuffle.  Every thread of the   */
+/* CTA must call it (T a multiple of 32).                                                        */
+
+__device__ __forceinline__ void partial_outputs(const float *cur, const float *head, const float *pend,
+                                                float *dst, uint32_t off, uint32_t i0, uint32_t i1,
+                                                uint32_t tid, uint32_t T)
+{
+    const uint32_t n        = i1 - i0;
+    if (n == 0)
+        return;
+    uint32_t G              = 1;
+    while ((G < 32) && (n * G * 2 <= T))
+        G                     <<= 1;
+    const uint32_t per_pass = T / G;
+    const uint32_t lane     = tid % G, grp = tid / G;
+    for (uint32_t base = 0; base < n; base += per_pass)            /* uniform trip count */
+    {
+        const uint32_t i        = i0 + base + grp;
+        const bool live         = (base + grp) < n;
+        double total            = 0.0;
+        if (live)
+        {
+            const uint32_t m        = off + i;
+            for (uint32_t j0 = lane; j0 <= m; j0 += 64 * G)
+            {
+                const uint32_t j1       = min(j0 + 64 * G, m + 1);
+                float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+                uint32_t j              = j0;
+                for ( ; j + 3 * G < j1; j += 4 * G)
+                {
+                    p0                      = fmaf(cur[j],         head[m - j],         p0);
+                    p1                      = fmaf(cur[j + G],     head[m - j - G],     p1);
+                    p2                      = fmaf(cur[j + 2 * G], head[m - j - 2 * G], p2);
+                    p3                      = fmaf(cur[j + 3 * G], head[m - j - 3 * G], p3);
+                }
+                for ( ; j < j1; j += G)
+                    p0                      = fmaf(cur[j], head[m - j], p0);
+                total                  += double((p0 + p1) + (p2 + p3));
+            }
+        }
+        for (uint32_t sft = G >> 1; sft > 0; sft >>= 1)
+            total                  += __shfl_xor_sync(0xffffffffu, total, sft);
+        if (live && (lane == 0))
+            dst[i]                  = pend[off + i] + float(total);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* k_frame : ranks 8..13, whole frames for every instance -- the block scheduler's "one launch    */
 /* per block".  grid = (jobs * splits, M / TB), TB / 4 threads.                                   */
 /*                                                                                             */
@@ -1535,7 +1604,10 @@ struct FrameCfg
     static constexpr int MINB   = (RANK >= 13) ? 2 : ((T >= 256) ? 4 : 8);  /* CTAs per SM (register cap) */
 };
 
-template <int RANK>
+/* GEN = the job-list form for the general path (a.jobs != NULL): per job any of P1 / FFT / MAC +
+ * inverse / P2 (see Job).  Launched WITHOUT programmatic serialisation -- every earlier launch has
+ * completed -- so ring_head only orders CTAs of this launch. */
+template <int RANK, bool GEN = false>
 __global__ void __launch_bounds__(FrameCfg<RANK>::T, FrameCfg<RANK>::MINB)
 k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs ra)
 {
@@ -1573,16 +1645,18 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     /* the instance / job tables are written by stream-ordered memcpys, never by a kernel */
     const Job job           = fetch_job(a, jobi);
     const InstDesc d        = a.inst[job.inst];
+    const bool split0       = (split == 0);
+    const bool fft_cta      = split0 && (tile == 0);
+    if (GEN && (!(job.flags & JOB_MAC)) && (!fft_cta))
+        return;                                 /* a job without a partition sum needs one CTA */
 
     uint32_t qa             = max(job.qa, d.q_lo);
     uint32_t qb             = min(job.qb, d.q_lo + d.nq);
-    uint32_t nq             = (qb > qa) ? (qb - qa) : 0;
+    uint32_t nq             = ((qb > qa) && ((!GEN) || (job.flags & JOB_MAC))) ? (qb - qa) : 0;
     uint32_t c0, c1;
     chunk_range(nq, split, a.splits, sh.bias, c0, c1);
     const uint32_t q0       = qa + c0, q1 = qa + c1;
     const uint32_t n_iter   = (q1 - q0 + QB - 1) / QB;
-    const bool split0       = (split == 0);
-    const bool fft_cta      = split0 && (tile == 0);
     /* Split 0 owns the partitions that need the NEWEST spectra: q = 0 the arriving frame's own
      * (written by this launch), q = 1 the previous frame's (published near the END of the previous
      * launch's partition stream, and CTAs of this launch may have become resident long before
@@ -1703,6 +1777,17 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
              * ring slot (-t) mod S.  Exception: the host knows the predecessor (STEP_EARLY_SRC). */
             if (!(a.flags & STEP_EARLY_SRC))
                 asm volatile("griddepcontrol.wait;" ::: "memory");
+            if (GEN && (job.n > 0))
+            {
+                /* P1: the call's samples that continue the frame in progress, answered at once */
+                for (uint32_t i = tid; i < job.n; i += T)
+                    d.cur[job.off + i]  = job.psrc[i];
+                __syncthreads();
+                partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, 0, job.n, tid, T);
+                __syncthreads();
+            }
+            if ((!GEN) || (job.flags & JOB_FFT))
+            {
             /* every stage buffer is idle here: two work buffers (one at rank 13) + the twiddle table */
             constexpr bool FFT_PP       = (RANK <= 12);
             constexpr uint32_t FFT_WORK = C::WORK * (FFT_PP ? 2 : 1);
@@ -1727,10 +1812,14 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
                  * acquire / release chain makes every older spectrum visible to whoever acquires
                  * the new value). */
                 uint32_t *hp    = a.ring_head + job.inst;
-                wait_ge<false>(hp, job.tlo, a.error, SPIN_ERR_RING);
-                const uint32_t head = job.tlo + 1u;
+                if (!GEN)
+                    wait_ge<false>(hp, job.tlo, a.error, SPIN_ERR_RING);
+                const uint32_t head = (GEN && (job.flags & JOB_FFT_PREV)) ? job.tlo : job.tlo + 1u;
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(hp), "r"(head) : "memory");
             }
+            }
+            if (GEN && (!(job.flags & JOB_MAC)))
+                return;
         }
         else if ((tid == 0) && (n_iter > 0))
         {
@@ -1796,9 +1885,19 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
             tws[i]          = a.tw[i];
         tw              = tws;                  /* visible after inv_body's first barrier */
     }
-    if (ra.mode == 0)
+    if (GEN || (ra.mode == 0))
     {
         inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, job.dst, a.tw, tw, false, int(tid));
+        if (GEN && (job.n2 > 0))
+        {
+            /* P2: the first samples of the frame that has just started, answered from the block
+             * (job.dst = the instance's pending block) the inverse transform has just produced */
+            __syncthreads();
+            for (uint32_t i = tid; i < job.n2; i += T)
+                d.cur[job.off2 + i] = job.psrc2[i];
+            __syncthreads();
+            partial_outputs(d.cur, d.head, job.dst, job.pdst2, job.off2, 0, job.n2, tid, T);
+        }
         FRAME_STAMP(3);
         return;
     }
@@ -1874,7 +1973,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
 /* ------------------------------------------------------------------------------------------- */
 /* Partial-call path (calls that do not complete whole frames, or a non-zero phase)              */
 
-/* cur[off .. off+n) = src[0 .. n) */
+/* cur[off .. off+n) = psrc[0 .. n)   (first half of a large P1 segment; k_partial follows) */
 __global__ void k_store(const StepArgs a)
 {
     for (uint32_t jb = blockIdx.y; jb < a.n_jobs; jb += gridDim.y)
@@ -1882,35 +1981,39 @@ __global__ void k_store(const StepArgs a)
         const Job job       = a.jobs[jb];
         float *cur          = a.inst[job.inst].cur;
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x)
-            cur[job.off + i]    = job.src[i];
+            cur[job.off + i]    = job.psrc[i];
     }
 }
 
-/* dst[m - off] = pend[m] + sum_{j <= m} cur[j] * head[m - j],  m in [off, off+n):
- * zero latency for any call size -- the samples of the frame in progress against taps [0, F)
- * in direct form (reference: dsp::convolve and the raising levels, Convolver.cpp:251-262,295). */
-__global__ void k_partial(const StepArgs a)
+/* pdst[i] = pend[off + i] + own-frame term, i < n: grid.x CTAs share the outputs of one job
+ * (after k_store: only `cur` is read, so pdst == psrc is safe). */
+__global__ void __launch_bounds__(256)
+k_partial(const StepArgs a)
 {
     for (uint32_t jb = blockIdx.y; jb < a.n_jobs; jb += gridDim.y)
     {
         const Job job       = a.jobs[jb];
         const InstDesc &d   = a.inst[job.inst];
-        const float *cur    = d.cur;
-        const float *head   = d.head;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < job.n; i += gridDim.x * blockDim.x)
-        {
-            uint32_t m      = job.off + i;
-            double total    = 0.0;
-            for (uint32_t j0 = 0; j0 <= m; j0 += 128)
-            {
-                uint32_t j1     = min(j0 + 128, m + 1);
-                float part      = 0.0f;
-                for (uint32_t j = j0; j < j1; ++j)
-                    part            = fmaf(cur[j], head[m - j], part);
-                total          += double(part);
-            }
-            job.dst[i]      = d.pend[m] + float(total);
-        }
+        const uint32_t per  = (job.n + gridDim.x - 1) / gridDim.x;
+        const uint32_t i0   = min(job.n, blockIdx.x * per), i1 = min(job.n, i0 + per);
+        partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, i0, i1, threadIdx.x, blockDim.x);
+    }
+}
+
+/* Both in ONE launch for steps in which no frame completes (a call inside a frame): one CTA per
+ * job stores the samples and answers them. */
+__global__ void __launch_bounds__(256)
+k_partial_fused(const StepArgs a)
+{
+    for (uint32_t jb = blockIdx.x; jb < a.n_jobs; jb += gridDim.x)
+    {
+        const Job job       = a.jobs[jb];
+        const InstDesc &d   = a.inst[job.inst];
+        for (uint32_t i = threadIdx.x; i < job.n; i += blockDim.x)
+            d.cur[job.off + i]  = job.psrc[i];
+        __syncthreads();
+        partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, 0, job.n, threadIdx.x, blockDim.x);
+        __syncthreads();
     }
 }
 

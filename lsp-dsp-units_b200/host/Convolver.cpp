@@ -92,18 +92,42 @@ namespace lsp
         void Convolver::dump(IStateDumper *v) const
         {
         #ifdef B200CONV_WITH_STATE_DUMPER
+            // The reference's 18 fields, same names and order (reference :315-337), with the values
+            // the reference object would hold after the same history (b200conv_get_dump); pointer
+            // fields report the device buffer that plays the same part.  Engine extras follow.
+            b200conv_dump_t d;
             b200conv_state_t st;
+            ::memset(&d, 0, sizeof(d));
             ::memset(&st, 0, sizeof(st));
             if (pEngine != NULL)
+            {
+                b200conv_get_dump(pEngine, 0, &d);
                 b200conv_get_state(pEngine, 0, &st);
+            }
+
+            v->write("pDataBuffer", d.vDataBuffer);
+            v->write("vFrame", d.vFrame);
+            v->write("vConvBuffer", d.vConvBuffer);
+            v->write("vTaskData", d.vTaskData);
+            v->write("vConvData", d.vConvData);
+            v->write("vDirectData", d.vDirectData);
+
+            v->write("nDataBufferSize", d.nDataBufferSize);
+            v->write("nDirectSize", d.nDirectSize);
+            v->write("nFrameSize", d.nFrameSize);
+            v->write("nFrameOff", d.nFrameOff);
+            v->write("nConvSize", d.nConvSize);
+            v->write("nLevels", d.nLevels);
+            v->write("nBlocks", d.nBlocks);
+            v->write("nBlocksDone", d.nBlocksDone);
+            v->write("nRank", d.nRank);
+            v->write("nBlkInit", d.nBlkInit);
+            v->write("fBlkCoef", d.fBlkCoef);
+
+            v->write("vData", d.vData);
 
             v->write("pEngine", static_cast<const void *>(pEngine));
             v->write("nDevice", nDevice);
-            v->write("nFrameSize", st.frame_size);
-            v->write("nFrameOff", st.frame_off);
-            v->write("nConvSize", st.conv_size);
-            v->write("nRank", st.rank);
-            v->write("nBins", st.bins);
             v->write("nPartitions", st.partitions);
             v->write("nPartOffset", st.part_offset);
             v->write("nFrames", static_cast<unsigned long long>(st.frames));

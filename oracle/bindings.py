@@ -234,3 +234,50 @@ class CpuEqualizer:
                 self._h = None
         except Exception:
             pass
+
+
+# ---- SyncChirpProcessor::do_linear_convolutions (oracle/chirp_oracle.c) ---------------------------
+
+class _ChirpPlan(ctypes.Structure):
+    _fields_ = [(n, _SZ) for n in ("partition_size", "conv_rank", "image", "allocation_size")]
+
+
+def _chirp_lib():
+    lib = ctypes.CDLL(os.path.join(_HERE, "liboracle.so"))
+    SZP = ctypes.POINTER(_SZ)
+    lib.orc_chirp_plan.argtypes = [ctypes.POINTER(_ChirpPlan), SZP, SZP, SZP, SZP, SZP, SZP, _SZ, _SZ, _SZ]
+    lib.orc_chirp_plan.restype = None
+    lib.orc_chirp_linear_convolutions.argtypes = [_FP, ctypes.POINTER(_FP), SZP, _SZ, _FP, _SZ, _SZ, ctypes.c_float]
+    lib.orc_chirp_linear_convolutions.restype = ctypes.c_int
+    return lib
+
+
+def chirp_plan(in_len, inverse_len, part_size_limit):
+    """calculateConvolutionPartitionSize + calculateConvolutionParameters
+    (SyncChirpProcessor.cpp:1224-1250, 1299-1331) -> dict of scalars and per-channel lists."""
+    n = len(in_len)
+    arr = lambda: (_SZ * n)()
+    plan, parts, padded, prep, clen, align = _ChirpPlan(), arr(), arr(), arr(), arr(), arr()
+    _chirp_lib().orc_chirp_plan(ctypes.byref(plan), parts, padded, prep, clen, align, (_SZ * n)(*in_len), n,
+                                inverse_len, part_size_limit)
+    out = {k: int(getattr(plan, k)) for k, _ in _ChirpPlan._fields_}
+    out.update(partitions=list(parts), padded=list(padded), prepends=list(prep), conv_lengths=list(clen),
+               align_offsets=list(align))
+    return out
+
+
+def chirp_linear_convolutions(inputs, inverse, part_size_limit, scale):
+    """SyncChirpProcessor::do_linear_convolutions (:1374-1508) on plain arrays: returns the
+    [nchannels][allocation_size] float32 result."""
+    inputs = [np.ascontiguousarray(x, dtype=np.float32) for x in inputs]
+    inverse = np.ascontiguousarray(inverse, dtype=np.float32)
+    n = len(inputs)
+    lens = [x.size for x in inputs]
+    plan = chirp_plan(lens, inverse.size, part_size_limit)
+    res = np.empty((n, plan["allocation_size"]), dtype=np.float32)
+    rc = _chirp_lib().orc_chirp_linear_convolutions(_ptr(res), (_FP * n)(*[_ptr(x) for x in inputs]),
+                                                    (_SZ * n)(*lens), n, _ptr(inverse), inverse.size,
+                                                    part_size_limit, scale)
+    if rc != 0:
+        raise RuntimeError("orc_chirp_linear_convolutions failed")
+    return res

@@ -70,3 +70,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, f)
+
+
+@pytest.mark.parametrize("in_len,inv_len,limit", [
+    ([1000], 300, 256), ([5000, 3000, 5000], 4096, 1024), ([40000, 100], 9000, 0),
+    ([70000], 70000, 32768), ([128, 129, 127], 128, 128), ([10], 3, 1), ([2000], 2500, 100000),
+])
+def test_chirp_plan_matches_the_reference_arithmetic(pkg, in_len, inv_len, limit):
+    """b200conv_chirp_plan is host arithmetic (SyncChirpProcessor.cpp:1224-1250,1299-1331): checked
+    here against the CPU restatement and the independent model, no GPU needed."""
+    import chirp_model
+    from oracle import bindings
+    pkg.lib()
+    got = pkg.chirp_plan(in_len, inv_len, limit)
+    assert got == bindings.chirp_plan(in_len, inv_len, limit)
+    assert got == chirp_model.plan(in_len, inv_len, limit)

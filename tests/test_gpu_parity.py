@@ -801,3 +801,43 @@ def test_batch_fed_its_own_previous_output(pkg, n, taps, rank):
         y = np.convolve(hist, h)[i * F:(i + 1) * F]
         assert rel_err(got[(i + 1) * F:(i + 2) * F], y) <= 10 * TOL
         cur = got[(i + 1) * F:(i + 2) * F].astype(np.float64)
+
+
+@pytest.mark.parametrize("taps,rank,phase,calls", [
+    (65536, 11, 0.0, [1024] * 3 + [100, 28, 128, 768, 1, 1023]),
+    (5000, 9, 0.37, [31] * 40),
+    (70000, 13, 0.9, [333] * 30),
+    (200, 12, 0.0, [256, 256, 1536, 2048, 7]),
+    (129, 8, 0.5, [64, 64, 128, 1, 127]),
+    (300000, 16, 0.0, [31, 4096, 28641, 32768, 5]),
+    (31, 9, 0.0, [31] * 10),
+])
+def test_dump_fields_match_the_reference_scheduler(pkg, taps, rank, phase, calls):
+    """Convolver::dump (Convolver.cpp:315-337): the 11 scalar fields the engine reports must equal
+    the reference scheduler's after the same init / process history -- including nBlocksDone, which
+    the reference raises at 128-sample boundaries and the engine reproduces arithmetically."""
+    names = {"nDataBufferSize": "data_buffer_size", "nDirectSize": "direct_size", "nFrameSize": "frame_size",
+             "nFrameOff": "frame_off", "nConvSize": "conv_size", "nLevels": "levels", "nBlocks": "blocks",
+             "nBlocksDone": "blocks_done", "nRank": "rank", "nBlkInit": "blk_init", "fBlkCoef": "blk_coef"}
+    ir = synth.decaying_ir(1, taps)
+    ref = CpuConvolver("oracle")
+    b = pkg.ConvolverBatch(1, 0)
+    d = b.dump(0)
+    assert all(not d[k] for k in d)                     # construct(): NULL / 0
+    assert ref.init(ir, rank, phase) and b.init(0, ir, rank, phase)
+
+    def same(where):
+        want, got = ref.state(), b.dump(0)
+        for k, o in names.items():
+            assert got[k] == want[o], (where, k, got[k], want[o])
+        assert all(got[k] for k in ("vDataBuffer", "vFrame", "vTaskData", "vConvData", "vDirectData", "vData"))
+
+    same("after init")
+    x = synth.noise(3, sum(calls))
+    pos = 0
+    for i, n in enumerate(calls):
+        ref.process(x[pos:pos + n])
+        b.process(x[None, pos:pos + n])
+        pos += n
+        same("after call %d (%d samples)" % (i, n))
+    b.close()

@@ -5,7 +5,8 @@ import ctypes
 import numpy as np
 import pytest
 
-from oracle.bindings import CpuConvolver
+import synth
+from oracle.bindings import CpuConvolver, direct_convolve
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -146,3 +147,60 @@ def test_large_batches_take_the_staged_transforms(pkg, rank, count):
     want = np.fft.irfft(np.fft.rfft(a.astype(np.float64), n, axis=1) * np.fft.rfft(h.astype(np.float64), n)[None, :],
                         n, axis=1)
     assert np.max(np.abs(dst.cpu().numpy() - want)) <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("in_len,inv_len,limit", [
+    ([1000], 300, 256), ([5000, 3000, 4999], 4096, 1024), ([20000, 100], 9000, 128),
+    ([300, 700], 512, 128), ([2000], 2500, 4096), ([120000, 120000, 90000, 120000], 48000, 0),
+    ([70000], 96000, 32768),
+])
+def test_chirp_linear_convolutions_match_the_reference_operator(pkg, in_len, inv_len, limit):
+    """Row f1: SyncChirpProcessor::do_linear_convolutions (SyncChirpProcessor.cpp:1374-1508) --
+    prepend-padded inverse filter, per-channel align offsets, scale over the first vConvLengths
+    samples -- against the CPU restatement of that operator AND the float64 model, at the
+    reference's partition-rank rule (:1224-1250)."""
+    import chirp_model
+    from oracle import bindings
+    inputs = [synth.noise(40 + c, n) for c, n in enumerate(in_len)]
+    inverse = synth.decaying_ir(41, inv_len)[::-1].copy()
+    scale = 0.37
+    got = pkg.chirp_linear_convolutions(inputs, inverse, limit, scale, device=0)
+    want = bindings.chirp_linear_convolutions(inputs, inverse, limit, scale)
+    truth, pl = chirp_model.linear_convolutions(inputs, inverse, limit, scale)
+    assert got.shape == want.shape == truth.shape
+    peak = float(np.max(np.abs(truth)))
+    assert np.max(np.abs(got - want.astype(np.float64))) <= 1e-5 * peak
+    assert np.max(np.abs(got - truth)) <= 1e-5 * peak
+    # layout: nothing before the align offset
+    for ch in range(len(in_len)):
+        assert not got[ch, :pl["align_offsets"][ch]].any()
+
+
+def test_chirp_rejects_partitions_below_the_engine_ranks(pkg):
+    with pytest.raises(pkg.B200ConvError):
+        pkg.chirp_linear_convolutions([synth.noise(1, 100)], synth.noise(2, 50), 64, 1.0, device=0)
+
+
+def test_shared_impulse_response_instances(pkg):
+    """b200conv_init_shared: many channels through one reverb share one set of IR spectra; the
+    lender cannot go away while borrowed from."""
+    n, taps, rank, F = 6, 30000, 10, 512
+    ir = synth.decaying_ir(3, taps)
+    b = pkg.ConvolverBatch(n, 0)
+    assert b.init(0, ir, rank, 0.0)
+    for c in range(1, n):
+        assert b.init_shared(c, 0 if c < 4 else 2, 0.25 * (c % 2))      # borrowing from a borrower resolves to the owner
+    x = np.stack([synth.noise(60 + c, 12 * F) for c in range(n)])
+    out = np.concatenate([b.process(x[:, i * 300:(i + 1) * 300].copy()) for i in range(12 * F // 300)], axis=1)
+    for c in range(n):
+        want = direct_convolve(x[c], ir, out.shape[1])
+        assert np.max(np.abs(out[c] - want)) <= 1e-5 * np.max(np.abs(want))
+    with pytest.raises(pkg.B200ConvError):
+        b.destroy(0)
+    with pytest.raises(pkg.B200ConvError):
+        b.init(0, ir[:100], rank, 0.0)
+    for c in range(1, n):
+        b.destroy(c)
+    b.destroy(0)
+    assert b.rank(0) == 0
+    b.close()

@@ -45,6 +45,39 @@ def test_facade_dump_compiles_against_the_reference_state_dumper(tmp_path):
     assert out.returncode == 0, out.stderr
 
 
+def _build_dump_probe(tmp_path):
+    exe = str(tmp_path / "dump_probe")
+    out = subprocess.run(
+        ["g++", "-std=c++11", "-O1", "-DB200CONV_WITH_STATE_DUMPER", "-DLSP_DSP_UNITS_BUILTIN",
+         "-I", os.path.join(HOST, "include"), "-I", os.path.join(ge.ROOT, "include"),
+         "-I", REF_INC, "-I", os.path.join(ge.ROOT, "oracle", "shim"),
+         os.path.join(HOST, "dump_probe.cpp"), os.path.join(HOST, "Convolver.cpp"),
+         "/root/reference/src/main/iface/IStateDumper.cpp",
+         "-L", ge.PKG_DIR, "-lb200conv", "-Wl,-rpath," + ge.PKG_DIR, "-o", exe],
+        capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INC), reason="needs the reference headers")
+def test_facade_dump_runs_and_writes_the_reference_fields_in_order(tmp_path):
+    """dump() is RUN through the reference's IStateDumper: the first 18 writes carry the names of
+    Convolver.cpp:317-336 in the reference's order (taken from the verbatim build of the reference
+    class), engine extras follow.  Un-initialised object: no GPU needed."""
+    from oracle.bindings import CpuConvolver
+    ge.load().build()
+    exe = _build_dump_probe(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    fields = [ln.split("=") for ln in out.stdout.split()]
+    n_ref, ref_names = CpuConvolver("reference").dump_names()
+    assert n_ref == 18
+    assert [f[0] for f in fields[:18]] == ref_names
+    # construct(): every pointer NULL, every scalar 0 (Convolver.cpp:46-69)
+    assert all(v in ("null", "0") for _, v in fields[:18])
+    assert [f[0] for f in fields[18:]] == ["pEngine", "nDevice", "nPartitions", "nPartOffset", "nFrames"]
+
+
 @pytest.mark.gpu
 def test_host_utest_on_gpu():
     exe = os.path.join(HOST, "utest_convolver")

@@ -35,6 +35,10 @@ CONFIGS = {
     9: ("64 ch x 10 s IR, rank 13, 4096 blocks",      64,  480000,  13, 4096, (0.0,),        "ranks 12..16: k_fwd -> k_mac -> k_inv per block (not fused yet)"),
     10: ("64 ch x 10 s IR, rank 16, 32768 blocks",    64,  480000,  16, 32768, (0.0,),       "largest rank"),
     11: ("4096 mono x 1024-tap IR, 8192-sample calls",  4096, 1024,    11, 8192, (0.0,),        "one partition: the transforms alone (k_fwd + k_inv over 32768 frames per call)"),
+    12: ("1 x 200000 taps, rank 16, 31-sample calls",   1,   200000,  16, 31,   (0.0,),        "calls inside a frame: store + direct-form head in one launch"),
+    13: ("64 ch x 10 s IR, rank 14, 8192 blocks",     64,  480000,  14, 8192, (0.0,),        ""),
+    14: ("64 ch x 10 s IR, rank 15, 16384 blocks",    64,  480000,  15, 16384, (0.0,),       ""),
+    15: ("8 x 60000 taps, rank 10, 77-sample calls",  8,   60000,   10, 77,   (0.0, 0.37),   "utest-like unaligned calls: one launch per step"),
     5: ("cfg5 8 ch x 120 s IR on ONE GPU",            8,   5760000, 11, 1024, (0.0,),        "all 5625 partitions on one GPU; the 8-way split is 1/8 of this per GPU + a 32 KiB all-reduce"),
 }
 
