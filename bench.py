@@ -194,13 +194,16 @@ def run_strong_cfg3(pkg, args, rank, local_rank, world, barrier, peak):
     g = torch.Generator(device="cuda").manual_seed(0x5EED1000 + rank)
     src = torch.rand((n, 64 * BLOCK), generator=g, device="cuda") * 2.0 - 1.0
     dst = torch.empty_like(src)
-    stream = torch.cuda.Stream()
+    # the batch's OWN stream: there the engine knows every enqueued operation and may run a block's
+    # input transform ahead of the previous block's tail (option "early_src", include/b200conv.h)
+    stream = torch.cuda.ExternalStream(b.stream())
     sp, dp = src.data_ptr(), dst.data_ptr()
 
     def call(t):
         o = 4 * (t % 64) * BLOCK
-        b.process_device(dp + o, sp + o, 64 * BLOCK, BLOCK, stream.cuda_stream)
+        b.process_device(dp + o, sp + o, 64 * BLOCK, BLOCK, None)
 
+    torch.cuda.synchronize()                    # the buffers were filled on torch's current stream
     with torch.cuda.stream(stream):
         for t in range(frames):                 # fill the ring
             call(t)
@@ -238,7 +241,7 @@ def run_cfg5(pkg, args, rank, local_rank, world, barrier, peak):
     conv = sharding.PartitionShardedConvolver(pkg, C5, RANK, local_rank, reduce="fused")
     assert conv.init(irs), "device allocation failed"
     p_lo, p_hi, _, _ = sharding.partition_shard(TAPS5, F, world, rank)
-    stream = torch.cuda.Stream()
+    stream = torch.cuda.ExternalStream(conv.batch.stream())    # the batch's own stream (see run_strong_cfg3)
 
     # ---- parity over the whole IR length: 16 blocks of noise, then silence --------------------
     nz = 16
@@ -247,10 +250,11 @@ def run_cfg5(pkg, args, rank, local_rank, world, barrier, peak):
     head = torch.rand((C5, nz * BLOCK), generator=g, device="cuda") * 2.0 - 1.0
     zeros = torch.zeros((C5, BLOCK), device="cuda")
     out = torch.empty((C5, total * BLOCK), device="cuda")
+    torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         for t in range(total):
             src = head[:, t * BLOCK:(t + 1) * BLOCK] if t < nz else zeros
-            conv.process_device(out[:, t * BLOCK:(t + 1) * BLOCK], src, BLOCK, stream)
+            conv.process_device(out[:, t * BLOCK:(t + 1) * BLOCK], src, BLOCK, None)
         stream.synchronize()
     err = None
     if rank == 0:
@@ -278,9 +282,10 @@ def run_cfg5(pkg, args, rank, local_rank, world, barrier, peak):
 
     def call(t):                                # lean host path: the block period is ~15 us at 8 GPUs
         o = 4 * (t % 64) * BLOCK
-        raw.process_device(dp + o, sp + o, 64 * BLOCK, BLOCK, stream.cuda_stream)
+        raw.process_device(dp + o, sp + o, 64 * BLOCK, BLOCK, None)
 
     blocks = 2000
+    torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         for t in range(256):
             call(t)

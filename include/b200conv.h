@@ -211,6 +211,13 @@ void   *b200conv_stream(b200conv_batch_t *h);
  *                 comes back once per audio block: nothing competes with the delivering launch);
  *                 1 (default) = automatic: early only while the caller keeps the GPU busy, i.e. the
  *                 previous ahead-of-time sum was still running when the call arrived
+ *   "early_src"   when a one-launch-per-block kernel may transform its input block before every
+ *                 earlier launch of the stream has completed (it may when no launch still in flight
+ *                 writes that block; this takes the transform out of the launch-to-launch chain,
+ *                 which matters for small batches): 0 = never; 1 (default) = on the batch's own
+ *                 stream, where the library knows everything that is enqueued; 2 = on a caller's
+ *                 stream too -- the caller promises that no kernel it enqueues between two calls
+ *                 signals programmatic launch completion before it has written the input block
  *   "zero_copy"   1 (default) = b200conv_process_planar lets the kernels read / write page-locked
  *                 host matrices directly (no staging copies); 0 = always stage */
 int     b200conv_set_option(b200conv_batch_t *h, const char *name, int value);

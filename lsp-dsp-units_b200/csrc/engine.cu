@@ -285,6 +285,13 @@ static MacPlan plan_mac(uint32_t rank, uint32_t jobs, uint32_t max_nq, int sm_co
     if (splits > 32)    splits = 32;
     if (splits < 1)     splits = 1;
     p.splits        = splits;
+    if ((tune_stages <= 0) && (jobs * p.tiles * splits <= 2u * uint32_t(sm_count)))
+    {
+        /* a grid this small is latency-bound, not bandwidth-bound (at most two CTAs per SM): keep
+         * four stages in flight per CTA instead of two */
+        p.sh.NS         = 4;
+        p.smem          = size_t(2) * p.sh.NS * p.sh.QB * p.sh.TB * sizeof(float2) + p.sh.NS * sizeof(uint64_t) + 16;
+    }
     return p;
 }
 
@@ -464,6 +471,92 @@ static int make_twiddles(uint32_t rank, float2 **out)
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* k_frame launches in flight, per stream                                                       */
+/*                                                                                             */
+/* A k_frame launch carries the programmatic-serialisation attribute, so it may become resident   */
+/* while earlier k_frame launches of the SAME stream -- of this batch or of another one -- are    */
+/* still in their inverse-transform tails.  Reading the caller's input block that early           */
+/* (STEP_EARLY_SRC: the transform does not wait for griddepcontrol.wait, which takes the          */
+/* transform out of the launch-to-launch dependency chain) is safe only if no launch that may     */
+/* still be running writes that block.  This table remembers the output ranges of the k_frame     */
+/* launches enqueued on a stream since its last full dependency (any other operation this library  */
+/* enqueues there, or a host synchronisation); a launch whose input overlaps one of them keeps the */
+/* in-kernel wait.  An early transform also writes ring slot (-t) mod S, last read by the launch    */
+/* RING_SPARE + 1 blocks ago: after FRAME_CHAIN_MAX (< RING_SPARE) launches in a row an            */
+/* early-capable launch is launched WITHOUT the attribute (a full dependency), which bounds the     */
+/* table and proves that reader complete.  Launches that keep the in-kernel wait need no bound.     */
+
+namespace
+{
+    const uint32_t FRAME_CHAIN_MAX = 24;
+    struct FrameHistory
+    {
+        cudaStream_t    st      = nullptr;
+        int             dev     = -1;
+        uint32_t        n       = 0;        /* > FRAME_CHAIN_MAX: more launches in flight than the table holds */
+        uint64_t        stamp   = 0;
+        uintptr_t       lo[FRAME_CHAIN_MAX], hi[FRAME_CHAIN_MAX];
+    };
+    std::mutex      g_hist_lock;
+    FrameHistory    g_hist[32];
+    uint64_t        g_hist_clock = 0;
+
+    FrameHistory *hist_find(cudaStream_t st, int dev, bool create)
+    {
+        FrameHistory *lru = &g_hist[0];
+        for (FrameHistory &h : g_hist)
+        {
+            if ((h.dev == dev) && (h.st == st))
+                return &h;
+            if (h.stamp < lru->stamp)
+                lru     = &h;
+        }
+        if (!create)
+            return nullptr;
+        /* an evicted entry is forgotten: its stream's next launch finds no history, which is safe
+         * only because eviction makes that launch serial (n = FRAME_CHAIN_MAX) */
+        lru->st     = st;
+        lru->dev    = dev;
+        lru->n      = FRAME_CHAIN_MAX + 1;
+        return lru;
+    }
+
+    /* a full dependency has been (or is about to be) enqueued on `st`, or `st` was synchronised */
+    void hist_reset(cudaStream_t st, int dev)
+    {
+        std::lock_guard<std::mutex> lock(g_hist_lock);
+        FrameHistory *h = hist_find(st, dev, false);
+        if (h != nullptr)
+            h->n        = 0;
+    }
+
+    /* Registers a k_frame launch that reads [s_lo, s_hi) and writes [d_lo, d_hi).  `capable`: the
+     * launch would like to transform its input early.  *early: it may; *serial: launch it without
+     * programmatic serialisation (only ever asked of a capable launch). */
+    void hist_launch(cudaStream_t st, int dev, bool capable, uintptr_t s_lo, uintptr_t s_hi,
+                     uintptr_t d_lo, uintptr_t d_hi, bool *early, bool *serial)
+    {
+        std::lock_guard<std::mutex> lock(g_hist_lock);
+        FrameHistory *h = hist_find(st, dev, true);
+        h->stamp        = ++g_hist_clock;
+        *serial         = capable && (h->n >= FRAME_CHAIN_MAX);
+        if (*serial)
+            h->n            = 0;
+        bool clash      = (h->n > FRAME_CHAIN_MAX);
+        for (uint32_t i = 0; (i < h->n) && (i < FRAME_CHAIN_MAX); ++i)
+            clash          |= (s_lo < h->hi[i]) && (h->lo[i] < s_hi);
+        *early          = capable && (!clash);
+        if (h->n < FRAME_CHAIN_MAX)
+        {
+            h->lo[h->n]     = d_lo;
+            h->hi[h->n]     = d_hi;
+        }
+        if (h->n <= FRAME_CHAIN_MAX)
+            h->n           += 1;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* batch                                                                                        */
 
 struct Instance
@@ -491,7 +584,10 @@ static const size_t JOB_RING_MAX = size_t(1) << 15;    /* job upload ring: 64 en
 static const size_t JOB_RING_MIN = size_t(1) << 10;
 static const size_t JOB_DIRECT   = 64;                  /* up to this many jobs a step the kernels read the
                                                            page-locked list in place (no upload copy)        */
-static const size_t RING_SPARE = 8;
+static const size_t RING_SPARE = 32;                    /* spare ring slots: frames transformed ahead of a multi-frame
+                                                           MAC pass (8), and k_frame launches in flight (FRAME_CHAIN_MAX) */
+static_assert(FRAME_CHAIN_MAX < RING_SPARE, "k_frame launches in flight must fit the spare ring slots");
+static const uint64_t EARLY_MAX_BYTES = 150000000ull;  /* launches that stream more than this per block keep the in-kernel wait */
 static const size_t PART_MAX   = 1024;                  /* samples one P1 / P2 segment of a fused step answers */
 
 struct b200conv_batch
@@ -538,6 +634,7 @@ struct b200conv_batch
     bool                    last_was_frame = false; /* the last launch on the stream was a k_frame of this batch */
     bool                    host_io     = false;    /* the running call reads / writes page-locked host matrices */
     int                     opt_fused   = 1, opt_bias = 6, opt_pdl = 1, opt_zero_copy = 1, opt_multi = 8;
+    int                     opt_early_src = 1;      /* 0 never, 1 on the batch's own stream, 2 on any stream */
     uint32_t               *d_tickets   = nullptr;  /* k_frame: one arrival counter per job */
     uint32_t               *d_ring_head = nullptr;  /* k_frame: frames published per instance */
     uint32_t               *h_error     = nullptr;  /* page-locked, device-mapped: a bounded in-kernel wait gave up */
@@ -571,12 +668,13 @@ struct b200conv_batch
 typedef b200conv_batch Batch;
 
 static cudaError_t launch_mac(Batch *b, const StepArgs &a, const MacPlan &p, uint32_t jobs, cudaStream_t st,
-                              bool fused = false)
+                              bool fused = false, bool serial = false)
 {
     auto go = [&]() -> cudaError_t
     {
         if (fused)
-            return launch_frame(a, p, jobs, b->d_tickets, b->reduce, (b->opt_pdl != 0) && (!b->profiling), st);
+            return launch_frame(a, p, jobs, b->d_tickets, b->reduce,
+                                (b->opt_pdl != 0) && (!b->profiling) && (!serial), st);
         return launch_mac_raw(a, p, jobs, st);
     };
     if (!b->profiling)
@@ -634,7 +732,10 @@ static cudaError_t quiesce(Batch *b)
 {
     cudaError_t e = cudaSuccess;
     if (b->stream)
+    {
         e = cudaStreamSynchronize(b->stream);
+        hist_reset(b->stream, b->device);
+    }
     if ((e == cudaSuccess) && b->last_foreign && (b->ev_last != nullptr))
         e = cudaEventSynchronize(b->ev_last);
     b->last_foreign = false;
@@ -696,6 +797,7 @@ static int upload_tables(Batch *b, cudaStream_t st)
 {
     if (!b->desc_dirty)
         return B200CONV_OK;
+    hist_reset(st, b->device);          /* the copies below are full dependencies */
     for (size_t i = 0; i < b->n; ++i)
     {
         b->h_ring_head[i]   = uint32_t(b->inst[i].frames);
@@ -970,8 +1072,8 @@ static int init_range_impl(b200conv_batch_t *b, size_t idx, const float *data, s
     const size_t F      = size_t(1) << (rank - 1);
     const size_t bins   = (count + F - 1) >> (rank - 1);    /* Convolver.cpp:93 */
     const size_t nq     = bins + 1;                         /* folded overlap: one extra row */
-    /* spare slots: one for the overlapped single-frame launches (k_frame), RING_SPARE - 1 so that
-     * up to RING_SPARE frames can be transformed ahead of one multi-frame MAC pass */
+    /* spare slots: frames transformed ahead of one multi-frame MAC pass (up to 8), and the k_frame
+     * launches that may be in flight when a launch writes its slot early (FrameHistory) */
     const size_t S      = part_offset + nq + RING_SPARE;
     if ((part_offset + nq) >= (size_t(1) << 31))
         return fail(B200CONV_ERR_ARG, "impulse response too long");
@@ -1211,6 +1313,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             mp.sh.NS        = (tf == 8) ? 8 : (tf == 4) ? 6 : 4;
             mp.smem         = size_t(2) * mp.sh.NS * mp.sh.QB * mp.sh.TB * sizeof(float2) + 2 * mp.sh.NS * sizeof(uint64_t) + 16;
             TRY(ensure_ypart(b, size_t(nact) * tf * mp.splits * F * sizeof(float2), st));
+            hist_reset(st, b->device);
             a.ypart         = b->ypart;
             a.n_jobs        = nact * tf;
             CU(launch_fwd(a, nact * tf, st));
@@ -1228,7 +1331,23 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
         }
         if (fused && (!used_multi))
         {
-            /* one launch per block for all instances x partitions */
+            /* one launch per block for all instances x partitions.  May its input transform run
+             * ahead of the launches still in flight on this stream? (FrameHistory) */
+            bool early = false, serial = false;
+            {
+                /* worth it only while the transform is a visible share of the block: a launch that
+                 * streams for tens of microseconds hides the chain anyway */
+                const bool capable = (b->opt_pdl != 0) && (!b->profiling) && (per_frame_bytes <= EARLY_MAX_BYTES) &&
+                                     ((b->opt_early_src == 2) || ((b->opt_early_src == 1) && (st == b->stream)));
+                const uintptr_t s_lo = reinterpret_cast<uintptr_t>(src + f * F);
+                const uintptr_t d_lo = reinterpret_cast<uintptr_t>(dst + f * F);
+                hist_launch(st, b->device, capable, s_lo, s_lo + ((b->n - 1) * stride + F) * sizeof(float),
+                            d_lo, d_lo + ((b->n - 1) * dst_stride + F) * sizeof(float), &early, &serial);
+            }
+            if (early)
+                a.flags        |= STEP_EARLY_SRC;
+            else
+                a.flags        &= ~uint32_t(STEP_EARLY_SRC);
             if (eager && b->pend_ready && (b->pend_t == b->t_batch + f) && (!tables_changed))
             {
                 /* partitions q >= 1 were summed ahead of time (launch_pending_mac): transform the
@@ -1241,14 +1360,13 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
                 af.rows         = b->pend_splits + 1;
                 af.row0         = b->pend_splits;
                 af.flags       |= STEP_HEAD_ONLY;
-                /* the predecessor on the own stream is this batch's pending MAC, which never
-                 * touches the caller's input block: fetch and transform it under that MAC */
-                if (st == b->stream)
-                    af.flags       |= STEP_EARLY_SRC;
-                CU(launch_mac(b, af, fp, nact, st, true));
+                /* (the predecessor on the own stream is this batch's pending MAC, which never
+                 * touches the caller's input block: with STEP_EARLY_SRC the block is fetched and
+                 * transformed under that MAC) */
+                CU(launch_mac(b, af, fp, nact, st, true, serial));
             }
             else
-                CU(launch_mac(b, a, plan, nact, st, true));
+                CU(launch_mac(b, a, plan, nact, st, true, serial));
             b->pend_ready   = false;
             b->last_was_frame = (st == b->stream) && (!b->profiling);
             b->stats.launches       += 1;
@@ -1258,6 +1376,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             MacPlan sp      = plan;
             sp.sh.bias      = 0;
             b->pend_ready   = false;
+            hist_reset(st, b->device);
             CU(launch_fwd(a, nact, st));
             CU(launch_mac(b, a, sp, nact, st));
             TRY(attach_park(b, a, nact, st));
@@ -1365,6 +1484,7 @@ static int process_general_fused(Batch *b, float *dst, size_t dst_stride, const 
 {
     const size_t F      = size_t(1) << (b->rank - 1);
     TRY(upload_tables(b, st));
+    hist_reset(st, b->device);          /* launched without programmatic serialisation */
     std::vector<size_t> &pos = b->g_pos;
     std::vector<Job> &jobs = b->g_jobs;
     for (uint32_t i : b->active)
@@ -1533,6 +1653,7 @@ static int process_general_staged(Batch *b, float *dst, size_t dst_stride, const
 {
     const size_t F      = size_t(1) << (b->rank - 1);
     TRY(upload_tables(b, st));
+    hist_reset(st, b->device);
     std::vector<size_t> &pos = b->g_pos;
     std::vector<Job> &fft = b->g_fft, &mac = b->g_mac, &part = b->g_part;
     for (uint32_t i : b->active)
@@ -1726,6 +1847,8 @@ static int process_device2_impl(b200conv_batch_t *b, float *dst, size_t dst_stri
         CU(cudaStreamWaitEvent(st, b->ev_pend, 0));     /* a pending MAC may still be running on the own stream */
 
     /* not initialised -> zeros (Convolver.cpp:219-223) */
+    if (b->active.size() < b->n)
+        hist_reset(st, b->device);
     for (size_t i = 0; i < b->n; )
     {
         if (b->inst[i].active) { ++i; continue; }
@@ -1780,6 +1903,7 @@ static int finish_sync_call(Batch *b)
         b->pend_inflight = true;
     }
     CU(cudaEventSynchronize(b->ev_done));
+    hist_reset(b->stream, b->device);   /* every launch that delivered this block has completed */
     return check_device_error(b);
 }
 
@@ -1832,6 +1956,7 @@ extern "C" int b200conv_process(b200conv_batch_t *b, float *const *dst, const fl
         for (size_t i = 0; i < b->n; ++i)
             if (b->inst[i].active)
                 memcpy(b->h_in + i * c, src[i] + done, c * sizeof(float));
+        hist_reset(b->stream, b->device);
         CU(cudaMemcpyAsync(b->d_in, b->h_in, b->n * c * sizeof(float), cudaMemcpyHostToDevice, b->stream));
         b->eager_call = true;
         int rc = b200conv_process_device(b, b->d_out, b->d_in, c, c, b->stream);
@@ -1900,6 +2025,7 @@ extern "C" int b200conv_process_planar(b200conv_batch_t *b, float *dst, const fl
         if (c > cap)
             c = cap;
         TRY(ensure_staging(b, b->n * c));
+        hist_reset(b->stream, b->device);
         CU(cudaMemcpy2DAsync(b->d_in, c * sizeof(float), src + done, stride * sizeof(float),
                              c * sizeof(float), b->n, cudaMemcpyHostToDevice, b->stream));
         b->eager_call = true;
@@ -2090,6 +2216,7 @@ extern "C" int b200conv_set_option(b200conv_batch_t *b, const char *name, int va
     else if (!strcmp(name, "zero_copy") && (value >= 0) && (value <= 1))    b->opt_zero_copy = value;
     else if (!strcmp(name, "eager") && (value >= 0) && (value <= 1))        b->opt_eager = value;
     else if (!strcmp(name, "early_pend") && (value >= 0) && (value <= 2))   b->opt_early_pend = value;
+    else if (!strcmp(name, "early_src") && (value >= 0) && (value <= 2))    b->opt_early_src = value;
     else if (!strcmp(name, "multi_frame") && ((value == 0) || (value == 1) || (value == 2) || (value == 4) || (value == 8)))
         b->opt_multi = (value == 1) ? 0 : value;
     else
@@ -2124,15 +2251,15 @@ extern "C" int b200conv_reduce_prepare(b200conv_batch_t *b, int grank, int world
     TRY(b200conv_reduce_disconnect(b));
 
     /* exchange buffer (identical layout on every rank):
-     *   slots    [DEPTH][world][channels][F] floats
-     *   flags    [DEPTH][world][channels]    sequence numbers (block + 1)
-     *   consumed [world][channels]           blocks consumed, written by the consuming rank      */
+     *   words    [DEPTH][world][channels][F] x { sample bits, sequence number = block + 1 }
+     *   consumed [world][channels]           blocks consumed, written by the consuming rank
+     *   scratch  [channels][F] floats        this rank's own block (local use only)                */
     const size_t F          = size_t(1) << (b->rank - 1);
     const size_t C          = b->n;
-    b->xchg_slots_bytes     = size_t(REDUCE_DEPTH) * world * C * F * sizeof(float);
-    b->xchg_flags_off       = (b->xchg_slots_bytes + 127) & ~size_t(127);
-    b->xchg_consumed_off    = (b->xchg_flags_off + size_t(REDUCE_DEPTH) * world * C * sizeof(uint32_t) + 127) & ~size_t(127);
-    size_t total            = b->xchg_consumed_off + size_t(world) * C * sizeof(uint32_t);
+    b->xchg_slots_bytes     = size_t(REDUCE_DEPTH) * world * C * F * sizeof(uint2);
+    b->xchg_consumed_off    = (b->xchg_slots_bytes + 127) & ~size_t(127);
+    b->xchg_flags_off       = (b->xchg_consumed_off + size_t(world) * C * sizeof(uint32_t) + 127) & ~size_t(127);   /* scratch */
+    size_t total            = b->xchg_flags_off + C * F * sizeof(float);
     CU(cudaMalloc(&b->xchg, total));
     CU(cudaMemset(b->xchg, 0, total));
     cudaIpcMemHandle_t hnd;
@@ -2180,10 +2307,10 @@ extern "C" int b200conv_reduce_connect(b200conv_batch_t *b, const unsigned char 
     for (uint32_t g = 0; g < r.world; ++g)
     {
         unsigned char *base = (g == r.grank) ? b->xchg : static_cast<unsigned char *>(b->xchg_peer[g]);
-        r.slots[g]          = reinterpret_cast<float *>(base);
-        r.flags[g]          = reinterpret_cast<uint32_t *>(base + b->xchg_flags_off);
+        r.words[g]          = reinterpret_cast<uint2 *>(base);
         r.consumed[g]       = reinterpret_cast<uint32_t *>(base + b->xchg_consumed_off);
     }
+    r.scratch               = reinterpret_cast<float *>(b->xchg + b->xchg_flags_off);
     r.t0                    = uint32_t(frames);
     r.mode                  = (r.world > 1) ? 1u : 0u;
     *b->h_error             = 0;

@@ -108,12 +108,13 @@ enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
  * no collective library call, no host in the loop, no root: an ALL-TO-ALL exchange after which
  * every rank holds the summed block (added in rank order, hence bit-identical on all ranks).
  *   every rank g : the CTA that finishes channel c of block b inverse-transforms its partial
- *                  spectrum, stores the block into slot [b % depth][g][c] of EVERY rank's exchange
- *                  buffer (posted peer stores), fences once at system scope and stores the sequence
- *                  number b + 1 into flag [b % depth][g][c] of every rank;
- *                  then waits until its own flags [b % depth][p][c] read b + 1 for all p, adds the
- *                  world slots, writes the output block, and tells every rank that it has consumed
- *                  block b of channel c (the slot is reused by block b + depth).
+ *                  spectrum and stores the block into slot [b % depth][g][c] of EVERY peer's exchange
+ *                  buffer as 8-byte words { sample bits, sequence number b + 1 } (posted peer stores;
+ *                  an 8-byte store is never torn, so a word whose sequence number matches carries
+ *                  its sample: no fence, no separate flag, one NVLink crossing of latency);
+ *                  then polls its own slots [b % depth][p][c] word by word until the sequence numbers
+ *                  read b + 1, adds the world blocks, writes the output block, and tells every rank
+ *                  that it has consumed block b of channel c (the slot is reused by block b + depth).
  * Sequence numbers, not resettable counters: a late peer can never be mistaken for the next
  * block.  All waits are bounded (a peer that never shows up raises *error instead of hanging the
  * GPU; the host then fails the next call). */
@@ -126,9 +127,9 @@ struct ReduceArgs
     uint32_t    t0;                                 /* frame counter (low 32 bits) at connect time */
     uint32_t    channels;                           /* instances per rank */
     uint32_t    frame;                              /* F */
-    float      *slots[REDUCE_MAX_WORLD];            /* rank p's [depth][world][channels][F]  (p == grank: local) */
-    uint32_t   *flags[REDUCE_MAX_WORLD];            /* rank p's [depth][world][channels] arrival sequence numbers */
+    uint2      *words[REDUCE_MAX_WORLD];            /* rank p's [depth][world][channels][F] {bits, seq}  (p == grank: local) */
     uint32_t   *consumed[REDUCE_MAX_WORLD];         /* rank p's [world][channels]: blocks rank g has consumed, written by g */
+    float      *scratch;                            /* local [channels][F]: this rank's own block */
 };
 
 __device__ __forceinline__ uint64_t global_ns()
@@ -1519,13 +1520,22 @@ k_mac_multi(const StepArgs a, const MacShape sh)
 /* for any call size:                                                                           */
 /*     dst[i] = pend[off + i] + sum_{j <= off + i} cur[j] * head[off + i - j],   i in [i0, i1)     */
 /* Parallel across outputs AND taps: a group of G lanes (a power of two, inside one warp) shares    */
-/* one output, lane l takes the taps j = l, l + G, ...; fp32 products in four independent chains,    */
-/* runs of <= 64 terms per lane, run totals in fp64, group totals by shuffle.  Every thread of the   */
-/* CTA must call it (T a multiple of 32).                                                        */
+/* one output, lane l takes the taps j = l, l + G, ... .  The taps are walked in tiles of PO_TILE:   */
+/* the CTA stages cur[tile] and the matching window of `head` in shared memory with coalesced       */
+/* loads (all in flight at once -- a serial chain of dependent global loads per tap is what made     */
+/* the first version latency-bound), then every group sums its output's share of the tile from      */
+/* shared memory: fp32 products in four independent chains, chain totals added in fp64 per tile,     */
+/* group totals by shuffle.  Samples newer than the group's newest output are never read (`cur`      */
+/* beyond them is stale), taps beyond an output's own index meet a zero in the head window.          */
+/* Every thread of the CTA must call it (T a multiple of 32, T <= PO_MAXT).                          */
+
+constexpr uint32_t PO_TILE  = 2048;
+constexpr uint32_t PO_MAXT  = 512;
+constexpr uint32_t PO_SMEM_FLOATS = 2 * PO_TILE + PO_MAXT;     /* cur tile | head window */
 
 __device__ __forceinline__ void partial_outputs(const float *cur, const float *head, const float *pend,
                                                 float *dst, uint32_t off, uint32_t i0, uint32_t i1,
-                                                uint32_t tid, uint32_t T)
+                                                uint32_t tid, uint32_t T, float *po_smem)
 {
     const uint32_t n        = i1 - i0;
     if (n == 0)
@@ -1533,30 +1543,48 @@ __device__ __forceinline__ void partial_outputs(const float *cur, const float *h
     uint32_t G              = 1;
     while ((G < 32) && (n * G * 2 <= T))
         G                     <<= 1;
-    const uint32_t per_pass = T / G;
+    const uint32_t per_pass = T / G;                                /* outputs per window */
     const uint32_t lane     = tid % G, grp = tid / G;
-    for (uint32_t base = 0; base < n; base += per_pass)            /* uniform trip count */
+    float *cs               = po_smem;                              /* cs[j - j0]                      */
+    float *hs               = po_smem + PO_TILE;                    /* hs[k] = head[hbase + k]          */
+
+    for (uint32_t base = 0; base < n; base += per_pass)            /* uniform trip counts throughout */
     {
-        const uint32_t i        = i0 + base + grp;
-        const bool live         = (base + grp) < n;
+        const uint32_t ia       = i0 + base;                        /* window of outputs [ia, ib) */
+        const uint32_t ib       = min(ia + per_pass, i1);
+        const uint32_t i        = ia + grp;
+        const bool live         = i < ib;
+        const uint32_t m_max    = off + ib - 1;                     /* newest sample of the window */
         double total            = 0.0;
-        if (live)
+        for (uint32_t j0 = 0; j0 <= m_max; j0 += PO_TILE)
         {
-            const uint32_t m        = off + i;
-            for (uint32_t j0 = lane; j0 <= m; j0 += 64 * G)
+            /* head indices needed: (off + i) - j for i in [ia, ib), j in [j0, j0 + TILE) */
+            const int32_t hbase     = int32_t(off + ia) - int32_t(j0) - int32_t(PO_TILE) + 1;
+            const uint32_t hcount   = PO_TILE + (ib - ia) - 1;
+            /* taps of this tile that exist: [j0, j0 + kend), kend a multiple of the 4 G stride */
+            const uint32_t kend     = min(PO_TILE, (m_max - j0 + 4 * G) & ~(4 * G - 1));
+            __syncthreads();                                        /* previous tile / window consumed */
+            for (uint32_t k = tid; k < kend; k += T)
+                cs[k]                   = (j0 + k <= m_max) ? cur[j0 + k] : 0.0f;
+            for (uint32_t k = (PO_TILE - kend) + tid; k < hcount; k += T)
             {
-                const uint32_t j1       = min(j0 + 64 * G, m + 1);
+                const int32_t h         = hbase + int32_t(k);
+                hs[k]                   = (h >= 0) ? head[h] : 0.0f;
+            }
+            __syncthreads();
+            if (live)
+            {
+                /* head[(off + i) - j] = hs[(i - ia) + (TILE - 1) - (j - j0)] */
+                const float *hp         = hs + (i - ia) + (PO_TILE - 1);
                 float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
-                uint32_t j              = j0;
-                for ( ; j + 3 * G < j1; j += 4 * G)
+                #pragma unroll 2
+                for (uint32_t k = lane; k < kend; k += 4 * G)
                 {
-                    p0                      = fmaf(cur[j],         head[m - j],         p0);
-                    p1                      = fmaf(cur[j + G],     head[m - j - G],     p1);
-                    p2                      = fmaf(cur[j + 2 * G], head[m - j - 2 * G], p2);
-                    p3                      = fmaf(cur[j + 3 * G], head[m - j - 3 * G], p3);
+                    p0                      = fmaf(cs[k],         hp[-int32_t(k)],         p0);
+                    p1                      = fmaf(cs[k + G],     hp[-int32_t(k + G)],     p1);
+                    p2                      = fmaf(cs[k + 2 * G], hp[-int32_t(k + 2 * G)], p2);
+                    p3                      = fmaf(cs[k + 3 * G], hp[-int32_t(k + 3 * G)], p3);
                 }
-                for ( ; j < j1; j += G)
-                    p0                      = fmaf(cur[j], head[m - j], p0);
                 total                  += double((p0 + p1) + (p2 + p3));
             }
         }
@@ -1721,6 +1749,23 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
         while ((issued < NS) && (issued < n_main))
             issue_next();
 
+    float *po               = nullptr;
+    if constexpr (GEN)
+    {
+        __shared__ float po_scratch[PO_SMEM_FLOATS];
+        po                      = po_scratch;
+        if (fft_cta && (job.n > 0))
+        {
+            /* P1: the call's samples that continue the frame in progress, answered at once (from
+             * the OLD pending block) while the first partition stages are in flight */
+            for (uint32_t i = tid; i < job.n; i += T)
+                d.cur[job.off + i]  = job.psrc[i];
+            __syncthreads();
+            partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, 0, job.n, tid, T, po);
+            __syncthreads();
+        }
+    }
+
     float4 acc[MAC_VPT];
     #pragma unroll
     for (int v = 0; v < MAC_VPT; ++v)
@@ -1777,15 +1822,6 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
              * ring slot (-t) mod S.  Exception: the host knows the predecessor (STEP_EARLY_SRC). */
             if (!(a.flags & STEP_EARLY_SRC))
                 asm volatile("griddepcontrol.wait;" ::: "memory");
-            if (GEN && (job.n > 0))
-            {
-                /* P1: the call's samples that continue the frame in progress, answered at once */
-                for (uint32_t i = tid; i < job.n; i += T)
-                    d.cur[job.off + i]  = job.psrc[i];
-                __syncthreads();
-                partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, 0, job.n, tid, T);
-                __syncthreads();
-            }
             if ((!GEN) || (job.flags & JOB_FFT))
             {
             /* every stage buffer is idle here: two work buffers (one at rank 13) + the twiddle table */
@@ -1896,7 +1932,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
             for (uint32_t i = tid; i < job.n2; i += T)
                 d.cur[job.off2 + i] = job.psrc2[i];
             __syncthreads();
-            partial_outputs(d.cur, d.head, job.dst, job.pdst2, job.off2, 0, job.n2, tid, T);
+            partial_outputs(d.cur, d.head, job.dst, job.pdst2, job.off2, 0, job.n2, tid, T, po);
         }
         FRAME_STAMP(3);
         return;
@@ -1908,8 +1944,8 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     const uint32_t ch       = job.inst;
     const uint32_t blk      = job.tlo - ra.t0;          /* block number since the ranks connected */
     const uint32_t s        = blk % uint32_t(REDUCE_DEPTH);
-    const size_t   slot_of_g = ((size_t(s) * W + g) * ra.channels + ch) * F;    /* same offset in every rank's buffer */
-    const size_t   flag_of_g = (size_t(s) * W + g) * ra.channels + ch;
+    const uint32_t seq      = blk + 1u;
+    const size_t   word_of_g = ((size_t(s) * W + g) * ra.channels + ch) * F;   /* same offset in every rank's buffer */
 
     /* slot s is free on rank p once p has consumed block blk - DEPTH of this channel */
     if ((tid < W) && (tid != g) && (blk >= uint32_t(REDUCE_DEPTH)))
@@ -1917,56 +1953,67 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
                       a.error, SPIN_ERR_PEER);
     __syncthreads();
 
-    float *mine             = ra.slots[g] + slot_of_g;
+    float *mine             = ra.scratch + size_t(ch) * F;
     inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, mine, a.tw, tw, false, int(tid));
     __syncthreads();
-    for (uint32_t i = tid; i < F / 4; i += T)
+
+    /* send: two samples and their sequence numbers per 16-byte store, to every peer */
+    for (uint32_t i = tid; i < F / 2; i += T)
     {
-        const float4 v      = reinterpret_cast<const float4 *>(mine)[i];
+        const float2 v      = reinterpret_cast<const float2 *>(mine)[i];
+        const uint32_t b0   = __float_as_uint(v.x), b1 = __float_as_uint(v.y);
         for (uint32_t p = 0; p < W; ++p)
             if (p != g)
-                reinterpret_cast<float4 *>(ra.slots[p] + slot_of_g)[i] = v;     /* posted peer stores */
+                asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                             :: "l"(ra.words[p] + word_of_g + 2 * i), "r"(b0), "r"(seq), "r"(b1), "r"(seq) : "memory");
     }
-    /* the barrier orders every thread's peer stores before thread 0, whose (cumulative)
-     * system-scope fence then publishes the whole block: one fence, then plain flag stores */
-    __syncthreads();
-    if (tid == 0)
+
+    /* receive and add in rank order (bit-identical on every rank) */
     {
-        __threadfence_system();
-        for (uint32_t p = 0; p < W; ++p)
-            if (p != g)
-                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(ra.flags[p] + flag_of_g), "r"(blk + 1u) : "memory");
-    }
-    if ((tid < W) && (tid != g))
-    {
-        /* equality on a sequence number: a late block of an earlier round can never satisfy it */
-        const uint32_t *fp  = ra.flags[g] + (size_t(s) * W + tid) * ra.channels + ch;
-        wait_ge<true>(fp, blk + 1u, a.error, SPIN_ERR_PEER);
-    }
-    __syncthreads();
-    {
-        const float *base   = ra.slots[g] + (size_t(s) * W * ra.channels + ch) * F;
-        const size_t gstep  = size_t(ra.channels) * F;
-        for (uint32_t i = tid; i < F / 4; i += T)
+        const uint64_t deadline = global_ns() + SPIN_LIMIT_NS;
+        const bool dst8     = (reinterpret_cast<uintptr_t>(job.dst) & 7) == 0;
+        for (uint32_t i = tid; i < F / 2; i += T)
         {
-            float4 sum          = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            for (uint32_t p = 0; p < W; ++p)                        /* rank order: bit-identical on every rank */
+            float2 sum          = make_float2(0.0f, 0.0f);
+            for (uint32_t p = 0; p < W; ++p)
             {
-                const float4 v      = __ldcg(reinterpret_cast<const float4 *>(base + p * gstep) + i);
-                sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                float2 v;
+                if (p == g)
+                    v                   = reinterpret_cast<const float2 *>(mine)[i];
+                else
+                {
+                    const uint2 *wp     = ra.words[g] + ((size_t(s) * W + p) * ra.channels + ch) * F + 2 * i;
+                    uint32_t b0, s0, b1, s1;
+                    for (uint32_t spins = 1; ; ++spins)
+                    {
+                        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(b0), "=r"(s0), "=r"(b1), "=r"(s1) : "l"(wp) : "memory");
+                        if ((s0 == seq) && (s1 == seq))
+                            break;
+                        if (((spins & 255u) == 0) && (global_ns() > deadline))
+                        {
+                            spin_fail(a.error, SPIN_ERR_PEER);
+                            break;
+                        }
+                    }
+                    v                   = make_float2(__uint_as_float(b0), __uint_as_float(b1));
+                }
+                sum.x              += v.x;
+                sum.y              += v.y;
             }
-            if ((reinterpret_cast<uintptr_t>(job.dst) & 15) == 0)
-                reinterpret_cast<float4 *>(job.dst)[i] = sum;
+            if (dst8)
+                reinterpret_cast<float2 *>(job.dst)[i] = sum;
             else
             {
-                job.dst[4 * i] = sum.x; job.dst[4 * i + 1] = sum.y; job.dst[4 * i + 2] = sum.z; job.dst[4 * i + 3] = sum.w;
+                job.dst[2 * i]      = sum.x;
+                job.dst[2 * i + 1]  = sum.y;
             }
         }
     }
     __syncthreads();
     if ((tid < W) && (tid != g))
         asm volatile("st.relaxed.sys.global.u32 [%0], %1;"
-                     :: "l"(ra.consumed[tid] + size_t(g) * ra.channels + ch), "r"(blk + 1u) : "memory");
+                     :: "l"(ra.consumed[tid] + size_t(g) * ra.channels + ch), "r"(seq) : "memory");
     FRAME_STAMP(3);
 }
 
@@ -1990,13 +2037,14 @@ __global__ void k_store(const StepArgs a)
 __global__ void __launch_bounds__(256)
 k_partial(const StepArgs a)
 {
+    __shared__ float po[PO_SMEM_FLOATS];
     for (uint32_t jb = blockIdx.y; jb < a.n_jobs; jb += gridDim.y)
     {
         const Job job       = a.jobs[jb];
         const InstDesc &d   = a.inst[job.inst];
         const uint32_t per  = (job.n + gridDim.x - 1) / gridDim.x;
         const uint32_t i0   = min(job.n, blockIdx.x * per), i1 = min(job.n, i0 + per);
-        partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, i0, i1, threadIdx.x, blockDim.x);
+        partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, i0, i1, threadIdx.x, blockDim.x, po);
     }
 }
 
@@ -2005,6 +2053,7 @@ k_partial(const StepArgs a)
 __global__ void __launch_bounds__(256)
 k_partial_fused(const StepArgs a)
 {
+    __shared__ float po[PO_SMEM_FLOATS];
     for (uint32_t jb = blockIdx.x; jb < a.n_jobs; jb += gridDim.x)
     {
         const Job job       = a.jobs[jb];
@@ -2012,7 +2061,7 @@ k_partial_fused(const StepArgs a)
         for (uint32_t i = threadIdx.x; i < job.n; i += blockDim.x)
             d.cur[job.off + i]  = job.psrc[i];
         __syncthreads();
-        partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, 0, job.n, threadIdx.x, blockDim.x);
+        partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, 0, job.n, threadIdx.x, blockDim.x, po);
         __syncthreads();
     }
 }

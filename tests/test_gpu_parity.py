@@ -765,6 +765,47 @@ def test_cascaded_batches_on_one_stream(pkg, n, taps, rank):
     assert rel_err(outs[0][0], want) <= TOL
 
 
+@pytest.mark.parametrize("n,taps,rank,own", [(8, 20000, 11, True), (64, 100000, 10, True), (8, 20000, 11, False)])
+def test_early_input_transform_is_bit_identical_and_respects_overlap(pkg, n, taps, rank, own):
+    """Option "early_src": on the batch's own stream (or, with value 2, on a caller's) a block's input
+    transform may run before the previous block's tail has finished -- unless a launch in flight
+    writes that input.  Three patterns per setting: independent buffers (early), feedback
+    (src(t) = dst(t-1): must fall back to the in-kernel wait), and a long back-to-back run that
+    crosses the bounded chain length.  All must equal the serialised (pdl = 0) run bit for bit."""
+    torch = pytest.importorskip("torch")
+    F = 1 << (rank - 1)
+    frames = 70
+    irs = [0.5 * synth.decaying_ir(c, taps) for c in range(2)]
+    g = torch.Generator(device="cuda").manual_seed(21)
+    src = torch.rand((n, frames * F), generator=g, device="cuda") * 2 - 1
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    results = []
+    for pdl, early in ((1, 2 if not own else 1), (0, 0)):
+        b = pkg.ConvolverBatch(n, 0)
+        b.set_option("pdl", pdl)
+        b.set_option("early_src", early)
+        for c in range(n):
+            assert b.init(c, irs[c % 2], rank, 0.0)
+        stream = None if own else st.cuda_stream
+        dst = torch.zeros_like(src)
+        fb = torch.zeros((n, (frames + 1) * F), device="cuda")
+        fb[:, :F] = src[:, :F]
+        torch.cuda.synchronize()
+        for i in range(frames):                             # independent buffers
+            b.process_device(dst.data_ptr() + 4 * i * F, src.data_ptr() + 4 * i * F, frames * F, F, stream)
+        for i in range(frames):                             # feedback
+            b.process_device(fb.data_ptr() + 4 * (i + 1) * F, fb.data_ptr() + 4 * i * F, (frames + 1) * F, F, stream)
+        b.sync()
+        st.synchronize()
+        results.append((dst.cpu().numpy(), fb.cpu().numpy()))
+        b.close()
+    assert np.array_equal(results[0][0], results[1][0])
+    assert np.array_equal(results[0][1], results[1][1])
+    want = direct_convolve(src[0].cpu().numpy(), irs[0], frames * F)
+    assert rel_err(results[0][0][0], want) <= TOL
+
+
 @pytest.mark.parametrize("n,taps,rank", [(8, 20000, 11), (64, 100000, 10)])
 def test_batch_fed_its_own_previous_output(pkg, n, taps, rank):
     """Feedback: block t's input is block t-1's OUTPUT buffer (same stream, back to back).  The
