@@ -387,34 +387,32 @@ static cudaError_t launch_frame_r(const StepArgs &a, const MacPlan &p, uint32_t 
 /* the job-list form (general path): no programmatic serialisation, no cross-GPU reduce */
 template <int RANK>
 static cudaError_t launch_frame_gen_r(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
-                                      cudaStream_t st)
+                                      const JobPack &pack, cudaStream_t st)
 {
     static size_t attr_smem[MAX_DEVICES] = { 0 };
     int dev = current_device();
     if (p.smem > attr_smem[dev])
     {
-        cudaError_t e = cudaFuncSetAttribute(k_frame<RANK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem));
+        cudaError_t e = cudaFuncSetAttribute(k_frame_gen<RANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem));
         if (e != cudaSuccess)
             return e;
         attr_smem[dev] = p.smem;
     }
-    ReduceArgs ra;
-    memset(&ra, 0, sizeof(ra));
-    k_frame<RANK, true><<<dim3(jobs * p.splits, p.tiles), p.threads, p.smem, st>>>(a, p.sh, tickets, ra);
+    k_frame_gen<RANK><<<dim3(jobs * p.splits, p.tiles), p.threads, p.smem, st>>>(a, p.sh, tickets, pack);
     return cudaGetLastError();
 }
 
 static cudaError_t launch_frame_gen(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
-                                    cudaStream_t st)
+                                    const JobPack &pack, cudaStream_t st)
 {
     switch (a.rank)
     {
-        case 8:  return launch_frame_gen_r<8>(a, p, jobs, tickets, st);
-        case 9:  return launch_frame_gen_r<9>(a, p, jobs, tickets, st);
-        case 10: return launch_frame_gen_r<10>(a, p, jobs, tickets, st);
-        case 11: return launch_frame_gen_r<11>(a, p, jobs, tickets, st);
-        case 12: return launch_frame_gen_r<12>(a, p, jobs, tickets, st);
-        case 13: return launch_frame_gen_r<13>(a, p, jobs, tickets, st);
+        case 8:  return launch_frame_gen_r<8>(a, p, jobs, tickets, pack, st);
+        case 9:  return launch_frame_gen_r<9>(a, p, jobs, tickets, pack, st);
+        case 10: return launch_frame_gen_r<10>(a, p, jobs, tickets, pack, st);
+        case 11: return launch_frame_gen_r<11>(a, p, jobs, tickets, pack, st);
+        case 12: return launch_frame_gen_r<12>(a, p, jobs, tickets, pack, st);
+        case 13: return launch_frame_gen_r<13>(a, p, jobs, tickets, pack, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -582,8 +580,6 @@ struct Instance
 
 static const size_t JOB_RING_MAX = size_t(1) << 15;    /* job upload ring: 64 entries per instance, within these bounds */
 static const size_t JOB_RING_MIN = size_t(1) << 10;
-static const size_t JOB_DIRECT   = 64;                  /* up to this many jobs a step the kernels read the
-                                                           page-locked list in place (no upload copy)        */
 static const size_t RING_SPARE = 32;                    /* spare ring slots: frames transformed ahead of a multi-frame
                                                            MAC pass (8), and k_frame launches in flight (FRAME_CHAIN_MAX) */
 static_assert(FRAME_CHAIN_MAX < RING_SPARE, "k_frame launches in flight must fit the spare ring slots");
@@ -613,14 +609,15 @@ struct b200conv_batch
     float2                 *ypart       = nullptr;
     size_t                  ypart_bytes = 0;
 
-    Job                    *h_jobs      = nullptr;  /* page-locked, device-mapped */
-    Job                    *h_jobs_dev  = nullptr;  /* ... its device alias */
+    Job                    *h_jobs      = nullptr;  /* page-locked */
     Job                    *d_jobs      = nullptr;
     size_t                  job_cap     = 0;
     size_t                  job_pos     = 0;
     /* general-path scratch, sized once at create: process() never allocates */
     std::vector<size_t>     g_pos;
     std::vector<Job>        g_jobs, g_fft, g_mac, g_part;
+    double                 *d_partials  = nullptr;  /* k_partial_tiles: [job][tile][PT_MAXN] */
+    size_t                  partials_jobs = 0;
     bool                    uniform_stale = false;  /* instances advanced one by one: t_delta must be refreshed */
 
     float                  *h_in = nullptr, *h_out = nullptr;   /* pinned staging */
@@ -960,8 +957,7 @@ static int create_impl(b200conv_batch_t **out, int device, size_t instances)
         if (b->job_cap < JOB_RING_MIN)  b->job_cap = JOB_RING_MIN;
         if (b->job_cap > JOB_RING_MAX)  b->job_cap = JOB_RING_MAX;
         if (b->job_cap < 3 * instances) b->job_cap = 3 * instances;    /* one unfused step: three lists */
-        CU_BRK(cudaHostAlloc(&b->h_jobs, b->job_cap * sizeof(Job), cudaHostAllocMapped | cudaHostAllocPortable));
-        CU_BRK(cudaHostGetDevicePointer(&b->h_jobs_dev, b->h_jobs, 0));
+        CU_BRK(cudaMallocHost(&b->h_jobs, b->job_cap * sizeof(Job)));
         CU_BRK(cudaMalloc(&b->d_jobs, b->job_cap * sizeof(Job)));
         CU_BRK(cudaMemset(b->d_desc, 0, instances * sizeof(InstDesc)));
         CU_BRK(cudaMalloc(&b->d_tickets, instances * sizeof(uint32_t)));
@@ -996,6 +992,7 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
         if (t) cudaFree(t);
     if (b->ypart)       cudaFree(b->ypart);
     if (b->park)        cudaFree(b->park);
+    if (b->d_partials)  cudaFree(b->d_partials);
     if (b->d_desc)      cudaFree(b->d_desc);
     if (b->d_active)    cudaFree(b->d_active);
     if (b->d_tickets)   cudaFree(b->d_tickets);
@@ -1454,16 +1451,20 @@ static inline uint32_t slot_of(const Instance &in, uint64_t t)
     return uint32_t((tm == 0) ? 0 : in.S - tm);
 }
 
-/* Where the kernels of one step find its job list: up to JOB_DIRECT jobs are read in place from
- * the page-locked, device-mapped ring (no copy operation in the stream -- a real-time call is one
- * kernel launch); longer lists are uploaded. */
-static int publish_jobs(Batch *b, size_t at, size_t count, cudaStream_t st, const Job **dev)
+/* Where the kernels of one step find its job list: up to JOB_PACK jobs ride in the kernel's
+ * parameter space (*dev = NULL: no copy operation in the stream -- a real-time call is one kernel
+ * launch); longer lists are uploaded from the page-locked ring. */
+static int publish_jobs(Batch *b, const Job *list, size_t count, cudaStream_t st, JobPack *pack, const Job **dev)
 {
-    if (count <= JOB_DIRECT)
+    if (count <= JOB_PACK)
     {
-        *dev        = b->h_jobs_dev + at;
+        memcpy(pack->j, list, count * sizeof(Job));
+        *dev        = nullptr;
         return B200CONV_OK;
     }
+    size_t at   = 0;
+    TRY(reserve_jobs(b, count, st, &at));
+    memcpy(b->h_jobs + at, list, count * sizeof(Job));
     TRY(push_jobs(b, at, count, st));
     *dev        = b->d_jobs + at;
     return B200CONV_OK;
@@ -1607,16 +1608,14 @@ static int process_general_fused(Batch *b, float *dst, size_t dst_stride, const 
         if (jobs.empty())
             break;
 
-        size_t at = 0;
-        TRY(reserve_jobs(b, jobs.size(), st, &at));
-        memcpy(b->h_jobs + at, jobs.data(), jobs.size() * sizeof(Job));
         StepArgs a  = base_args(b);
-        TRY(publish_jobs(b, at, jobs.size(), st, &a.jobs));
+        JobPack pack;
+        TRY(publish_jobs(b, jobs.data(), jobs.size(), st, &pack, &a.jobs));
         a.n_jobs    = uint32_t(jobs.size());
         if ((n_mac == 0) && (n_fft == 0))
         {
             /* every job sits inside a frame: store + answer, one CTA per job */
-            k_partial_fused<<<a.n_jobs, 256, 0, st>>>(a);
+            k_partial_fused<<<a.n_jobs, 256, 0, st>>>(a, pack);
             CU(cudaGetLastError());
             b->stats.launches += 1;
             continue;
@@ -1627,7 +1626,7 @@ static int process_general_fused(Batch *b, float *dst, size_t dst_stride, const 
         TRY(ensure_ypart(b, jobs.size() * plan.splits * F * sizeof(float2), st));
         a.ypart     = b->ypart;
         a.splits    = plan.splits;
-        CU(launch_frame_gen(a, plan, a.n_jobs, b->d_tickets, st));
+        CU(launch_frame_gen(a, plan, a.n_jobs, b->d_tickets, pack, st));
         b->stats.launches       += 1;
         if (n_mac > 0)
         {
@@ -1751,26 +1750,62 @@ static int process_general_staged(Batch *b, float *dst, size_t dst_stride, const
         if (total == 0)
             break;
 
+        /* the transform / MAC lists are uploaded (their kernels take device lists); a short list of
+         * samples to answer rides in the launch parameters */
+        size_t maxn = 0;
+        for (const Job &pj : part)
+            if (pj.n > maxn) maxn = pj.n;
+        const bool part_packed = (!part.empty()) && (maxn <= 256) && (part.size() <= JOB_PACK);
+        const size_t n_up = (part_packed ? 0 : part.size()) + fft.size() + mac.size();
+        const size_t part_up = part_packed ? 0 : part.size();
         size_t at = 0;
-        TRY(reserve_jobs(b, total, st, &at));
-        Job *hj = b->h_jobs + at;
-        if (!part.empty())  memcpy(hj, part.data(), part.size() * sizeof(Job));
-        if (!fft.empty())   memcpy(hj + part.size(), fft.data(), fft.size() * sizeof(Job));
-        if (!mac.empty())   memcpy(hj + part.size() + fft.size(), mac.data(), mac.size() * sizeof(Job));
-        const Job *dj = nullptr;
-        TRY(publish_jobs(b, at, total, st, &dj));
+        if (n_up > 0)
+        {
+            TRY(reserve_jobs(b, n_up, st, &at));
+            Job *hj = b->h_jobs + at;
+            if (part_up > 0)    memcpy(hj, part.data(), part.size() * sizeof(Job));
+            if (!fft.empty())   memcpy(hj + part_up, fft.data(), fft.size() * sizeof(Job));
+            if (!mac.empty())   memcpy(hj + part_up + fft.size(), mac.data(), mac.size() * sizeof(Job));
+            TRY(push_jobs(b, at, n_up, st));
+        }
+        const Job *dj = b->d_jobs + at;
 
         StepArgs a  = base_args(b);
         if (!part.empty())
         {
-            a.jobs      = dj;
+            a.jobs      = part_packed ? nullptr : dj;
             a.n_jobs    = uint32_t(part.size());
-            size_t maxn = 0;
+            size_t deepest = 0;
             for (const Job &pj : part)
-                if (pj.n > maxn) maxn = pj.n;
-            if (maxn <= 256)
+                if (size_t(pj.off) + pj.n > deepest) deepest = size_t(pj.off) + pj.n;
+            const uint32_t max_tiles = uint32_t((F + PO_TILE - 1) / PO_TILE);
+            if ((maxn <= PT_MAXN) && (deepest > 2 * PO_TILE) && (a.n_jobs <= 65535u))
             {
-                k_partial_fused<<<a.n_jobs, 256, 0, st>>>(a);
+                /* deep inside a long frame: the tap tiles of every job side by side */
+                if (part.size() > b->partials_jobs)
+                {
+                    CU(cudaStreamSynchronize(st));
+                    if (b->d_partials) cudaFree(b->d_partials);
+                    b->d_partials       = nullptr;
+                    b->partials_jobs    = 0;
+                    size_t want         = (part.size() < 16) ? 16 : part.size();    /* outside the steady state only */
+                    CU(cudaMalloc(&b->d_partials, want * max_tiles * PT_MAXN * sizeof(double)));
+                    b->partials_jobs    = want;
+                }
+                JobPack pack;
+                if (part_packed)
+                    memcpy(pack.j, part.data(), part.size() * sizeof(Job));
+                dim3 gt(uint32_t((deepest - 1) / PO_TILE + 1), a.n_jobs);
+                k_partial_tiles<<<gt, 256, 0, st>>>(a, pack, b->d_partials, b->d_tickets, max_tiles);
+                CU(cudaGetLastError());
+                b->stats.launches += 1;
+            }
+            else if (maxn <= 256)
+            {
+                JobPack pack;
+                if (part_packed)
+                    memcpy(pack.j, part.data(), part.size() * sizeof(Job));
+                k_partial_fused<<<a.n_jobs, 256, 0, st>>>(a, pack);
                 CU(cudaGetLastError());
                 b->stats.launches += 1;
             }
@@ -1788,7 +1823,7 @@ static int process_general_staged(Batch *b, float *dst, size_t dst_stride, const
         }
         if (!fft.empty())
         {
-            a.jobs      = dj + part.size();
+            a.jobs      = dj + part_up;
             a.n_jobs    = uint32_t(fft.size());
             CU(launch_fwd(a, a.n_jobs, st));
             b->stats.launches++;
@@ -1799,7 +1834,7 @@ static int process_general_staged(Batch *b, float *dst, size_t dst_stride, const
                                     b->sm_count, b->tune_splits, b->tune_stages);
             TRY(ensure_ypart(b, mac.size() * plan.splits * F * sizeof(float2), st));
             a.ypart     = b->ypart;
-            a.jobs      = dj + part.size() + fft.size();
+            a.jobs      = dj + part_up + fft.size();
             a.n_jobs    = uint32_t(mac.size());
             a.splits    = plan.splits;
             CU(launch_mac(b, a, plan, a.n_jobs, st));
@@ -1811,7 +1846,9 @@ static int process_general_staged(Batch *b, float *dst, size_t dst_stride, const
         }
     }
 
-    b->desc_dirty = true;       /* ring_head was bypassed; per-instance frame counters moved */
+    /* ring_head was bypassed and the per-instance frame counters moved: both matter only to a
+     * k_frame launch, which refreshes the tables first (uniform_stale) */
+    b->uniform_stale = true;
     b->pend_ready = false;
     return B200CONV_OK;
 }

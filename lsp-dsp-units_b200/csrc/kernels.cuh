@@ -69,6 +69,15 @@ struct Job                          /* explicit work item (general path, init, p
 enum { JOB_FFT = 1, JOB_MAC = 2,
        JOB_FFT_PREV = 4 /* the transformed frame is t - 1 (the MAC prepares frame t): publish t, not t + 1 */ };
 
+/* A short job list travels in the kernel's parameter space (constant bank: no copy operation in
+ * the stream, no trip across PCIe or to DRAM before a CTA knows what to do) -- the latency of a
+ * real-time call is one kernel launch.  Longer lists are uploaded to device memory (StepArgs::jobs). */
+constexpr uint32_t JOB_PACK = 16;
+struct JobPack
+{
+    Job j[JOB_PACK];
+};
+
 struct StepArgs                     /* by-value kernel argument */
 {
     const InstDesc *inst;
@@ -1635,9 +1644,9 @@ struct FrameCfg
 /* GEN = the job-list form for the general path (a.jobs != NULL): per job any of P1 / FFT / MAC +
  * inverse / P2 (see Job).  Launched WITHOUT programmatic serialisation -- every earlier launch has
  * completed -- so ring_head only orders CTAs of this launch. */
-template <int RANK, bool GEN = false>
-__global__ void __launch_bounds__(FrameCfg<RANK>::T, FrameCfg<RANK>::MINB)
-k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs ra)
+template <int RANK, bool GEN>
+__device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh, uint32_t *tickets,
+                                           const ReduceArgs &ra, const Job *pack)
 {
     using C = FftCfg<RANK, FrameCfg<RANK>::T>;
     constexpr uint32_t M = C::M, T = C::T, TB = FrameCfg<RANK>::TB;
@@ -1671,7 +1680,7 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     __syncthreads();
 
     /* the instance / job tables are written by stream-ordered memcpys, never by a kernel */
-    const Job job           = fetch_job(a, jobi);
+    const Job job           = (GEN && (a.jobs == nullptr)) ? pack[jobi] : fetch_job(a, jobi);
     const InstDesc d        = a.inst[job.inst];
     const bool split0       = (split == 0);
     const bool fft_cta      = split0 && (tile == 0);
@@ -2017,6 +2026,23 @@ k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs
     FRAME_STAMP(3);
 }
 
+template <int RANK>
+__global__ void __launch_bounds__(FrameCfg<RANK>::T, FrameCfg<RANK>::MINB)
+k_frame(const StepArgs a, const MacShape sh, uint32_t *tickets, const ReduceArgs ra)
+{
+    frame_body<RANK, false>(a, sh, tickets, ra, nullptr);
+}
+
+/* the job-list form; a.jobs == NULL: the (at most JOB_PACK) jobs are in `pack` */
+template <int RANK>
+__global__ void __launch_bounds__(FrameCfg<RANK>::T, FrameCfg<RANK>::MINB)
+k_frame_gen(const StepArgs a, const MacShape sh, uint32_t *tickets, const __grid_constant__ JobPack pack)
+{
+    ReduceArgs ra;
+    ra.mode = 0;
+    frame_body<RANK, true>(a, sh, tickets, ra, pack.j);
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* Partial-call path (calls that do not complete whole frames, or a non-zero phase)              */
 
@@ -2051,18 +2077,110 @@ k_partial(const StepArgs a)
 /* Both in ONE launch for steps in which no frame completes (a call inside a frame): one CTA per
  * job stores the samples and answers them. */
 __global__ void __launch_bounds__(256)
-k_partial_fused(const StepArgs a)
+k_partial_fused(const StepArgs a, const __grid_constant__ JobPack pack)
 {
     __shared__ float po[PO_SMEM_FLOATS];
     for (uint32_t jb = blockIdx.x; jb < a.n_jobs; jb += gridDim.x)
     {
-        const Job job       = a.jobs[jb];
+        const Job job       = (a.jobs == nullptr) ? pack.j[jb] : a.jobs[jb];
         const InstDesc &d   = a.inst[job.inst];
         for (uint32_t i = threadIdx.x; i < job.n; i += blockDim.x)
             d.cur[job.off + i]  = job.psrc[i];
         __syncthreads();
         partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, 0, job.n, threadIdx.x, blockDim.x, po);
         __syncthreads();
+    }
+}
+
+/* k_partial_tiles : the same answer for a call deep inside a LONG frame (ranks 14..16: up to 32768
+ * taps per output sample), with the tap tiles spread over grid.x CTAs instead of walked one after
+ * the other: CTA (t, job) sums tile t for every output of the job (fp64 partial per output, into
+ * `partials` [job][tile][PT_MAXN]), the last CTA of a job to finish (ticket) adds the tiles in
+ * order -- deterministic -- and delivers.  n <= PT_MAXN outputs per job; the new samples are read
+ * from the caller's segment (never from `cur`), and the segment's outputs are written only after
+ * every CTA has taken its ticket, so pdst == psrc is safe. */
+constexpr uint32_t PT_MAXN = 256;
+
+__global__ void __launch_bounds__(256)
+k_partial_tiles(const StepArgs a, const __grid_constant__ JobPack pack, double *partials, uint32_t *tickets,
+                uint32_t max_tiles)
+{
+    __shared__ float po[PO_SMEM_FLOATS];
+    __shared__ uint32_t last;
+    const uint32_t tid      = threadIdx.x, T = blockDim.x;
+    const uint32_t jb       = blockIdx.y, tile = blockIdx.x;
+    const Job job           = (a.jobs == nullptr) ? pack.j[jb] : a.jobs[jb];
+    const InstDesc d        = a.inst[job.inst];
+    const uint32_t n        = job.n, off = job.off;
+    const uint32_t m_max    = off + n - 1;
+    const uint32_t tiles    = m_max / PO_TILE + 1;
+    if (tile >= tiles)
+        return;
+
+    uint32_t G              = 1;
+    while ((G < 32) && (n * G * 2 <= T))
+        G                     <<= 1;
+    const uint32_t lane     = tid % G, i = tid / G;             /* one window: T / G >= n */
+    const bool live         = i < n;
+    float *cs               = po, *hs = po + PO_TILE;
+    const uint32_t j0       = tile * PO_TILE;
+    const int32_t hbase     = int32_t(off) - int32_t(j0) - int32_t(PO_TILE) + 1;
+    const uint32_t hcount   = PO_TILE + n - 1;
+    const uint32_t kend     = min(PO_TILE, (m_max - j0 + 4 * G) & ~(4 * G - 1));
+    for (uint32_t k = tid; k < kend; k += T)
+    {
+        const uint32_t j        = j0 + k;
+        cs[k]                   = (j < off) ? d.cur[j] : ((j <= m_max) ? job.psrc[j - off] : 0.0f);
+    }
+    for (uint32_t k = (PO_TILE - kend) + tid; k < hcount; k += T)
+    {
+        const int32_t h         = hbase + int32_t(k);
+        hs[k]                   = (h >= 0) ? d.head[h] : 0.0f;
+    }
+    __syncthreads();
+    double total            = 0.0;
+    if (live)
+    {
+        const float *hp         = hs + i + (PO_TILE - 1);
+        float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+        #pragma unroll 2
+        for (uint32_t k = lane; k < kend; k += 4 * G)
+        {
+            p0                      = fmaf(cs[k],         hp[-int32_t(k)],         p0);
+            p1                      = fmaf(cs[k + G],     hp[-int32_t(k + G)],     p1);
+            p2                      = fmaf(cs[k + 2 * G], hp[-int32_t(k + 2 * G)], p2);
+            p3                      = fmaf(cs[k + 3 * G], hp[-int32_t(k + 3 * G)], p3);
+        }
+        total                   = double((p0 + p1) + (p2 + p3));
+    }
+    for (uint32_t sft = G >> 1; sft > 0; sft >>= 1)
+        total                  += __shfl_xor_sync(0xffffffffu, total, sft);
+    double *mine            = partials + (size_t(jb) * max_tiles + tile) * PT_MAXN;
+    if (live && (lane == 0))
+        mine[i]                 = total;
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+    {
+        const uint32_t old      = atomicAdd(&tickets[jb], 1u);
+        last                    = (old == tiles - 1) ? 1u : 0u;
+        if (last)
+            tickets[jb]             = 0;
+    }
+    __syncthreads();
+    if (!last)
+        return;
+    __threadfence();
+    const double *all       = partials + size_t(jb) * max_tiles * PT_MAXN;
+    for (uint32_t o = tid; o < n; o += T)
+    {
+        double sum              = 0.0;
+        for (uint32_t t = 0; t < tiles; ++t)
+            sum                    += __ldcg(all + size_t(t) * PT_MAXN + o);
+        const float x           = job.psrc[o];
+        job.pdst[o]             = d.pend[off + o] + float(sum);
+        d.cur[off + o]          = x;
     }
 }
 

@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--multi", type=int, default=8)
     ap.add_argument("--no-host", action="store_true")
     ap.add_argument("--eager", type=int, default=1)
+    ap.add_argument("--caller-stream", action="store_true", help="enqueue on a torch stream instead of the batch's own")
     args = ap.parse_args()
     pkg = ge.load()
     peak = 6546.2
@@ -74,11 +75,13 @@ def main():
         frames = max(8, min(512, int(2e8 // (n * block))))
         src = torch.rand((n, frames * block), device="cuda") * 2 - 1
         dst = torch.empty_like(src)
-        st = torch.cuda.Stream()
+        # the batch's own stream (there the engine may run a block's input transform early)
+        st = torch.cuda.ExternalStream(b.stream()) if not args.caller_stream else torch.cuda.Stream()
+        torch.cuda.synchronize()
         def run():
             for i in range(frames):
                 b.process_device(dst.data_ptr() + 4 * i * block, src.data_ptr() + 4 * i * block,
-                                 frames * block, block, st.cuda_stream)
+                                 frames * block, block, st.cuda_stream if args.caller_stream else None)
         with torch.cuda.stream(st):
             run()
             torch.cuda.synchronize()
