@@ -239,7 +239,9 @@ def run_cfg5(pkg, args, rank, local_rank, world, barrier, peak):
     bins5 = (TAPS5 + F - 1) // F
     irs = [synth.decaying_ir(100 + c, TAPS5) for c in range(C5)]
     conv = sharding.PartitionShardedConvolver(pkg, C5, RANK, local_rank, reduce="fused")
+    t_init = time.perf_counter()
     assert conv.init(irs), "device allocation failed"
+    init_ms = (time.perf_counter() - t_init) * 1e3
     p_lo, p_hi, _, _ = sharding.partition_shard(TAPS5, F, world, rank)
     stream = torch.cuda.ExternalStream(conv.batch.stream())    # the batch's own stream (see run_strong_cfg3)
 
@@ -305,6 +307,7 @@ def run_cfg5(pkg, args, rank, local_rank, world, barrier, peak):
         "algorithmic_bytes_per_block_per_gpu": per_gpu_bytes,
         "share_of_hbm_roofline_per_gpu": per_gpu_bytes / (us * 1e-6) / 1e9 / peak,
         "max_err_vs_float64_of_peak": err,
+        "init_ms": init_ms, "init_bytes_h2d_this_gpu": C5 * (min(TAPS5, p_hi * F) - p_lo * F) * 4,
         "parity_span": "%d blocks = the whole IR length + %d (every partition of every rank contributes)" % (total, nz),
         "all_ranks_bit_identical": bool(int(flags) & 2 == 0),
         "peer_wait_timed_out": bool(int(flags) & 1),
@@ -330,6 +333,7 @@ def main():
     ap.add_argument("--pdl", type=int, default=1)
     ap.add_argument("--zero-copy", type=int, default=1)
     ap.add_argument("--eager", type=int, default=1)
+    ap.add_argument("--no-facade", action="store_true", help="skip the C++ facade / pointer-table e2e legs")
     ap.add_argument("--extras-timeout", type=int, default=420)
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra multi-GPU shapes (cfg3 strong scaling, cfg5 partition split)")
@@ -377,9 +381,10 @@ def main():
     # depend on the values, parity at full size is covered by tests/.
     base = rank * INSTANCES
     irs = [synth.decaying_ir(base + c, TAPS) for c in range(8)]
-    for c in range(INSTANCES):
-        ok = batch.init(c, irs[c % 8], RANK, 0.0)
-        assert ok, "device allocation failed"
+    t_init = time.perf_counter()
+    ok = batch.init_many(list(range(INSTANCES)), [irs[c % 8] for c in range(INSTANCES)], RANK)
+    assert ok, "device allocation failed"
+    init_ms = (time.perf_counter() - t_init) * 1e3      # 64 x Convolver::init: upload + 30 016 partition transforms
     frames = args.frames_per_step
     n = frames * BLOCK
     g = torch.Generator(device="cuda").manual_seed(0x5EED0000 + rank)
@@ -453,6 +458,19 @@ def main():
     e2e_value = world * args.steps * e2e_frames * BLOCK * INSTANCES / float(t.item())
     io_bytes = e2e_frames * INSTANCES * BLOCK * 4
 
+    # ---- the reference-facing call itself: 64 x lsp::dspu::Convolver::process (C++ facade, pageable
+    #      buffers, serial loop) and the explicit coalescing API b200conv_process (pointer table) -----
+    facade = None
+    exe = os.path.join(ROOT, "lsp-dsp-units_b200", "host", "bench_facade")
+    if rank == 0 and world == 1 and os.path.exists(exe) and not args.no_facade:
+        try:
+            env = dict(os.environ, B200CONV_DEVICE=str(local_rank))
+            out = subprocess.run([exe, str(INSTANCES), str(TAPS), str(RANK), str(BLOCK), "200"],
+                                 capture_output=True, text=True, timeout=300, env=env)
+            facade = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as exc:
+            facade = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     peak, peak_src = hbm_peak()
     extras = {}
     batch.close()
@@ -510,6 +528,7 @@ def main():
                 "l2": "working set 2 x 246 MB (IR spectra + input-spectrum ring) per GPU streams "
                       "once per call: inputs larger than the 126 MB L2, no flush needed",
                 "sharding": "independent channels per rank, no collective",
+                "init_ms": init_ms, "init_bytes_h2d": INSTANCES * TAPS * 4,
                 "value_share_of_hbm_roofline": value / world * (16 * BINS + 24) / (peak * 1e9),
             },
             "clocks": clocks,
@@ -528,6 +547,10 @@ def main():
                          "isolated_frac": bytes_per_launch / (iso_ms * 1e-3) / 1e9 / peak if iso_ms > 0 else None,
                          "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src},
         }
+        if facade is not None:
+            for k in ("facade_64x_process", "pointer_table_pageable", "error"):
+                if k in facade:
+                    line["e2e"][k] = facade[k]
         line.update(extras)
         if (world == 1) and (not args.no_cpu_baseline):
             cores = min(os.cpu_count() or 1, INSTANCES)

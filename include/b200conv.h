@@ -113,6 +113,15 @@ int     b200conv_init(b200conv_batch_t *h, size_t idx, const float *data, size_t
 int     b200conv_init_range(b200conv_batch_t *h, size_t idx, const float *data, size_t count,
                             size_t rank, float phase, size_t part_offset);
 
+/* Convolver::init for `count` instances in ONE call (the IR ingest of a whole plugin / render job):
+ * instance idx[k] gets data[k][0 .. counts[k]) with phases[k] (NULL: 0) and part_offsets[k] (NULL:
+ * 0); counts[k] == 0 destroys it.  One device allocation, one staged asynchronous upload, one
+ * transform launch over every partition of every instance.  Same rank rule, same failure
+ * guarantee as b200conv_init (nothing changes unless everything was allocated). */
+int     b200conv_init_many(b200conv_batch_t *h, size_t count, const size_t *idx, const float *const *data,
+                           const size_t *counts, size_t rank, const float *phases,
+                           const size_t *part_offsets);
+
 /* Convolver::init for instance `idx` with the SAME impulse response and rank as the initialised
  * instance `src_idx` (many channels through one reverb): the device IR spectra are shared, only the
  * input-spectrum ring and the frame buffers are new.  The lender cannot be destroyed or

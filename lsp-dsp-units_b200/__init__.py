@@ -78,6 +78,8 @@ _SIGNATURES = {
     "b200conv_free": (None, [_VP]),
     "b200conv_init": (ctypes.c_int, [_VP, _SZ, _FP, _SZ, _SZ, ctypes.c_float]),
     "b200conv_init_range": (ctypes.c_int, [_VP, _SZ, _FP, _SZ, _SZ, ctypes.c_float, _SZ]),
+    "b200conv_init_many": (ctypes.c_int, [_VP, _SZ, ctypes.POINTER(_SZ), ctypes.POINTER(_FP), ctypes.POINTER(_SZ), _SZ,
+                                          _FP, ctypes.POINTER(_SZ)]),
     "b200conv_init_shared": (ctypes.c_int, [_VP, _SZ, _SZ, ctypes.c_float]),
     "b200conv_destroy": (ctypes.c_int, [_VP, _SZ]),
     "b200conv_process": (ctypes.c_int, [_VP, ctypes.POINTER(_FP), ctypes.POINTER(_FP), _SZ]),
@@ -165,6 +167,21 @@ class ConvolverBatch:
         False only on allocation failure (previous state kept), like the reference."""
         data = np.ascontiguousarray(data, dtype=np.float32)
         rc = lib().b200conv_init_range(self._h, idx, _ptr(data), data.size, rank, phase, part_offset)
+        if rc == ERR_NOMEM:
+            return False
+        _check(rc)
+        return True
+
+    def init_many(self, indices, irs, rank, phases=None, part_offsets=None):
+        """``Convolver::init`` for many instances in one call (one allocation, one upload, one
+        transform launch); an empty IR destroys its instance.  False on allocation failure."""
+        irs = [np.ascontiguousarray(x, dtype=np.float32) for x in irs]
+        n = len(indices)
+        assert len(irs) == n
+        ph = (ctypes.c_float * n)(*(phases if phases is not None else [0.0] * n))
+        po = (_SZ * n)(*(part_offsets if part_offsets is not None else [0] * n))
+        rc = lib().b200conv_init_many(self._h, n, (_SZ * n)(*indices), (_FP * n)(*[_ptr(x) for x in irs]),
+                                      (_SZ * n)(*[x.size for x in irs]), rank, ph, po)
         if rc == ERR_NOMEM:
             return False
         _check(rc)

@@ -11,6 +11,7 @@
 #include "b200conv.h"
 #include "kernels.cuh"
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -557,6 +558,13 @@ namespace
 /* ------------------------------------------------------------------------------------------- */
 /* batch                                                                                        */
 
+struct Slab                         /* one device allocation shared by the instances of one init call */
+{
+    void       *base        = nullptr;
+    size_t      refs        = 0;
+};
+static void slab_release(Slab *s);
+
 struct Instance
 {
     bool        active      = false;
@@ -574,6 +582,7 @@ struct Instance
     float2     *G           = nullptr;
     float2     *ring        = nullptr;
     float      *aux         = nullptr;  /* cur | pend | head, F floats each */
+    Slab       *slab        = nullptr;  /* != NULL: G (unless borrowed), ring and aux live in this slab */
     long        g_owner     = -1;       /* >= 0: G belongs to that instance (b200conv_init_shared) */
     size_t      g_sharers   = 0;        /* instances borrowing this one's G */
 };
@@ -621,6 +630,7 @@ struct b200conv_batch
     bool                    uniform_stale = false;  /* instances advanced one by one: t_delta must be refreshed */
 
     float                  *h_in = nullptr, *h_out = nullptr;   /* pinned staging */
+    float                  *h_in_dev = nullptr, *h_out_dev = nullptr;  /* ... as the device addresses them */
     float                  *d_in = nullptr, *d_out = nullptr;
     size_t                  stage_floats = 0;
 
@@ -754,10 +764,15 @@ static int check_device_error(Batch *b)
 
 static void free_instance_buffers(Instance &in)
 {
-    if (in.G && (in.g_owner < 0))   cudaFree(in.G);
-    if (in.ring)    cudaFree(in.ring);
-    if (in.aux)     cudaFree(in.aux);
-    in.G = nullptr; in.ring = nullptr; in.aux = nullptr;
+    if (in.slab != nullptr)
+        slab_release(in.slab);          /* the last instance of the slab frees it */
+    else
+    {
+        if (in.G && (in.g_owner < 0))   cudaFree(in.G);
+        if (in.ring)    cudaFree(in.ring);
+        if (in.aux)     cudaFree(in.aux);
+    }
+    in.G = nullptr; in.ring = nullptr; in.aux = nullptr; in.slab = nullptr;
 }
 
 static void rebuild_tables(Batch *b)
@@ -1037,141 +1052,267 @@ extern "C" int b200conv_destroy(b200conv_batch_t *b, size_t idx)
     return B200CONV_OK;
 }
 
-static int init_range_impl(b200conv_batch_t *b, size_t idx, const float *data, size_t count,
-                                   size_t rank, float phase, size_t part_offset)
+/* Convolver::init for MANY instances at once (Convolver.cpp:77-215 per instance):
+ *   - ONE device allocation (slab) holds the IR spectra, the input-spectrum ring and the frame
+ *     buffers of all of them, allocated before any old state is touched (:103-108);
+ *   - the impulse responses go up through a double-buffered page-locked staging area, the copy of
+ *     chunk k + 1 into it overlapping the transfer of chunk k;
+ *   - ONE transform launch covers every partition of every instance (the per-partition
+ *     fastconv_parse of :183-197), one more forms the folded spectra and keeps taps [0, F).
+ * counts[i] == 0 destroys instance idx[i] (:80-84). */
+static const size_t INIT_STAGE_FLOATS = size_t(4) << 20;        /* 16 MiB per staging buffer */
+
+static void slab_release(Slab *s)
 {
-    if ((b == nullptr) || (idx >= b->n))
-        return fail(B200CONV_ERR_ARG, "b200conv_init: bad handle or index");
-    if (count == 0)                                         /* Convolver.cpp:80-84 */
-        return b200conv_destroy(b, idx);
-    if (data == nullptr)
-        return fail(B200CONV_ERR_ARG, "b200conv_init: NULL impulse response");
+    if ((s != nullptr) && (--s->refs == 0))
+    {
+        cudaFree(s->base);
+        delete s;
+    }
+}
+
+static int init_many_impl(b200conv_batch_t *b, size_t count, const size_t *idx, const float *const *data,
+                          const size_t *counts, size_t rank, const float *phases, const size_t *part_offsets)
+{
+    if ((b == nullptr) || (count == 0) || (idx == nullptr) || (data == nullptr) || (counts == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_init_many: bad arguments");
 
     /* Convolver.cpp:87 : clamp through a signed value */
     long r = long(rank);
     if (r < B200CONV_RANK_MIN) r = B200CONV_RANK_MIN;
     if (r > B200CONV_RANK_MAX) r = B200CONV_RANK_MAX;
     rank = size_t(r);
+    const size_t F      = size_t(1) << (rank - 1);
 
+    std::vector<char> touched(b->n, 0);
+    size_t live = 0, rows_total = 0, slab_floats = 0;
+    for (size_t k = 0; k < count; ++k)
+    {
+        if ((idx[k] >= b->n) || touched[idx[k]])
+            return fail(B200CONV_ERR_ARG, "b200conv_init_many: index %zu out of range or repeated", idx[k]);
+        touched[idx[k]]     = 1;
+        if (b->inst[idx[k]].g_sharers > 0)
+            return fail(B200CONV_ERR_STATE, "instance %zu lends its IR spectra to %zu other instance(s): destroy those first",
+                        idx[k], b->inst[idx[k]].g_sharers);
+        if (counts[k] == 0)
+            continue;
+        if (data[k] == nullptr)
+            return fail(B200CONV_ERR_ARG, "b200conv_init: NULL impulse response");
+        const size_t po     = (part_offsets != nullptr) ? part_offsets[k] : 0;
+        const size_t bins   = (counts[k] + F - 1) >> (rank - 1);    /* Convolver.cpp:93 */
+        if ((po + bins + 1) >= (size_t(1) << 31))
+            return fail(B200CONV_ERR_ARG, "impulse response too long");
+        ++live;
+        rows_total         += bins;
+        /* G: bins + 1 rows | ring: S rows (float2 [F]) | aux: 3 F floats */
+        slab_floats        += 2 * F * (bins + 1) + 2 * F * (po + bins + 1 + RING_SPARE) + 3 * F;
+    }
     for (size_t i = 0; i < b->n; ++i)
-        if ((i != idx) && b->inst[i].active && (b->inst[i].rank != rank))
+        if ((!touched[i]) && b->inst[i].active && (live > 0) && (b->inst[i].rank != rank))
             return fail(B200CONV_ERR_ARG, "all instances of a batch share one rank (%zu active, %zu requested)",
                         b->inst[i].rank, rank);
-
-    if (b->inst[idx].g_sharers > 0)
-        return fail(B200CONV_ERR_STATE, "instance %zu lends its IR spectra to %zu other instance(s): destroy those first",
-                    idx, b->inst[idx].g_sharers);
 
     ENTER_DEVICE(b);
     CU(quiesce(b));                 /* the tables and buffers below may be in use by queued launches */
     cudaStream_t st = b->stream;
 
-    const size_t F      = size_t(1) << (rank - 1);
-    const size_t bins   = (count + F - 1) >> (rank - 1);    /* Convolver.cpp:93 */
-    const size_t nq     = bins + 1;                         /* folded overlap: one extra row */
-    /* spare slots: frames transformed ahead of one multi-frame MAC pass (up to 8), and the k_frame
-     * launches that may be in flight when a launch writes its slot early (FrameHistory) */
-    const size_t S      = part_offset + nq + RING_SPARE;
-    if ((part_offset + nq) >= (size_t(1) << 31))
-        return fail(B200CONV_ERR_ARG, "impulse response too long");
-
+    if (live == 0)
+    {
+        for (size_t k = 0; k < count; ++k)
+            TRY(b200conv_destroy(b, idx[k]));
+        return B200CONV_OK;
+    }
     if (b->tw[rank] == nullptr)
         TRY(make_twiddles(uint32_t(rank), &b->tw[rank]));
 
+    const bool trace = (getenv("B200CONV_INIT_TRACE") != nullptr);
+    auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now_ms();
+    double t_alloc = 0.0, t_upload = 0.0;
+
     /* Allocate everything new before touching the old state (Convolver.cpp:103-108). */
-    Instance fresh;
-    float *irdev = nullptr;
+    float *slab_mem = nullptr, *irdev = nullptr, *stage[2] = { nullptr, nullptr };
     float2 *H = nullptr;
-    cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = cudaMalloc(&fresh.G, nq * F * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMalloc(&fresh.ring, S * F * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMalloc(&fresh.aux, 3 * F * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&irdev, bins * F * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&H, bins * F * sizeof(float2));
+    FoldDesc *d_fold = nullptr;
+    cudaEvent_t ev[2] = { nullptr, nullptr };
+    std::vector<FoldDesc> fold(live);
+    std::vector<Instance> fresh(live);
+    Slab *slab = new Slab();
+    auto cleanup = [&](bool keep_slab)
+    {
+        if (irdev)      cudaFree(irdev);
+        if (H)          cudaFree(H);
+        if (d_fold)     cudaFree(d_fold);
+        for (int i = 0; i < 2; ++i)
+        {
+            if (stage[i])   cudaFreeHost(stage[i]);
+            if (ev[i])      cudaEventDestroy(ev[i]);
+        }
+        if (!keep_slab)
+        {
+            if (slab_mem)   cudaFree(slab_mem);
+            delete slab;
+        }
+    };
+    const size_t stage_floats = (rows_total * F < INIT_STAGE_FLOATS) ? rows_total * F : INIT_STAGE_FLOATS;
+    cudaError_t e = cudaMalloc(&slab_mem, slab_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&irdev, rows_total * F * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&H, rows_total * F * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&d_fold, live * sizeof(FoldDesc));
+    for (int i = 0; (i < 2) && (e == cudaSuccess); ++i)
+    {
+        e = cudaMallocHost(&stage[i], stage_floats * sizeof(float));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess)
     {
-        free_instance_buffers(fresh);
-        if (irdev) cudaFree(irdev);
-        if (H)     cudaFree(H);
+        cleanup(false);
         cudaGetLastError();
-        return fail(B200CONV_ERR_NOMEM, "device allocation failed for %zu taps: %s", count, cudaGetErrorString(e));
+        return fail(B200CONV_ERR_NOMEM, "allocation failed for %zu impulse response(s): %s", live, cudaGetErrorString(e));
+    }
+    slab->base  = slab_mem;
+    slab->refs  = live;
+    t_alloc     = now_ms();
+
+    /* carve the slab: all IR spectra first, then ring + frame buffers (one memset clears those) */
+    size_t at = 0, slot = 0, row = 0;
+    for (size_t k = 0; k < count; ++k)
+    {
+        if (counts[k] == 0) continue;
+        fresh[slot].G   = reinterpret_cast<float2 *>(slab_mem + at);
+        at             += 2 * F * (((counts[k] + F - 1) >> (rank - 1)) + 1);
+        ++slot;
+    }
+    const size_t clear_from = at;
+    slot = 0;
+    for (size_t k = 0; k < count; ++k)
+    {
+        if (counts[k] == 0) continue;
+        const size_t po     = (part_offsets != nullptr) ? part_offsets[k] : 0;
+        const size_t bins   = (counts[k] + F - 1) >> (rank - 1);
+        Instance &in        = fresh[slot];
+        in.ring             = reinterpret_cast<float2 *>(slab_mem + at);
+        at                 += 2 * F * (po + bins + 1 + RING_SPARE);
+        in.aux              = slab_mem + at;
+        at                 += 3 * F;
+        in.slab             = slab;
+        in.active           = true;
+        in.conv_size        = counts[k];
+        in.rank             = rank;
+        in.F                = F;
+        in.bins             = bins;
+        in.nq               = bins + 1;                     /* folded overlap: one extra row */
+        in.q_lo             = po;
+        in.S                = po + bins + 1 + RING_SPARE;
+        float fo            = ((phases != nullptr) ? phases[k] : 0.0f) * float(F);     /* Convolver.cpp:140, fp32 */
+        in.off              = ((fo > 0.0f) && (fo < 1.8e19f)) ? (size_t(fo) % F) : 0;
+        in.off0             = in.off;
+        fold[slot].G        = in.G;
+        fold[slot].head     = (po == 0) ? in.aux + 2 * F : nullptr;
+        fold[slot].h_row    = row;
+        fold[slot].bins     = uint32_t(bins);
+        fold[slot].pad      = 0;
+        row                += bins;
+        ++slot;
     }
 
     int rc = B200CONV_OK;
     do
     {
         #define CU_BRK(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(B200CONV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); break; } }
-        CU_BRK(cudaMemsetAsync(irdev, 0, bins * F * sizeof(float), st));
-        CU_BRK(cudaMemcpyAsync(irdev, data, count * sizeof(float), cudaMemcpyHostToDevice, st));
-        CU_BRK(cudaMemsetAsync(fresh.ring, 0, S * F * sizeof(float2), st));
-        CU_BRK(cudaMemsetAsync(fresh.aux, 0, 3 * F * sizeof(float), st));
-        b->stats.h2d_bytes += count * sizeof(float);
+        CU_BRK(cudaMemsetAsync(slab_mem + clear_from, 0, (slab_floats - clear_from) * sizeof(float), st));
+        CU_BRK(cudaMemsetAsync(irdev, 0, rows_total * F * sizeof(float), st));      /* the zero padding of every last partition */
+        CU_BRK(cudaMemcpyAsync(d_fold, fold.data(), live * sizeof(FoldDesc), cudaMemcpyHostToDevice, st));
+
+        /* upload: host -> staging buffer (CPU copy) -> device (DMA), two buffers in flight */
+        int which = 0;
+        bool used[2] = { false, false };
+        row = 0;
+        for (size_t k = 0; (k < count) && (rc == B200CONV_OK); ++k)
+        {
+            if (counts[k] == 0) continue;
+            const size_t bins   = (counts[k] + F - 1) >> (rank - 1);
+            for (size_t done = 0; done < counts[k]; )
+            {
+                size_t c    = counts[k] - done;
+                if (c > stage_floats)   c = stage_floats;
+                if (used[which])
+                    CU_BRK(cudaEventSynchronize(ev[which]));
+                memcpy(stage[which], data[k] + done, c * sizeof(float));
+                CU_BRK(cudaMemcpyAsync(irdev + row * F + done, stage[which], c * sizeof(float), cudaMemcpyHostToDevice, st));
+                CU_BRK(cudaEventRecord(ev[which], st));
+                used[which] = true;
+                which      ^= 1;
+                done       += c;
+            }
+            b->stats.h2d_bytes += counts[k] * sizeof(float);
+            row        += bins;
+        }
+        if (rc != B200CONV_OK) break;
+        t_upload    = now_ms();
 
         /* H_p = spectrum of taps [pF, (p+1)F) zero padded -- the per-partition fastconv_parse of
-         * Convolver.cpp:183-197, batched over partitions on the device */
+         * Convolver.cpp:183-197 for every partition of every instance, one launch */
         StepArgs a  = base_args(b);
         a.rank      = uint32_t(rank);
         a.tw        = b->tw[rank];
-        for (size_t p0 = 0; p0 < bins; p0 += b->job_cap)
+        a.jobs      = nullptr;
+        a.flags     = STEP_LINEAR_JOBS;
+        a.src       = irdev;
+        a.dst       = reinterpret_cast<float *>(H);
+        for (size_t j0 = 0; j0 < rows_total; j0 += (size_t(1) << 30))
         {
-            size_t cnt  = (bins - p0 < b->job_cap) ? bins - p0 : b->job_cap;
-            size_t pos  = 0;
-            if ((rc = reserve_jobs(b, cnt, st, &pos)) != B200CONV_OK) break;
-            for (size_t p = 0; p < cnt; ++p)
-            {
-                Job &j  = b->h_jobs[pos + p];
-                memset(&j, 0, sizeof(j));
-                j.src   = irdev + (p0 + p) * F;
-                j.spec  = H + (p0 + p) * F;
-            }
-            if ((rc = push_jobs(b, pos, cnt, st)) != B200CONV_OK) break;
-            a.jobs      = b->d_jobs + pos;
-            a.n_jobs    = uint32_t(cnt);
+            const size_t cnt = (rows_total - j0 < (size_t(1) << 30)) ? rows_total - j0 : (size_t(1) << 30);
+            a.src       = irdev + j0 * F;
+            a.dst       = reinterpret_cast<float *>(H + j0 * F);
             CU_BRK(launch_fwd(a, uint32_t(cnt), st));
             b->stats.launches++;
         }
         if (rc != B200CONV_OK) break;
 
-        dim3 grid(uint32_t((F + 255) / 256), uint32_t((nq < 65535) ? nq : 65535));
-        k_fold<<<grid, 256, 0, st>>>(fresh.G, H, uint32_t(bins), uint32_t(F));
+        size_t max_bins = 0;
+        for (const FoldDesc &fd : fold)
+            max_bins    = (fd.bins > max_bins) ? fd.bins : max_bins;
+        dim3 grid(uint32_t((F + 255) / 256), uint32_t((max_bins + 1 < 1024) ? max_bins + 1 : 1024),
+                  uint32_t((live < 64) ? live : 64));
+        k_fold_many<<<grid, 256, 0, st>>>(d_fold, uint32_t(live), H, irdev, uint32_t(F));
         CU_BRK(cudaGetLastError());
         b->stats.launches++;
-
-        if (part_offset == 0)
-            CU_BRK(cudaMemcpyAsync(fresh.aux + 2 * F, irdev, F * sizeof(float), cudaMemcpyDeviceToDevice, st));
         CU_BRK(cudaStreamSynchronize(st));
         #undef CU_BRK
     } while (false);
 
-    cudaFree(irdev);
-    cudaFree(H);
+    const double t_done = now_ms();
+    cleanup(rc == B200CONV_OK);
     if (rc != B200CONV_OK)
-    {
-        free_instance_buffers(fresh);
         return rc;
-    }
+    if (trace)
+        fprintf(stderr, "b200conv_init_many: %zu instances, %.1f MB: alloc %.2f ms, upload (enqueue) %.2f ms, "
+                        "transforms + drain %.2f ms, release %.2f ms\n", live, rows_total * F * 4e-6,
+                t_alloc - t_start, t_upload - t_alloc, t_done - t_upload, now_ms() - t_done);
 
     /* swap in (Convolver.cpp:108-142) */
-    Instance &in    = b->inst[idx];
-    if (in.g_owner >= 0)
-        b->inst[size_t(in.g_owner)].g_sharers -= 1;
-    free_instance_buffers(in);
-    in              = fresh;
-    in.active       = true;
-    in.conv_size    = count;
-    in.rank         = rank;
-    in.F            = F;
-    in.bins         = bins;
-    in.nq           = nq;
-    in.q_lo         = part_offset;
-    in.S            = S;
-    float fo        = phase * float(F);                     /* Convolver.cpp:140, fp32 */
-    in.off          = ((fo > 0.0f) && (fo < 1.8e19f)) ? (size_t(fo) % F) : 0;
-    in.off0         = in.off;
-    in.frames       = 0;
-    in.pend_valid   = false;
+    slot = 0;
+    for (size_t k = 0; k < count; ++k)
+    {
+        Instance &in    = b->inst[idx[k]];
+        if (in.g_owner >= 0)
+            b->inst[size_t(in.g_owner)].g_sharers -= 1;
+        free_instance_buffers(in);
+        in              = (counts[k] == 0) ? Instance() : fresh[slot++];
+    }
     rebuild_tables(b);
     return B200CONV_OK;
+}
+
+static int init_range_impl(b200conv_batch_t *b, size_t idx, const float *data, size_t count,
+                           size_t rank, float phase, size_t part_offset)
+{
+    if ((b == nullptr) || (idx >= b->n))
+        return fail(B200CONV_ERR_ARG, "b200conv_init: bad handle or index");
+    if (count == 0)                                         /* Convolver.cpp:80-84 */
+        return b200conv_destroy(b, idx);
+    return init_many_impl(b, 1, &idx, &data, &count, rank, &phase, &part_offset);
 }
 
 extern "C" int b200conv_init(b200conv_batch_t *b, size_t idx, const float *data, size_t count,
@@ -1357,9 +1498,12 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
                 af.rows         = b->pend_splits + 1;
                 af.row0         = b->pend_splits;
                 af.flags       |= STEP_HEAD_ONLY;
-                /* (the predecessor on the own stream is this batch's pending MAC, which never
-                 * touches the caller's input block: with STEP_EARLY_SRC the block is fetched and
-                 * transformed under that MAC) */
+                /* A synchronous host call on the own stream: every launch that delivered an earlier
+                 * block has completed (the caller has its output), and the predecessor in the
+                 * stream is this batch's pending MAC, which never touches the caller's input block
+                 * -- the block is fetched and transformed under that MAC whatever the launch size. */
+                if ((st == b->stream) && (b->opt_pdl != 0) && (b->opt_early_src != 0))
+                    af.flags       |= STEP_EARLY_SRC;
                 CU(launch_mac(b, af, fp, nact, st, true, serial));
             }
             else
@@ -1957,6 +2101,8 @@ static int ensure_staging(Batch *b, size_t floats)
     b->stage_floats = 0;
     CU(cudaMallocHost(&b->h_in, floats * sizeof(float)));
     CU(cudaMallocHost(&b->h_out, floats * sizeof(float)));
+    CU(cudaHostGetDevicePointer(&b->h_in_dev, b->h_in, 0));
+    CU(cudaHostGetDevicePointer(&b->h_out_dev, b->h_out, 0));
     CU(cudaMalloc(&b->d_in, floats * sizeof(float)));
     CU(cudaMalloc(&b->d_out, floats * sizeof(float)));
     b->stage_floats = floats;
@@ -1993,13 +2139,27 @@ extern "C" int b200conv_process(b200conv_batch_t *b, float *const *dst, const fl
         for (size_t i = 0; i < b->n; ++i)
             if (b->inst[i].active)
                 memcpy(b->h_in + i * c, src[i] + done, c * sizeof(float));
-        hist_reset(b->stream, b->device);
-        CU(cudaMemcpyAsync(b->d_in, b->h_in, b->n * c * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+        /* the gathered block sits in page-locked memory: short blocks are read and written by the
+         * kernels in place across PCIe (no copy operations in the stream), long ones are copied */
+        const bool in_place = (b->opt_zero_copy != 0) && (b->n * c * sizeof(float) <= (size_t(4) << 20));
         b->eager_call = true;
-        int rc = b200conv_process_device(b, b->d_out, b->d_in, c, c, b->stream);
+        int rc;
+        if (in_place)
+        {
+            b->host_io      = true;
+            rc              = b200conv_process_device(b, b->h_out_dev, b->h_in_dev, c, c, b->stream);
+            b->host_io      = false;
+        }
+        else
+        {
+            hist_reset(b->stream, b->device);
+            CU(cudaMemcpyAsync(b->d_in, b->h_in, b->n * c * sizeof(float), cudaMemcpyHostToDevice, b->stream));
+            rc              = b200conv_process_device(b, b->d_out, b->d_in, c, c, b->stream);
+        }
         b->eager_call = false;
         TRY(rc);
-        CU(cudaMemcpyAsync(b->h_out, b->d_out, b->n * c * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
+        if (!in_place)
+            CU(cudaMemcpyAsync(b->h_out, b->d_out, b->n * c * sizeof(float), cudaMemcpyDeviceToHost, b->stream));
         if (done + c >= count)
             TRY(finish_sync_call(b));
         else
@@ -2784,6 +2944,13 @@ extern "C" int b200conv_init_range(b200conv_batch_t *b, size_t idx, const float 
 extern "C" int b200conv_init_shared(b200conv_batch_t *b, size_t idx, size_t src_idx, float phase)
 {
     try { return init_shared_impl(b, idx, src_idx, phase); }
+    catch (const std::bad_alloc &) { return fail(B200CONV_ERR_NOMEM, "out of host memory"); }
+}
+
+extern "C" int b200conv_init_many(b200conv_batch_t *b, size_t count, const size_t *idx, const float *const *data,
+                                  const size_t *counts, size_t rank, const float *phases, const size_t *part_offsets)
+{
+    try { return init_many_impl(b, count, idx, data, counts, rank, phases, part_offsets); }
     catch (const std::bad_alloc &) { return fail(B200CONV_ERR_NOMEM, "out of host memory"); }
 }
 

@@ -105,6 +105,8 @@ struct StepArgs                     /* by-value kernel argument */
 };
 
 enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
+       STEP_LINEAR_JOBS = 64 /* IR ingest: job j transforms src + j * F into the row dst + j * 2 F (one
+                                contiguous slab of zero-padded partitions -> one slab of spectra) */,
        STEP_HOST_IO = 8 /* src / dst are page-locked HOST matrices: no bulk-copy staging */,
        STEP_WAIT_HEAD = 16 /* k_mac launched early (programmatic serialization) behind a k_frame:
                               poll ring_head before touching the newest spectra */,
@@ -206,6 +208,18 @@ __device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
 {
     if (a.jobs != nullptr)
         return a.jobs[j];
+    if (a.flags & STEP_LINEAR_JOBS)
+    {
+        const uint64_t F    = 1ull << (a.rank - 1);
+        Job r;
+        r.src               = a.src + uint64_t(j) * F;
+        r.spec              = reinterpret_cast<float2 *>(a.dst) + uint64_t(j) * F;
+        r.dst               = nullptr;
+        r.psrc = r.psrc2    = nullptr;
+        r.pdst = r.pdst2    = nullptr;
+        r.inst = r.slot0 = r.qa = r.qb = r.off = r.n = r.off2 = r.n2 = r.tlo = r.flags = 0;
+        return r;
+    }
 
     /* uniform mode: every active instance sits on a frame boundary and receives whole frames */
     const uint32_t F    = 1u << (a.rank - 1);
@@ -2199,6 +2213,36 @@ __global__ void k_fold(float2 *G, const float2 *H, uint32_t bins, uint32_t M)
         float2 prev     = (q > 0) ? H[uint64_t(q - 1) * M + k] : make_float2(0.0f, 0.0f);
         float sgn       = (k & 1) ? -1.0f : 1.0f;
         G[uint64_t(q) * M + k] = make_float2(cur.x + sgn * prev.x, cur.y + sgn * prev.y);
+    }
+}
+
+/* The same for many instances in one launch (batched IR ingest): instance i folds rows
+ * H[h_row .. h_row + bins) into its G (bins + 1 rows) and keeps taps [0, F) in `head`. */
+struct FoldDesc
+{
+    float2         *G;
+    float          *head;           /* NULL: no time-domain head (partition-range shard with part_offset > 0) */
+    uint64_t        h_row;          /* first row of this instance in the H / padded-IR slabs */
+    uint32_t        bins;
+    uint32_t        pad;
+};
+
+__global__ void k_fold_many(const FoldDesc *desc, uint32_t n, const float2 *H, const float *ir, uint32_t M)
+{
+    for (uint32_t i = blockIdx.z; i < n; i += gridDim.z)
+    {
+        const FoldDesc d    = desc[i];
+        const float2 *Hi    = H + d.h_row * M;
+        for (uint32_t q = blockIdx.y; q <= d.bins; q += gridDim.y)
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < M; k += gridDim.x * blockDim.x)
+        {
+            float2 cur      = (q < d.bins) ? Hi[uint64_t(q) * M + k] : make_float2(0.0f, 0.0f);
+            float2 prev     = (q > 0) ? Hi[uint64_t(q - 1) * M + k] : make_float2(0.0f, 0.0f);
+            float sgn       = (k & 1) ? -1.0f : 1.0f;
+            d.G[uint64_t(q) * M + k] = make_float2(cur.x + sgn * prev.x, cur.y + sgn * prev.y);
+            if ((q == 0) && (d.head != nullptr))
+                d.head[k]       = ir[d.h_row * M + k];
+        }
     }
 }
 

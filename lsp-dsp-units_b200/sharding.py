@@ -98,12 +98,13 @@ class PartitionShardedConvolver:
 
     def init(self, irs, phase=0.0):
         """``irs``: one full-length impulse response per channel (every rank passes the same)."""
-        ok = True
-        for c, ir in enumerate(irs):
+        shards, offsets = [], []
+        for ir in irs:
             p_lo, p_hi, t_lo, t_hi = partition_shard(len(ir), self.frame, self.world, self.rank)
             # a rank with an empty range still takes part in the exchange: a 1-tap zero IR
-            taps = ir[t_lo:t_hi] if t_hi > t_lo else ir[:1] * 0
-            ok = self.batch.init(c, taps, self.rank_fft, phase, part_offset=p_lo) and ok
+            shards.append(ir[t_lo:t_hi] if t_hi > t_lo else ir[:1] * 0)
+            offsets.append(p_lo)
+        ok = self.batch.init_many(list(range(len(irs))), shards, self.rank_fft, [phase] * len(irs), offsets)
         if ok and self.reduce == "fused":
             import torch
             mine = self.batch.reduce_prepare(self.rank, self.world)

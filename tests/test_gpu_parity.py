@@ -882,3 +882,42 @@ def test_dump_fields_match_the_reference_scheduler(pkg, taps, rank, phase, calls
         pos += n
         same("after call %d (%d samples)" % (i, n))
     b.close()
+
+
+def test_init_many_equals_one_by_one(pkg):
+    """b200conv_init_many (one slab, one staged upload, one transform launch for all instances) must
+    leave exactly the state N x b200conv_init leaves: bit-identical outputs, ragged lengths, phases,
+    partition-range shards, a zero-length entry that destroys its instance, and re-initialisation of a
+    subset while the other instances keep their history."""
+    rank, F, n = 10, 512, 7
+    lens = [30000, 1, 511, 513, 0, 70000, 4096]
+    phases = [0.0, 0.5, 0.25, 0.0, 0.0, 0.9, 0.0]
+    offs = [0, 0, 0, 0, 0, 0, 3]
+    irs = [synth.decaying_ir(c, max(L, 1))[:L] for c, L in enumerate(lens)]
+    x = np.stack([synth.noise(80 + c, 9 * F + 77) for c in range(n)])
+    a, b = pkg.ConvolverBatch(n, 0), pkg.ConvolverBatch(n, 0)
+    assert a.init(4, synth.decaying_ir(9, 100), rank, 0.0) and b.init(4, synth.decaying_ir(9, 100), rank, 0.0)
+    for c in range(n):
+        assert a.init(c, irs[c], rank, phases[c], part_offset=offs[c])
+    assert b.init_many(list(range(n)), irs, rank, phases, offs)
+    assert a.rank(4) == 0 and b.rank(4) == 0            # the zero-length entry destroyed instance 4
+    for c in range(n):
+        assert a.state(c) == b.state(c)
+    step = 300
+    for i in range(0, x.shape[1], step):
+        ya, yb = a.process(x[:, i:i + step].copy()), b.process(x[:, i:i + step].copy())
+        assert np.array_equal(ya, yb)
+    # re-initialise two instances in one call: the others keep their history
+    new = [synth.decaying_ir(50, 2000), synth.decaying_ir(51, 9000)]
+    for c, ir in zip((2, 5), new):
+        assert a.init(c, ir, rank, 0.0)
+    assert b.init_many([2, 5], new, rank)
+    for i in range(0, 4 * F, step):
+        blk = x[:, i:i + step].copy()
+        assert np.array_equal(a.process(blk), b.process(blk))
+    # a rank clash fails as a whole and changes nothing
+    with pytest.raises(pkg.B200ConvError):
+        b.init_many([0], [irs[0]], rank + 1)
+    assert b.rank(0) == rank
+    a.close()
+    b.close()
