@@ -20,6 +20,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace b200conv;
@@ -90,13 +91,33 @@ static uint32_t resident_grid(uint32_t jobs, int threads, size_t smem)
     return (jobs < cap) ? jobs : uint32_t(cap);
 }
 
+/* <<< >>> with the programmatic-serialisation attribute when `pdl` (the kernel then starts as soon
+ * as every CTA of its predecessor in the stream has started, and orders itself with
+ * griddepcontrol.wait) */
+template <typename K, typename... Args>
+static cudaError_t launch_k(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim             = grid;
+    cfg.blockDim            = block;
+    cfg.dynamicSmemBytes    = smem;
+    cfg.stream              = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id              = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs               = attr;
+    cfg.numAttrs            = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 static uint32_t rows_per_job_host(const StepArgs &a)
 {
     return (a.rows != 0) ? a.rows : a.splits;
 }
 
 template <int RANK>
-static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t st)
+static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t st, bool pdl)
 {
     using C = FftCfg<RANK>;
     static bool attr_set[MAX_DEVICES] = { false };
@@ -113,7 +134,7 @@ static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t s
         /* many jobs per CTA and device-resident input: prefetch the next job's input (k_fwd_staged) */
         constexpr size_t SS = StageCfg<RANK>::FWD_SMEM;
         const uint32_t cap  = resident_grid(grid, C::T, SS);
-        if ((grid >= 2 * cap) && !(a.flags & STEP_HOST_IO))
+        if ((grid >= 2 * cap) && !(a.flags & STEP_HOST_IO) && (!pdl))
         {
             static bool attr_staged[MAX_DEVICES] = { false };
             if ((!attr_staged[dev]) && (SS > 48 * 1024))
@@ -123,7 +144,7 @@ static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t s
                     return e;
             }
             attr_staged[dev] = true;
-            k_fwd_staged<RANK><<<cap, C::T, SS, st>>>(a);
+            k_fwd_staged<RANK><<<cap, C::T, SS, st>>>(a);      /* (never part of a programmatic chain) */
             return cudaGetLastError();
         }
     }
@@ -142,16 +163,14 @@ static cudaError_t launch_fwd_r(const StepArgs &a, uint32_t grid, cudaStream_t s
                     return e;
             }
             attr_half[dev] = true;
-            k_fwd_half<RANK><<<resident_grid(2 * grid, H::T, H::SMEM), H::T, H::SMEM, st>>>(a);
-            return cudaGetLastError();
+            return launch_k(k_fwd_half<RANK>, dim3(resident_grid(2 * grid, H::T, H::SMEM)), dim3(H::T), H::SMEM, st, pdl, a);
         }
     }
-    k_fwd<RANK><<<resident_grid(grid, C::T, C::SMEM), C::T, C::SMEM, st>>>(a);
-    return cudaGetLastError();
+    return launch_k(k_fwd<RANK>, dim3(resident_grid(grid, C::T, C::SMEM)), dim3(C::T), C::SMEM, st, pdl, a);
 }
 
 template <int RANK, int RG>
-static cudaError_t launch_inv_rg(const StepArgs &a, uint32_t grid, cudaStream_t st)
+static cudaError_t launch_inv_rg(const StepArgs &a, uint32_t grid, cudaStream_t st, bool pdl)
 {
     using C = FftCfg<RANK>;
     static bool attr_set[MAX_DEVICES] = { false };
@@ -163,12 +182,11 @@ static cudaError_t launch_inv_rg(const StepArgs &a, uint32_t grid, cudaStream_t 
             return e;
     }
     attr_set[dev] = true;
-    k_inv<RANK, RG><<<resident_grid(grid, C::T, C::SMEM), C::T, C::SMEM, st>>>(a);
-    return cudaGetLastError();
+    return launch_k(k_inv<RANK, RG>, dim3(resident_grid(grid, C::T, C::SMEM)), dim3(C::T), C::SMEM, st, pdl, a);
 }
 
 template <int RANK>
-static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t st)
+static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t st, bool pdl, uint32_t *tickets)
 {
     using C = FftCfg<RANK>;
     if constexpr (C::PP)
@@ -176,7 +194,7 @@ static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t s
         /* one partial row per job and many jobs per CTA: prefetch the next row (k_inv_staged) */
         constexpr size_t SS = StageCfg<RANK>::INV_SMEM;
         const uint32_t cap  = resident_grid(grid, C::T, SS);
-        if ((rows_per_job_host(a) == 1) && (grid >= 2 * cap) && ((reinterpret_cast<uintptr_t>(a.ypart) & 15) == 0))
+        if ((rows_per_job_host(a) == 1) && (grid >= 2 * cap) && ((reinterpret_cast<uintptr_t>(a.ypart) & 15) == 0) && (!pdl))
         {
             static bool attr_staged[MAX_DEVICES] = { false };
             int dev = current_device();
@@ -206,20 +224,20 @@ static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t s
                     return e;
             }
             attr_half[dev] = true;
-            k_inv_half<RANK><<<resident_grid(2 * grid, H::T, H::SMEM), H::T, H::SMEM, st>>>(a);
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess)
+            /* with a ticket array the second half to finish combines; otherwise an element-wise launch */
+            cudaError_t e = launch_k(k_inv_half<RANK>, dim3(resident_grid(2 * grid, H::T, H::SMEM)), dim3(H::T),
+                                     H::SMEM, st, pdl, a, tickets);
+            if ((e != cudaSuccess) || (tickets != nullptr))
                 return e;
             const uint32_t F = 1u << (RANK - 1);
             dim3 cg((F / 256 < 32) ? F / 256 : 32, (grid < 4096) ? grid : 4096);
-            k_inv_combine<<<cg, 256, 0, st>>>(a);
-            return cudaGetLastError();
+            return launch_k(k_inv_combine, cg, dim3(256), 0, st, pdl, a);
         }
     }
     /* the row-group size only matters on the ping-pong ranks (FftCfg::PP) */
     if (FftCfg<RANK>::PP && (rows_per_job_host(a) <= 2))
-        return launch_inv_rg<RANK, 2>(a, grid, st);
-    return launch_inv_rg<RANK, 8>(a, grid, st);
+        return launch_inv_rg<RANK, 2>(a, grid, st, pdl);
+    return launch_inv_rg<RANK, 8>(a, grid, st, pdl);
 }
 
 #define RANK_SWITCH(fn, rank, ...)                                      \
@@ -237,18 +255,21 @@ static cudaError_t launch_inv_r(const StepArgs &a, uint32_t grid, cudaStream_t s
     }
 
 /* `jobs` frame transforms (the kernels loop over them with a resident grid) */
-static cudaError_t launch_fwd(const StepArgs &args, uint32_t jobs, cudaStream_t st)
+static cudaError_t launch_fwd(const StepArgs &args, uint32_t jobs, cudaStream_t st, bool pdl = false)
 {
     StepArgs a  = args;
     a.n_jobs    = jobs;
-    RANK_SWITCH(launch_fwd_r, a.rank, a, jobs, st)
+    RANK_SWITCH(launch_fwd_r, a.rank, a, jobs, st, pdl)
 }
 
-static cudaError_t launch_inv(const StepArgs &args, uint32_t jobs, cudaStream_t st)
+/* tickets: one zeroed counter per job (NULL: none available) -- lets the half-frame inverse of the
+ * big ranks combine its halves itself */
+static cudaError_t launch_inv(const StepArgs &args, uint32_t jobs, cudaStream_t st, bool pdl = false,
+                              uint32_t *tickets = nullptr)
 {
     StepArgs a  = args;
     a.n_jobs    = jobs;
-    RANK_SWITCH(launch_inv_r, a.rank, a, jobs, st)
+    RANK_SWITCH(launch_inv_r, a.rank, a, jobs, st, pdl, tickets)
 }
 
 struct MacPlan
@@ -625,6 +646,12 @@ struct b200conv_batch
     /* general-path scratch, sized once at create: process() never allocates */
     std::vector<size_t>     g_pos;
     std::vector<Job>        g_jobs, g_fft, g_mac, g_part;
+    /* IR ingest (b200conv_init_many): scratch that stays with the batch between calls */
+    void                   *init_scratch = nullptr; /* device: padded taps | spectra | fold table of one round */
+    size_t                  init_scratch_bytes = 0;
+    float                  *init_stage[2] = { nullptr, nullptr };   /* page-locked upload staging */
+    size_t                  init_stage_floats = 0;
+    cudaEvent_t             init_ev[2]  = { nullptr, nullptr };
     double                 *d_partials  = nullptr;  /* k_partial_tiles: [job][tile][PT_MAXN] */
     size_t                  partials_jobs = 0;
     bool                    uniform_stale = false;  /* instances advanced one by one: t_delta must be refreshed */
@@ -675,14 +702,14 @@ struct b200conv_batch
 typedef b200conv_batch Batch;
 
 static cudaError_t launch_mac(Batch *b, const StepArgs &a, const MacPlan &p, uint32_t jobs, cudaStream_t st,
-                              bool fused = false, bool serial = false)
+                              bool fused = false, bool serial = false, bool chain = false)
 {
     auto go = [&]() -> cudaError_t
     {
         if (fused)
             return launch_frame(a, p, jobs, b->d_tickets, b->reduce,
                                 (b->opt_pdl != 0) && (!b->profiling) && (!serial), st);
-        return launch_mac_raw(a, p, jobs, st);
+        return launch_mac_raw(a, p, jobs, st, chain);
     };
     if (!b->profiling)
         return go();
@@ -1008,6 +1035,12 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     if (b->ypart)       cudaFree(b->ypart);
     if (b->park)        cudaFree(b->park);
     if (b->d_partials)  cudaFree(b->d_partials);
+    if (b->init_scratch) cudaFree(b->init_scratch);
+    for (int i = 0; i < 2; ++i)
+    {
+        if (b->init_stage[i])   cudaFreeHost(b->init_stage[i]);
+        if (b->init_ev[i])      cudaEventDestroy(b->init_ev[i]);
+    }
     if (b->d_desc)      cudaFree(b->d_desc);
     if (b->d_active)    cudaFree(b->d_active);
     if (b->d_tickets)   cudaFree(b->d_tickets);
@@ -1060,7 +1093,11 @@ extern "C" int b200conv_destroy(b200conv_batch_t *b, size_t idx)
  *   - ONE transform launch covers every partition of every instance (the per-partition
  *     fastconv_parse of :183-197), one more forms the folded spectra and keeps taps [0, F).
  * counts[i] == 0 destroys instance idx[i] (:80-84). */
-static const size_t INIT_STAGE_FLOATS = size_t(4) << 20;        /* 16 MiB per staging buffer */
+static const size_t INIT_STAGE_FLOATS  = size_t(4) << 20;      /* 16 MiB per page-locked staging buffer */
+static const size_t INIT_CHUNK_FLOATS  = size_t(16) << 20;     /* padded IR samples transformed per round: 64 MiB of taps,
+                                                                   128 MiB of spectra -- bounded scratch, whatever the job */
+static const size_t INIT_KEEP_BYTES    = size_t(64) << 20;     /* device scratch up to this size stays with the batch */
+static const int    INIT_COPY_THREADS  = 4;                    /* host threads filling one staging buffer */
 
 static void slab_release(Slab *s)
 {
@@ -1069,6 +1106,27 @@ static void slab_release(Slab *s)
         cudaFree(s->base);
         delete s;
     }
+}
+
+/* pageable -> page-locked copy, split over a few host threads above 1 MiB (one core moves ~8 GB/s,
+ * less than PCIe 5 takes) */
+static void staged_copy(float *dst, const float *src, size_t n)
+{
+    if (n < (size_t(1) << 18))
+    {
+        memcpy(dst, src, n * sizeof(float));
+        return;
+    }
+    std::thread pool[INIT_COPY_THREADS - 1];
+    const size_t per = (n + INIT_COPY_THREADS - 1) / INIT_COPY_THREADS;
+    for (int t = 1; t < INIT_COPY_THREADS; ++t)
+    {
+        const size_t lo = (per * t < n) ? per * t : n, hi = (lo + per < n) ? lo + per : n;
+        pool[t - 1]     = std::thread([=]() { if (hi > lo) memcpy(dst + lo, src + lo, (hi - lo) * sizeof(float)); });
+    }
+    memcpy(dst, src, ((per < n) ? per : n) * sizeof(float));
+    for (int t = 1; t < INIT_COPY_THREADS; ++t)
+        pool[t - 1].join();
 }
 
 static int init_many_impl(b200conv_batch_t *b, size_t count, const size_t *idx, const float *const *data,
@@ -1085,7 +1143,7 @@ static int init_many_impl(b200conv_batch_t *b, size_t count, const size_t *idx, 
     const size_t F      = size_t(1) << (rank - 1);
 
     std::vector<char> touched(b->n, 0);
-    size_t live = 0, rows_total = 0, slab_floats = 0;
+    size_t live = 0, rows_total = 0, slab_floats = 0, rows_max = 0;
     for (size_t k = 0; k < count; ++k)
     {
         if ((idx[k] >= b->n) || touched[idx[k]])
@@ -1104,6 +1162,7 @@ static int init_many_impl(b200conv_batch_t *b, size_t count, const size_t *idx, 
             return fail(B200CONV_ERR_ARG, "impulse response too long");
         ++live;
         rows_total         += bins;
+        rows_max            = (bins > rows_max) ? bins : rows_max;
         /* G: bins + 1 rows | ring: S rows (float2 [F]) | aux: 3 F floats */
         slab_floats        += 2 * F * (bins + 1) + 2 * F * (po + bins + 1 + RING_SPARE) + 3 * F;
     }
@@ -1128,59 +1187,68 @@ static int init_many_impl(b200conv_batch_t *b, size_t count, const size_t *idx, 
     const bool trace = (getenv("B200CONV_INIT_TRACE") != nullptr);
     auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now_ms();
-    double t_alloc = 0.0, t_upload = 0.0;
+
+    /* Scratch, bounded whatever the job: the instances are transformed in rounds of whole instances
+     * whose padded IRs fit INIT_CHUNK_FLOATS (a single longer IR gets a round of its own). */
+    size_t chunk_rows   = INIT_CHUNK_FLOATS / F;
+    if (chunk_rows < rows_max)      chunk_rows = rows_max;
+    if (chunk_rows > rows_total)    chunk_rows = rows_total;
+    const size_t stage_floats   = (rows_total * F < INIT_STAGE_FLOATS) ? rows_total * F : INIT_STAGE_FLOATS;
+    const size_t scratch_bytes  = chunk_rows * F * (sizeof(float) + sizeof(float2)) + live * sizeof(FoldDesc) + 256;
 
     /* Allocate everything new before touching the old state (Convolver.cpp:103-108). */
-    float *slab_mem = nullptr, *irdev = nullptr, *stage[2] = { nullptr, nullptr };
-    float2 *H = nullptr;
-    FoldDesc *d_fold = nullptr;
-    cudaEvent_t ev[2] = { nullptr, nullptr };
-    std::vector<FoldDesc> fold(live);
-    std::vector<Instance> fresh(live);
-    Slab *slab = new Slab();
-    auto cleanup = [&](bool keep_slab)
+    float *slab_mem = nullptr;
+    cudaError_t e = cudaMalloc(&slab_mem, slab_floats * sizeof(float));
+    if ((e == cudaSuccess) && (scratch_bytes > b->init_scratch_bytes))
     {
-        if (irdev)      cudaFree(irdev);
-        if (H)          cudaFree(H);
-        if (d_fold)     cudaFree(d_fold);
+        if (b->init_scratch) cudaFree(b->init_scratch);
+        b->init_scratch         = nullptr;
+        b->init_scratch_bytes   = 0;
+        e = cudaMalloc(&b->init_scratch, scratch_bytes);
+        if (e == cudaSuccess)
+            b->init_scratch_bytes   = scratch_bytes;
+    }
+    if ((e == cudaSuccess) && (stage_floats > b->init_stage_floats))
+    {
         for (int i = 0; i < 2; ++i)
         {
-            if (stage[i])   cudaFreeHost(stage[i]);
-            if (ev[i])      cudaEventDestroy(ev[i]);
+            if (b->init_stage[i]) cudaFreeHost(b->init_stage[i]);
+            b->init_stage[i]        = nullptr;
         }
-        if (!keep_slab)
-        {
-            if (slab_mem)   cudaFree(slab_mem);
-            delete slab;
-        }
-    };
-    const size_t stage_floats = (rows_total * F < INIT_STAGE_FLOATS) ? rows_total * F : INIT_STAGE_FLOATS;
-    cudaError_t e = cudaMalloc(&slab_mem, slab_floats * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&irdev, rows_total * F * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&H, rows_total * F * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMalloc(&d_fold, live * sizeof(FoldDesc));
-    for (int i = 0; (i < 2) && (e == cudaSuccess); ++i)
-    {
-        e = cudaMallocHost(&stage[i], stage_floats * sizeof(float));
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+        b->init_stage_floats    = 0;
+        for (int i = 0; (i < 2) && (e == cudaSuccess); ++i)
+            e = cudaMallocHost(&b->init_stage[i], stage_floats * sizeof(float));
+        if (e == cudaSuccess)
+            b->init_stage_floats    = stage_floats;
     }
+    for (int i = 0; (i < 2) && (e == cudaSuccess); ++i)
+        if (b->init_ev[i] == nullptr)
+            e = cudaEventCreateWithFlags(&b->init_ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess)
     {
-        cleanup(false);
+        if (slab_mem) cudaFree(slab_mem);
         cudaGetLastError();
         return fail(B200CONV_ERR_NOMEM, "allocation failed for %zu impulse response(s): %s", live, cudaGetErrorString(e));
     }
-    slab->base  = slab_mem;
-    slab->refs  = live;
-    t_alloc     = now_ms();
+    float *irdev        = reinterpret_cast<float *>(b->init_scratch);
+    float2 *H           = reinterpret_cast<float2 *>(irdev + chunk_rows * F);
+    FoldDesc *d_fold    = reinterpret_cast<FoldDesc *>(reinterpret_cast<unsigned char *>(H + chunk_rows * F) + 128);
+    Slab *slab          = new Slab();
+    slab->base          = slab_mem;
+    slab->refs          = live;
+    const double t_alloc = now_ms();
 
     /* carve the slab: all IR spectra first, then ring + frame buffers (one memset clears those) */
-    size_t at = 0, slot = 0, row = 0;
+    std::vector<FoldDesc> fold(live);
+    std::vector<Instance> fresh(live);
+    std::vector<size_t> which_k(live);
+    size_t at = 0, slot = 0;
     for (size_t k = 0; k < count; ++k)
     {
         if (counts[k] == 0) continue;
         fresh[slot].G   = reinterpret_cast<float2 *>(slab_mem + at);
         at             += 2 * F * (((counts[k] + F - 1) >> (rank - 1)) + 1);
+        which_k[slot]   = k;
         ++slot;
     }
     const size_t clear_from = at;
@@ -1209,87 +1277,105 @@ static int init_many_impl(b200conv_batch_t *b, size_t count, const size_t *idx, 
         in.off0             = in.off;
         fold[slot].G        = in.G;
         fold[slot].head     = (po == 0) ? in.aux + 2 * F : nullptr;
-        fold[slot].h_row    = row;
+        fold[slot].h_row    = 0;                            /* within its round, set below */
         fold[slot].bins     = uint32_t(bins);
         fold[slot].pad      = 0;
-        row                += bins;
         ++slot;
     }
 
     int rc = B200CONV_OK;
+    double t_upload = 0.0;
     do
     {
         #define CU_BRK(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = fail(B200CONV_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); break; } }
         CU_BRK(cudaMemsetAsync(slab_mem + clear_from, 0, (slab_floats - clear_from) * sizeof(float), st));
-        CU_BRK(cudaMemsetAsync(irdev, 0, rows_total * F * sizeof(float), st));      /* the zero padding of every last partition */
-        CU_BRK(cudaMemcpyAsync(d_fold, fold.data(), live * sizeof(FoldDesc), cudaMemcpyHostToDevice, st));
 
-        /* upload: host -> staging buffer (CPU copy) -> device (DMA), two buffers in flight */
         int which = 0;
         bool used[2] = { false, false };
-        row = 0;
-        for (size_t k = 0; (k < count) && (rc == B200CONV_OK); ++k)
+        for (size_t s0 = 0; (s0 < live) && (rc == B200CONV_OK); )
         {
-            if (counts[k] == 0) continue;
-            const size_t bins   = (counts[k] + F - 1) >> (rank - 1);
-            for (size_t done = 0; done < counts[k]; )
+            /* one round: instances s0 .. s1-1 */
+            size_t s1 = s0, rows = 0;
+            while ((s1 < live) && ((s1 == s0) || (rows + fold[s1].bins <= chunk_rows)))
             {
-                size_t c    = counts[k] - done;
-                if (c > stage_floats)   c = stage_floats;
-                if (used[which])
-                    CU_BRK(cudaEventSynchronize(ev[which]));
-                memcpy(stage[which], data[k] + done, c * sizeof(float));
-                CU_BRK(cudaMemcpyAsync(irdev + row * F + done, stage[which], c * sizeof(float), cudaMemcpyHostToDevice, st));
-                CU_BRK(cudaEventRecord(ev[which], st));
-                used[which] = true;
-                which      ^= 1;
-                done       += c;
+                fold[s1].h_row  = rows;
+                rows           += fold[s1].bins;
+                ++s1;
             }
-            b->stats.h2d_bytes += counts[k] * sizeof(float);
-            row        += bins;
-        }
-        if (rc != B200CONV_OK) break;
-        t_upload    = now_ms();
+            const double t_round = now_ms();
+            CU_BRK(cudaMemsetAsync(irdev, 0, rows * F * sizeof(float), st));    /* the zero padding of every last partition */
+            CU_BRK(cudaMemcpyAsync(d_fold, fold.data() + s0, (s1 - s0) * sizeof(FoldDesc), cudaMemcpyHostToDevice, st));
 
-        /* H_p = spectrum of taps [pF, (p+1)F) zero padded -- the per-partition fastconv_parse of
-         * Convolver.cpp:183-197 for every partition of every instance, one launch */
-        StepArgs a  = base_args(b);
-        a.rank      = uint32_t(rank);
-        a.tw        = b->tw[rank];
-        a.jobs      = nullptr;
-        a.flags     = STEP_LINEAR_JOBS;
-        a.src       = irdev;
-        a.dst       = reinterpret_cast<float *>(H);
-        for (size_t j0 = 0; j0 < rows_total; j0 += (size_t(1) << 30))
-        {
-            const size_t cnt = (rows_total - j0 < (size_t(1) << 30)) ? rows_total - j0 : (size_t(1) << 30);
-            a.src       = irdev + j0 * F;
-            a.dst       = reinterpret_cast<float *>(H + j0 * F);
-            CU_BRK(launch_fwd(a, uint32_t(cnt), st));
+            /* upload: host -> staging buffer (CPU copy, a few threads) -> device (DMA), two buffers in flight */
+            for (size_t sl = s0; (sl < s1) && (rc == B200CONV_OK); ++sl)
+            {
+                const size_t k  = which_k[sl];
+                for (size_t done = 0; done < counts[k]; )
+                {
+                    size_t c    = counts[k] - done;
+                    if (c > b->init_stage_floats)   c = b->init_stage_floats;
+                    if (used[which])
+                        CU_BRK(cudaEventSynchronize(b->init_ev[which]));
+                    staged_copy(b->init_stage[which], data[k] + done, c);
+                    CU_BRK(cudaMemcpyAsync(irdev + fold[sl].h_row * F + done, b->init_stage[which], c * sizeof(float),
+                                           cudaMemcpyHostToDevice, st));
+                    CU_BRK(cudaEventRecord(b->init_ev[which], st));
+                    used[which] = true;
+                    which      ^= 1;
+                    done       += c;
+                }
+                b->stats.h2d_bytes += counts[k] * sizeof(float);
+            }
+            if (rc != B200CONV_OK) break;
+            t_upload   += now_ms() - t_round;
+
+            /* H_p = spectrum of taps [pF, (p+1)F) zero padded -- the per-partition fastconv_parse of
+             * Convolver.cpp:183-197 for every partition of every instance of the round, one launch */
+            StepArgs a  = base_args(b);
+            a.rank      = uint32_t(rank);
+            a.tw        = b->tw[rank];
+            a.jobs      = nullptr;
+            a.flags     = STEP_LINEAR_JOBS;
+            a.src       = irdev;
+            a.dst       = reinterpret_cast<float *>(H);
+            CU_BRK(launch_fwd(a, uint32_t(rows), st));
             b->stats.launches++;
+
+            size_t max_bins = 0;
+            for (size_t sl = s0; sl < s1; ++sl)
+                max_bins    = (fold[sl].bins > max_bins) ? fold[sl].bins : max_bins;
+            dim3 grid(uint32_t((F + 255) / 256), uint32_t((max_bins + 1 < 1024) ? max_bins + 1 : 1024),
+                      uint32_t((s1 - s0 < 64) ? s1 - s0 : 64));
+            k_fold_many<<<grid, 256, 0, st>>>(d_fold, uint32_t(s1 - s0), H, irdev, uint32_t(F));
+            CU_BRK(cudaGetLastError());
+            b->stats.launches++;
+            s0          = s1;
         }
         if (rc != B200CONV_OK) break;
-
-        size_t max_bins = 0;
-        for (const FoldDesc &fd : fold)
-            max_bins    = (fd.bins > max_bins) ? fd.bins : max_bins;
-        dim3 grid(uint32_t((F + 255) / 256), uint32_t((max_bins + 1 < 1024) ? max_bins + 1 : 1024),
-                  uint32_t((live < 64) ? live : 64));
-        k_fold_many<<<grid, 256, 0, st>>>(d_fold, uint32_t(live), H, irdev, uint32_t(F));
-        CU_BRK(cudaGetLastError());
-        b->stats.launches++;
         CU_BRK(cudaStreamSynchronize(st));
         #undef CU_BRK
     } while (false);
 
     const double t_done = now_ms();
-    cleanup(rc == B200CONV_OK);
+    if (b->init_scratch_bytes > INIT_KEEP_BYTES)
+    {
+        /* a big job's scratch goes back; small ones (a plugin re-loading its IR) keep theirs */
+        cudaStreamSynchronize(st);
+        cudaFree(b->init_scratch);
+        b->init_scratch         = nullptr;
+        b->init_scratch_bytes   = 0;
+    }
     if (rc != B200CONV_OK)
+    {
+        cudaStreamSynchronize(st);
+        cudaFree(slab_mem);
+        delete slab;
         return rc;
+    }
     if (trace)
-        fprintf(stderr, "b200conv_init_many: %zu instances, %.1f MB: alloc %.2f ms, upload (enqueue) %.2f ms, "
-                        "transforms + drain %.2f ms, release %.2f ms\n", live, rows_total * F * 4e-6,
-                t_alloc - t_start, t_upload - t_alloc, t_done - t_upload, now_ms() - t_done);
+        fprintf(stderr, "b200conv_init_many: %zu instances, %.1f MB of taps: alloc %.2f ms, upload (enqueue) %.2f ms, "
+                        "all rounds + drain %.2f ms, release %.2f ms\n", live, rows_total * F * 4e-6,
+                t_alloc - t_start, t_upload, t_done - t_alloc, now_ms() - t_done);
 
     /* swap in (Convolver.cpp:108-142) */
     slot = 0;
@@ -1518,10 +1604,18 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             sp.sh.bias      = 0;
             b->pend_ready   = false;
             hist_reset(st, b->device);
-            CU(launch_fwd(a, nact, st));
-            CU(launch_mac(b, a, sp, nact, st));
-            TRY(attach_park(b, a, nact, st));
-            CU(launch_inv(a, nact, st));
+            /* Ranks 14..16: the three kernels of a block are chained with programmatic serialisation --
+             * the partition stream of q >= 1 runs beside the block's own transform (which only the
+             * stage with q = 0 needs, taken last, STEP_AFTER_FWD), table staging overlaps the launch
+             * before; every kernel orders itself with griddepcontrol.wait. */
+            const bool chain = (b->rank >= 14) && (b->opt_pdl != 0) && (!b->profiling);
+            TRY(attach_park(b, a, nact, st));       /* (may synchronise: before the chain starts) */
+            CU(launch_fwd(a, nact, st, chain));
+            StepArgs am     = a;
+            if (chain)
+                am.flags       |= STEP_AFTER_FWD;
+            CU(launch_mac(b, am, sp, nact, st, false, false, chain));
+            CU(launch_inv(a, nact, st, chain, b->d_tickets));      /* nact <= instances counters */
             b->stats.launches       += 3;
         }
         b->stats.mac_launches   += 1;

@@ -105,6 +105,9 @@ struct StepArgs                     /* by-value kernel argument */
 };
 
 enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
+       STEP_AFTER_FWD = 128 /* k_mac launched with programmatic serialisation right behind the k_fwd of the
+                               SAME block (three-kernel path, ranks 14..16): the CTAs of split 0 take the
+                               stage that needs the arriving frame's spectrum last, after griddepcontrol.wait */,
        STEP_LINEAR_JOBS = 64 /* IR ingest: job j transforms src + j * F into the row dst + j * 2 F (one
                                 contiguous slab of zero-padded partitions -> one slab of spectra) */,
        STEP_HOST_IO = 8 /* src / dst are page-locked HOST matrices: no bulk-copy staging */,
@@ -307,7 +310,12 @@ struct FftCfg
     static constexpr int TW_PRE = P - NS0;                              /* 3 * (NS0 + 4 NS0 + ... + P/4) */
     static constexpr int TW_POST = TW_PRE + P;
     static constexpr int TW_TOTAL = TW_POST + M / 2 + 1;
-    static constexpr size_t SMEM = (size_t(WORK) * (PP ? 2 : 1) + (TWS ? TW_TOTAL : 0)) * sizeof(float2);
+    /* Ranks >= 13 have no room for the whole table next to the work buffer, but the passes need only
+     * ONE factor per butterfly (w^2, w^3 by multiplication): a compact copy of the r = 1 third of
+     * every pass, (P - NS0) / 3 entries (44 KiB at rank 16), keeps the dependent twiddle loads of
+     * every pass on chip instead of in L2. */
+    static constexpr int TWC_N  = (P - NS0) / 3;
+    static constexpr size_t SMEM = (size_t(WORK) * (PP ? 2 : 1) + (TWS ? TW_TOTAL : TWC_N)) * sizeof(float2);
 };
 
 /* Transforms the NH sequences held in A; returns the buffer that holds the result (A or B). */
@@ -326,9 +334,12 @@ __device__ __forceinline__ float2 rot90(float2 z)       /* forward: -i z ; inver
     return INV ? make_float2(-z.y, z.x) : make_float2(z.y, -z.x);
 }
 
-template <int RANK, bool INV, bool PP, int TT = 0, bool WMUL = (RANK >= 12), bool FAST1 = true, int NHO = 0>
+/* TWC: `tw` is the compact table (see FftCfg::TWC_N): pass Ns at offset (Ns - NS0) / 3, r = 1 only. */
+template <int RANK, bool INV, bool PP, int TT = 0, bool WMUL = (RANK >= 12), bool FAST1 = true, int NHO = 0,
+          bool TWC = false>
 __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *tw, int tid)
 {
+    static_assert((!TWC) || WMUL, "fft_smem: the compact table holds one factor per butterfly");
     using C = FftCfg<RANK, TT, NHO>;
     constexpr int P = C::P, T = C::T, BPT = C::BPT, NH = C::NH;
 
@@ -483,7 +494,7 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
         if (!PP)
             __syncthreads();
 
-        const float2 *tws = tw + (Ns - C::NS0);     /* this pass: 3 * Ns entries, r-major (see FftCfg) */
+        const float2 *tws = tw + (TWC ? (Ns - C::NS0) / 3 : (Ns - C::NS0));    /* this pass: 3 * Ns entries, r-major (see FftCfg) */
         #pragma unroll
         for (int i = 0; i < BPT; ++i)
         {
@@ -545,11 +556,13 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
 /* twg = twiddle table in global memory (used next to the global loads), tw = the table the      */
 /* transform passes read (shared-memory copy when the caller staged one, else twg).              */
 
-template <int RANK, bool PP, int TT = 0, bool SMEM_OUT = false, bool WM = (RANK >= 12), int NHO = 0>
+template <int RANK, bool PP, int TT = 0, bool SMEM_OUT = false, bool WM = (RANK >= 12), int NHO = 0, bool TWC = false>
 __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src, float2 *out,
                                          const float2 *twg, const float2 *tw, int tid,
                                          float2 **smem_out = nullptr, int only_pass = -1)
 {
+    /* TWC: `tw` is the compact pass table (fft_smem); every other lookup goes to twg */
+    const float2 *twx       = TWC ? twg : tw;
     /* only_pass (one resident half, NH == 1): 0 = even bins only, 1 = odd bins only -- the two
      * halves of a frame are independent all the way to the output row (k_fwd_half) */
     /* SMEM_OUT (ping-pong ranks only): the bins go to whichever work buffer the transform did
@@ -563,55 +576,120 @@ __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src,
     {
         if ((only_pass >= 0) && (pass != only_pass))
             continue;
+        /* The streaming phases (this load and the split pass below) run at one CTA per SM on the big
+         * ranks: their global loads are issued LB at a time before the first use, or each thread
+         * would sit out a full memory latency per element (profiles/: 60 % of the rank-16 transform
+         * was long-scoreboard stall in these two loops). */
+        static_assert(P % T == 0, "fwd_body: whole rounds");
+        constexpr int LB = (P / T >= 8) ? 8 : (P / T);
         const bool src8 = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
-        for (int m = tid; m < P; m += T)
+        const bool need_w = (NH == 2) || (pass == 1);
+        #pragma unroll 1
+        for (int m0 = tid; m0 < P; m0 += LB * T)
         {
-            float2 z    = src8 ? reinterpret_cast<const float2 *>(src)[m]
-                               : make_float2(src[2 * m], src[2 * m + 1]);
-            float2 zb   = cmul(z, twg[C::TW_PRE + m]);          /* w_M^m */
-            if (NH == 2)    { A[m] = z; A[P + m] = zb; }
-            else            { A[m] = (pass == 0) ? z : zb; }
+            float2 z[LB], w[LB];
+            #pragma unroll
+            for (int u = 0; u < LB; ++u)
+            {
+                const int m = m0 + u * T;
+                z[u]        = src8 ? reinterpret_cast<const float2 *>(src)[m]
+                                   : make_float2(src[2 * m], src[2 * m + 1]);
+                w[u]        = need_w ? twg[C::TW_PRE + m] : make_float2(1.0f, 0.0f);     /* w_M^m */
+            }
+            #pragma unroll
+            for (int u = 0; u < LB; ++u)
+            {
+                const int m = m0 + u * T;
+                float2 zb   = cmul(z[u], w[u]);
+                if (NH == 2)    { A[m] = z[u]; A[P + m] = zb; }
+                else            { A[m] = (pass == 0) ? z[u] : zb; }
+            }
         }
         __syncthreads();
 
-        const float2 *R = fft_smem<RANK, false, PP, TT, WM, true, NHO>(A, B, tw, tid);
+        const float2 *R = fft_smem<RANK, false, PP, TT, WM, true, NHO, TWC>(A, B, tw, tid);
         if (SMEM_OUT)
         {
             out         = (R == A) ? B : A;
             *smem_out   = out;
         }
 
-        /* split post-pass over pairs (k, M-k), k = 0 .. M/2; thread 0 takes k = 0 and k = M/2 */
-        for (int k = tid; k < M / 2; k += T)
+        /* split post-pass over pairs (k, M-k), k = 0 .. M/2; thread 0 takes k = 0 and k = M/2.
+         * One resident half: only the bins k = 2 i + pass of its parity. */
+        constexpr int KSTEP = (NH == 2) ? 1 : 2;
+        constexpr int KN    = (M / 2) / KSTEP;                  /* bins visited per pass */
+        constexpr int LK    = (KN / T >= 8) ? 8 : ((KN / T >= 1) ? (KN / T) : 1);
+        #pragma unroll 1
+        for (int i0 = tid; i0 < KN; i0 += LK * T)
         {
-            if (k == 0)
+            float2 w[LK];
+            #pragma unroll
+            for (int u = 0; u < LK; ++u)
             {
-                if ((NH == 2) || (pass == 0))
+                const int k = (i0 + u * T) * KSTEP + ((NH == 2) ? 0 : pass);
+                w[u]        = (i0 + u * T < KN) ? twx[C::TW_POST + k] : make_float2(0.0f, 0.0f);
+            }
+            #pragma unroll
+            for (int u = 0; u < LK; ++u)
+            {
+                if (i0 + u * T >= KN)
+                    continue;
+                const int k = (i0 + u * T) * KSTEP + ((NH == 2) ? 0 : pass);
+                if (k == 0)
                 {
                     float2 z0   = R[0];                         /* Z[0]: (DC, Nyquist) */
                     out[0]      = make_float2(z0.x + z0.y, z0.x - z0.y);
                     float2 zh   = R[P / 2];                     /* Z[M/2] pairs with itself: X = conj(Z) */
                     out[M / 2]  = make_float2(zh.x, -zh.y);
+                    continue;
                 }
-                continue;
+                const int par = k & 1;
+                const float2 *half  = R + ((NH == 2) ? par * P : 0);
+                int ik      = k >> 1;
+                int im      = par ? (P - 1 - ik) : (P - ik);
+                float2 zk   = half[ik], zm = half[im];
+                /* e = (zk + conj(zm))/2 ; o = (zk - conj(zm))/2 ; X[k] = e - i w^k o */
+                float2 e    = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                float2 o    = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
+                float2 wo   = cmul(w[u], o);
+                out[k]      = make_float2(e.x + wo.y, e.y - wo.x);
+                /* X[M-k] = conj(e) - i conj(w) conj(o) = conj(e) - i conj(wo) */
+                out[M - k]  = make_float2(e.x - wo.y, -e.y - wo.x);
             }
-            int par     = k & 1;
-            if ((NH == 1) && (par != pass))
-                continue;
-            const float2 *half  = R + ((NH == 2) ? par * P : 0);
-            int ik      = k >> 1;
-            int im      = par ? (P - 1 - ik) : (P - ik);
-            float2 zk   = half[ik], zm = half[im];
-            /* e = (zk + conj(zm))/2 ; o = (zk - conj(zm))/2 ; X[k] = e - i w^k o */
-            float2 e    = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-            float2 o    = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
-            float2 wo   = cmul(tw[C::TW_POST + k], o);
-            out[k]      = make_float2(e.x + wo.y, e.y - wo.x);
-            /* X[M-k] = conj(e) - i conj(w) conj(o) = conj(e) - i conj(wo) */
-            out[M - k]  = make_float2(e.x - wo.y, -e.y - wo.x);
         }
         if (NH == 1)
             __syncthreads();
+    }
+}
+
+/* copies the r = 1 third of every radix-4 pass of the global table into the compact shared-memory one */
+template <typename C>
+__device__ __forceinline__ void stage_compact_twiddles(float2 *twc, const float2 *twg, int tid)
+{
+    /* entry e of the compact table is entry pass_base(e) * 3 + (e - pass_base(e)) ... walked flat so
+     * that a thread's loads are independent of each other (all in flight at once) */
+    constexpr int LT = 4;
+    #pragma unroll 1
+    for (int e0 = tid; e0 < C::TWC_N; e0 += LT * C::T)
+    {
+        float2 v[LT];
+        int at[LT];
+        #pragma unroll
+        for (int u = 0; u < LT; ++u)
+        {
+            const int e = e0 + u * C::T;
+            /* pass with Ns entries starts at compact offset (Ns - NS0) / 3: Ns = the largest
+             * NS0 * 4^j with (Ns - NS0) / 3 <= e */
+            int Ns = C::NS0;
+            while ((4 * Ns - C::NS0) / 3 <= e)
+                Ns <<= 2;
+            at[u]       = e;
+            v[u]        = (e < C::TWC_N) ? twg[(Ns - C::NS0) + (e - (Ns - C::NS0) / 3)] : make_float2(0.0f, 0.0f);
+        }
+        #pragma unroll
+        for (int u = 0; u < LT; ++u)
+            if (at[u] < C::TWC_N)
+                twc[at[u]]  = v[u];
     }
 }
 
@@ -621,6 +699,7 @@ k_fwd(const StepArgs a)
 {
     using C = FftCfg<RANK>;
     extern __shared__ float2 sm[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     float2 *A               = sm;
     float2 *B               = C::PP ? sm + C::WORK : nullptr;
     const float2 *tw        = a.tw;
@@ -632,13 +711,23 @@ k_fwd(const StepArgs a)
         tw                  = tws;
         __syncthreads();
     }
+    else
+    {
+        float2 *twc         = sm + C::WORK;
+        stage_compact_twiddles<C>(twc, a.tw, threadIdx.x);
+        tw                  = twc;
+        __syncthreads();
+    }
+    /* (three-kernel path with programmatic serialisation: the table staging above overlaps the
+     * previous launch; everything below reads what earlier launches wrote) */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     /* grid-stride over the jobs: a launch over many frames (IR ingest, multi-frame calls) keeps
      * one resident set of CTAs and stages the twiddle table once per CTA; these launches are
      * throughput-bound, so every twiddle comes from the shared-memory copy (one load per butterfly) */
     for (uint32_t j = blockIdx.x; j < a.n_jobs; j += gridDim.x)
     {
         const Job job           = fetch_job(a, j);
-        fwd_body<RANK, C::PP, 0, false, true>(A, B, job.src, job.spec, tw, tw, threadIdx.x);
+        fwd_body<RANK, C::PP, 0, false, true, 0, !C::TWS>(A, B, job.src, job.spec, a.tw, tw, threadIdx.x);
         __syncthreads();            /* the work buffers are reused by the next job */
     }
 }
@@ -654,11 +743,16 @@ k_fwd_half(const StepArgs a)
     using C = FftCfg<RANK, 0, 1>;
     static_assert(!C::PP && !C::TWS, "k_fwd_half: ranks 13..16");
     extern __shared__ float2 sm[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    float2 *twc             = sm + C::WORK;
+    stage_compact_twiddles<C>(twc, a.tw, threadIdx.x);
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (uint32_t w = blockIdx.x; w < 2 * a.n_jobs; w += gridDim.x)
     {
         const Job job           = fetch_job(a, w >> 1);
-        fwd_body<RANK, false, 0, false, true, 1>(sm, nullptr, job.src, job.spec, a.tw, a.tw, threadIdx.x,
-                                                 nullptr, int(w & 1u));
+        fwd_body<RANK, false, 0, false, true, 1, true>(sm, nullptr, job.src, job.spec, a.tw, twc, threadIdx.x,
+                                                       nullptr, int(w & 1u));
         __syncthreads();
     }
 }
@@ -675,11 +769,12 @@ k_fwd_half(const StepArgs a)
  * MODE bit 2 (INV_STAGED, ping-pong ranks): yp is ONE spectrum row in shared memory. */
 enum { INV_OLA = 1, INV_PRESUMMED = 2, INV_STAGED = 4 };
 
-template <int RANK, bool PP, int RG = 8, int TT = 0, int MODE = 0, bool WM = (RANK >= 12), int NHO = 0>     /* RG: partial rows loaded per round (registers) */
+template <int RANK, bool PP, int RG = 8, int TT = 0, int MODE = 0, bool WM = (RANK >= 12), int NHO = 0, bool TWC = false>     /* RG: partial rows loaded per round (registers) */
 __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp, uint32_t splits,
                                          float *dst, const float2 *twg, const float2 *tw, bool full, int tid,
                                          int only_pass = -1)
 {
+    const float2 *twx       = TWC ? twg : tw;      /* TWC: `tw` is the compact pass table (fft_smem) */
     /* only_pass (one resident half, NH == 1; k_inv_half): 0 = the odd bins' half, 1 = the even
      * bins' half; either way dst receives that half's F scaled samples and nothing is combined */
     static_assert((!(MODE & INV_PRESUMMED)) || PP, "inv_body: INV_PRESUMMED needs the second work buffer");
@@ -735,24 +830,33 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
             __syncthreads();
         }
 
+        /* UB bins per round, each with its mirror (k = 0 pairs with M/2: both self-paired specials
+         * ride in thread 0's first slot).  One resident half visits only the bins k = 2 i + want of
+         * its parity.  Without a second work buffer (ranks >= 13, one CTA per SM) the partial rows and
+         * the twiddles come straight from global memory / L2: eight bins per round keep enough loads
+         * in flight to cover that latency. */
+        constexpr int KSTEP     = (NH == 2) ? 1 : 2;
+        constexpr int ROUNDS    = ITER / KSTEP;
+        constexpr int UB        = PP ? 2 : ((ROUNDS >= 8) ? 8 : ROUNDS);
+        static_assert((ROUNDS >= 1) && (ROUNDS % UB == 0), "inv_body: whole rounds");
         #pragma unroll 1
-        for (int it0 = 0; it0 < ITER; it0 += 2)
+        for (int it0 = 0; it0 < ROUNDS; it0 += UB)
         {
-            /* Two bins per round, each with its mirror (k = 0 pairs with M/2: both self-paired
-             * specials ride in thread 0's first slot). */
-            int k[2], km[2];
+            int k[UB], km[UB];
+            float2 wk[UB];
             #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < UB; ++u)
             {
-                k[u]        = tid + (it0 + u) * T;
+                k[u]        = (tid + (it0 + u) * T) * KSTEP + ((NH == 2) ? 0 : want);
                 km[u]       = (k[u] == 0) ? (M / 2) : (M - k[u]);
+                wk[u]       = twg[C::TW_POST + k[u]];
             }
-            float2 yk[2], ym[2];
+            float2 yk[UB], ym[UB];
             if (PP)
             {
                 const float2 *Y = (MODE & INV_STAGED) ? yp : B;
                 #pragma unroll
-                for (int u = 0; u < 2; ++u)
+                for (int u = 0; u < UB; ++u)
                 {
                     yk[u]       = Y[k[u]];
                     ym[u]       = Y[km[u]];
@@ -761,13 +865,13 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
             else
             {
                 #pragma unroll
-                for (int u = 0; u < 2; ++u)
+                for (int u = 0; u < UB; ++u)
                     yk[u] = ym[u] = make_float2(0.0f, 0.0f);
                 for (uint32_t s = 0; s < splits; ++s)
                 {
                     const float2 *row = yp + uint64_t(s) * M;
                     #pragma unroll
-                    for (int u = 0; u < 2; ++u)
+                    for (int u = 0; u < UB; ++u)
                     {
                         yk[u]       = cadd(yk[u], __ldcg(row + k[u]));
                         ym[u]       = cadd(ym[u], __ldcg(row + km[u]));
@@ -776,11 +880,9 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
             }
 
             #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < UB; ++u)
             {
                 int par     = k[u] & 1;
-                if ((NH == 1) && (par != want))
-                    continue;
                 float2 *half = A + ((NH == 2) ? par * P : 0);
                 if (k[u] == 0)
                 {
@@ -792,7 +894,7 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
                 /* e = yk + conj(ym) ; o = conj(w^k) (yk - conj(ym)) ; Z[k] = e + i o ; Z[M-k] = conj(e) + i conj(o) */
                 float2 e    = make_float2(yk[u].x + ym[u].x, yk[u].y - ym[u].y);
                 float2 df   = make_float2(yk[u].x - ym[u].x, yk[u].y + ym[u].y);
-                float2 o    = cmulc(df, twg[C::TW_POST + k[u]]);
+                float2 o    = cmulc(df, wk[u]);
                 int ik      = k[u] >> 1;
                 int im      = par ? (P - 1 - ik) : (P - ik);
                 half[ik]    = make_float2(e.x - o.y, e.y + o.x);
@@ -801,23 +903,40 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
         }
         __syncthreads();
 
-        const float2 *R = fft_smem<RANK, true, PP, TT, WM, true, NHO>(A, B, tw, tid);
+        const float2 *R = fft_smem<RANK, true, PP, TT, WM, true, NHO, TWC>(A, B, tw, tid);
 
-        /* z[m] = (A[m] + conj(w_M^m) B[m]) / N ; z[m + P] = (A[m] - conj(w_M^m) B[m]) / N */
-        for (int m = tid; m < P; m += T)
+        /* z[m] = (A[m] + conj(w_M^m) B[m]) / N ; z[m + P] = (A[m] - conj(w_M^m) B[m]) / N
+         * (global loads -- the twiddle, the parked half -- LBO at a time before the first use) */
+        constexpr int LBO = (P / T >= 8) ? 8 : (P / T);
+        const bool need_w   = (NH == 2) || (pass == 0);
+        const bool need_pk  = (NH == 1) && (pass != 0) && (only_pass != 1);
+        #pragma unroll 1
+        for (int m0 = tid; m0 < P; m0 += LBO * T)
         {
+        float2 wv[LBO], pkv[LBO];
+        #pragma unroll
+        for (int u = 0; u < LBO; ++u)
+        {
+            const int m = m0 + u * T;
+            wv[u]       = need_w ? twx[C::TW_PRE + m] : make_float2(1.0f, 0.0f);
+            pkv[u]      = need_pk ? make_float2(dst[2 * m], dst[2 * m + 1]) : make_float2(0.0f, 0.0f);
+        }
+        #pragma unroll
+        for (int u = 0; u < LBO; ++u)
+        {
+            const int m = m0 + u * T;
             float2 lo, hi;
             if (NH == 2)
             {
                 float2 av   = R[m];
-                float2 bv   = cmulc(R[P + m], tw[C::TW_PRE + m]);
+                float2 bv   = cmulc(R[P + m], wv[u]);
                 lo          = make_float2((av.x + bv.x) * scale, (av.y + bv.y) * scale);
                 hi          = make_float2((av.x - bv.x) * scale, (av.y - bv.y) * scale);
             }
             else if (pass == 0)
             {
                 /* park conj(w) B / N where the result will go; the same thread reads it back */
-                float2 bv   = cmulc(R[m], tw[C::TW_PRE + m]);
+                float2 bv   = cmulc(R[m], wv[u]);
                 dst[2 * m]      = bv.x * scale;
                 dst[2 * m + 1]  = bv.y * scale;
                 continue;
@@ -831,7 +950,7 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
             else
             {
                 float2 av   = R[m];
-                float2 pk   = make_float2(dst[2 * m], dst[2 * m + 1]);
+                float2 pk   = pkv[u];
                 lo          = make_float2(av.x * scale + pk.x, av.y * scale + pk.y);
                 hi          = make_float2(av.x * scale - pk.x, av.y * scale - pk.y);
             }
@@ -859,6 +978,7 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
                 }
             }
         }
+        }
         if (NH == 1)
             __syncthreads();
     }
@@ -878,6 +998,7 @@ k_inv(const StepArgs a)
 {
     using C = FftCfg<RANK>;
     extern __shared__ float2 sm[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     float2 *A               = sm;
     float2 *B               = C::PP ? sm + C::WORK : nullptr;
     const float2 *tw        = a.tw;
@@ -889,11 +1010,19 @@ k_inv(const StepArgs a)
         tw                  = tws;
         __syncthreads();
     }
+    else
+    {
+        float2 *twc         = sm + C::WORK;
+        stage_compact_twiddles<C>(twc, a.tw, threadIdx.x);
+        tw                  = twc;
+        __syncthreads();
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");     /* the partial rows of the launch before */
     for (uint32_t j = blockIdx.x; j < a.n_jobs; j += gridDim.x)
     {
         const Job job           = fetch_job(a, j);
-        inv_body<RANK, C::PP, RG, 0, 0, true>(A, B, a.ypart + uint64_t(j) * rows_per_job(a) * C::M, rows_per_job(a),
-                                              job.dst, tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
+        inv_body<RANK, C::PP, RG, 0, 0, true, 0, !C::TWS>(A, B, a.ypart + uint64_t(j) * rows_per_job(a) * C::M, rows_per_job(a),
+                                                          job.dst, a.tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
         __syncthreads();
     }
 }
@@ -904,24 +1033,77 @@ k_inv(const StepArgs a)
  * park[job][half] and an element-wise launch combines them. */
 template <int RANK>
 __global__ void __launch_bounds__(FftCfg<RANK, 0, 1>::T)
-k_inv_half(const StepArgs a)
+k_inv_half(const StepArgs a, uint32_t *tickets)
 {
+    __shared__ uint32_t last;
     using C = FftCfg<RANK, 0, 1>;
     static_assert(!C::PP && !C::TWS, "k_inv_half: ranks 13..16");
     extern __shared__ float2 sm[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    float2 *twc             = sm + C::WORK;
+    stage_compact_twiddles<C>(twc, a.tw, threadIdx.x);
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t rows = rows_per_job(a);
     for (uint32_t w = blockIdx.x; w < 2 * a.n_jobs; w += gridDim.x)
     {
         const uint32_t j = w >> 1, half = w & 1u;       /* half 0: odd bins, half 1: even bins */
-        inv_body<RANK, false, 8, 0, 0, true, 1>(sm, nullptr, a.ypart + uint64_t(j) * rows * C::M, rows,
-                                                a.park + (uint64_t(j) * 2 + half) * C::M, a.tw, a.tw, false,
-                                                threadIdx.x, int(half));
+        inv_body<RANK, false, 8, 0, 0, true, 1, true>(sm, nullptr, a.ypart + uint64_t(j) * rows * C::M, rows,
+                                                      a.park + (uint64_t(j) * 2 + half) * C::M, a.tw, twc, false,
+                                                      threadIdx.x, int(half));
+        if (tickets != nullptr)
+        {
+            /* the second half of a frame to finish combines: y[i] = e[i] + o[i] (and e[i] - o[i] for
+             * the upper half of a full inverse) -- no separate element-wise launch */
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                const uint32_t old  = atomicAdd(&tickets[j], 1u);
+                last                = (old == 1u) ? 1u : 0u;
+                if (last)
+                    tickets[j]          = 0;
+            }
+            __syncthreads();
+            if (last)
+            {
+                __threadfence();
+                const Job job       = fetch_job(a, j);
+                const bool full     = (a.flags & INV_FULL) != 0;
+                const float4 *o4    = reinterpret_cast<const float4 *>(a.park + uint64_t(j) * 2 * C::M);
+                const float4 *e4    = o4 + C::M / 4;
+                const bool al       = (reinterpret_cast<uintptr_t>(job.dst) & 15) == 0;
+                for (uint32_t i = threadIdx.x; i < uint32_t(C::M) / 4; i += C::T)
+                {
+                    const float4 ev = __ldcg(e4 + i), ov = __ldcg(o4 + i);
+                    const float4 lo = make_float4(ev.x + ov.x, ev.y + ov.y, ev.z + ov.z, ev.w + ov.w);
+                    const float4 hi = make_float4(ev.x - ov.x, ev.y - ov.y, ev.z - ov.z, ev.w - ov.w);
+                    if (al)
+                    {
+                        reinterpret_cast<float4 *>(job.dst)[i]  = lo;
+                        if (full)
+                            reinterpret_cast<float4 *>(job.dst)[C::M / 4 + i] = hi;
+                    }
+                    else
+                    {
+                        job.dst[4 * i] = lo.x; job.dst[4 * i + 1] = lo.y; job.dst[4 * i + 2] = lo.z; job.dst[4 * i + 3] = lo.w;
+                        if (full)
+                        {
+                            float *d2 = job.dst + C::M;
+                            d2[4 * i] = hi.x; d2[4 * i + 1] = hi.y; d2[4 * i + 2] = hi.z; d2[4 * i + 3] = hi.w;
+                        }
+                    }
+                }
+            }
+        }
         __syncthreads();
     }
 }
 
 __global__ void k_inv_combine(const StepArgs a)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t F    = 1u << (a.rank - 1);
     const bool full     = (a.flags & INV_FULL) != 0;
     for (uint32_t j = blockIdx.y; j < a.n_jobs; j += gridDim.y)
@@ -1238,11 +1420,24 @@ k_mac(const StepArgs a, const MacShape sh)
     __syncthreads();
 
     /* Stage-ring bookkeeping is incremental (next stage buffer, next partition, next ring slot):
-     * no integer division inside the streaming loop. */
-    uint32_t f_it = 0, f_s = 0, f_q = q0;
-    uint32_t f_slot         = uint32_t((uint64_t(job.slot0) + q0) % d.S);
+     * no integer division inside the streaming loop.  STEP_AFTER_FWD: the CTAs of split 0 visit
+     * their stages in the order 1, 2, ..., n_iter - 1, 0 -- stage 0 holds partition q = 0, whose
+     * ring row the k_fwd launch right before this one is still writing. */
+    const uint32_t late     = ((a.flags & STEP_AFTER_FWD) && (split == 0) && (n_iter > 0)) ? 1u : 0u;
+    const uint32_t slot_q0  = uint32_t((uint64_t(job.slot0) + q0) % d.S);
+    uint32_t f_it = 0, f_s = 0, f_q = q0 + late * QB;
+    uint32_t f_slot         = slot_q0 + late * QB;
+    if (f_slot >= d.S)      f_slot -= d.S;
     auto issue_next = [&]()
     {
+        if (late && (f_it == n_iter - 1))
+        {
+            /* the rotated first stage: every earlier launch (the transform of this block) is complete */
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+            f_q             = q0;
+            f_slot          = slot_q0;
+        }
         uint32_t rows   = min(QB, q1 - f_q);
         float2 *g       = sG + size_t(f_s) * stage_elems;
         float2 *x       = sX + size_t(f_s) * stage_elems;
@@ -1281,9 +1476,11 @@ k_mac(const StepArgs a, const MacShape sh)
         acc[v]      = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     float dny       = 0.0f;         /* sum of Im*Im of the thread's first bin: Nyquist fix-up for bin 0 */
 
-    uint32_t c_s = 0, c_par = 0, c_q = q0;
+    uint32_t c_s = 0, c_par = 0, c_q = q0 + late * QB;
     for (uint32_t it = 0; it < n_iter; ++it)
     {
+        if (late && (it == n_iter - 1))
+            c_q             = q0;
         uint32_t rows   = min(QB, q1 - c_q);
         mbar_wait(&full[c_s], c_par);
 
