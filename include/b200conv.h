@@ -241,7 +241,9 @@ int     b200conv_set_option(b200conv_batch_t *h, const char *name, int value);
  *   apply       : dst[i][0 .. 2^rank) += IFFT(c1[i] * c2[i]) / 2^rank
  *   parse_apply : dst[i][0 .. 2^rank) += IFFT(c[i] * parse(src[i])) / 2^rank
  *   restore     : dst[i][0 .. 2^rank)  = IFFT(image[i]) / 2^rank
- * Enqueued on `stream` (NULL = default stream of `device`). */
+ * Enqueued on `stream` (NULL = default stream of `device`) and truly stream-ordered: no host
+ * synchronisation, no lock on the data path, no job upload (row i of every operand is problem i);
+ * scratch comes from the stream-ordered allocator (cudaMallocAsync on `stream`). */
 int     b200conv_fastconv_parse(int device, float *image, const float *src, size_t rank,
                                 size_t count, void *stream);
 int     b200conv_fastconv_apply(int device, float *dst, const float *c1, const float *c2,

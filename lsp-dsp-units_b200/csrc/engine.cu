@@ -2641,79 +2641,58 @@ extern "C" int b200conv_reduce_status(b200conv_batch_t *b, int *timed_out)
 /* ------------------------------------------------------------------------------------------- */
 /* fastconv primitives on the device                                                            */
 
+/* Stream-ordered: nothing here synchronises, takes a lock on the data path or uploads a job list.
+ * Problem i lives at row i of each operand, so the kernels derive their jobs from the base
+ * pointers (STEP_LINEAR_JOBS); scratch comes from the stream-ordered allocator
+ * (cudaMallocAsync / cudaFreeAsync on the caller's stream).  The only shared state is the
+ * per-device twiddle table of a rank, built once. */
 namespace
 {
-    struct PrimCtx
-    {
-        float2     *tw[B200CONV_RANK_MAX + 1] = { nullptr };
-        Job        *d_jobs      = nullptr;
-        size_t      job_cap     = 0;
-        float      *scratch     = nullptr;      /* images / time rows */
-        size_t      scratch_bytes = 0;
-    };
     std::mutex  g_prim_lock;
-    PrimCtx     g_prim[64];
+    float2     *g_prim_tw[MAX_DEVICES][B200CONV_RANK_MAX + 1] = { { nullptr } };
 
-    int prim_prepare(int device, size_t rank, size_t count, size_t scratch_bytes, PrimCtx **out)
+    int prim_twiddles(int device, size_t rank, size_t count, float2 **tw)
     {
-        if ((rank < B200CONV_RANK_MIN) || (rank > B200CONV_RANK_MAX) || (count == 0))
+        if ((rank < B200CONV_RANK_MIN) || (rank > B200CONV_RANK_MAX) || (count == 0) || (count >= (size_t(1) << 31)))
             return fail(B200CONV_ERR_ARG, "fastconv: rank %zu / count %zu not supported", rank, count);
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
         if ((e != cudaSuccess) || (n == 0))
             return fail(B200CONV_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(e));
-        if ((device < 0) || (device >= n) || (device >= 64))
+        if ((device < 0) || (device >= n) || (device >= MAX_DEVICES))
             return fail(B200CONV_ERR_ARG, "device %d out of range", device);
-        PrimCtx &c = g_prim[device];
-        if (c.tw[rank] == nullptr)
-            TRY(make_twiddles(uint32_t(rank), &c.tw[rank]));
-        if (count > c.job_cap)
-        {
-            CU(cudaDeviceSynchronize());
-            if (c.d_jobs) cudaFree(c.d_jobs);
-            c.d_jobs = nullptr; c.job_cap = 0;
-            CU(cudaMalloc(&c.d_jobs, count * sizeof(Job)));
-            c.job_cap = count;
-        }
-        if (scratch_bytes > c.scratch_bytes)
-        {
-            CU(cudaDeviceSynchronize());
-            if (c.scratch) cudaFree(c.scratch);
-            c.scratch = nullptr; c.scratch_bytes = 0;
-            CU(cudaMalloc(&c.scratch, scratch_bytes));
-            c.scratch_bytes = scratch_bytes;
-        }
-        *out = &c;
+        std::lock_guard<std::mutex> lock(g_prim_lock);      /* first use of a (device, rank) builds the table */
+        if (g_prim_tw[device][rank] == nullptr)
+            TRY(make_twiddles(uint32_t(rank), &g_prim_tw[device][rank]));
+        *tw         = g_prim_tw[device][rank];
         return B200CONV_OK;
     }
 
-    /* rows: job i reads src + i*src_step, writes spec + i*spec_step / dst + i*dst_step */
-    int prim_jobs(PrimCtx *c, size_t count, const float *src, size_t src_step, float2 *spec,
-                  size_t spec_step, float *dst, size_t dst_step, cudaStream_t st)
-    {
-        std::vector<Job> jobs(count);
-        for (size_t i = 0; i < count; ++i)
-        {
-            memset(&jobs[i], 0, sizeof(Job));
-            jobs[i].src     = (src != nullptr) ? src + i * src_step : nullptr;
-            jobs[i].spec    = (spec != nullptr) ? spec + i * spec_step : nullptr;
-            jobs[i].dst     = (dst != nullptr) ? dst + i * dst_step : nullptr;
-        }
-        CU(cudaMemcpyAsync(c->d_jobs, jobs.data(), count * sizeof(Job), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));      /* `jobs` is pageable and about to go out of scope */
-        return B200CONV_OK;
-    }
-
-    StepArgs prim_args(PrimCtx *c, size_t rank, size_t count)
+    /* job i: transform input src + i * F, spectrum row spec + i * M, inverse output dst + i * dst_step */
+    StepArgs prim_args(const float2 *tw, size_t rank, size_t count, const float *src, float *fwd_out_or_inv_dst,
+                       size_t dst_step, uint32_t flags)
     {
         StepArgs a;
         memset(&a, 0, sizeof(a));
-        a.jobs      = c->d_jobs;
-        a.tw        = c->tw[rank];
+        a.tw        = tw;
         a.rank      = uint32_t(rank);
         a.n_jobs    = uint32_t(count);
         a.splits    = 1;
+        a.src       = src;
+        a.dst       = fwd_out_or_inv_dst;
+        a.stride_dst = dst_step;
+        a.flags     = STEP_LINEAR_JOBS | flags;
         return a;
+    }
+
+    /* ranks 13..16: scratch for the half-frame inverse (NULL when the launch will not use it) */
+    int prim_park(size_t rank, size_t count, cudaStream_t st, float **park)
+    {
+        *park       = nullptr;
+        if ((rank < 13) || ((rank < 16) && (count > 2 * MAX_FEW_JOBS)))
+            return B200CONV_OK;
+        CU(cudaMallocAsync(park, count * (size_t(2) << (rank - 1)) * sizeof(float), st));
+        return B200CONV_OK;
     }
 }
 
@@ -2730,89 +2709,104 @@ extern "C" int b200conv_fastconv_parse(int device, float *image, const float *sr
                                        size_t count, void *stream)
 {
     ENTER_PRIM_DEVICE(device);
-    std::lock_guard<std::mutex> lock(g_prim_lock);
-    PrimCtx *c = nullptr;
-    TRY(prim_prepare(device, rank, count, 0, &c));
-    cudaStream_t st = cudaStream_t(stream);
-    size_t F = size_t(1) << (rank - 1);
-    TRY(prim_jobs(c, count, src, F, reinterpret_cast<float2 *>(image), F, nullptr, 0, st));
-    StepArgs a = prim_args(c, rank, count);
-    CU(launch_fwd(a, uint32_t(count), st));
-    CU(cudaStreamSynchronize(st));
+    float2 *tw = nullptr;
+    TRY(prim_twiddles(device, rank, count, &tw));
+    if ((image == nullptr) || (src == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_fastconv_parse: NULL buffer");
+    StepArgs a = prim_args(tw, rank, count, src, image, 0, 0);
+    CU(launch_fwd(a, uint32_t(count), cudaStream_t(stream)));
     return B200CONV_OK;
 }
 
-static int prim_inverse(PrimCtx *c, float *dst, const float2 *images, size_t rank, size_t count,
-                        bool accumulate, float *time_scratch, cudaStream_t st)
+/* dst[i][0 .. 2^rank) (+)= IFFT(images[i]) / 2^rank; `images` may be clobbered by nobody: the
+ * inverse reads it once */
+static int prim_inverse(const float2 *tw, float *dst, const float2 *images, size_t rank, size_t count,
+                        bool accumulate, cudaStream_t st)
 {
-    size_t N = size_t(1) << rank;
-    float *out = accumulate ? time_scratch : dst;
-    TRY(prim_jobs(c, count, nullptr, 0, nullptr, 0, out, N, st));
-    StepArgs a = prim_args(c, rank, count);
-    a.ypart     = const_cast<float2 *>(images);
-    a.flags     = INV_FULL;
-    CU(launch_inv(a, uint32_t(count), st));
+    const size_t N  = size_t(1) << rank;
+    float *rows = nullptr, *park = nullptr;
     if (accumulate)
+        CU(cudaMallocAsync(&rows, count * N * sizeof(float), st));
+    int rc = prim_park(rank, count, st, &park);
+    if (rc == B200CONV_OK)
     {
-        uint64_t total = uint64_t(count) * N;
-        uint32_t grid = uint32_t((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-        k_accumulate<<<grid, 256, 0, st>>>(dst, time_scratch, total);
-        CU(cudaGetLastError());
+        StepArgs a  = prim_args(tw, rank, count, nullptr, accumulate ? rows : dst, N, INV_FULL);
+        a.ypart     = const_cast<float2 *>(images);
+        a.park      = park;
+        cudaError_t e = launch_inv(a, uint32_t(count), st);
+        if ((e == cudaSuccess) && accumulate)
+        {
+            uint64_t total  = uint64_t(count) * N;
+            uint32_t grid   = uint32_t((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+            k_accumulate<<<grid, 256, 0, st>>>(dst, rows, total);
+            e               = cudaGetLastError();
+        }
+        if (e != cudaSuccess)
+            rc              = fail(B200CONV_ERR_CUDA, "fastconv inverse failed: %s", cudaGetErrorString(e));
     }
-    CU(cudaStreamSynchronize(st));
-    return B200CONV_OK;
+    if (rows)   cudaFreeAsync(rows, st);
+    if (park)   cudaFreeAsync(park, st);
+    return rc;
 }
 
 extern "C" int b200conv_fastconv_restore(int device, float *dst, const float *image, size_t rank,
                                          size_t count, void *stream)
 {
     ENTER_PRIM_DEVICE(device);
-    std::lock_guard<std::mutex> lock(g_prim_lock);
-    PrimCtx *c = nullptr;
-    TRY(prim_prepare(device, rank, count, 0, &c));
-    return prim_inverse(c, dst, reinterpret_cast<const float2 *>(image), rank, count, false, nullptr,
-                        cudaStream_t(stream));
+    float2 *tw = nullptr;
+    TRY(prim_twiddles(device, rank, count, &tw));
+    if ((dst == nullptr) || (image == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_fastconv_restore: NULL buffer");
+    return prim_inverse(tw, dst, reinterpret_cast<const float2 *>(image), rank, count, false, cudaStream_t(stream));
 }
 
 extern "C" int b200conv_fastconv_apply(int device, float *dst, const float *c1, const float *c2,
                                        size_t rank, size_t count, void *stream)
 {
     ENTER_PRIM_DEVICE(device);
-    std::lock_guard<std::mutex> lock(g_prim_lock);
-    size_t N = size_t(1) << rank, M = N / 2;
-    PrimCtx *c = nullptr;
-    /* scratch: product images (count*M float2) + time rows (count*N floats) */
-    TRY(prim_prepare(device, rank, count, count * M * sizeof(float2) + count * N * sizeof(float), &c));
+    float2 *tw = nullptr;
+    TRY(prim_twiddles(device, rank, count, &tw));
+    if ((dst == nullptr) || (c1 == nullptr) || (c2 == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_fastconv_apply: NULL buffer");
     cudaStream_t st = cudaStream_t(stream);
-    float2 *prod    = reinterpret_cast<float2 *>(c->scratch);
-    float *rows     = c->scratch + count * M * 2;
+    const size_t M  = size_t(1) << (rank - 1);
+    float2 *prod    = nullptr;
+    CU(cudaMallocAsync(&prod, count * M * sizeof(float2), st));
     uint64_t total  = uint64_t(count) * M;
     uint32_t grid   = uint32_t((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
     k_cmul<<<grid, 256, 0, st>>>(prod, reinterpret_cast<const float2 *>(c1),
                                  reinterpret_cast<const float2 *>(c2), uint32_t(M), total);
-    CU(cudaGetLastError());
-    return prim_inverse(c, dst, prod, rank, count, true, rows, st);
+    int rc = (cudaGetLastError() == cudaSuccess) ? prim_inverse(tw, dst, prod, rank, count, true, st)
+                                                 : fail(B200CONV_ERR_CUDA, "k_cmul launch failed");
+    cudaFreeAsync(prod, st);
+    return rc;
 }
 
 extern "C" int b200conv_fastconv_parse_apply(int device, float *dst, const float *cimg, const float *src,
                                              size_t rank, size_t count, void *stream)
 {
     ENTER_PRIM_DEVICE(device);
-    std::lock_guard<std::mutex> lock(g_prim_lock);
-    size_t N = size_t(1) << rank, M = N / 2;
-    PrimCtx *c = nullptr;
-    TRY(prim_prepare(device, rank, count, count * M * sizeof(float2) + count * N * sizeof(float), &c));
+    float2 *tw = nullptr;
+    TRY(prim_twiddles(device, rank, count, &tw));
+    if ((dst == nullptr) || (cimg == nullptr) || (src == nullptr))
+        return fail(B200CONV_ERR_ARG, "b200conv_fastconv_parse_apply: NULL buffer");
     cudaStream_t st = cudaStream_t(stream);
-    float2 *prod    = reinterpret_cast<float2 *>(c->scratch);
-    float *rows     = c->scratch + count * M * 2;
-    TRY(prim_jobs(c, count, src, M, prod, M, nullptr, 0, st));
-    StepArgs a = prim_args(c, rank, count);
-    CU(launch_fwd(a, uint32_t(count), st));
-    uint64_t total  = uint64_t(count) * M;
-    uint32_t grid   = uint32_t((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
-    k_cmul<<<grid, 256, 0, st>>>(prod, prod, reinterpret_cast<const float2 *>(cimg), uint32_t(M), total);
-    CU(cudaGetLastError());
-    return prim_inverse(c, dst, prod, rank, count, true, rows, st);
+    const size_t M  = size_t(1) << (rank - 1);
+    float2 *prod    = nullptr;
+    CU(cudaMallocAsync(&prod, count * M * sizeof(float2), st));
+    StepArgs a      = prim_args(tw, rank, count, src, reinterpret_cast<float *>(prod), 0, 0);
+    cudaError_t e   = launch_fwd(a, uint32_t(count), st);
+    if (e == cudaSuccess)
+    {
+        uint64_t total  = uint64_t(count) * M;
+        uint32_t grid   = uint32_t((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+        k_cmul<<<grid, 256, 0, st>>>(prod, prod, reinterpret_cast<const float2 *>(cimg), uint32_t(M), total);
+        e               = cudaGetLastError();
+    }
+    int rc = (e == cudaSuccess) ? prim_inverse(tw, dst, prod, rank, count, true, st)
+                                : fail(B200CONV_ERR_CUDA, "fastconv_parse_apply failed: %s", cudaGetErrorString(e));
+    cudaFreeAsync(prod, st);
+    return rc;
 }
 
 extern "C" int b200conv_convolve(int device, float *dst, size_t dst_stride, const float *src, size_t src_stride,

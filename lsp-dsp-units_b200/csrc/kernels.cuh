@@ -108,8 +108,8 @@ enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
        STEP_AFTER_FWD = 128 /* k_mac launched with programmatic serialisation right behind the k_fwd of the
                                SAME block (three-kernel path, ranks 14..16): the CTAs of split 0 take the
                                stage that needs the arriving frame's spectrum last, after griddepcontrol.wait */,
-       STEP_LINEAR_JOBS = 64 /* IR ingest: job j transforms src + j * F into the row dst + j * 2 F (one
-                                contiguous slab of zero-padded partitions -> one slab of spectra) */,
+       STEP_LINEAR_JOBS = 64 /* IR ingest / the fastconv primitives: forward job j transforms src + j * F into
+                                the spectrum row (float2 *) dst + j * F; inverse job j writes dst + j * stride_dst */,
        STEP_HOST_IO = 8 /* src / dst are page-locked HOST matrices: no bulk-copy staging */,
        STEP_WAIT_HEAD = 16 /* k_mac launched early (programmatic serialization) behind a k_frame:
                               poll ring_head before touching the newest spectra */,
@@ -217,7 +217,7 @@ __device__ __forceinline__ Job fetch_job(const StepArgs &a, uint32_t j)
         Job r;
         r.src               = a.src + uint64_t(j) * F;
         r.spec              = reinterpret_cast<float2 *>(a.dst) + uint64_t(j) * F;
-        r.dst               = nullptr;
+        r.dst               = a.dst + uint64_t(j) * a.stride_dst;       /* inverse transforms: output row */
         r.psrc = r.psrc2    = nullptr;
         r.pdst = r.pdst2    = nullptr;
         r.inst = r.slot0 = r.qa = r.qb = r.off = r.n = r.off2 = r.n2 = r.tlo = r.flags = 0;
