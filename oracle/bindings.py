@@ -281,3 +281,92 @@ def chirp_linear_convolutions(inputs, inverse, part_size_limit, scale):
     if rc != 0:
         raise RuntimeError("orc_chirp_linear_convolutions failed")
     return res
+
+
+# ---- lsp::dspu::SpectralProcessor, the reference class itself (oracle/ref_wrap_spectral.cpp) -------
+
+class CpuSpectralProcessor:
+    """The reference's own ``dspu::SpectralProcessor`` (SpectralProcessor.cpp compiled verbatim into
+    ``oracle/_ref``) with one of two host callbacks: ``bind_complex(H)`` multiplies the packed complex
+    spectrum (``2**rank`` bins) by ``H``, ``bind_gain(g)`` scales bin ``k`` by the real ``g[k]``."""
+
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(_HERE, "_ref", "libref_convolver.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            lib = ctypes.CDLL(os.path.join(_HERE, "_ref", "libref_convolver.so"))
+            lib.refsp_create.restype = ctypes.c_void_p
+            lib.refsp_create.argtypes = [_SZ]
+            lib.refsp_free.argtypes = [ctypes.c_void_p]
+            lib.refsp_set_rank.argtypes = [ctypes.c_void_p, _SZ]
+            lib.refsp_set_phase.argtypes = [ctypes.c_void_p, ctypes.c_float]
+            for name in ("refsp_rank", "refsp_latency", "refsp_remaining"):
+                getattr(lib, name).restype = _SZ
+                getattr(lib, name).argtypes = [ctypes.c_void_p]
+            lib.refsp_reset.argtypes = [ctypes.c_void_p]
+            lib.refsp_update_settings.argtypes = [ctypes.c_void_p]
+            lib.refsp_bind.argtypes = [ctypes.c_void_p, ctypes.c_int, _FP, _SZ]
+            lib.refsp_process.argtypes = [ctypes.c_void_p, _FP, _FP, _SZ]
+            cls._lib = lib
+        return cls._lib
+
+    def __init__(self, max_rank):
+        self._h = self.lib().refsp_create(max_rank)
+
+    def set_rank(self, rank):
+        self.lib().refsp_set_rank(self._h, rank)
+
+    def set_phase(self, phase):
+        self.lib().refsp_set_phase(self._h, phase)
+
+    def rank(self):
+        return int(self.lib().refsp_rank(self._h))
+
+    def latency(self):
+        return int(self.lib().refsp_latency(self._h))
+
+    def remaining(self):
+        return int(self.lib().refsp_remaining(self._h))
+
+    def reset(self):
+        self.lib().refsp_reset(self._h)
+
+    def update_settings(self):
+        self.lib().refsp_update_settings(self._h)
+
+    def unbind(self):
+        self.lib().refsp_bind(self._h, 0, None, 0)
+
+    def bind_complex(self, H):
+        H = np.ascontiguousarray(H, dtype=np.complex64).view(np.float32)
+        self.lib().refsp_bind(self._h, 1, _ptr(H), H.size)
+
+    def bind_gain(self, g):
+        g = np.ascontiguousarray(g, dtype=np.float32)
+        self.lib().refsp_bind(self._h, 2, _ptr(g), g.size)
+
+    def process(self, src):
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        out = np.empty_like(src)
+        self.lib().refsp_process(self._h, _ptr(out), _ptr(src), src.size)
+        return out
+
+    def run(self, src, step):
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        out = np.zeros_like(src)
+        for i in range(0, src.size, step):
+            out[i:i + step] = self.process(src[i:i + step])
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                self.lib().refsp_free(self._h)
+                self._h = None
+        except Exception:
+            pass

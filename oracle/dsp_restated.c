@@ -211,3 +211,97 @@ void rs_fastconv_restore(float *dst, float *src, size_t rank)
     for (size_t i = 0; i < n; ++i)
         dst[i]      = src[i] * k;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* The primitives lsp::dspu::SpectralProcessor calls (SpectralProcessor.cpp:163-183): element-wise
+ * products, real <-> packed complex, and the packed (interleaved re / im, natural bin order)
+ * complex FFT pair.  The reverse transform is normalised by 1 / N, as the reference relies on
+ * (window -> FFT -> IFFT -> window -> overlap-add reproduces the input when the callback leaves
+ * the spectrum alone). */
+
+void rs_mul3(float *dst, const float *a, const float *b, size_t count)
+{
+    for (size_t i = 0; i < count; ++i)
+        dst[i]  = a[i] * b[i];
+}
+
+void rs_fmadd3(float *dst, const float *a, const float *b, size_t count)
+{
+    for (size_t i = 0; i < count; ++i)
+        dst[i] += a[i] * b[i];
+}
+
+void rs_pcomplex_r2c(float *dst, const float *src, size_t count)
+{
+    /* forwards: the reference converts in place with src = dst + count (SpectralProcessor.cpp:164),
+     * where the write index 2 i + 1 never passes the read index count + i */
+    for (size_t i = 0; i < count; ++i)
+    {
+        float v     = src[i];
+        dst[2*i]    = v;
+        dst[2*i+1]  = 0.0f;
+    }
+}
+
+void rs_pcomplex_c2r(float *dst, const float *src, size_t count)
+{
+    for (size_t i = 0; i < count; ++i)      /* forwards: dst may alias src */
+        dst[i]      = src[2*i];
+}
+
+static void rs_packed_fft(float *dst, const float *src, size_t rank, int inverse)
+{
+    rs_dsp_init();
+    const size_t n = (size_t)1 << rank;
+    /* bit-reversal copy (in place when dst == src) */
+    if (dst != src)
+    {
+        for (size_t i = 0; i < n; ++i)
+        {
+            size_t j = 0;
+            for (size_t b = 0; b < rank; ++b)
+                j  |= ((i >> b) & 1) << (rank - 1 - b);
+            dst[2*j]    = src[2*i];
+            dst[2*j+1]  = src[2*i+1];
+        }
+    }
+    else
+    {
+        for (size_t i = 0; i < n; ++i)
+        {
+            size_t j = 0;
+            for (size_t b = 0; b < rank; ++b)
+                j  |= ((i >> b) & 1) << (rank - 1 - b);
+            if (j > i)
+            {
+                float tr = dst[2*i], ti = dst[2*i+1];
+                dst[2*i] = dst[2*j]; dst[2*i+1] = dst[2*j+1];
+                dst[2*j] = tr;       dst[2*j+1] = ti;
+            }
+        }
+    }
+    /* decimation in time, natural order out */
+    for (size_t h = 1; h < n; h <<= 1)
+    {
+        const float *wr = &rs_tw_re[h], *wi = &rs_tw_im[h];
+        for (size_t b = 0; b < n; b += 2*h)
+            for (size_t j = 0; j < h; ++j)
+            {
+                float c = wr[j], s = inverse ? -wi[j] : wi[j];
+                float *p = &dst[2*(b + j)], *q = &dst[2*(b + j + h)];
+                float tr = q[0] * c - q[1] * s;
+                float ti = q[0] * s + q[1] * c;
+                q[0] = p[0] - tr;  q[1] = p[1] - ti;
+                p[0] += tr;        p[1] += ti;
+            }
+    }
+    if (inverse)
+    {
+        const float k = 1.0f / (float)n;
+        for (size_t i = 0; i < 2*n; ++i)
+            dst[i]     *= k;
+    }
+}
+
+void rs_packed_direct_fft(float *dst, const float *src, size_t rank)   { rs_packed_fft(dst, src, rank, 0); }
+void rs_packed_reverse_fft(float *dst, const float *src, size_t rank)  { rs_packed_fft(dst, src, rank, 1); }

@@ -58,6 +58,16 @@ void rs_fastconv_parse_apply(float *dst, float *tmp, const float *c, const float
 /* dst[0 .. 2^rank) = Re(IFFT(src)) / 2^rank ; src clobbered (store, not add) */
 void rs_fastconv_restore(float *dst, float *src, size_t rank);
 
+/* ---- the primitives of lsp::dspu::SpectralProcessor (SpectralProcessor.cpp:163-183) ---------- */
+void rs_mul3(float *dst, const float *a, const float *b, size_t count);            /* dst = a * b   */
+void rs_fmadd3(float *dst, const float *a, const float *b, size_t count);          /* dst += a * b  */
+void rs_pcomplex_r2c(float *dst, const float *src, size_t count);                  /* (re, 0) pairs */
+void rs_pcomplex_c2r(float *dst, const float *src, size_t count);                  /* real parts    */
+/* complex FFT of 2^rank points, interleaved re / im, natural order in and out; dst may equal src;
+ * the reverse transform is scaled by 1 / 2^rank */
+void rs_packed_direct_fft(float *dst, const float *src, size_t rank);
+void rs_packed_reverse_fft(float *dst, const float *src, size_t rank);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,13 +1,17 @@
 /*
  * oracle/shim -- TEST INFRASTRUCTURE.  Stand-in for lsp-common-lib's
  * <lsp-plug.in/common/alloc.h>: alloc_aligned / free_aligned as used at
- * reference Convolver.cpp:73,104.
+ * reference Convolver.cpp:73,104 and SpectralProcessor.cpp:72,80.
  */
 #ifndef ORACLE_SHIM_COMMON_ALLOC_H_
 #define ORACLE_SHIM_COMMON_ALLOC_H_
 
 #include <lsp-plug.in/common/types.h>
 #include <stdlib.h>
+
+#ifndef DEFAULT_ALIGN
+    #define DEFAULT_ALIGN       0x10        /* lsp-common-lib's default (used at SpectralProcessor.cpp:72) */
+#endif
 
 namespace lsp
 {

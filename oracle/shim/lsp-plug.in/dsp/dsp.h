@@ -31,6 +31,14 @@ namespace lsp
             { rs_fastconv_parse_apply(dst, tmp, c, src, rank); }
         inline void fastconv_restore(float *dst, float *src, size_t rank)
             { rs_fastconv_restore(dst, src, rank); }
+
+        /* SpectralProcessor.cpp:163-183 */
+        inline void mul3(float *dst, const float *a, const float *b, size_t count)     { rs_mul3(dst, a, b, count); }
+        inline void fmadd3(float *dst, const float *a, const float *b, size_t count)   { rs_fmadd3(dst, a, b, count); }
+        inline void pcomplex_r2c(float *dst, const float *src, size_t count)           { rs_pcomplex_r2c(dst, src, count); }
+        inline void pcomplex_c2r(float *dst, const float *src, size_t count)           { rs_pcomplex_c2r(dst, src, count); }
+        inline void packed_direct_fft(float *dst, const float *src, size_t rank)       { rs_packed_direct_fft(dst, src, rank); }
+        inline void packed_reverse_fft(float *dst, const float *src, size_t rank)      { rs_packed_reverse_fft(dst, src, rank); }
     }
 }
 
