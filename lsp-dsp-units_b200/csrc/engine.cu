@@ -509,13 +509,35 @@ static int make_twiddles(uint32_t rank, float2 **out)
 namespace
 {
     const uint32_t FRAME_CHAIN_MAX = 24;
+
+    /* the rows of one block in a planar matrix: row i covers [lo + i * stride, + len) bytes */
+    struct BlockRows
+    {
+        uintptr_t   lo;
+        size_t      stride, len, rows;
+        uintptr_t hi() const    { return lo + ((rows > 0) ? (rows - 1) * stride : 0) + len; }
+    };
+
+    bool rows_overlap(const BlockRows &a, const BlockRows &b)
+    {
+        if ((a.lo >= b.hi()) || (b.lo >= a.hi()))
+            return false;
+        if ((a.stride == b.stride) && (a.stride >= a.len) && (a.stride >= b.len) && (a.stride > 0))
+        {
+            /* two column blocks of matrices with one row pitch: compare the column offsets */
+            const size_t d  = (b.lo >= a.lo) ? (b.lo - a.lo) % a.stride : (a.stride - (a.lo - b.lo) % a.stride) % a.stride;
+            return (d < a.len) || (d + b.len > a.stride);
+        }
+        return true;                        /* different pitches: the enclosing intervals decide */
+    }
+
     struct FrameHistory
     {
         cudaStream_t    st      = nullptr;
         int             dev     = -1;
         uint32_t        n       = 0;        /* > FRAME_CHAIN_MAX: more launches in flight than the table holds */
         uint64_t        stamp   = 0;
-        uintptr_t       lo[FRAME_CHAIN_MAX], hi[FRAME_CHAIN_MAX];
+        BlockRows       out[FRAME_CHAIN_MAX];
     };
     std::mutex      g_hist_lock;
     FrameHistory    g_hist[32];
@@ -534,7 +556,7 @@ namespace
         if (!create)
             return nullptr;
         /* an evicted entry is forgotten: its stream's next launch finds no history, which is safe
-         * only because eviction makes that launch serial (n = FRAME_CHAIN_MAX) */
+         * only because eviction makes that launch conservative (n = FRAME_CHAIN_MAX + 1) */
         lru->st     = st;
         lru->dev    = dev;
         lru->n      = FRAME_CHAIN_MAX + 1;
@@ -550,11 +572,12 @@ namespace
             h->n        = 0;
     }
 
-    /* Registers a k_frame launch that reads [s_lo, s_hi) and writes [d_lo, d_hi).  `capable`: the
-     * launch would like to transform its input early.  *early: it may; *serial: launch it without
-     * programmatic serialisation (only ever asked of a capable launch). */
-    void hist_launch(cudaStream_t st, int dev, bool capable, uintptr_t s_lo, uintptr_t s_hi,
-                     uintptr_t d_lo, uintptr_t d_hi, bool *early, bool *serial)
+    /* Registers a k_frame launch that reads the block `in` and writes the block `out`.  `capable`:
+     * the launch would like to transform its input early.  *early: it may (no launch in flight
+     * writes its input); *serial: launch it without programmatic serialisation (only ever asked of
+     * a capable launch); *dst_clash: a launch that may be in flight writes (part of) `out` too. */
+    void hist_launch(cudaStream_t st, int dev, bool capable, const BlockRows &in, const BlockRows &out,
+                     bool *early, bool *serial, bool *dst_clash)
     {
         std::lock_guard<std::mutex> lock(g_hist_lock);
         FrameHistory *h = hist_find(st, dev, true);
@@ -562,15 +585,16 @@ namespace
         *serial         = capable && (h->n >= FRAME_CHAIN_MAX);
         if (*serial)
             h->n            = 0;
-        bool clash      = (h->n > FRAME_CHAIN_MAX);
+        bool clash      = (h->n > FRAME_CHAIN_MAX), wclash = clash;
         for (uint32_t i = 0; (i < h->n) && (i < FRAME_CHAIN_MAX); ++i)
-            clash          |= (s_lo < h->hi[i]) && (h->lo[i] < s_hi);
-        *early          = capable && (!clash);
-        if (h->n < FRAME_CHAIN_MAX)
         {
-            h->lo[h->n]     = d_lo;
-            h->hi[h->n]     = d_hi;
+            clash          |= rows_overlap(h->out[i], in);
+            wclash         |= rows_overlap(h->out[i], out);
         }
+        *early          = capable && (!clash);
+        *dst_clash      = wclash;
+        if (h->n < FRAME_CHAIN_MAX)
+            h->out[h->n]    = out;
         if (h->n <= FRAME_CHAIN_MAX)
             h->n           += 1;
     }
@@ -669,7 +693,11 @@ struct b200conv_batch
     bool                    host_io     = false;    /* the running call reads / writes page-locked host matrices */
     int                     opt_fused   = 1, opt_bias = 6, opt_pdl = 1, opt_zero_copy = 1, opt_multi = 8;
     int                     opt_early_src = 1;      /* 0 never, 1 on the batch's own stream, 2 on any stream */
-    uint32_t               *d_tickets   = nullptr;  /* k_frame: one arrival counter per job */
+    uint32_t               *d_tickets   = nullptr;  /* k_frame: [FRAME_SLOTS][instances] arrival counters */
+    uint32_t               *d_slot_done = nullptr;  /* k_frame: [FRAME_SLOTS][instances], see FRAME_SLOTS in kernels.cuh */
+    uint32_t                frame_seq   = 0;        /* sequence number of the next k_frame launch */
+    size_t                  ypart_slot_bytes = 0;   /* ypart holds FRAME_SLOTS slots of this size */
+    std::vector<uint32_t>   h_slot_done;
     uint32_t               *d_ring_head = nullptr;  /* k_frame: frames published per instance */
     uint32_t               *h_error     = nullptr;  /* page-locked, device-mapped: a bounded in-kernel wait gave up */
     std::vector<uint32_t>   h_ring_head;
@@ -684,6 +712,7 @@ struct b200conv_batch
     bool                    pend_ready  = false;
     uint64_t                pend_t      = 0;        /* batch frame counter the pending rows belong to */
     uint32_t                pend_splits = 0;
+    uint32_t                pend_seq    = 0;        /* sequence number of the k_frame launch the pending rows are for */
     cudaEvent_t             ev_done     = nullptr;  /* output of the current block is complete */
     cudaEvent_t             ev_pend     = nullptr;  /* the pending MAC launched after it is complete */
     bool                    pend_inflight = false;
@@ -707,8 +736,14 @@ static cudaError_t launch_mac(Batch *b, const StepArgs &a, const MacPlan &p, uin
     auto go = [&]() -> cudaError_t
     {
         if (fused)
-            return launch_frame(a, p, jobs, b->d_tickets, b->reduce,
+        {
+            const uint32_t slot = a.seq % uint32_t(FRAME_SLOTS);
+            ReduceArgs ra   = b->reduce;
+            if (ra.mode != 0)
+                ra.scratch     += size_t(slot) * ra.channels * ra.frame;
+            return launch_frame(a, p, jobs, b->d_tickets + size_t(slot) * b->n, ra,
                                 (b->opt_pdl != 0) && (!b->profiling) && (!serial), st);
+        }
         return launch_mac_raw(a, p, jobs, st, chain);
     };
     if (!b->profiling)
@@ -844,6 +879,10 @@ static int upload_tables(Batch *b, cudaStream_t st)
             b->h_desc[i].t_delta = int64_t(b->inst[i].frames) - int64_t(b->t_batch);
     }
     CU(cudaMemcpyAsync(b->d_ring_head, b->h_ring_head.data(), b->n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    /* every earlier k_frame launch has completed when these copies run: all slots are free */
+    for (uint32_t &v : b->h_slot_done)
+        v                   = b->frame_seq;
+    CU(cudaMemcpyAsync(b->d_slot_done, b->h_slot_done.data(), b->h_slot_done.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     /* pageable sources: cudaMemcpyAsync stages them before returning */
     CU(cudaMemcpyAsync(b->d_desc, b->h_desc.data(), b->n * sizeof(InstDesc), cudaMemcpyHostToDevice, st));
     if (!b->active.empty())
@@ -853,19 +892,31 @@ static int upload_tables(Batch *b, cudaStream_t st)
     return B200CONV_OK;
 }
 
+/* `bytes` of partial rows per launch; the buffer holds FRAME_SLOTS such slots (pipelined k_frame
+ * launches rotate through them, every other user takes slot 0) */
 static int ensure_ypart(Batch *b, size_t bytes, cudaStream_t st)
 {
-    if (bytes <= b->ypart_bytes)
+    if (bytes <= b->ypart_slot_bytes)
         return B200CONV_OK;
+    CU(quiesce(b));
     CU(cudaStreamSynchronize(st));
     if (b->ypart)
         cudaFree(b->ypart);
     b->ypart        = nullptr;
     b->ypart_bytes  = 0;
-    size_t want     = bytes + bytes / 4;
-    CU(cudaMalloc(&b->ypart, want));
-    b->ypart_bytes  = want;
+    b->ypart_slot_bytes = 0;
+    size_t want     = (bytes + bytes / 4 + 255) & ~size_t(255);
+    CU(cudaMalloc(&b->ypart, want * FRAME_SLOTS));
+    b->ypart_bytes  = want * FRAME_SLOTS;
+    b->ypart_slot_bytes = want;
+    b->pend_ready   = false;
     return B200CONV_OK;
+}
+
+static float2 *ypart_slot(const Batch *b, uint32_t seq)
+{
+    return reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(b->ypart) +
+                                      size_t(seq % uint32_t(FRAME_SLOTS)) * b->ypart_slot_bytes);
 }
 
 /* Ranks 13..16 with few frames per launch: scratch for the half-frame inverse transform
@@ -974,6 +1025,7 @@ static int create_impl(b200conv_batch_t **out, int device, size_t instances)
     b->inst.resize(instances);
     b->h_desc.resize(instances);
     b->h_ring_head.assign(instances, 0);
+    b->h_slot_done.assign(FRAME_SLOTS * instances, 0);
     b->g_pos.assign(instances, 0);
     b->g_jobs.reserve(instances);
     b->g_fft.reserve(instances);
@@ -1002,8 +1054,10 @@ static int create_impl(b200conv_batch_t **out, int device, size_t instances)
         CU_BRK(cudaMallocHost(&b->h_jobs, b->job_cap * sizeof(Job)));
         CU_BRK(cudaMalloc(&b->d_jobs, b->job_cap * sizeof(Job)));
         CU_BRK(cudaMemset(b->d_desc, 0, instances * sizeof(InstDesc)));
-        CU_BRK(cudaMalloc(&b->d_tickets, instances * sizeof(uint32_t)));
-        CU_BRK(cudaMemset(b->d_tickets, 0, instances * sizeof(uint32_t)));
+        CU_BRK(cudaMalloc(&b->d_tickets, FRAME_SLOTS * instances * sizeof(uint32_t)));
+        CU_BRK(cudaMemset(b->d_tickets, 0, FRAME_SLOTS * instances * sizeof(uint32_t)));
+        CU_BRK(cudaMalloc(&b->d_slot_done, FRAME_SLOTS * instances * sizeof(uint32_t)));
+        CU_BRK(cudaMemset(b->d_slot_done, 0, FRAME_SLOTS * instances * sizeof(uint32_t)));
         CU_BRK(cudaHostAlloc(&b->h_error, 64, cudaHostAllocMapped | cudaHostAllocPortable));
         *b->h_error = 0;
         CU_BRK(cudaMalloc(&b->d_ring_head, instances * sizeof(uint32_t)));
@@ -1044,6 +1098,7 @@ extern "C" void b200conv_free(b200conv_batch_t *b)
     if (b->d_desc)      cudaFree(b->d_desc);
     if (b->d_active)    cudaFree(b->d_active);
     if (b->d_tickets)   cudaFree(b->d_tickets);
+    if (b->d_slot_done) cudaFree(b->d_slot_done);
     if (b->d_ring_head) cudaFree(b->d_ring_head);
     if (b->h_error)     cudaFreeHost(b->h_error);
     if (b->d_jobs)      cudaFree(b->d_jobs);
@@ -1557,22 +1612,28 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
         {
             /* one launch per block for all instances x partitions.  May its input transform run
              * ahead of the launches still in flight on this stream? (FrameHistory) */
-            bool early = false, serial = false;
+            bool early = false, serial = false, dst_clash = false;
             {
                 /* worth it only while the transform is a visible share of the block: a launch that
                  * streams for tens of microseconds hides the chain anyway */
                 const bool capable = (b->opt_pdl != 0) && (!b->profiling) && (per_frame_bytes <= EARLY_MAX_BYTES) &&
                                      ((b->opt_early_src == 2) || ((b->opt_early_src == 1) && (st == b->stream)));
-                const uintptr_t s_lo = reinterpret_cast<uintptr_t>(src + f * F);
-                const uintptr_t d_lo = reinterpret_cast<uintptr_t>(dst + f * F);
-                hist_launch(st, b->device, capable, s_lo, s_lo + ((b->n - 1) * stride + F) * sizeof(float),
-                            d_lo, d_lo + ((b->n - 1) * dst_stride + F) * sizeof(float), &early, &serial);
+                const BlockRows in  = { reinterpret_cast<uintptr_t>(src + f * F), stride * sizeof(float), F * sizeof(float), b->n };
+                const BlockRows out = { reinterpret_cast<uintptr_t>(dst + f * F), dst_stride * sizeof(float), F * sizeof(float), b->n };
+                hist_launch(st, b->device, capable, in, out, &early, &serial, &dst_clash);
             }
+            a.flags        &= ~uint32_t(STEP_EARLY_SRC | STEP_ORDER_DST);
             if (early)
                 a.flags        |= STEP_EARLY_SRC;
-            else
-                a.flags        &= ~uint32_t(STEP_EARLY_SRC);
-            if (eager && b->pend_ready && (b->pend_t == b->t_batch + f) && (!tables_changed))
+            if (dst_clash)
+                a.flags        |= STEP_ORDER_DST;
+            /* pipelined tails (FRAME_SLOTS in kernels.cuh): this launch's rows, tickets and sequence number */
+            a.seq           = b->frame_seq;
+            a.n_cap         = uint32_t(b->n);
+            a.slot_done     = ((b->opt_pdl != 0) && (!b->profiling)) ? b->d_slot_done : nullptr;
+            a.ypart         = ypart_slot(b, a.seq);
+            b->frame_seq   += 1;
+            if (eager && b->pend_ready && (b->pend_t == b->t_batch + f) && (!tables_changed) && (b->pend_seq == a.seq))
             {
                 /* partitions q >= 1 were summed ahead of time (launch_pending_mac): transform the
                  * input, add partition 0, invert -- one CTA per instance */
@@ -1652,10 +1713,12 @@ static int launch_pending_mac(Batch *b, cudaStream_t st)
     MacPlan plan    = plan_mac(uint32_t(b->rank), nact, uint32_t(b->max_nq), b->sm_count,
                                b->tune_splits, b->tune_stages);
     const size_t F  = size_t(1) << (b->rank - 1);
-    if (size_t(nact) * (plan.splits + 1) * F * sizeof(float2) > b->ypart_bytes)
+    if (size_t(nact) * (plan.splits + 1) * F * sizeof(float2) > b->ypart_slot_bytes)
         return B200CONV_OK;                 /* sized by the next process call */
 
     StepArgs a      = base_args(b);
+    a.ypart         = ypart_slot(b, b->frame_seq);      /* the slot of the k_frame launch that will add partition 0 */
+    b->pend_seq     = b->frame_seq;
     a.splits        = plan.splits;
     a.rows          = plan.splits + 1;
     a.row0          = 0;
@@ -2544,13 +2607,13 @@ extern "C" int b200conv_reduce_prepare(b200conv_batch_t *b, int grank, int world
     /* exchange buffer (identical layout on every rank):
      *   words    [DEPTH][world][channels][F] x { sample bits, sequence number = block + 1 }
      *   consumed [world][channels]           blocks consumed, written by the consuming rank
-     *   scratch  [channels][F] floats        this rank's own block (local use only)                */
+     *   scratch  [FRAME_SLOTS][channels][F]  this rank's own block, one per launch in flight (local) */
     const size_t F          = size_t(1) << (b->rank - 1);
     const size_t C          = b->n;
     b->xchg_slots_bytes     = size_t(REDUCE_DEPTH) * world * C * F * sizeof(uint2);
     b->xchg_consumed_off    = (b->xchg_slots_bytes + 127) & ~size_t(127);
     b->xchg_flags_off       = (b->xchg_consumed_off + size_t(world) * C * sizeof(uint32_t) + 127) & ~size_t(127);   /* scratch */
-    size_t total            = b->xchg_flags_off + C * F * sizeof(float);
+    size_t total            = b->xchg_flags_off + size_t(FRAME_SLOTS) * C * F * sizeof(float);
     CU(cudaMalloc(&b->xchg, total));
     CU(cudaMemset(b->xchg, 0, total));
     cudaIpcMemHandle_t hnd;

@@ -88,6 +88,10 @@ struct StepArgs                     /* by-value kernel argument */
     float          *park;           /* k_inv_half: [job][2][F] half results (odd, even); NULL = not available */
     uint32_t       *ring_head;      /* [instance] frames whose spectrum is in the ring (low 32 bits) */
     uint32_t       *error;          /* host-mapped word: set when a bounded in-kernel wait gave up    */
+    uint32_t       *slot_done;      /* k_frame: [FRAME_SLOTS][n_cap] sequence number + 1 of the launch whose tail
+                                       last finished with that (slot, instance); NULL: launches are not pipelined */
+    uint32_t        seq;            /* k_frame: sequence number of this launch (its slot is seq % FRAME_SLOTS) */
+    uint32_t        n_cap;          /* k_frame: instances of the batch (row pitch of slot_done)        */
     uint32_t        rows;           /* partial rows per job in ypart (0 = splits); a launch writes rows
                                        row0 .. row0 + splits - 1, the inverse transform sums all `rows` */
     uint32_t        row0;
@@ -113,6 +117,9 @@ enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
        STEP_HOST_IO = 8 /* src / dst are page-locked HOST matrices: no bulk-copy staging */,
        STEP_WAIT_HEAD = 16 /* k_mac launched early (programmatic serialization) behind a k_frame:
                               poll ring_head before touching the newest spectra */,
+       STEP_ORDER_DST = 256 /* k_frame: the output block overlaps the output block of a launch that may still
+                               be in flight: this launch's tail writes it only after the previous launch's
+                               tail for the same instance has finished */,
        STEP_EARLY_SRC = 32 /* k_frame: the input block may be read before griddepcontrol.wait -- set by
                               the host only when the predecessor on the stream is this batch's own pending
                               k_mac and the input is a caller-owned HOST block no kernel writes */ };
@@ -132,6 +139,18 @@ enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
  * Sequence numbers, not resettable counters: a late peer can never be mistaken for the next
  * block.  All waits are bounded (a peer that never shows up raises *error instead of hanging the
  * GPU; the host then fails the next call). */
+/* k_frame launches of one batch are pipelined FRAME_SLOTS deep: launch s keeps its partial rows, its
+ * tickets (and, sharded, its own output block) in slot s % FRAME_SLOTS, so the tail of block t --
+ * sum of the partial rows, inverse transform, cross-GPU exchange -- overlaps the partition stream
+ * AND the tail of block t + 1 instead of gating it.  What orders the launches:
+ *   slot reuse     slot_done[slot][instance] holds s + 1 once the tail of launch s (the previous user
+ *                  of the slot is launch s - FRAME_SLOTS) has finished; CTAs of launch s poll for
+ *                  s + 1 - FRAME_SLOTS before their first write into the slot (bounded; in steady
+ *                  state it is long there);
+ *   output order   only if the host sees overlapping output blocks (STEP_ORDER_DST);
+ *   completion     the tail CTAs execute griddepcontrol.wait as their LAST instruction, so launch
+ *                  s completes after launch s - 1 (stream order for whatever follows). */
+constexpr int FRAME_SLOTS      = 4;
 constexpr int REDUCE_MAX_WORLD = 8;
 constexpr int REDUCE_DEPTH     = 4;
 struct ReduceArgs
@@ -1837,8 +1856,8 @@ __device__ __forceinline__ void partial_outputs(const float *cur, const float *h
 /* its own dst) is final when it is read, whoever that producer was.                             */
 #ifdef B200CONV_TIMING
 /* developer instrumentation (tools/frame_timeline.py): per-CTA timestamps of the last k_frame launch */
-__device__ unsigned long long g_frame_times[8192 * 4];
-#define FRAME_STAMP(slot)   do { if ((threadIdx.x == 0) && (blockIdx.x < 8192)) g_frame_times[blockIdx.x * 4 + (slot)] = global_ns(); } while (0)
+__device__ unsigned long long g_frame_times[8192 * 8];
+#define FRAME_STAMP(slot)   do { if ((threadIdx.x == 0) && (blockIdx.x < 8192)) g_frame_times[blockIdx.x * 8 + (slot)] = global_ns(); } while (0)
 #else
 #define FRAME_STAMP(slot)   do { } while (0)
 #endif
@@ -2101,8 +2120,23 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
     }
     FRAME_STAMP(1);
 
-    /* partial rows, tickets and the output block are shared with the previous launch's tail */
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool pipelined    = (!GEN) && (a.slot_done != nullptr);
+    uint32_t *my_done       = pipelined ? a.slot_done + size_t(a.seq % uint32_t(FRAME_SLOTS)) * a.n_cap + job.inst : nullptr;
+    if (pipelined)
+    {
+        /* the slot (partial rows, tickets) was last used by launch seq - FRAME_SLOTS: its tail for
+         * this instance must have finished (see FRAME_SLOTS) */
+        if (tid == 0)
+            wait_ge<false>(my_done, a.seq + 1u - uint32_t(FRAME_SLOTS), a.error, SPIN_ERR_RING);
+        __syncthreads();
+    }
+    if ((!pipelined) || (a.flags & STEP_HEAD_ONLY))
+    {
+        /* not pipelined: partial rows, tickets and the output block are shared with the previous
+         * launch's tail.  STEP_HEAD_ONLY: the other rows of this job come from the pending MAC launched
+         * right before -- a true dependency on that launch's completion. */
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     const uint32_t rows = rows_per_job(a);
     float2 *yrow    = a.ypart + uint64_t(jobi) * rows * M;
@@ -2127,6 +2161,27 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
     if (*flag == 0)
         return;
     __threadfence();
+    if (pipelined && (a.flags & STEP_ORDER_DST))
+    {
+        /* the caller re-uses an output block that a launch in flight also writes: keep the order */
+        if (tid == 0)
+            wait_ge<false>(a.slot_done + size_t((a.seq + uint32_t(FRAME_SLOTS) - 1u) % uint32_t(FRAME_SLOTS)) * a.n_cap + job.inst,
+                           a.seq, a.error, SPIN_ERR_RING);
+        __syncthreads();
+    }
+    /* end of a pipelined tail: release the slot, then let the launch complete in stream order */
+    auto tail_done = [&]()
+    {
+        if (!pipelined)
+            return;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0)
+        {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(my_done), "r"(a.seq + 1u) : "memory");
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+        }
+    };
 
     /* The inverse transform is the exposed tail of the launch: twiddles go to shared memory
      * (the stage buffers are idle now) so that its dependent loads stay on chip. */
@@ -2155,6 +2210,7 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
             partial_outputs(d.cur, d.head, job.dst, job.pdst2, job.off2, 0, job.n2, tid, T, po);
         }
         FRAME_STAMP(3);
+        tail_done();
         return;
     }
 
@@ -2174,8 +2230,10 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
     __syncthreads();
 
     float *mine             = ra.scratch + size_t(ch) * F;
+    FRAME_STAMP(4);
     inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, mine, a.tw, tw, false, int(tid));
     __syncthreads();
+    FRAME_STAMP(5);
 
     /* send: two samples and their sequence numbers per 16-byte store, to every peer */
     for (uint32_t i = tid; i < F / 2; i += T)
@@ -2188,6 +2246,7 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
                              :: "l"(ra.words[p] + word_of_g + 2 * i), "r"(b0), "r"(seq), "r"(b1), "r"(seq) : "memory");
     }
 
+    FRAME_STAMP(6);
     /* receive and add in rank order (bit-identical on every rank) */
     {
         const uint64_t deadline = global_ns() + SPIN_LIMIT_NS;
@@ -2235,6 +2294,7 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
         asm volatile("st.relaxed.sys.global.u32 [%0], %1;"
                      :: "l"(ra.consumed[tid] + size_t(g) * ra.channels + ch), "r"(seq) : "memory");
     FRAME_STAMP(3);
+    tail_done();
 }
 
 template <int RANK>

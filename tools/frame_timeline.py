@@ -28,10 +28,10 @@ for bias in (6, 12):
     src = torch.rand((n, F), device="cuda"); dst = torch.empty_like(src)
     for _ in range(20):
         b.process_device(dst.data_ptr(), src.data_ptr(), F, F); b.sync()
-    buf = (ctypes.c_ulonglong * (512 * 4))()
+    buf = (ctypes.c_ulonglong * (512 * 8))()
     lib.b200conv_debug_frame_times.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
-    assert lib.b200conv_debug_frame_times(buf, 512 * 4) == 0
-    t = np.array(buf[:], dtype=np.float64).reshape(512, 4)
+    assert lib.b200conv_debug_frame_times(buf, 512 * 8) == 0
+    t = np.array(buf[:], dtype=np.float64).reshape(512, 8)[:, :4]
     t0 = t[:, 0].min()
     start, stream_end, ticket, tail_end = [(t[:, k] - t0) / 1e3 for k in range(4)]
     fft = np.arange(512) % 8 == 0
