@@ -1632,7 +1632,8 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             a.n_cap         = uint32_t(b->n);
             a.slot_done     = ((b->opt_pdl != 0) && (!b->profiling)) ? b->d_slot_done : nullptr;
             a.ypart         = ypart_slot(b, a.seq);
-            b->frame_seq   += 1;
+            if (a.slot_done != nullptr)
+                b->frame_seq   += 1;            /* only pipelined launches take part in the slot rotation */
             if (eager && b->pend_ready && (b->pend_t == b->t_batch + f) && (!tables_changed) && (b->pend_seq == a.seq))
             {
                 /* partitions q >= 1 were summed ahead of time (launch_pending_mac): transform the
@@ -2531,6 +2532,8 @@ extern "C" int b200conv_set_profiling(b200conv_batch_t *b, int enable)
     if (b == nullptr)
         return fail(B200CONV_ERR_ARG, "b200conv_set_profiling: NULL handle");
     b->profiling    = (enable != 0);
+    b->desc_dirty   = true;     /* profiled launches are not pipelined: the slot counters are re-seeded */
+    b->pend_ready   = false;
     return B200CONV_OK;
 }
 

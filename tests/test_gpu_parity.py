@@ -921,3 +921,57 @@ def test_init_many_equals_one_by_one(pkg):
     assert b.rank(0) == rank
     a.close()
     b.close()
+
+
+def test_switching_between_pipelined_profiled_and_synchronous_calls(pkg):
+    """The sequence bench.py runs on one batch: back-to-back device calls on a caller's stream
+    (pipelined launches), a profiled pass (every launch bracketed by events: not pipelined), and
+    then synchronous host calls on page-locked buffers (the batch's own stream, eager pending MAC).
+    The slot bookkeeping of the pipelined launches must survive every switch: outputs stay
+    correct and no in-kernel wait times out."""
+    torch = pytest.importorskip("torch")
+    n, taps, rank, F = 8, 60000, 11, 1024
+    irs = [synth.decaying_ir(c, taps) for c in range(2)]
+    b = pkg.ConvolverBatch(n, 0)
+    for c in range(n):
+        assert b.init(c, irs[c % 2], rank, 0.0)
+    blocks = 30
+    x = np.stack([synth.noise(300 + c, 4 * blocks * F) for c in range(n)])
+    src = torch.from_numpy(x).cuda()
+    dst = torch.zeros_like(src)
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    pos = 0
+
+    def device_calls(count, stream):
+        nonlocal pos
+        for _ in range(count):
+            b.process_device(dst.data_ptr() + 4 * pos, src.data_ptr() + 4 * pos, src.shape[1], F, stream)
+            pos += F
+
+    device_calls(blocks, st.cuda_stream)
+    st.synchronize()
+    b.set_profiling(True)
+    device_calls(blocks // 2, st.cuda_stream)
+    torch.cuda.synchronize()
+    ms, launches = b.profile()
+    assert launches == blocks // 2 and ms > 0
+    b.set_profiling(False)
+    device_calls(blocks // 2, None)                      # the batch's own stream
+    b.sync()
+    out = dst.cpu().numpy()
+    hs = torch.empty((n, F)).pin_memory()
+    hd = torch.empty((n, F)).pin_memory()
+    for _ in range(blocks):                             # synchronous calls on page-locked buffers
+        hs.copy_(torch.from_numpy(x[:, pos:pos + F]))
+        b.process(hs.numpy(), hd.numpy())
+        out[:, pos:pos + F] = hd.numpy()
+        pos += F
+    device_calls(blocks, None)
+    b.sync()
+    out[:, pos - blocks * F:pos] = dst[:, pos - blocks * F:pos].cpu().numpy()
+    assert not b.reduce_timed_out()
+    for c in (0, 5):
+        want = direct_convolve(x[c], irs[c % 2], pos)
+        assert rel_err(out[c, :pos], want) <= TOL
+    b.close()
