@@ -356,6 +356,53 @@ size_t  b200conv_eq_fir_size(const b200conv_eq_t *e);
 size_t  b200conv_eq_latency(const b200conv_eq_t *e);
 size_t  b200conv_eq_instances(const b200conv_eq_t *e);
 
+/* ---- SpectralProcessor ("next" row f4 of the scope table) ------------------------------------ */
+
+/* lsp::dspu::SpectralProcessor for a batch of instances (reference
+ * include/lsp-plug.in/dsp-units/util/SpectralProcessor.h, src/main/util/SpectralProcessor.cpp): an
+ * STFT with a sine window before and after the spectral operation, frames of N = 2^rank samples
+ * every N / 2, N samples of latency.  ONE launch per process call for all instances, whatever
+ * their phases and the call size.
+ *
+ *   b200conv_sp_create        N x SpectralProcessor::init(max_rank) (:58-75); ranks 7..15
+ *   b200conv_sp_set_rank      set_rank (:133-141) for the whole batch (one launch shape): ignored
+ *                             when equal to the current rank or above max_rank; drops history and
+ *                             every bound table (tables are rank-specific: bind again)
+ *   b200conv_sp_set_phase     set_phase (:127-131), per instance, clamped to [0, 1]; takes effect at
+ *                             the next process call like the reference's update_settings (:107-125):
+ *                             buffers cleared, first transform after N/2 - size_t(N * (phase / 2)) samples
+ *   b200conv_sp_bind_complex  the reference binds a HOST callback that edits the packed complex
+ *   b200conv_sp_bind_gain     spectrum (spectral_processor_func_t, SpectralProcessor.h:38); on the
+ *   b200conv_sp_unbind        device the spectral operation is a per-instance table instead:
+ *                             spectrum[k] *= H[k] (`table`: 2^rank packed complex bins, host) or
+ *                             spectrum[k] *= g[k] (`gain`: 2^rank real values, host).  Any table is
+ *                             allowed -- the result is Re(IFFT(X H)) exactly as the reference's with
+ *                             that callback.  Unbound (:174-175): the frames are only windowed.
+ *   b200conv_sp_process_*     SpectralProcessor::process(dst, src, count) (:143-199) for all
+ *                             instances: device matrices [instances][stride] (stream-ordered, dst ==
+ *                             src allowed) or one planar host matrix (synchronous)
+ *   b200conv_sp_reset         reset() (:247-257);  b200conv_sp_remaining  remaining() (:241-245);
+ *   b200conv_sp_latency       latency() = 2^rank */
+typedef struct b200conv_sp b200conv_sp_t;
+
+int     b200conv_sp_create(b200conv_sp_t **out, int device, size_t instances, size_t max_rank);
+void    b200conv_sp_free(b200conv_sp_t *s);
+int     b200conv_sp_set_rank(b200conv_sp_t *s, size_t rank);
+int     b200conv_sp_set_phase(b200conv_sp_t *s, size_t idx, float phase);
+int     b200conv_sp_bind_complex(b200conv_sp_t *s, size_t idx, const float *table);
+int     b200conv_sp_bind_gain(b200conv_sp_t *s, size_t idx, const float *gain);
+int     b200conv_sp_unbind(b200conv_sp_t *s, size_t idx);
+int     b200conv_sp_process_device(b200conv_sp_t *s, float *dst, size_t dst_stride, const float *src,
+                                   size_t src_stride, size_t count, void *stream);
+int     b200conv_sp_process_planar(b200conv_sp_t *s, float *dst, const float *src, size_t stride, size_t count);
+int     b200conv_sp_reset(b200conv_sp_t *s);
+int     b200conv_sp_sync(b200conv_sp_t *s);
+void   *b200conv_sp_stream(b200conv_sp_t *s);
+size_t  b200conv_sp_rank(const b200conv_sp_t *s);
+size_t  b200conv_sp_latency(const b200conv_sp_t *s);
+size_t  b200conv_sp_remaining(const b200conv_sp_t *s, size_t idx);
+size_t  b200conv_sp_instances(const b200conv_sp_t *s);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 const char *b200conv_last_error(void);      /* thread-local text of the last failure */

@@ -123,6 +123,22 @@ _SIGNATURES = {
     "b200conv_eq_fir_size": (_SZ, [_VP]),
     "b200conv_eq_latency": (_SZ, [_VP]),
     "b200conv_eq_instances": (_SZ, [_VP]),
+    "b200conv_sp_create": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_int, _SZ, _SZ]),
+    "b200conv_sp_free": (None, [_VP]),
+    "b200conv_sp_set_rank": (ctypes.c_int, [_VP, _SZ]),
+    "b200conv_sp_set_phase": (ctypes.c_int, [_VP, _SZ, ctypes.c_float]),
+    "b200conv_sp_bind_complex": (ctypes.c_int, [_VP, _SZ, _FP]),
+    "b200conv_sp_bind_gain": (ctypes.c_int, [_VP, _SZ, _FP]),
+    "b200conv_sp_unbind": (ctypes.c_int, [_VP, _SZ]),
+    "b200conv_sp_process_device": (ctypes.c_int, [_VP, _VP, _SZ, _VP, _SZ, _SZ, _VP]),
+    "b200conv_sp_process_planar": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ]),
+    "b200conv_sp_reset": (ctypes.c_int, [_VP]),
+    "b200conv_sp_sync": (ctypes.c_int, [_VP]),
+    "b200conv_sp_stream": (_VP, [_VP]),
+    "b200conv_sp_rank": (_SZ, [_VP]),
+    "b200conv_sp_latency": (_SZ, [_VP]),
+    "b200conv_sp_remaining": (_SZ, [_VP, _SZ]),
+    "b200conv_sp_instances": (_SZ, [_VP]),
     "b200conv_last_error": (ctypes.c_char_p, []),
     "b200conv_version": (ctypes.c_char_p, []),
 }
@@ -483,3 +499,76 @@ class EqualizerBatch:
 
     def stream(self):
         return lib().b200conv_eq_stream(self._h)
+
+
+class SpectralProcessorBatch:
+    """``instances`` x ``lsp::dspu::SpectralProcessor`` on one GPU (``b200conv_sp_*``): same method
+    names and meaning as the reference class; the host callback of the reference is replaced by a
+    per-instance spectral table (``bind_complex`` / ``bind_gain``)."""
+
+    def __init__(self, instances, max_rank, device=-1):
+        self._h = _VP()
+        _check(lib().b200conv_sp_create(ctypes.byref(self._h), device, instances, max_rank))
+        self.instances = instances
+
+    def close(self):
+        if self._h:
+            lib().b200conv_sp_free(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_rank(self, rank):
+        _check(lib().b200conv_sp_set_rank(self._h, rank))
+
+    def set_phase(self, idx, phase):
+        _check(lib().b200conv_sp_set_phase(self._h, idx, phase))
+
+    def get_rank(self):
+        return int(lib().b200conv_sp_rank(self._h))
+
+    def latency(self):
+        return int(lib().b200conv_sp_latency(self._h))
+
+    def remaining(self, idx):
+        return int(lib().b200conv_sp_remaining(self._h, idx))
+
+    def bind_complex(self, idx, table):
+        t = np.ascontiguousarray(table, dtype=np.complex64).view(np.float32)
+        if t.size != 2 << self.get_rank():
+            raise ValueError("table must hold 2**rank complex bins")
+        _check(lib().b200conv_sp_bind_complex(self._h, idx, _ptr(t)))
+
+    def bind_gain(self, idx, gain):
+        g = np.ascontiguousarray(gain, dtype=np.float32)
+        if g.size != 1 << self.get_rank():
+            raise ValueError("gain must hold 2**rank values")
+        _check(lib().b200conv_sp_bind_gain(self._h, idx, _ptr(g)))
+
+    def unbind(self, idx):
+        _check(lib().b200conv_sp_unbind(self._h, idx))
+
+    def reset(self):
+        _check(lib().b200conv_sp_reset(self._h))
+
+    def process(self, src):
+        """src: [instances][samples] float32 (host) -> same shape (synchronous)."""
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        if src.ndim != 2 or src.shape[0] != self.instances:
+            raise ValueError("expected [instances][samples]")
+        out = np.empty_like(src)
+        _check(lib().b200conv_sp_process_planar(self._h, out.ctypes.data, src.ctypes.data, src.shape[1], src.shape[1]))
+        return out
+
+    def process_device(self, dst_ptr, dst_stride, src_ptr, src_stride, samples, stream=None):
+        _check(lib().b200conv_sp_process_device(self._h, dst_ptr, dst_stride, src_ptr, src_stride, samples, stream))
+
+    def sync(self):
+        _check(lib().b200conv_sp_sync(self._h))
+
+    def stream(self):
+        return lib().b200conv_sp_stream(self._h)

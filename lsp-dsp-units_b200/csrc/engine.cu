@@ -3068,6 +3068,8 @@ extern "C" int b200conv_chirp_linear_convolutions(int device, float *result, siz
 }
 
 #include "equalizer.cuh"
+#include "spectral.cuh"
+#include "spectral_host.cuh"
 
 #ifdef B200CONV_TIMING
 /* developer instrumentation: copies the per-CTA timestamps of the last k_frame launch */
