@@ -156,7 +156,8 @@ struct EqCfg
     static constexpr size_t OFF_BAR = OFF_IB + (PIPE ? C::M * sizeof(float) : 0);
     static constexpr size_t SMEM    = PIPE ? OFF_BAR + 2 * sizeof(uint64_t) : C::SMEM;
     static constexpr int    XPT     = PIPE ? C::M / C::T : 1;           /* input samples per thread */
-    static constexpr int    MINB    = (RANK == 11) ? 5 : (RANK == 12) ? 2 : (RANK == 10) ? 1 : 0;     /* measured (profiles/r1_equalizer.jsonl); 0: left to the compiler */
+    static constexpr int    MINB    = (RANK == 11) ? 5 : (RANK == 12) ? 2 : (RANK == 13) ? 2 : (RANK == 10) ? 1 : 0;     /* measured (profiles/); 0: left to the compiler.
+                                                                           rank 13: two 512-thread CTAs per SM need <= 64 registers (the batched loads of the transform bodies would take 94) */
 };
 
 template <int RANK>
@@ -183,6 +184,14 @@ k_eq(const EqArgs a)
         tw                  = tws;
     }
     const float2 *twg       = tw;           /* the shared-memory copy serves every twiddle read */
+    if ((!C::TWS) && a.do_block)
+    {
+        /* ranks >= 13: the compact pass table (one factor per butterfly) next to the work buffer */
+        float2 *twc         = A + C::WORK;
+        stage_compact_twiddles<C>(twc, a.tw, tid);
+        tw                  = twc;
+        twg                 = a.tw;
+    }
     if (pipe && (tid == 0))
     {
         mbar_init(&bars[0], 1);
@@ -265,7 +274,7 @@ k_eq(const EqArgs a)
                 }
                 else
                 {
-                    fwd_body<RANK, C::PP>(A, B, ib, xs, twg, tw, tid);
+                    fwd_body<RANK, C::PP, 0, false, (RANK >= 12), 0, !C::TWS>(A, B, ib, xs, twg, tw, tid);
                     __syncthreads();
                     for (int k = tid; k < M; k += T)
                     {
@@ -273,14 +282,14 @@ k_eq(const EqArgs a)
                         ys[k]       = (k == 0) ? make_float2(x.x * h.x, x.y * h.y) : cmul(x, h);
                     }
                     __syncthreads();
-                    inv_body<RANK, C::PP, 8, 0, INV_OLA>(A, B, ys, 1, ob, twg, tw, true, tid);
+                    inv_body<RANK, C::PP, 8, 0, INV_OLA, (RANK >= 12), 0, !C::TWS>(A, B, ys, 1, ob, twg, tw, true, tid);
                 }
             }
             else
             {
                 /* hand-over block (:486-501): both results in full, then the ramps.  Positions
                  * [F/2, F/2 + F) fade from the old to the new result, the rest of the tail is new. */
-                fwd_body<RANK, C::PP>(A, B, E::PIPE ? ibs : ib, xs, twg, tw, tid);
+                fwd_body<RANK, C::PP, 0, false, (RANK >= 12), 0, !C::TWS>(A, B, E::PIPE ? ibs : ib, xs, twg, tw, tid);
                 __syncthreads();
                 if (E::PIPE && (tid == 0) && more)
                 {
@@ -296,7 +305,7 @@ k_eq(const EqArgs a)
                         ys[k]       = (k == 0) ? make_float2(x.x * h.x, x.y * h.y) : cmul(x, h);
                     }
                     __syncthreads();
-                    inv_body<RANK, C::PP>(A, B, ys, 1, v ? c1 : c0, twg, tw, true, tid);
+                    inv_body<RANK, C::PP, 8, 0, 0, (RANK >= 12), 0, !C::TWS>(A, B, ys, 1, v ? c1 : c0, twg, tw, true, tid);
                     __syncthreads();
                 }
                 constexpr int half      = F / 2;
