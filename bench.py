@@ -239,9 +239,8 @@ def run_cfg5(pkg, args, rank, local_rank, world, barrier, peak):
     bins5 = (TAPS5 + F - 1) // F
     irs = [synth.decaying_ir(100 + c, TAPS5) for c in range(C5)]
     conv = sharding.PartitionShardedConvolver(pkg, C5, RANK, local_rank, reduce="fused")
-    t_init = time.perf_counter()
     assert conv.init(irs), "device allocation failed"
-    init_ms = (time.perf_counter() - t_init) * 1e3
+    init_ms, connect_ms = conv.init_ms, conv.connect_ms
     p_lo, p_hi, _, _ = sharding.partition_shard(TAPS5, F, world, rank)
     stream = torch.cuda.ExternalStream(conv.batch.stream())    # the batch's own stream (see run_strong_cfg3)
 
@@ -308,6 +307,7 @@ def run_cfg5(pkg, args, rank, local_rank, world, barrier, peak):
         "share_of_hbm_roofline_per_gpu": per_gpu_bytes / (us * 1e-6) / 1e9 / peak,
         "max_err_vs_float64_of_peak": err,
         "init_ms": init_ms, "init_bytes_h2d_this_gpu": C5 * (min(TAPS5, p_hi * F) - p_lo * F) * 4,
+        "reduce_connect_ms": connect_ms,
         "parity_span": "%d blocks = the whole IR length + %d (every partition of every rank contributes)" % (total, nz),
         "all_ranks_bit_identical": bool(int(flags) & 2 == 0),
         "peer_wait_timed_out": bool(int(flags) & 1),

@@ -104,13 +104,19 @@ class PartitionShardedConvolver:
             # a rank with an empty range still takes part in the exchange: a 1-tap zero IR
             shards.append(ir[t_lo:t_hi] if t_hi > t_lo else ir[:1] * 0)
             offsets.append(p_lo)
+        import time
+        t0 = time.perf_counter()
         ok = self.batch.init_many(list(range(len(irs))), shards, self.rank_fft, [phase] * len(irs), offsets)
+        self.init_ms = (time.perf_counter() - t0) * 1e3         # IR upload + partition transforms of this rank's share
+        self.connect_ms = 0.0
         if ok and self.reduce == "fused":
             import torch
+            t0 = time.perf_counter()
             mine = self.batch.reduce_prepare(self.rank, self.world)
             self.batch.reduce_connect(exchange_handles(mine, self.group, torch.device("cuda", self.device)))
             self._dist.barrier(self.group)      # nobody stores into a buffer its owner has not opened yet
             self.connected = True
+            self.connect_ms = (time.perf_counter() - t0) * 1e3  # IPC handle exchange, peer mappings, barrier
         return ok
 
     def process_device(self, dst, src, count, stream=None):
