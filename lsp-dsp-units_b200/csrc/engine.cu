@@ -537,7 +537,7 @@ namespace
         int             dev     = -1;
         uint32_t        n       = 0;        /* > FRAME_CHAIN_MAX: more launches in flight than the table holds */
         uint64_t        stamp   = 0;
-        BlockRows       out[FRAME_CHAIN_MAX];
+        BlockRows       out[FRAME_CHAIN_MAX], in[FRAME_CHAIN_MAX];
     };
     std::mutex      g_hist_lock;
     FrameHistory    g_hist[32];
@@ -575,7 +575,8 @@ namespace
     /* Registers a k_frame launch that reads the block `in` and writes the block `out`.  `capable`:
      * the launch would like to transform its input early.  *early: it may (no launch in flight
      * writes its input); *serial: launch it without programmatic serialisation (only ever asked of
-     * a capable launch); *dst_clash: a launch that may be in flight writes (part of) `out` too. */
+     * a capable launch); *dst_clash: a launch that may be in flight writes OR READS (part of) `out`
+     * -- this launch must not write before those have completed. */
     void hist_launch(cudaStream_t st, int dev, bool capable, const BlockRows &in, const BlockRows &out,
                      bool *early, bool *serial, bool *dst_clash)
     {
@@ -589,12 +590,15 @@ namespace
         for (uint32_t i = 0; (i < h->n) && (i < FRAME_CHAIN_MAX); ++i)
         {
             clash          |= rows_overlap(h->out[i], in);
-            wclash         |= rows_overlap(h->out[i], out);
+            wclash         |= rows_overlap(h->out[i], out) || rows_overlap(h->in[i], out);
         }
         *early          = capable && (!clash);
         *dst_clash      = wclash;
         if (h->n < FRAME_CHAIN_MAX)
+        {
             h->out[h->n]    = out;
+            h->in[h->n]     = in;
+        }
         if (h->n <= FRAME_CHAIN_MAX)
             h->n           += 1;
     }
@@ -1626,7 +1630,8 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             if (early)
                 a.flags        |= STEP_EARLY_SRC;
             if (dst_clash)
-                a.flags        |= STEP_ORDER_DST;
+                a.flags        |= STEP_ORDER_DST;  /* e.g. a cascade re-using one hand-over block: the tail of the
+                                                      next launch must not overwrite what a launch in flight reads */
             /* pipelined tails (FRAME_SLOTS in kernels.cuh): this launch's rows, tickets and sequence number */
             a.seq           = b->frame_seq;
             a.n_cap         = uint32_t(b->n);

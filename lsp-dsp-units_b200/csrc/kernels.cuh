@@ -117,9 +117,10 @@ enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
        STEP_HOST_IO = 8 /* src / dst are page-locked HOST matrices: no bulk-copy staging */,
        STEP_WAIT_HEAD = 16 /* k_mac launched early (programmatic serialization) behind a k_frame:
                               poll ring_head before touching the newest spectra */,
-       STEP_ORDER_DST = 256 /* k_frame: the output block overlaps the output block of a launch that may still
-                               be in flight: this launch's tail writes it only after the previous launch's
-                               tail for the same instance has finished */,
+       STEP_ORDER_DST = 256 /* k_frame: the output block overlaps a block that a launch which may still be in
+                               flight writes or reads (a buffer re-used every call, a cascade's hand-over
+                               block): this launch keeps the full griddepcontrol.wait before its first
+                               shared write, i.e. its tail starts after every earlier launch has completed */,
        STEP_EARLY_SRC = 32 /* k_frame: the input block may be read before griddepcontrol.wait -- set by
                               the host only when the predecessor on the stream is this batch's own pending
                               k_mac and the input is a caller-owned HOST block no kernel writes */ };
@@ -147,7 +148,9 @@ enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
  *                  of the slot is launch s - FRAME_SLOTS) has finished; CTAs of launch s poll for
  *                  s + 1 - FRAME_SLOTS before their first write into the slot (bounded; in steady
  *                  state it is long there);
- *   output order   only if the host sees overlapping output blocks (STEP_ORDER_DST);
+ *   output blocks  a launch whose output block overlaps a block that a launch in flight writes or reads
+ *                  (the host's launch history sees it: STEP_ORDER_DST) keeps the full
+ *                  griddepcontrol.wait before its first shared write;
  *   completion     the tail CTAs execute griddepcontrol.wait as their LAST instruction, so launch
  *                  s completes after launch s - 1 (stream order for whatever follows). */
 constexpr int FRAME_SLOTS      = 4;
@@ -2130,11 +2133,12 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
             wait_ge<false>(my_done, a.seq + 1u - uint32_t(FRAME_SLOTS), a.error, SPIN_ERR_RING);
         __syncthreads();
     }
-    if ((!pipelined) || (a.flags & STEP_HEAD_ONLY))
+    if ((!pipelined) || (a.flags & (STEP_HEAD_ONLY | STEP_ORDER_DST)))
     {
         /* not pipelined: partial rows, tickets and the output block are shared with the previous
          * launch's tail.  STEP_HEAD_ONLY: the other rows of this job come from the pending MAC launched
-         * right before -- a true dependency on that launch's completion. */
+         * right before -- a true dependency on that launch's completion.  STEP_ORDER_DST: the output
+         * block is still in use by a launch in flight. */
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
 
@@ -2161,14 +2165,6 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
     if (*flag == 0)
         return;
     __threadfence();
-    if (pipelined && (a.flags & STEP_ORDER_DST))
-    {
-        /* the caller re-uses an output block that a launch in flight also writes: keep the order */
-        if (tid == 0)
-            wait_ge<false>(a.slot_done + size_t((a.seq + uint32_t(FRAME_SLOTS) - 1u) % uint32_t(FRAME_SLOTS)) * a.n_cap + job.inst,
-                           a.seq, a.error, SPIN_ERR_RING);
-        __syncthreads();
-    }
     /* end of a pipelined tail: release the slot, then let the launch complete in stream order */
     auto tail_done = [&]()
     {

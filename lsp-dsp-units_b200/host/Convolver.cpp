@@ -72,10 +72,13 @@ namespace lsp
             if (count == 0)
                 return;
 
-            // a batch of one is a 1 x count planar matrix: page-locked buffers are read and
-            // written by the kernels directly, others are staged.  The reference has no error
-            // channel here; a device failure yields silence.
-            if (b200conv_process_planar(pEngine, dst, src, count, count) != B200CONV_OK)
+            // A batch of one.  The caller's buffers are ordinary pageable memory (Convolver.h:95):
+            // the pointer-table call gathers the block into page-locked memory which the kernels
+            // then read and write in place across PCIe -- no copy operations in the stream.  The
+            // reference has no error channel here; a device failure yields silence.
+            float *d = dst;
+            const float *s = src;
+            if (b200conv_process(pEngine, &d, &s, count) != B200CONV_OK)
                 ::memset(dst, 0, count * sizeof(float));
         }
 

@@ -113,6 +113,48 @@ def _equalizer_worker(rank, world, port, result):
     dist.destroy_process_group()
 
 
+def _handles_worker(rank, world, port, result):
+    """The transport of the fused reduce's set-up: every rank contributes a 64-byte handle and gets
+    all of them back in rank order (gloo, CPU tensors); and the all-to-all sum itself, modelled on
+    the host: every rank adds the partial blocks of all ranks in RANK ORDER, so every rank ends
+    with the same bits (what the kernel tails do over NVLink)."""
+    sharding = _setup(rank, world, port)
+    import engine_model as em
+    import synth
+    mine = bytes([(17 * rank + i) % 251 for i in range(sharding.HANDLE_BYTES)])
+    every = sharding.exchange_handles(mine, device=None)
+    ok = (len(every) == world) and all(every[r] == bytes([(17 * r + i) % 251 for i in range(sharding.HANDLE_BYTES)])
+                                       for r in range(world))
+    try:
+        sharding.exchange_handles(b"short")
+        ok = False
+    except ValueError:
+        pass
+    R, F, L, blocks = 9, 256, 7000, 10
+    ir, x = synth.decaying_ir(4, L), synth.noise(4, blocks * F)
+    p_lo, p_hi, t_lo, t_hi = sharding.partition_shard(L, F, world, rank)
+    conv = em.ModelConvolver(ir[t_lo:t_hi], R, 0.0, part_offset=p_lo)
+    out = np.empty(blocks * F, np.float32)
+    for b in range(blocks):
+        part = torch.from_numpy(conv.process(x[b * F:(b + 1) * F]).astype(np.float32).copy())
+        slots = [torch.empty_like(part) for _ in range(world)]
+        dist.all_gather(slots, part)                        # every rank's block lands in every rank's slots
+        acc = torch.zeros_like(part)
+        for r in range(world):                              # rank order: bit-identical everywhere
+            acc += slots[r]
+        out[b * F:(b + 1) * F] = acc.numpy()
+    want = np.convolve(x.astype(np.float64), ir.astype(np.float64))[:blocks * F]
+    err = float(np.max(np.abs(out - want)) / np.max(np.abs(want)))
+    mine_out = torch.from_numpy(out.copy())
+    ref = mine_out.clone()
+    dist.broadcast(ref, src=0)
+    same = torch.tensor([int(torch.equal(ref, mine_out))])
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        result.put(("handles", ok, err, bool(same.item())))
+    dist.destroy_process_group()
+
+
 def _run(worker, port):
     ctx = mp.get_context("spawn")
     result = ctx.Queue()
@@ -139,6 +181,11 @@ def test_channel_shards_no_collective_gloo_world2():
 def test_equalizer_instances_shard_by_instance_gloo_world2():
     tag, complete, err = _run(_equalizer_worker, 29613)
     assert tag == "equalizer" and complete and err <= 1e-9
+
+
+def test_handle_exchange_and_all_to_all_sum_gloo_world2():
+    tag, ok, err, same = _run(_handles_worker, 29614)
+    assert tag == "handles" and ok and same and err <= 1e-5
 
 
 def test_shard_plans_cover_everything():
