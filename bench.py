@@ -126,7 +126,7 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     threads = min(cores, INSTANCES)
-    # bounded sample per step: ~2 s of CPU work (one convolver per thread, 96 blocks each)
+    # bounded sample per step: a few seconds of CPU work (one convolver per thread, 192 blocks each)
     blocks = args.cpu_blocks
     rates = []
     t0 = time.time()
@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=BINS)
     ap.add_argument("--e2e-frames", type=int, default=BINS)
-    ap.add_argument("--cpu-blocks", type=int, default=96)
+    ap.add_argument("--cpu-blocks", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--splits", type=int, default=0)
     ap.add_argument("--stages", type=int, default=0)

@@ -307,13 +307,9 @@ static MacPlan plan_mac(uint32_t rank, uint32_t jobs, uint32_t max_nq, int sm_co
     if (splits > 32)    splits = 32;
     if (splits < 1)     splits = 1;
     p.splits        = splits;
-    if ((tune_stages <= 0) && (jobs * p.tiles * splits <= 2u * uint32_t(sm_count)))
-    {
-        /* a grid this small is latency-bound, not bandwidth-bound (at most two CTAs per SM): keep
-         * four stages in flight per CTA instead of two */
-        p.sh.NS         = 4;
-        p.smem          = size_t(2) * p.sh.NS * p.sh.QB * p.sh.TB * sizeof(float2) + p.sh.NS * sizeof(uint64_t) + 16;
-    }
+    /* (deeper stage rings for small, latency-bound grids were measured and bought nothing:
+     * tools/ab_stages.py, 2 / 3 / 4 stages within 1 % on cfg 1 and cfg 2, two stages 5-8 % ahead at
+     * 8 channels per GPU) */
     return p;
 }
 
