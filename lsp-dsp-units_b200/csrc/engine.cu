@@ -637,7 +637,9 @@ static const size_t JOB_RING_MIN = size_t(1) << 10;
 static const size_t RING_SPARE = 32;                    /* spare ring slots: frames transformed ahead of a multi-frame
                                                            MAC pass (8), and k_frame launches in flight (FRAME_CHAIN_MAX) */
 static_assert(FRAME_CHAIN_MAX < RING_SPARE, "k_frame launches in flight must fit the spare ring slots");
-static const uint64_t EARLY_MAX_BYTES = 150000000ull;  /* launches that stream more than this per block keep the in-kernel wait */
+static const uint64_t EARLY_MAX_BYTES = 450000000ull;  /* launches that stream more than this per block (~70 us) keep the
+                                                           in-kernel wait: they hide the chain anyway, and spare themselves
+                                                           the serialised launch every FRAME_CHAIN_MAX blocks */
 static const size_t PART_MAX   = 1024;                  /* samples one P1 / P2 segment of a fused step answers */
 
 struct b200conv_batch
