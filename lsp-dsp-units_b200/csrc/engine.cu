@@ -402,10 +402,11 @@ static cudaError_t launch_frame_r(const StepArgs &a, const MacPlan &p, uint32_t 
     return cudaLaunchKernelEx(&cfg, k_frame<RANK>, a, p.sh, tickets, ra);
 }
 
-/* the job-list form (general path): no programmatic serialisation, no cross-GPU reduce */
+/* the job-list form (general path): no cross-GPU reduce; with `pdl` its prologue (and the launch
+ * latency) hides under the tail of the launch before it -- every CTA then waits for that launch */
 template <int RANK>
 static cudaError_t launch_frame_gen_r(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
-                                      const JobPack &pack, cudaStream_t st)
+                                      const JobPack &pack, bool pdl, cudaStream_t st)
 {
     static size_t attr_smem[MAX_DEVICES] = { 0 };
     int dev = current_device();
@@ -416,21 +417,20 @@ static cudaError_t launch_frame_gen_r(const StepArgs &a, const MacPlan &p, uint3
             return e;
         attr_smem[dev] = p.smem;
     }
-    k_frame_gen<RANK><<<dim3(jobs * p.splits, p.tiles), p.threads, p.smem, st>>>(a, p.sh, tickets, pack);
-    return cudaGetLastError();
+    return launch_k(k_frame_gen<RANK>, dim3(jobs * p.splits, p.tiles), dim3(p.threads), p.smem, st, pdl, a, p.sh, tickets, pack);
 }
 
 static cudaError_t launch_frame_gen(const StepArgs &a, const MacPlan &p, uint32_t jobs, uint32_t *tickets,
-                                    const JobPack &pack, cudaStream_t st)
+                                    const JobPack &pack, bool pdl, cudaStream_t st)
 {
     switch (a.rank)
     {
-        case 8:  return launch_frame_gen_r<8>(a, p, jobs, tickets, pack, st);
-        case 9:  return launch_frame_gen_r<9>(a, p, jobs, tickets, pack, st);
-        case 10: return launch_frame_gen_r<10>(a, p, jobs, tickets, pack, st);
-        case 11: return launch_frame_gen_r<11>(a, p, jobs, tickets, pack, st);
-        case 12: return launch_frame_gen_r<12>(a, p, jobs, tickets, pack, st);
-        case 13: return launch_frame_gen_r<13>(a, p, jobs, tickets, pack, st);
+        case 8:  return launch_frame_gen_r<8>(a, p, jobs, tickets, pack, pdl, st);
+        case 9:  return launch_frame_gen_r<9>(a, p, jobs, tickets, pack, pdl, st);
+        case 10: return launch_frame_gen_r<10>(a, p, jobs, tickets, pack, pdl, st);
+        case 11: return launch_frame_gen_r<11>(a, p, jobs, tickets, pack, pdl, st);
+        case 12: return launch_frame_gen_r<12>(a, p, jobs, tickets, pack, pdl, st);
+        case 13: return launch_frame_gen_r<13>(a, p, jobs, tickets, pack, pdl, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -568,10 +568,23 @@ namespace
             h->n        = 0;
     }
 
+    /* Kernels that let their successor start early (griddepcontrol.launch_dependents) but are not
+     * registered below -- the job-list form, the three-kernel blocks of ranks 14..16, multi-frame
+     * passes -- have been enqueued on `st`: what they write is unknown to the table, so the next
+     * k_frame launch there is launched without the attribute (it starts when they have completed). */
+    void hist_unknown(cudaStream_t st, int dev)
+    {
+        std::lock_guard<std::mutex> lock(g_hist_lock);
+        FrameHistory *h = hist_find(st, dev, true);
+        h->stamp        = ++g_hist_clock;
+        h->n            = FRAME_CHAIN_MAX + 1;
+    }
+
     /* Registers a k_frame launch that reads the block `in` and writes the block `out`.  `capable`:
      * the launch would like to transform its input early.  *early: it may (no launch in flight
-     * writes its input); *serial: launch it without programmatic serialisation (only ever asked of
-     * a capable launch); *dst_clash: a launch that may be in flight writes OR READS (part of) `out`
+     * writes its input); *serial: launch it without programmatic serialisation (asked of a capable
+     * launch every FRAME_CHAIN_MAX, and of any launch when the table does not know what is in
+     * flight: hist_unknown, an evicted entry); *dst_clash: a launch that may be in flight writes OR READS (part of) `out`
      * -- this launch must not write before those have completed. */
     void hist_launch(cudaStream_t st, int dev, bool capable, const BlockRows &in, const BlockRows &out,
                      bool *early, bool *serial, bool *dst_clash)
@@ -579,7 +592,7 @@ namespace
         std::lock_guard<std::mutex> lock(g_hist_lock);
         FrameHistory *h = hist_find(st, dev, true);
         h->stamp        = ++g_hist_clock;
-        *serial         = capable && (h->n >= FRAME_CHAIN_MAX);
+        *serial         = (capable && (h->n >= FRAME_CHAIN_MAX)) || (h->n > FRAME_CHAIN_MAX);
         if (*serial)
             h->n            = 0;
         bool clash      = (h->n > FRAME_CHAIN_MAX), wclash = clash;
@@ -1601,6 +1614,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             CU(launch_mac_multi(a, mp, nact, tf, st));
             TRY(attach_park(b, a, size_t(nact) * tf, st));
             CU(launch_inv(a, nact * tf, st));
+            hist_unknown(st, b->device);
             b->stats.launches       += 3;
             b->stats.mac_launches   += 1;
             b->stats.mac_algo_bytes += per_frame_bytes * tf;
@@ -1681,6 +1695,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
                 am.flags       |= STEP_AFTER_FWD;
             CU(launch_mac(b, am, sp, nact, st, false, false, chain));
             CU(launch_inv(a, nact, st, chain, b->d_tickets));      /* nact <= instances counters */
+            hist_unknown(st, b->device);
             b->stats.launches       += 3;
         }
         b->stats.mac_launches   += 1;
@@ -1790,7 +1805,7 @@ static int process_general_fused(Batch *b, float *dst, size_t dst_stride, const 
 {
     const size_t F      = size_t(1) << (b->rank - 1);
     TRY(upload_tables(b, st));
-    hist_reset(st, b->device);          /* launched without programmatic serialisation */
+    hist_reset(st, b->device);          /* every CTA of the job-list form waits for all earlier launches */
     std::vector<size_t> &pos = b->g_pos;
     std::vector<Job> &jobs = b->g_jobs;
     for (uint32_t i : b->active)
@@ -1928,10 +1943,11 @@ static int process_general_fused(Batch *b, float *dst, size_t dst_stride, const 
         MacPlan plan = plan_mac(uint32_t(b->rank), uint32_t(jobs.size()), uint32_t((max_nq > 0) ? max_nq : 2),
                                 b->sm_count, b->tune_splits, b->tune_stages);
         plan.sh.bias = 0;
-        TRY(ensure_ypart(b, jobs.size() * plan.splits * F * sizeof(float2), st));
+        /* one more row per job: the direct-form answers that the job's CTAs share out (k_frame_gen) */
+        TRY(ensure_ypart(b, jobs.size() * (plan.splits + 1) * F * sizeof(float2), st));
         a.ypart     = b->ypart;
         a.splits    = plan.splits;
-        CU(launch_frame_gen(a, plan, a.n_jobs, b->d_tickets, pack, st));
+        CU(launch_frame_gen(a, plan, a.n_jobs, b->d_tickets, pack, (b->opt_pdl != 0) && (!b->profiling), st));
         b->stats.launches       += 1;
         if (n_mac > 0)
         {
@@ -1940,6 +1956,7 @@ static int process_general_fused(Batch *b, float *dst, size_t dst_stride, const 
         }
     }
 
+    hist_unknown(st, b->device);
     b->uniform_stale = true;    /* per-instance frame counters moved independently of t_batch */
     b->pend_ready = false;
     return B200CONV_OK;
@@ -2153,6 +2170,7 @@ static int process_general_staged(Batch *b, float *dst, size_t dst_stride, const
 
     /* ring_head was bypassed and the per-instance frame counters moved: both matter only to a
      * k_frame launch, which refreshes the tables first (uniform_stale) */
+    hist_unknown(st, b->device);
     b->uniform_stale = true;
     b->pend_ready = false;
     return B200CONV_OK;

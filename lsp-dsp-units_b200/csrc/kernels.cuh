@@ -1771,13 +1771,31 @@ k_mac_multi(const StepArgs a, const MacShape sh)
 /* beyond them is stale), taps beyond an output's own index meet a zero in the head window.          */
 /* Every thread of the CTA must call it (T a multiple of 32, T <= PO_MAXT).                          */
 
+/* asynchronous global -> shared copies of single words (no register, no stall at the copy) */
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(uint32_t(__cvta_generic_to_shared(smem))), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 constexpr uint32_t PO_TILE  = 2048;
 constexpr uint32_t PO_MAXT  = 512;
 constexpr uint32_t PO_SMEM_FLOATS = 2 * PO_TILE + PO_MAXT;     /* cur tile | head window */
 
+/* xnew != NULL: the samples j >= off are taken from xnew[j - off] (the caller's block) instead of   */
+/* cur -- for CTAs that must not depend on another CTA's copy into `cur`; pend == NULL: the direct   */
+/* sum alone (the pending block is added later, by whoever produces it).                             */
 __device__ __forceinline__ void partial_outputs(const float *cur, const float *head, const float *pend,
                                                 float *dst, uint32_t off, uint32_t i0, uint32_t i1,
-                                                uint32_t tid, uint32_t T, float *po_smem)
+                                                uint32_t tid, uint32_t T, float *po_smem,
+                                                const float *xnew = nullptr)
 {
     const uint32_t n        = i1 - i0;
     if (n == 0)
@@ -1806,13 +1824,25 @@ __device__ __forceinline__ void partial_outputs(const float *cur, const float *h
             /* taps of this tile that exist: [j0, j0 + kend), kend a multiple of the 4 G stride */
             const uint32_t kend     = min(PO_TILE, (m_max - j0 + 4 * G) & ~(4 * G - 1));
             __syncthreads();                                        /* previous tile / window consumed */
+            /* asynchronous copies: every word of the tile is in flight at once (plain loads into
+             * shared memory were issued one round trip after the other) */
             for (uint32_t k = tid; k < kend; k += T)
-                cs[k]                   = (j0 + k <= m_max) ? cur[j0 + k] : 0.0f;
+            {
+                const uint32_t j        = j0 + k;
+                if (j > m_max)
+                    cs[k]                   = 0.0f;
+                else
+                    cp_async4(cs + k, ((xnew != nullptr) && (j >= off)) ? (xnew + (j - off)) : (cur + j));
+            }
             for (uint32_t k = (PO_TILE - kend) + tid; k < hcount; k += T)
             {
                 const int32_t h         = hbase + int32_t(k);
-                hs[k]                   = (h >= 0) ? head[h] : 0.0f;
+                if (h >= 0)
+                    cp_async4(hs + k, head + h);
+                else
+                    hs[k]                   = 0.0f;
             }
+            cp_async_wait_all();
             __syncthreads();
             if (live)
             {
@@ -1833,7 +1863,7 @@ __device__ __forceinline__ void partial_outputs(const float *cur, const float *h
         for (uint32_t sft = G >> 1; sft > 0; sft >>= 1)
             total                  += __shfl_xor_sync(0xffffffffu, total, sft);
         if (live && (lane == 0))
-            dst[i]                  = pend[off + i] + float(total);
+            dst[i]                  = ((pend != nullptr) ? pend[off + i] : 0.0f) + float(total);
     }
 }
 
@@ -1874,9 +1904,9 @@ struct FrameCfg
     static constexpr int MINB   = (RANK >= 13) ? 2 : ((T >= 256) ? 4 : 8);  /* CTAs per SM (register cap) */
 };
 
-/* GEN = the job-list form for the general path (a.jobs != NULL): per job any of P1 / FFT / MAC +
- * inverse / P2 (see Job).  Launched WITHOUT programmatic serialisation -- every earlier launch has
- * completed -- so ring_head only orders CTAs of this launch. */
+/* GEN = the job-list form for the general path: per job any of P1 / FFT / MAC + inverse / P2 (see
+ * Job).  Every CTA waits for all earlier launches right after its prologue (griddepcontrol.wait),
+ * so ring_head only orders CTAs of this launch. */
 template <int RANK, bool GEN>
 __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh, uint32_t *tickets,
                                            const ReduceArgs &ra, const Job *pack)
@@ -1919,6 +1949,12 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
     const bool fft_cta      = split0 && (tile == 0);
     if (GEN && (!(job.flags & JOB_MAC)) && (!fft_cta))
         return;                                 /* a job without a partition sum needs one CTA */
+    /* The job-list form touches per-instance state that the launch before it writes (the frame in
+     * progress, the pending block, ring rows without a ring_head hand-shake across launches): it
+     * orders itself behind every earlier launch HERE -- launched with programmatic serialisation
+     * it has become resident, set up its barriers and fetched its job under the predecessor's tail. */
+    if (GEN)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 
     uint32_t qa             = max(job.qa, d.q_lo);
     uint32_t qb             = min(job.qb, d.q_lo + d.nq);
@@ -1992,20 +2028,66 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
             issue_next();
 
     float *po               = nullptr;
+    /* GEN: a job with a partition sum has splits x tiles CTAs of which all but one idle once their
+     * chunk is streamed, while the direct-form answers (P1: the samples that continue the frame in
+     * progress; P2: the first samples of the next frame) were the longest stretch of the one CTA
+     * that also transforms.  So they are SPREAD: every other CTA of the job computes a slice of
+     * both direct sums while its first stages are in flight (P1 complete, with the OLD pending
+     * block; P2 without the new one) into the job's answer row behind the partial rows; the CTA
+     * that finishes the job copies them out (adding the new pending block to P2) after the ticket,
+     * i.e. after every CTA has read the caller's samples -- safe for in-place calls. */
+    const uint32_t n_cta    = a.splits * gridDim.y;
+    const bool spread       = GEN && ((job.flags & JOB_MAC) != 0) && (n_cta > 1);
+    constexpr uint32_t AW   = TB;           /* floats per answer array in the scratch: a segment has <= min(F, 1024) samples */
+    constexpr bool TW_FITS  = GEN && (3 * AW + 2 * uint32_t(C::TW_TOTAL) <= PO_SMEM_FLOATS);   /* ranks 8..10 */
+    const bool tw_early     = TW_FITS && fft_cta && (spread || ((job.n == 0) && (job.n2 == 0)));
+    float *ans1             = nullptr, *ans2 = nullptr;
     if constexpr (GEN)
     {
-        __shared__ float po_scratch[PO_SMEM_FLOATS];
+        __shared__ __align__(16) float po_scratch[PO_SMEM_FLOATS];
         po                      = po_scratch;
+        if (spread)
+        {
+            ans1                    = reinterpret_cast<float *>(a.ypart + (uint64_t(a.n_jobs) * rows_per_job(a) + jobi) * M);
+            ans2                    = ans1 + M;
+        }
+        if (tw_early)
+        {
+            /* this CTA's direct-form scratch is idle: the twiddles of its two transforms arrive
+             * there while the partition stream runs, instead of at the head of each transform */
+            float2 *tws             = reinterpret_cast<float2 *>(po + 3 * AW);
+            for (uint32_t i = tid; i < uint32_t(C::TW_TOTAL); i += T)
+                cp_async8(tws + i, a.tw + i);
+        }
         if (fft_cta && (job.n > 0))
         {
             /* P1: the call's samples that continue the frame in progress, answered at once (from
              * the OLD pending block) while the first partition stages are in flight */
             for (uint32_t i = tid; i < job.n; i += T)
                 d.cur[job.off + i]  = job.psrc[i];
-            __syncthreads();
-            partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, 0, job.n, tid, T, po);
-            __syncthreads();
+            __syncthreads();                    /* the transform below reads them back */
+            if (!spread)
+            {
+                partial_outputs(d.cur, d.head, d.pend, job.pdst, job.off, 0, job.n, tid, T, po);
+                __syncthreads();
+            }
         }
+        if (spread && (!fft_cta))
+        {
+            const uint32_t ci       = split * gridDim.y + tile - 1u, nc = n_cta - 1u;
+            if (job.n > 0)
+                partial_outputs(d.cur, d.head, d.pend, ans1, job.off,
+                                uint32_t((uint64_t(job.n) * ci) / nc), uint32_t((uint64_t(job.n) * (ci + 1)) / nc),
+                                tid, T, po, job.psrc);
+            if (job.n2 > 0)
+            {
+                __syncthreads();
+                partial_outputs(d.cur, d.head, nullptr, ans2, job.off2,
+                                uint32_t((uint64_t(job.n2) * ci) / nc), uint32_t((uint64_t(job.n2) * (ci + 1)) / nc),
+                                tid, T, po, job.psrc2);
+            }
+        }
+        FRAME_STAMP(4);
     }
 
     float4 acc[MAC_VPT];
@@ -2054,6 +2136,8 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
             issue_next();
     }
 
+    if (GEN)
+        FRAME_STAMP(5);
     if (split0)
     {
         if (fft_cta)
@@ -2071,7 +2155,12 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
             constexpr uint32_t FFT_WORK = C::WORK * (FFT_PP ? 2 : 1);
             float2 *wa          = stages, *wb = FFT_PP ? stages + C::WORK : nullptr;
             const float2 *tw    = a.tw;
-            if (FFT_WORK + uint32_t(C::TW_TOTAL) <= NS * 2 * stage_elems)
+            if (tw_early)
+            {
+                cp_async_wait_all();
+                tw                  = reinterpret_cast<const float2 *>(po + 3 * AW);    /* visible after fwd_body's first barrier */
+            }
+            else if (FFT_WORK + uint32_t(C::TW_TOTAL) <= NS * 2 * stage_elems)
             {
                 float2 *tws         = stages + FFT_WORK;
                 for (uint32_t i = tid; i < uint32_t(C::TW_TOTAL); i += T)
@@ -2096,6 +2185,8 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(hp), "r"(head) : "memory");
             }
             }
+            if (GEN)
+                FRAME_STAMP(6);
             if (GEN && (!(job.flags & JOB_MAC)))
                 return;
         }
@@ -2182,10 +2273,14 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
     /* The inverse transform is the exposed tail of the launch: twiddles go to shared memory
      * (the stage buffers are idle now) so that its dependent loads stay on chip. */
     constexpr bool TAIL_PP = (RANK <= 12);      /* two work buffers fit the (>= 2) stage buffers */
+    constexpr int  TAIL_RG = (RANK <= 9) ? 8 : 4;   /* partial rows in flight per round: the small CTAs of the small
+                                                       ranks have the registers, and their row sum is pure latency */
     constexpr uint32_t TAIL_WORK = C::WORK * (TAIL_PP ? 2 : 1);
     float2 *wa      = stages, *wb = TAIL_PP ? stages + C::WORK : nullptr;
     const float2 *tw = a.tw;
-    if (TAIL_WORK + uint32_t(C::TW_TOTAL) <= NS * 2 * stage_elems)
+    if (tw_early)
+        tw              = reinterpret_cast<const float2 *>(po + 3 * AW);     /* there since the forward transform */
+    else if (TAIL_WORK + uint32_t(C::TW_TOTAL) <= NS * 2 * stage_elems)
     {
         float2 *tws     = stages + TAIL_WORK;
         for (uint32_t i = tid; i < uint32_t(C::TW_TOTAL); i += T)
@@ -2194,8 +2289,34 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
     }
     if (GEN || (ra.mode == 0))
     {
-        inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, job.dst, a.tw, tw, false, int(tid));
-        if (GEN && (job.n2 > 0))
+        if (GEN && spread)
+        {
+            /* the spread answers (see above): every CTA of the job is past its ticket.  They and
+             * the samples of P2 travel to shared memory UNDER the inverse transform. */
+            for (uint32_t i = tid; i < job.n; i += T)
+                cp_async4(po + i, ans1 + i);
+            for (uint32_t i = tid; i < job.n2; i += T)
+            {
+                cp_async4(po + AW + i, ans2 + i);
+                cp_async4(po + 2 * AW + i, job.psrc2 + i);
+            }
+        }
+        inv_body<RANK, TAIL_PP, TAIL_RG, int(T)>(wa, wb, yrow, rows, job.dst, a.tw, tw, false, int(tid));
+        if (GEN)
+            FRAME_STAMP(7);
+        if (GEN && spread)
+        {
+            cp_async_wait_all();
+            __syncthreads();
+            for (uint32_t i = tid; i < job.n; i += T)
+                job.pdst[i]         = po[i];
+            for (uint32_t i = tid; i < job.n2; i += T)
+            {
+                d.cur[job.off2 + i] = po[2 * AW + i];
+                job.pdst2[i]        = job.dst[job.off2 + i] + po[AW + i];
+            }
+        }
+        else if (GEN && (job.n2 > 0))
         {
             /* P2: the first samples of the frame that has just started, answered from the block
              * (job.dst = the instance's pending block) the inverse transform has just produced */
@@ -2227,7 +2348,7 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
 
     float *mine             = ra.scratch + size_t(ch) * F;
     FRAME_STAMP(4);
-    inv_body<RANK, TAIL_PP, 4, int(T)>(wa, wb, yrow, rows, mine, a.tw, tw, false, int(tid));
+    inv_body<RANK, TAIL_PP, TAIL_RG, int(T)>(wa, wb, yrow, rows, mine, a.tw, tw, false, int(tid));
     __syncthreads();
     FRAME_STAMP(5);
 

@@ -975,3 +975,73 @@ def test_switching_between_pipelined_profiled_and_synchronous_calls(pkg):
         want = direct_convolve(x[c], irs[c % 2], pos)
         assert rel_err(out[c, :pos], want) <= TOL
     b.close()
+
+
+@pytest.mark.parametrize("n,taps,rank,step,phases", [(2, 60000, 9, 256, (0.0, 0.5)), (8, 30000, 10, 77, (0.0, 0.37)),
+                                                     (3, 20000, 12, 1500, (0.25,)), (70, 9000, 8, 100, (0.0, 0.6))])
+def test_spread_direct_form_answers_in_place_on_device(pkg, n, taps, rank, step, phases):
+    """The job-list launch shares the direct-form answers of a call (the samples that finish the frame
+    in progress, the first samples of the next one) among the CTAs of the job; the CTA that finishes
+    the job copies them out after every CTA has read the caller's samples.  So dst == src (in place,
+    device pointers, back-to-back launches with programmatic serialisation) must still be exact."""
+    torch = pytest.importorskip("torch")
+    calls = 60
+    irs = [synth.decaying_ir(c, taps) for c in range(2)]
+    x = np.stack([synth.noise(500 + c, calls * step) for c in range(n)])
+    outs = []
+    for pdl in (1, 0):
+        b = pkg.ConvolverBatch(n, 0)
+        b.set_option("pdl", pdl)
+        for c in range(n):
+            assert b.init(c, irs[c % 2], rank, phases[c % len(phases)])
+        buf = torch.from_numpy(x).cuda()
+        torch.cuda.synchronize()
+        for i in range(calls):
+            p = buf.data_ptr() + 4 * i * step
+            b.process_device(p, p, calls * step, step)
+        b.sync()
+        outs.append(buf.cpu().numpy())
+        b.close()
+    assert np.array_equal(outs[0], outs[1])
+    for c in (0, 1, n - 1):
+        assert rel_err(outs[0][c], direct_convolve(x[c], irs[c % 2], calls * step)) <= TOL
+
+
+def test_cascade_behind_a_batch_on_the_job_list_path(pkg):
+    """Batch A is called with sizes that take the job-list path (its launches let their successor
+    start early but are not in the launch history); batch B, on the same caller stream and allowed to
+    transform its input early ("early_src" = 2), reads A's output block: B's launch must not start
+    before A's has completed.  Equal to the serialised run bit for bit, and the right answer."""
+    torch = pytest.importorskip("torch")
+    n, rank, F = 4, 11, 1024
+    ira = [synth.decaying_ir(c, 30000) for c in range(2)]
+    irb = [synth.decaying_ir(10 + c, 15000) for c in range(2)]
+    frames = 40
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = torch.rand((n, frames * F), generator=g, device="cuda") * 2 - 1
+    st = torch.cuda.Stream()
+    outs = []
+    for pdl in (1, 0):
+        A, B = pkg.ConvolverBatch(n, 0), pkg.ConvolverBatch(n, 0)
+        for b, irs in ((A, ira), (B, irb)):
+            b.set_option("pdl", pdl)
+            b.set_option("early_src", 2 if pdl else 0)
+            for c in range(n):
+                assert b.init(c, irs[c % 2], rank, 0.0)
+        mid = torch.zeros((n, F), device="cuda")
+        dst = torch.zeros_like(src)
+        torch.cuda.synchronize()
+        for i in range(frames):
+            # A: the block in two uneven calls (job-list path), B: the whole block (one k_frame launch)
+            A.process_device(mid.data_ptr(), src.data_ptr() + 4 * i * F, frames * F, 300, st.cuda_stream, dst_stride=F)
+            A.process_device(mid.data_ptr() + 4 * 300, src.data_ptr() + 4 * (i * F + 300), frames * F, F - 300,
+                             st.cuda_stream, dst_stride=F)
+            B.process_device(dst.data_ptr() + 4 * i * F, mid.data_ptr(), F, F, st.cuda_stream, dst_stride=frames * F)
+        st.synchronize()
+        outs.append(dst.cpu().numpy())
+        A.close()
+        B.close()
+    assert np.array_equal(outs[0], outs[1])
+    x = src[1].cpu().numpy().astype(np.float64)
+    want = np.convolve(np.convolve(x, ira[1].astype(np.float64))[:frames * F], irb[1].astype(np.float64))[:frames * F]
+    assert rel_err(outs[0][1], want) <= TOL
