@@ -1662,6 +1662,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
                 af.splits       = 1;
                 af.rows         = b->pend_splits + 1;
                 af.row0         = b->pend_splits;
+                af.sum0         = b->pend_splits - 1;       /* the pending MAC folded its rows into this one */
                 af.flags       |= STEP_HEAD_ONLY;
                 /* A synchronous host call on the own stream: every launch that delivered an earlier
                  * block has completed (the caller has its output), and the predecessor in the
@@ -1742,6 +1743,7 @@ static int launch_pending_mac(Batch *b, cudaStream_t st)
     a.rows          = plan.splits + 1;
     a.row0          = 0;
     a.flags        |= STEP_FROM_Q1;
+    a.fold_tickets  = b->d_tickets + size_t(b->frame_seq % uint32_t(FRAME_SLOTS)) * b->n;   /* the slot's: idle until that launch */
     a.n_jobs        = nact;
     a.t_base        = b->t_batch;           /* the block about to arrive */
     a.frame0        = 0;

@@ -95,6 +95,10 @@ struct StepArgs                     /* by-value kernel argument */
     uint32_t        rows;           /* partial rows per job in ypart (0 = splits); a launch writes rows
                                        row0 .. row0 + splits - 1, the inverse transform sums all `rows` */
     uint32_t        row0;
+    uint32_t        sum0;           /* k_frame: the inverse transform sums rows sum0 .. rows - 1 (the pending
+                                       MAC has folded its rows into row sum0 = row0 - 1: fold_tickets)      */
+    uint32_t       *fold_tickets;   /* k_mac: [job] counters (zero between launches); != NULL: the last CTA of a job
+                                       adds the job's rows row0 .. row0 + splits - 1, in order, into the last one */
     const float    *src;            /* uniform mode: [instances][stride]                            */
     float          *dst;
     uint64_t        stride;         /* uniform mode: floats between instance rows of src            */
@@ -1389,9 +1393,53 @@ __device__ __forceinline__ void chunk_range(uint32_t nq, uint32_t split, uint32_
     c1              = len0 + uint32_t((uint64_t(rest) * split) / (splits - 1));
 }
 
+/* The eager pending MAC (synchronous host callers) has time that the launch which delivers the
+ * block has not: the last CTA of a job folds the job's rows into one, in the order the inverse
+ * transform would have added them, so that launch sums two rows instead of splits + 1.  Kept out
+ * of line: k_mac's register budget (4 CTAs per SM) belongs to the partition stream. */
+__device__ __noinline__ void fold_rows(uint32_t *ticket, float2 *job_rows, uint32_t splits, uint32_t n_cta, uint32_t M,
+                                       uint32_t tid, uint32_t T)
+{
+    __shared__ uint32_t fold_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+    {
+        uint32_t old    = atomicAdd(ticket, 1u);
+        uint32_t last   = (old == n_cta - 1) ? 1u : 0u;
+        if (last)
+            *ticket         = 0;
+        fold_last       = last;
+    }
+    __syncthreads();
+    if (fold_last == 0)
+        return;
+    __threadfence();
+    float4 *rows    = reinterpret_cast<float4 *>(job_rows);
+    const uint32_t C4 = M / 2;                                      /* float4 columns per row */
+    for (uint32_t c = tid; c < C4; c += T)
+    {
+        float4 sum      = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (uint32_t s0 = 0; s0 < splits; s0 += 8)
+        {
+            float4 v[8];
+            #pragma unroll
+            for (int r = 0; r < 8; ++r)
+                v[r]            = ld_cg_f4(rows + uint64_t(min(s0 + r, splits - 1)) * C4 + c);
+            #pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (s0 + r < splits)
+                {
+                    sum.x += v[r].x; sum.y += v[r].y; sum.z += v[r].z; sum.w += v[r].w;
+                }
+        }
+        rows[uint64_t(splits - 1) * C4 + c] = sum;
+    }
+}
+
 constexpr int MAC_VPT = 2;      /* float4 columns per thread; blockDim.x = TB / (2 * MAC_VPT) */
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_mac(const StepArgs a, const MacShape sh)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -1551,6 +1599,10 @@ k_mac(const StepArgs a, const MacShape sh)
     #pragma unroll
     for (int v = 0; v < MAC_VPT; ++v)
         yp[tid + v * T] = acc[v];
+
+    if (a.fold_tickets != nullptr)
+        fold_rows(a.fold_tickets + jobi, a.ypart + (uint64_t(jobi) * rows_per_job(a) + a.row0) * M, a.splits,
+                  a.splits * gridDim.y, M, tid, T);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -2235,6 +2287,8 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
 
     const uint32_t rows = rows_per_job(a);
     float2 *yrow    = a.ypart + uint64_t(jobi) * rows * M;
+    const float2 *ysum  = yrow + uint64_t(a.sum0) * M;              /* the rows the inverse transform adds */
+    const uint32_t nsum = rows - a.sum0;
     float4 *yp      = reinterpret_cast<float4 *>(yrow + uint64_t(a.row0 + split) * M + uint64_t(tile) * TB);
     #pragma unroll
     for (int v = 0; v < MAC_VPT; ++v)
@@ -2301,7 +2355,7 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
                 cp_async4(po + 2 * AW + i, job.psrc2 + i);
             }
         }
-        inv_body<RANK, TAIL_PP, TAIL_RG, int(T)>(wa, wb, yrow, rows, job.dst, a.tw, tw, false, int(tid));
+        inv_body<RANK, TAIL_PP, TAIL_RG, int(T)>(wa, wb, ysum, nsum, job.dst, a.tw, tw, false, int(tid));
         if (GEN)
             FRAME_STAMP(7);
         if (GEN && spread)
@@ -2348,7 +2402,7 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
 
     float *mine             = ra.scratch + size_t(ch) * F;
     FRAME_STAMP(4);
-    inv_body<RANK, TAIL_PP, TAIL_RG, int(T)>(wa, wb, yrow, rows, mine, a.tw, tw, false, int(tid));
+    inv_body<RANK, TAIL_PP, TAIL_RG, int(T)>(wa, wb, ysum, nsum, mine, a.tw, tw, false, int(tid));
     __syncthreads();
     FRAME_STAMP(5);
 
