@@ -178,6 +178,61 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
+def run_latency_configs(pkg, args, rank, local_rank, world, barrier, peak):
+    """BASELINE configs[0] and [1] -- the latency-bound shapes (mono 65 536 taps in 1024-sample calls;
+    stereo 192 000 taps, rank 9, 256-sample calls, phases 0 / 0.5: the job-list path) on ONE GPU:
+    device time per call back to back, and what a synchronous host call on page-locked buffers sees
+    when the host comes back once per millisecond."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    out = {}
+    for key, n, taps, rnk, block, phases in (("cfg1", 1, 65536, 11, 1024, (0.0,)), ("cfg2", 2, 192000, 9, 256, (0.0, 0.5))):
+        b = pkg.ConvolverBatch(n, local_rank)
+        for c in range(n):
+            assert b.init(c, synth.decaying_ir(c, taps), rnk, phases[c % len(phases)])
+        calls = 512
+        src = torch.rand((n, calls * block), device="cuda") * 2 - 1
+        dst = torch.empty_like(src)
+        st = torch.cuda.ExternalStream(b.stream())
+        torch.cuda.synchronize()
+
+        def run():
+            for i in range(calls):
+                b.process_device(dst.data_ptr() + 4 * i * block, src.data_ptr() + 4 * i * block, calls * block, block, None)
+        run()
+        b.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            e0.record(st)
+            for _ in range(4):
+                run()
+            e1.record(st)
+        torch.cuda.synchronize()
+        dev_us = e0.elapsed_time(e1) * 1e3 / (4 * calls)
+        hs = torch.rand((n, block)).pin_memory()
+        hd = torch.empty((n, block)).pin_memory()
+        a, o = hs.numpy(), hd.numpy()
+        lat = []
+        for i in range(260):
+            t_wait = time.perf_counter() + 1e-3
+            while time.perf_counter() < t_wait:
+                pass
+            t0 = time.perf_counter()
+            b.process(a, o)
+            lat.append((time.perf_counter() - t0) * 1e6)
+        lat = np.sort(np.array(lat[60:]))
+        out[key] = {"instances": n, "taps": taps, "rank": rnk, "call_samples": block,
+                    "device_us_per_call": dev_us, "host_call_us_median": float(lat[len(lat) // 2]),
+                    "host_call_us_p99": float(lat[int(len(lat) * 0.99)]),
+                    "block_period_us_at_48k": block / 48000.0 * 1e6}
+        b.close()
+    out["note"] = ("device: back-to-back calls on the batch's stream, CUDA events; host: synchronous calls on page-locked "
+                   "buffers, one per millisecond, wall clock around the call (python ctypes included)")
+    return out
+
+
 def run_strong_cfg3(pkg, args, rank, local_rank, world, barrier, peak):
     """BASELINE configs[2] read literally: the 64-channel batch sharded by channel over the ranks
     (64 / N channels per GPU, fixed total work), no collective."""
@@ -485,7 +540,10 @@ def main():
 
         def run_extras():
             torch.cuda.set_device(local_rank)
-            for name, fn in (("strong_cfg3", run_strong_cfg3), ("cfg5_split", run_cfg5)):
+            legs = [("strong_cfg3", run_strong_cfg3), ("cfg5_split", run_cfg5)]
+            if world == 1:
+                legs.append(("latency_configs", run_latency_configs))
+            for name, fn in legs:
                 try:
                     extras[name] = fn(pkg, args, rank, local_rank, world, barrier, peak)
                 except Exception as exc:

@@ -2126,12 +2126,15 @@ __device__ __forceinline__ void frame_body(const StepArgs &a, const MacShape &sh
         }
         if (spread && (!fft_cta))
         {
-            const uint32_t ci       = split * gridDim.y + tile - 1u, nc = n_cta - 1u;
-            if (job.n > 0)
+            /* a page-locked HOST block: every helper fetches the samples its slice needs across PCIe,
+             * so fewer, larger slices */
+            const uint32_t ci       = split * gridDim.y + tile - 1u;
+            const uint32_t nc       = (a.flags & STEP_HOST_IO) ? min(n_cta - 1u, 8u) : (n_cta - 1u);
+            if ((job.n > 0) && (ci < nc))
                 partial_outputs(d.cur, d.head, d.pend, ans1, job.off,
                                 uint32_t((uint64_t(job.n) * ci) / nc), uint32_t((uint64_t(job.n) * (ci + 1)) / nc),
                                 tid, T, po, job.psrc);
-            if (job.n2 > 0)
+            if ((job.n2 > 0) && (ci < nc))
             {
                 __syncthreads();
                 partial_outputs(d.cur, d.head, nullptr, ans2, job.off2,
