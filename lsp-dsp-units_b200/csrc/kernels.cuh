@@ -179,6 +179,16 @@ __device__ __forceinline__ uint64_t global_ns()
     return t;
 }
 
+#ifdef B200CONV_TIMING
+/* developer instrumentation (tools/frame_timeline.py, gen_timeline.py, chain_timeline.py): per-CTA timestamps of the last k_frame launch */
+__device__ unsigned long long g_frame_times[8192 * 8];
+#define FRAME_STAMP(slot)   do { if ((threadIdx.x == 0) && (blockIdx.x < 8192)) g_frame_times[blockIdx.x * 8 + (slot)] = global_ns(); } while (0)
+#define CHAIN_STAMP(id, slot) do { if ((threadIdx.x == 0) && ((id) < 8192)) g_frame_times[(id) * 8 + (slot)] = global_ns(); } while (0)
+#else
+#define FRAME_STAMP(slot)   do { } while (0)
+#define CHAIN_STAMP(id, slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
 {
     uint32_t v;
@@ -502,7 +512,83 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
         Ns = 2;
     }
 
-    for ( ; Ns < P; Ns <<= 2)
+    /* Radix-16 passes (two radix-4 layers fused in registers) where a thread owns at least 16 points
+     * per pass and the transform runs in place (ranks 14..16): the passes of these ranks are bound by
+     * shared-memory round trips and barriers, and there are half as many this way.  Leading radix-4
+     * passes bring Ns to >= 16 (their stores have the bank rotation below) and the remaining factor
+     * to a power of 16. */
+    constexpr bool USE16 = (!PP) && WMUL && FAST1 && (BPT >= 4) && ((NH * P / 16) % T == 0);
+    auto pass16 = [&](int Ns)
+    {
+        constexpr int IT16  = USE16 ? (NH * P / 16) / T : 1;
+        float2 v[IT16][16];
+        #pragma unroll
+        for (int i = 0; i < IT16; ++i)
+        {
+            int idx = tid + i * T;
+            int h   = idx / (P / 16), j = idx % (P / 16);
+            #pragma unroll
+            for (int r = 0; r < 16; ++r)
+                v[i][r] = in[h * P + j + r * (P / 16)];
+        }
+        __syncthreads();
+        /* exp(-2 pi i k / (16 Ns)) is the r = 1 entry of the radix-4 pass 4 Ns, its fourth power that of pass Ns */
+        const float2 *t1 = tw + (TWC ? (4 * Ns - C::NS0) / 3 : (4 * Ns - C::NS0));
+        const float2 *t4 = tw + (TWC ? (Ns - C::NS0) / 3 : (Ns - C::NS0));
+        #pragma unroll
+        for (int i = 0; i < IT16; ++i)
+        {
+            int idx = tid + i * T;
+            int h   = idx / (P / 16), j = idx % (P / 16);
+            int k   = j & (Ns - 1);
+            float2 (&x)[16] = v[i];
+            {
+                const float2 w1 = t1[k], w4 = t4[k];
+                const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1), w8 = cmul(w4, w4), w12 = cmul(w8, w4);
+                auto tw_mul = [&](float2 &z, float2 w) { z = INV ? cmulc(z, w) : cmul(z, w); };
+                tw_mul(x[1], w1);   tw_mul(x[2], w2);   tw_mul(x[3], w3);   tw_mul(x[4], w4);
+                tw_mul(x[5], cmul(w4, w1));  tw_mul(x[6], cmul(w4, w2));  tw_mul(x[7], cmul(w4, w3));
+                tw_mul(x[8], w8);
+                tw_mul(x[9], cmul(w8, w1));  tw_mul(x[10], cmul(w8, w2)); tw_mul(x[11], cmul(w8, w3));
+                tw_mul(x[12], w12);
+                tw_mul(x[13], cmul(w12, w1)); tw_mul(x[14], cmul(w12, w2)); tw_mul(x[15], cmul(w12, w3));
+            }
+            auto dft4 = [](float2 &a, float2 &b, float2 &c, float2 &d)
+            {
+                float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = rot90<INV>(csub(b, d));
+                a = cadd(s0, s2); b = cadd(s1, s3); c = csub(s0, s2); d = csub(s1, s3);
+            };
+            /* layer A: over s1 of x[4 s1 + s2]; result y[s2][r1] lands in x[4 r1 + s2] */
+            #pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2)
+                dft4(x[s2], x[4 + s2], x[8 + s2], x[12 + s2]);
+            /* y[s2][r1] *= w16^(s2 r1) */
+            {
+                const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+                auto cw = [&](float2 &z, float wr, float wi)     /* times (wr - i wi) forward, (wr + i wi) inverse */
+                {
+                    z = INV ? make_float2(z.x * wr - z.y * wi, z.y * wr + z.x * wi)
+                            : make_float2(z.x * wr + z.y * wi, z.y * wr - z.x * wi);
+                };
+                cw(x[4 * 1 + 1], c1, s1);   cw(x[4 * 1 + 2], r2, r2);   cw(x[4 * 1 + 3], s1, c1);
+                cw(x[4 * 2 + 1], r2, r2);   x[4 * 2 + 2] = rot90<INV>(x[4 * 2 + 2]);   cw(x[4 * 2 + 3], -r2, r2);
+                cw(x[4 * 3 + 1], s1, c1);   cw(x[4 * 3 + 2], -r2, r2);  cw(x[4 * 3 + 3], -c1, -s1);
+            }
+            /* layer B: over s2 of x[4 r1 + s2]; X[r1 + 4 r2] lands in x[4 r1 + r2] */
+            #pragma unroll
+            for (int r1 = 0; r1 < 4; ++r1)
+                dft4(x[4 * r1], x[4 * r1 + 1], x[4 * r1 + 2], x[4 * r1 + 3]);
+            float2 *o  = out + h * P + ((j - k) << 4) + k;
+            #pragma unroll
+            for (int r1 = 0; r1 < 4; ++r1)
+                #pragma unroll
+                for (int r2 = 0; r2 < 4; ++r2)
+                    o[(r1 + 4 * r2) * Ns]   = x[4 * r1 + r2];
+        }
+        __syncthreads();
+    };
+
+    auto pass4 = [&](int Ns)
     {
         float2 v[BPT][4];
         #pragma unroll
@@ -569,6 +655,25 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
         }
         __syncthreads();
         if (PP) { float2 *t = in; in = out; out = t; }
+    };
+
+    if constexpr (USE16)
+    {
+        /* remaining factor P / Ns = 4^m: radix-4 until Ns >= 16 and m is even, then radix-16 */
+        #pragma unroll 1
+        while ((Ns < 16) || (((31 - __clz(P / Ns)) & 3) != 0))
+        {
+            pass4(Ns);
+            Ns <<= 2;
+        }
+        #pragma unroll 1
+        for ( ; Ns < P; Ns <<= 4)
+            pass16(Ns);
+    }
+    else
+    {
+        for ( ; Ns < P; Ns <<= 2)
+            pass4(Ns);
     }
     return in;
 }
@@ -774,6 +879,7 @@ k_fwd_half(const StepArgs a)
     stage_compact_twiddles<C>(twc, a.tw, threadIdx.x);
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    CHAIN_STAMP(4096 + blockIdx.x, 0);
     for (uint32_t w = blockIdx.x; w < 2 * a.n_jobs; w += gridDim.x)
     {
         const Job job           = fetch_job(a, w >> 1);
@@ -781,6 +887,7 @@ k_fwd_half(const StepArgs a)
                                                        nullptr, int(w & 1u));
         __syncthreads();
     }
+    CHAIN_STAMP(4096 + blockIdx.x, 1);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -1069,7 +1176,9 @@ k_inv_half(const StepArgs a, uint32_t *tickets)
     float2 *twc             = sm + C::WORK;
     stage_compact_twiddles<C>(twc, a.tw, threadIdx.x);
     __syncthreads();
+    CHAIN_STAMP(4096 + 512 + blockIdx.x, 0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    CHAIN_STAMP(4096 + 512 + blockIdx.x, 1);
     const uint32_t rows = rows_per_job(a);
     for (uint32_t w = blockIdx.x; w < 2 * a.n_jobs; w += gridDim.x)
     {
@@ -1454,6 +1563,7 @@ k_mac(const StepArgs a, const MacShape sh)
     const uint32_t TB       = sh.TB, QB = sh.QB, NS = sh.NS;
     const uint32_t T        = blockDim.x;
     const uint32_t tid      = threadIdx.x;
+    CHAIN_STAMP(blockIdx.x + gridDim.x * blockIdx.y, 0);
     const uint32_t jobi     = blockIdx.x / a.splits;
     const uint32_t split    = blockIdx.x % a.splits;
     const uint32_t tile     = blockIdx.y;
@@ -1592,7 +1702,9 @@ k_mac(const StepArgs a, const MacShape sh)
     }
 
     /* launched early: the previous launch may still be reading the rows this one replaces */
+    CHAIN_STAMP(blockIdx.x + gridDim.x * blockIdx.y, 1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    CHAIN_STAMP(blockIdx.x + gridDim.x * blockIdx.y, 2);
 
     float4 *yp      = reinterpret_cast<float4 *>(a.ypart + (uint64_t(jobi) * rows_per_job(a) + a.row0 + split) * M
                                                  + uint64_t(tile) * TB);
@@ -1939,13 +2051,6 @@ __device__ __forceinline__ void partial_outputs(const float *cur, const float *h
 /* griddepcontrol.wait, i.e. when every earlier launch in the stream has completed and flushed -- */
 /* so a src that an earlier launch produced (two batches cascaded on one stream, or a batch fed   */
 /* its own dst) is final when it is read, whoever that producer was.                             */
-#ifdef B200CONV_TIMING
-/* developer instrumentation (tools/frame_timeline.py): per-CTA timestamps of the last k_frame launch */
-__device__ unsigned long long g_frame_times[8192 * 8];
-#define FRAME_STAMP(slot)   do { if ((threadIdx.x == 0) && (blockIdx.x < 8192)) g_frame_times[blockIdx.x * 8 + (slot)] = global_ns(); } while (0)
-#else
-#define FRAME_STAMP(slot)   do { } while (0)
-#endif
 
 template <int RANK>
 struct FrameCfg
