@@ -379,10 +379,85 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
     using C = FftCfg<RANK, TT, NHO>;
     constexpr int P = C::P, T = C::T, BPT = C::BPT, NH = C::NH;
 
+    constexpr bool USE16 = (!PP) && WMUL && FAST1 && (BPT >= 4) && ((NH * P / 16) % T == 0);
     float2 *in  = A;
     float2 *out = PP ? B : A;
     int Ns = 1;
-    if (FAST1 && (C::LOGP & 1))
+    if constexpr (FAST1 && USE16 && !(C::LOGP & 1))
+    {
+        /* radix-16, Ns = 1: no twiddles, outputs 16 j .. 16 j + 15 are contiguous (128 bytes per thread):
+         * eight 16-byte stores whose order is rotated per lane, so that the eight lanes of every
+         * quarter-warp cover all 32 banks */
+        constexpr int IT16  = USE16 ? (NH * P / 16) / T : 1;
+        float2 v[IT16][16];
+        #pragma unroll
+        for (int i = 0; i < IT16; ++i)
+        {
+            int idx = tid + i * T;
+            int h   = idx / (P / 16), j = idx % (P / 16);
+            #pragma unroll
+            for (int r = 0; r < 16; ++r)
+                v[i][r] = in[h * P + j + r * (P / 16)];
+        }
+        __syncthreads();
+        const int sw = tid & 7;
+        #pragma unroll
+        for (int i = 0; i < IT16; ++i)
+        {
+            int idx = tid + i * T;
+            int h   = idx / (P / 16), j = idx % (P / 16);
+            float2 (&x)[16] = v[i];
+            auto dft4 = [](float2 &a, float2 &b, float2 &c, float2 &d)
+            {
+                float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = rot90<INV>(csub(b, d));
+                a = cadd(s0, s2); b = cadd(s1, s3); c = csub(s0, s2); d = csub(s1, s3);
+            };
+            #pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2)
+                dft4(x[s2], x[4 + s2], x[8 + s2], x[12 + s2]);
+            {
+                const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+                auto cw = [&](float2 &z, float wr, float wi)
+                {
+                    z = INV ? make_float2(z.x * wr - z.y * wi, z.y * wr + z.x * wi)
+                            : make_float2(z.x * wr + z.y * wi, z.y * wr - z.x * wi);
+                };
+                cw(x[4 * 1 + 1], c1, s1);   cw(x[4 * 1 + 2], r2, r2);   cw(x[4 * 1 + 3], s1, c1);
+                cw(x[4 * 2 + 1], r2, r2);   x[4 * 2 + 2] = rot90<INV>(x[4 * 2 + 2]);   cw(x[4 * 2 + 3], -r2, r2);
+                cw(x[4 * 3 + 1], s1, c1);   cw(x[4 * 3 + 2], -r2, r2);  cw(x[4 * 3 + 3], -c1, -s1);
+            }
+            #pragma unroll
+            for (int r1 = 0; r1 < 4; ++r1)
+                dft4(x[4 * r1], x[4 * r1 + 1], x[4 * r1 + 2], x[4 * r1 + 3]);
+            /* output r = r1 + 4 r2 sits in x[4 r1 + r2]; chunk c = outputs 2 c, 2 c + 1 */
+            float4 c[8];
+            #pragma unroll
+            for (int n = 0; n < 8; ++n)
+            {
+                const int ra = 2 * n, rb = 2 * n + 1;
+                const float2 a = x[4 * (ra & 3) + (ra >> 2)], b = x[4 * (rb & 3) + (rb >> 2)];
+                c[n]    = make_float4(a.x, a.y, b.x, b.y);
+            }
+            /* e_n = chunk (n + sw) & 7, by a three-stage barrel rotation */
+            float4 d[8], e[8], f[8];
+            #pragma unroll
+            for (int n = 0; n < 8; ++n)
+                d[n]    = (sw & 1) ? c[(n + 1) & 7] : c[n];
+            #pragma unroll
+            for (int n = 0; n < 8; ++n)
+                e[n]    = (sw & 2) ? d[(n + 2) & 7] : d[n];
+            #pragma unroll
+            for (int n = 0; n < 8; ++n)
+                f[n]    = (sw & 4) ? e[(n + 4) & 7] : e[n];
+            float4 *row = reinterpret_cast<float4 *>(out + h * P + 16 * j);
+            #pragma unroll
+            for (int n = 0; n < 8; ++n)
+                row[(n + sw) & 7]   = f[n];
+        }
+        __syncthreads();
+        Ns = 16;
+    }
+    else if (FAST1 && (C::LOGP & 1))
     {
         constexpr int B8    = NH * P / 8;                       /* radix-8 butterflies */
         constexpr int IT8   = (B8 + T - 1) / T;
@@ -517,7 +592,6 @@ __device__ __forceinline__ float2 *fft_smem(float2 *A, float2 *B, const float2 *
      * shared-memory round trips and barriers, and there are half as many this way.  Leading radix-4
      * passes bring Ns to >= 16 (their stores have the bank rotation below) and the remaining factor
      * to a power of 16. */
-    constexpr bool USE16 = (!PP) && WMUL && FAST1 && (BPT >= 4) && ((NH * P / 16) % T == 0);
     auto pass16 = [&](int Ns)
     {
         constexpr int IT16  = USE16 ? (NH * P / 16) / T : 1;
