@@ -812,7 +812,9 @@ __device__ __forceinline__ void fwd_body(float2 *A, float2 *B, const float *src,
         }
         __syncthreads();
 
+        CHAIN_STAMP(4096 + blockIdx.x, 2);
         const float2 *R = fft_smem<RANK, false, PP, TT, WM, true, NHO, TWC>(A, B, tw, tid);
+        CHAIN_STAMP(4096 + blockIdx.x, 3);
         if (SMEM_OUT)
         {
             out         = (R == A) ? B : A;
@@ -1110,7 +1112,9 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
         }
         __syncthreads();
 
+        CHAIN_STAMP(4096 + 512 + blockIdx.x, 2);
         const float2 *R = fft_smem<RANK, true, PP, TT, WM, true, NHO, TWC>(A, B, tw, tid);
+        CHAIN_STAMP(4096 + 512 + blockIdx.x, 3);
 
         /* z[m] = (A[m] + conj(w_M^m) B[m]) / N ; z[m + P] = (A[m] - conj(w_M^m) B[m]) / N
          * (global loads -- the twiddle, the parked half -- LBO at a time before the first use) */
@@ -1282,24 +1286,42 @@ k_inv_half(const StepArgs a, uint32_t *tickets)
                 const float4 *o4    = reinterpret_cast<const float4 *>(a.park + uint64_t(j) * 2 * C::M);
                 const float4 *e4    = o4 + C::M / 4;
                 const bool al       = (reinterpret_cast<uintptr_t>(job.dst) & 15) == 0;
-                for (uint32_t i = threadIdx.x; i < uint32_t(C::M) / 4; i += C::T)
+                /* CB columns per round, all loads in flight before the first store (one round trip to
+                 * L2 per round instead of one per column: this loop is the exposed end of the block) */
+                constexpr uint32_t COLS = uint32_t(C::M) / 4 / C::T;
+                constexpr uint32_t CB   = (COLS % 4 == 0) ? 4 : ((COLS % 2 == 0) ? 2 : 1);
+                static_assert(COLS * C::T * 4 == uint32_t(C::M), "k_inv_half: whole columns per thread");
+                #pragma unroll 1
+                for (uint32_t c0 = 0; c0 < COLS; c0 += CB)
                 {
-                    const float4 ev = __ldcg(e4 + i), ov = __ldcg(o4 + i);
-                    const float4 lo = make_float4(ev.x + ov.x, ev.y + ov.y, ev.z + ov.z, ev.w + ov.w);
-                    const float4 hi = make_float4(ev.x - ov.x, ev.y - ov.y, ev.z - ov.z, ev.w - ov.w);
-                    if (al)
+                    float4 ev[CB], ov[CB];
+                    #pragma unroll
+                    for (uint32_t u = 0; u < CB; ++u)
                     {
-                        reinterpret_cast<float4 *>(job.dst)[i]  = lo;
-                        if (full)
-                            reinterpret_cast<float4 *>(job.dst)[C::M / 4 + i] = hi;
+                        const uint32_t i    = threadIdx.x + (c0 + u) * C::T;
+                        ev[u]               = ld_cg_f4(e4 + i);
+                        ov[u]               = ld_cg_f4(o4 + i);
                     }
-                    else
+                    #pragma unroll
+                    for (uint32_t u = 0; u < CB; ++u)
                     {
-                        job.dst[4 * i] = lo.x; job.dst[4 * i + 1] = lo.y; job.dst[4 * i + 2] = lo.z; job.dst[4 * i + 3] = lo.w;
-                        if (full)
+                        const uint32_t i    = threadIdx.x + (c0 + u) * C::T;
+                        const float4 lo = make_float4(ev[u].x + ov[u].x, ev[u].y + ov[u].y, ev[u].z + ov[u].z, ev[u].w + ov[u].w);
+                        const float4 hi = make_float4(ev[u].x - ov[u].x, ev[u].y - ov[u].y, ev[u].z - ov[u].z, ev[u].w - ov[u].w);
+                        if (al)
                         {
-                            float *d2 = job.dst + C::M;
-                            d2[4 * i] = hi.x; d2[4 * i + 1] = hi.y; d2[4 * i + 2] = hi.z; d2[4 * i + 3] = hi.w;
+                            reinterpret_cast<float4 *>(job.dst)[i]  = lo;
+                            if (full)
+                                reinterpret_cast<float4 *>(job.dst)[C::M / 4 + i] = hi;
+                        }
+                        else
+                        {
+                            job.dst[4 * i] = lo.x; job.dst[4 * i + 1] = lo.y; job.dst[4 * i + 2] = lo.z; job.dst[4 * i + 3] = lo.w;
+                            if (full)
+                            {
+                                float *d2 = job.dst + C::M;
+                                d2[4 * i] = hi.x; d2[4 * i + 1] = hi.y; d2[4 * i + 2] = hi.z; d2[4 * i + 3] = hi.w;
+                            }
                         }
                     }
                 }
@@ -1307,6 +1329,7 @@ k_inv_half(const StepArgs a, uint32_t *tickets)
         }
         __syncthreads();
     }
+    CHAIN_STAMP(4096 + 512 + blockIdx.x, 4);
 }
 
 __global__ void k_inv_combine(const StepArgs a)

@@ -39,6 +39,8 @@ t0 = fwd[:, 0].min()
 def us(x): return (x - t0) / 1e3
 print("rank %d, last block: times in us since the first transform CTA passed its wait" % rank)
 print("  k_fwd_half: %d CTAs, start %.1f .. %.1f, end %.1f .. %.1f" % (len(fwd), us(fwd[:, 0]).min(), us(fwd[:, 0]).max(), us(fwd[:, 1]).min(), us(fwd[:, 1]).max()))
+print("              passes start %.1f .. %.1f, passes end %.1f .. %.1f (median pass time %.1f us)" % (
+    us(fwd[:, 2]).min(), us(fwd[:, 2]).max(), us(fwd[:, 3]).min(), us(fwd[:, 3]).max(), np.median(fwd[:, 3] - fwd[:, 2]) / 1e3))
 fe = fwd[:, 1].max()
 print("  k_mac: %d CTAs; started before the transform ended: %d; start p0/p10/p50/p90/p100 = %s" % (
     len(mac), int((mac[:, 0] < fe).sum()), " ".join("%.1f" % v for v in np.percentile(us(mac[:, 0]), [0, 10, 50, 90, 100]))))
@@ -47,3 +49,6 @@ print("         stream end p0/p50/p100 = %s; after wait p0/p50/p100 = %s" % (
 dur = (mac[:, 1] - mac[:, 0]) / 1e3
 print("         per-CTA stream time p10/p50/p90 = %s us" % " ".join("%.1f" % v for v in np.percentile(dur, [10, 50, 90])))
 print("  k_inv_half: %d CTAs, resident %.1f .. %.1f, past wait %.1f .. %.1f" % (len(inv), us(inv[:, 0]).min(), us(inv[:, 0]).max(), us(inv[:, 1]).min(), us(inv[:, 1]).max()))
+print("              passes start %.1f .. %.1f, passes end %.1f .. %.1f (median pass time %.1f us)" % (
+    us(inv[:, 2]).min(), us(inv[:, 2]).max(), us(inv[:, 3]).min(), us(inv[:, 3]).max(), np.median(inv[:, 3] - inv[:, 2]) / 1e3))
+print("              end %.1f .. %.1f" % (us(inv[:, 4]).min(), us(inv[:, 4]).max()))
