@@ -279,12 +279,16 @@ struct MacPlan
     size_t      smem;
 };
 
+static int g_tune_tile = 0;         /* developer option "mac_tile": bins per k_mac CTA at ranks >= 14 (0 = 1024) */
+
 static MacPlan plan_mac(uint32_t rank, uint32_t jobs, uint32_t max_nq, int sm_count,
                         int tune_splits, int tune_stages)
 {
     MacPlan p;
     uint32_t M      = 1u << (rank - 1);
     p.sh.TB         = (M < 1024) ? M : 1024;
+    if ((rank >= 14) && (g_tune_tile > 0))
+        p.sh.TB         = uint32_t(g_tune_tile);
     p.sh.QB         = 1024 / p.sh.TB;
     p.sh.NS         = (tune_stages > 0) ? uint32_t(tune_stages) : 2;      /* measured: 2 x 16 KiB beats 3 (profiles/) */
     p.tiles         = M / p.sh.TB;
@@ -2589,6 +2593,7 @@ extern "C" int b200conv_set_option(b200conv_batch_t *b, const char *name, int va
     if ((b == nullptr) || (name == nullptr))
         return fail(B200CONV_ERR_ARG, "b200conv_set_option: bad arguments");
     if (!strcmp(name, "mac_splits") && (value >= 0) && (value <= 32))       b->tune_splits = value;
+    else if (!strcmp(name, "mac_tile") && ((value == 0) || (value == 256) || (value == 512) || (value == 1024))) g_tune_tile = value;
     else if (!strcmp(name, "mac_stages") && ((value == 0) || ((value >= 2) && (value <= 12)))) b->tune_stages = value;
     else if (!strcmp(name, "fused") && (value >= 0) && (value <= 1))        b->opt_fused = value;
     else if (!strcmp(name, "fft_bias") && (value >= 0) && (value <= 64))    b->opt_bias = value;

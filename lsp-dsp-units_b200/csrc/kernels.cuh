@@ -1719,13 +1719,27 @@ k_mac(const StepArgs a, const MacShape sh)
         float2 *g       = sG + size_t(f_s) * stage_elems;
         float2 *x       = sX + size_t(f_s) * stage_elems;
         mbar_expect_tx(&full[f_s], 2u * rows * row_bytes);
-        /* IR rows q .. q+rows-1 are contiguous when TB == M (QB > 1 only then) */
-        bulk_g2s(g, Gt + uint64_t(f_q - d.q_lo) * M, rows * row_bytes, &full[f_s], l2_stream);
-        /* ring slots (slot0 + q) mod S ascend with q: one copy, or two around the wrap */
-        uint32_t n1     = min(rows, d.S - f_slot);
-        bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s], l2_stream);
-        if (n1 < rows)
-            bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s], l2_stream);
+        if (TB == M)
+        {
+            /* IR rows q .. q+rows-1 are contiguous */
+            bulk_g2s(g, Gt + uint64_t(f_q - d.q_lo) * M, rows * row_bytes, &full[f_s], l2_stream);
+            /* ring slots (slot0 + q) mod S ascend with q: one copy, or two around the wrap */
+            uint32_t n1     = min(rows, d.S - f_slot);
+            bulk_g2s(x, Xt + uint64_t(f_slot) * M, n1 * row_bytes, &full[f_s], l2_stream);
+            if (n1 < rows)
+                bulk_g2s(x + size_t(n1) * TB, Xt, (rows - n1) * row_bytes, &full[f_s], l2_stream);
+        }
+        else
+        {
+            /* a bin tile of several partitions per stage (QB > 1 with TB < M): one copy per row */
+            for (uint32_t r = 0; r < rows; ++r)
+            {
+                uint32_t sl     = f_slot + r;
+                if (sl >= d.S)  sl -= d.S;
+                bulk_g2s(g + size_t(r) * TB, Gt + uint64_t(f_q + r - d.q_lo) * M, row_bytes, &full[f_s], l2_stream);
+                bulk_g2s(x + size_t(r) * TB, Xt + uint64_t(sl) * M, row_bytes, &full[f_s], l2_stream);
+            }
+        }
         ++f_it;
         f_q            += QB;
         f_slot         += QB;

@@ -1045,3 +1045,33 @@ def test_cascade_behind_a_batch_on_the_job_list_path(pkg):
     x = src[1].cpu().numpy().astype(np.float64)
     want = np.convolve(np.convolve(x, ira[1].astype(np.float64))[:frames * F], irb[1].astype(np.float64))[:frames * F]
     assert rel_err(outs[0][1], want) <= TOL
+
+
+def test_smaller_mac_bin_tiles_are_bit_identical(pkg):
+    """Developer option "mac_tile" (ranks >= 14): 512-bin k_mac tiles with two partitions per stage
+    (one bulk copy per row) must give the bits of the default 1024-bin tiles."""
+    torch = pytest.importorskip("torch")
+    n, taps, rank = 3, 150000, 14
+    F = 1 << (rank - 1)
+    irs = [synth.decaying_ir(c, taps) for c in range(2)]
+    x = np.stack([synth.noise(700 + c, 6 * F) for c in range(n)])
+    outs = []
+    try:
+        for tile in (0, 512):
+            b = pkg.ConvolverBatch(n, 0)
+            b.set_option("mac_tile", tile)
+            for c in range(n):
+                assert b.init(c, irs[c % 2], rank, 0.0)
+            src = torch.from_numpy(x).cuda()
+            dst = torch.zeros_like(src)
+            for i in range(6):
+                b.process_device(dst.data_ptr() + 4 * i * F, src.data_ptr() + 4 * i * F, 6 * F, F)
+            b.sync()
+            outs.append(dst.cpu().numpy())
+            b.close()
+    finally:
+        b = pkg.ConvolverBatch(1, 0)
+        b.set_option("mac_tile", 0)                     # process-wide knob: back to the default
+        b.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert rel_err(outs[0][1], direct_convolve(x[1], irs[1], 6 * F)) <= TOL
