@@ -717,7 +717,9 @@ struct b200conv_batch
     uint32_t                frame_seq   = 0;        /* sequence number of the next k_frame launch */
     size_t                  ypart_slot_bytes = 0;   /* ypart holds FRAME_SLOTS slots of this size */
     std::vector<uint32_t>   h_slot_done;
-    uint32_t               *d_ring_head = nullptr;  /* k_frame: frames published per instance */
+    uint32_t               *d_ring_head = nullptr;  /* k_frame: frames published per instance; [n] = chain head (StepArgs::chain_head) */
+    bool                    chain_valid = false;    /* the device word will hold chain_next once everything enqueued has run */
+    uint32_t                chain_next  = 0;
     uint32_t               *h_error     = nullptr;  /* page-locked, device-mapped: a bounded in-kernel wait gave up */
     std::vector<uint32_t>   h_ring_head;
 
@@ -891,6 +893,7 @@ static int upload_tables(Batch *b, cudaStream_t st)
     if (!b->desc_dirty)
         return B200CONV_OK;
     hist_reset(st, b->device);          /* the copies below are full dependencies */
+    b->chain_valid = false;
     for (size_t i = 0; i < b->n; ++i)
     {
         b->h_ring_head[i]   = uint32_t(b->inst[i].frames);
@@ -1079,8 +1082,8 @@ static int create_impl(b200conv_batch_t **out, int device, size_t instances)
         CU_BRK(cudaMemset(b->d_slot_done, 0, FRAME_SLOTS * instances * sizeof(uint32_t)));
         CU_BRK(cudaHostAlloc(&b->h_error, 64, cudaHostAllocMapped | cudaHostAllocPortable));
         *b->h_error = 0;
-        CU_BRK(cudaMalloc(&b->d_ring_head, instances * sizeof(uint32_t)));
-        CU_BRK(cudaMemset(b->d_ring_head, 0, instances * sizeof(uint32_t)));
+        CU_BRK(cudaMalloc(&b->d_ring_head, (instances + 1) * sizeof(uint32_t)));       /* + the chain head (k_mac) */
+        CU_BRK(cudaMemset(b->d_ring_head, 0, (instances + 1) * sizeof(uint32_t)));
         #undef CU_BRK
     } while (false);
 
@@ -1619,6 +1622,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             TRY(attach_park(b, a, size_t(nact) * tf, st));
             CU(launch_inv(a, nact * tf, st));
             hist_unknown(st, b->device);
+            b->chain_valid  = false;
             b->stats.launches       += 3;
             b->stats.mac_launches   += 1;
             b->stats.mac_algo_bytes += per_frame_bytes * tf;
@@ -1698,6 +1702,17 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             StepArgs am     = a;
             if (chain)
                 am.flags       |= STEP_AFTER_FWD;
+            {
+                /* "the spectra of all frames < t are final": published by the k_mac of block t - 1; whenever
+                 * that was not the launch before this one (first block, a multi-frame pass, the general
+                 * path, another frame counter) the word is seeded by a copy -- a full dependency */
+                const uint32_t t32 = uint32_t(a.t_base + a.frame0);
+                if ((!b->chain_valid) || (b->chain_next != t32))
+                    CU(cudaMemcpyAsync(b->d_ring_head + b->n, &t32, sizeof(t32), cudaMemcpyHostToDevice, st));
+                am.chain_head   = b->d_ring_head + b->n;
+                b->chain_valid  = true;
+                b->chain_next   = t32 + 1u;
+            }
             CU(launch_mac(b, am, sp, nact, st, false, false, chain));
             CU(launch_inv(a, nact, st, chain, b->d_tickets));      /* nact <= instances counters */
             hist_unknown(st, b->device);
@@ -1963,6 +1978,7 @@ static int process_general_fused(Batch *b, float *dst, size_t dst_stride, const 
     }
 
     hist_unknown(st, b->device);
+    b->chain_valid = false;
     b->uniform_stale = true;    /* per-instance frame counters moved independently of t_batch */
     b->pend_ready = false;
     return B200CONV_OK;
@@ -2177,6 +2193,7 @@ static int process_general_staged(Batch *b, float *dst, size_t dst_stride, const
     /* ring_head was bypassed and the per-instance frame counters moved: both matter only to a
      * k_frame launch, which refreshes the tables first (uniform_stale) */
     hist_unknown(st, b->device);
+    b->chain_valid = false;
     b->uniform_stale = true;
     b->pend_ready = false;
     return B200CONV_OK;

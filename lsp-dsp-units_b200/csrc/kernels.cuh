@@ -97,6 +97,12 @@ struct StepArgs                     /* by-value kernel argument */
     uint32_t        row0;
     uint32_t        sum0;           /* k_frame: the inverse transform sums rows sum0 .. rows - 1 (the pending
                                        MAC has folded its rows into row sum0 = row0 - 1: fold_tickets)      */
+    uint32_t       *chain_head;     /* k_mac in the three-kernel block (ranks 14..16), != NULL: one word per batch,
+                                       "the spectra of all frames < *chain_head are final".  The launch of block t
+                                       polls it for t before its first read of the ring (its own CTAs may be
+                                       running while the transforms of EARLIER blocks are still resident: every
+                                       kernel of the chain releases its successor at its top) and publishes
+                                       t + 1 once the transform of block t has completed. */
     uint32_t       *fold_tickets;   /* k_mac: [job] counters (zero between launches); != NULL: the last CTA of a job
                                        adds the job's rows row0 .. row0 + splits - 1, in order, into the last one */
     const float    *src;            /* uniform mode: [instances][stride]                            */
@@ -1749,6 +1755,11 @@ k_mac(const StepArgs a, const MacShape sh)
 
     if (tid == 0)
     {
+        if ((a.chain_head != nullptr) && (n_iter > 0))
+        {
+            wait_ge<false>(a.chain_head, uint32_t(a.t_base + a.frame0), a.error, SPIN_ERR_RING);
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
         if ((a.flags & STEP_WAIT_HEAD) && (n_iter > 0))
         {
             /* The eager pending MAC of a synchronous caller starts while the k_frame launch that
@@ -1816,6 +1827,8 @@ k_mac(const StepArgs a, const MacShape sh)
     CHAIN_STAMP(blockIdx.x + gridDim.x * blockIdx.y, 1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     CHAIN_STAMP(blockIdx.x + gridDim.x * blockIdx.y, 2);
+    if ((a.chain_head != nullptr) && (blockIdx.x == 0) && (blockIdx.y == 0) && (tid == 0))
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.chain_head), "r"(uint32_t(a.t_base + a.frame0) + 1u) : "memory");
 
     float4 *yp      = reinterpret_cast<float4 *>(a.ypart + (uint64_t(jobi) * rows_per_job(a) + a.row0 + split) * M
                                                  + uint64_t(tile) * TB);

@@ -1047,9 +1047,11 @@ def test_cascade_behind_a_batch_on_the_job_list_path(pkg):
     assert rel_err(outs[0][1], want) <= TOL
 
 
-def test_smaller_mac_bin_tiles_are_bit_identical(pkg):
+def test_smaller_mac_bin_tiles(pkg):
     """Developer option "mac_tile" (ranks >= 14): 512-bin k_mac tiles with two partitions per stage
-    (one bulk copy per row) must give the bits of the default 1024-bin tiles."""
+    (one bulk copy per row).  Not the bits of the default 1024-bin tiles -- the stage that holds
+    partition 0 is taken last, so two partitions per stage change the order of the fp32 sum -- but the
+    same answer to rounding."""
     torch = pytest.importorskip("torch")
     n, taps, rank = 3, 150000, 14
     F = 1 << (rank - 1)
@@ -1073,5 +1075,8 @@ def test_smaller_mac_bin_tiles_are_bit_identical(pkg):
         b = pkg.ConvolverBatch(1, 0)
         b.set_option("mac_tile", 0)                     # process-wide knob: back to the default
         b.close()
-    assert np.array_equal(outs[0], outs[1])
-    assert rel_err(outs[0][1], direct_convolve(x[1], irs[1], 6 * F)) <= TOL
+    for c in range(n):
+        want = direct_convolve(x[c], irs[c % 2], 6 * F)
+        assert rel_err(outs[0][c], want) <= TOL
+        assert rel_err(outs[1][c], want) <= TOL
+        assert rel_err(outs[1][c], outs[0][c].astype(np.float64)) <= 2e-6
