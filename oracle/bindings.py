@@ -370,3 +370,112 @@ class CpuSpectralProcessor:
                 self._h = None
         except Exception:
             pass
+
+
+# ---- lsp::dspu::SpectralSplitter, the reference class itself (oracle/ref_wrap_splitter.cpp) --------
+
+class CpuSpectralSplitter:
+    """The reference's own ``dspu::SpectralSplitter`` (SpectralSplitter.cpp compiled verbatim into
+    ``oracle/_ref``).  Handler ``h`` gets one of: ``bind_complex(h, H)`` (spectrum times a packed
+    complex table of ``2**rank`` bins), ``bind_gain(h, g)`` (real gain per bin: what ``FFTCrossover``
+    does per band), ``bind_sink(h)`` (no spectral function: the input frames themselves).  Every
+    bound handler has a sink; ``process`` returns ``[handlers][count]`` (rows of unbound handlers
+    stay zero)."""
+
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        path = os.path.join(_HERE, "_ref", "libref_convolver.so")
+        if not os.path.exists(path):
+            return False
+        try:
+            return hasattr(ctypes.CDLL(path), "refss_create")
+        except OSError:
+            return False
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            lib = ctypes.CDLL(os.path.join(_HERE, "_ref", "libref_convolver.so"))
+            lib.refss_create.restype = ctypes.c_void_p
+            lib.refss_create.argtypes = [_SZ, _SZ]
+            lib.refss_free.argtypes = [ctypes.c_void_p]
+            lib.refss_set_rank.argtypes = [ctypes.c_void_p, _SZ]
+            lib.refss_set_chunk_rank.argtypes = [ctypes.c_void_p, ctypes.c_long]
+            lib.refss_set_phase.argtypes = [ctypes.c_void_p, ctypes.c_float]
+            for name in ("refss_rank", "refss_latency", "refss_bindings"):
+                getattr(lib, name).restype = _SZ
+                getattr(lib, name).argtypes = [ctypes.c_void_p]
+            lib.refss_chunk_rank.restype = ctypes.c_long
+            lib.refss_chunk_rank.argtypes = [ctypes.c_void_p]
+            lib.refss_clear.argtypes = [ctypes.c_void_p]
+            lib.refss_update_settings.argtypes = [ctypes.c_void_p]
+            lib.refss_bind.restype = ctypes.c_int
+            lib.refss_bind.argtypes = [ctypes.c_void_p, _SZ, ctypes.c_int, _FP, _SZ]
+            lib.refss_process.argtypes = [ctypes.c_void_p, _FP, _SZ, _FP, _SZ]
+            cls._lib = lib
+        return cls._lib
+
+    def __init__(self, max_rank, handlers):
+        self.handlers = handlers
+        self._h = self.lib().refss_create(max_rank, handlers)
+        if not self._h:
+            raise ValueError("SpectralSplitter::init failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.lib().refss_free(self._h)
+            self._h = None
+
+    def set_rank(self, rank):
+        self.lib().refss_set_rank(self._h, rank)
+
+    def set_chunk_rank(self, rank):
+        self.lib().refss_set_chunk_rank(self._h, rank)
+
+    def set_phase(self, phase):
+        self.lib().refss_set_phase(self._h, phase)
+
+    def rank(self):
+        return int(self.lib().refss_rank(self._h))
+
+    def chunk_rank(self):
+        return int(self.lib().refss_chunk_rank(self._h))
+
+    def latency(self):
+        return int(self.lib().refss_latency(self._h))
+
+    def bindings(self):
+        return int(self.lib().refss_bindings(self._h))
+
+    def clear(self):
+        self.lib().refss_clear(self._h)
+
+    def update_settings(self):
+        self.lib().refss_update_settings(self._h)
+
+    def bind_complex(self, handler, H):
+        H = np.ascontiguousarray(H, dtype=np.complex64).view(np.float32)
+        return self.lib().refss_bind(self._h, handler, 1, _ptr(H), H.size)
+
+    def bind_gain(self, handler, gain):
+        gain = np.ascontiguousarray(gain, dtype=np.float32)
+        return self.lib().refss_bind(self._h, handler, 2, _ptr(gain), gain.size)
+
+    def bind_sink(self, handler):
+        return self.lib().refss_bind(self._h, handler, 3, None, 0)
+
+    def unbind(self, handler):
+        return self.lib().refss_bind(self._h, handler, 0, None, 0)
+
+    def process(self, src):
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        out = np.zeros((self.handlers, src.size), dtype=np.float32)
+        if src.size:
+            self.lib().refss_process(self._h, _ptr(out), src.size, _ptr(src), src.size)
+        return out
+
+    def run(self, src, step):
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        return np.concatenate([self.process(src[i:i + step]) for i in range(0, src.size, step)], axis=1)

@@ -1,7 +1,7 @@
 /*
  * oracle/shim -- TEST INFRASTRUCTURE.  Stand-in for lsp-common-lib's
  * <lsp-plug.in/common/alloc.h>: alloc_aligned / free_aligned as used at
- * reference Convolver.cpp:73,104 and SpectralProcessor.cpp:72,80.
+ * reference Convolver.cpp:73,104, SpectralProcessor.cpp:72,80 and SpectralSplitter.cpp:90-100.
  */
 #ifndef ORACLE_SHIM_COMMON_ALLOC_H_
 #define ORACLE_SHIM_COMMON_ALLOC_H_
@@ -26,6 +26,13 @@ namespace lsp
         if (rem != 0)
             p              += align - rem;
         return reinterpret_cast<T *>(p);
+    }
+
+    /* rounds `size` up to a multiple of `align` (SpectralSplitter.cpp:90) */
+    inline size_t align_size(size_t size, size_t align)
+    {
+        size_t rem      = size % align;
+        return (rem == 0) ? size : size + align - rem;
     }
 
     inline void free_aligned(uint8_t * &raw)
