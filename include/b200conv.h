@@ -403,6 +403,57 @@ size_t  b200conv_sp_latency(const b200conv_sp_t *s);
 size_t  b200conv_sp_remaining(const b200conv_sp_t *s, size_t idx);
 size_t  b200conv_sp_instances(const b200conv_sp_t *s);
 
+/* ---- scope-table row f4, second sibling: lsp::dspu::SpectralSplitter, batched --------------------
+ * Reference: src/main/util/SpectralSplitter.cpp (+ include/lsp-plug.in/dsp-units/util/SpectralSplitter.h).
+ * One forward transform of the last 2^rank input samples every 2^(chunk_rank - 1) samples, shared by
+ * all bound handlers ("bands"); each band applies its function to the spectrum, transforms back,
+ * windows with sin^2 and overlap-adds into its own output stream (latency 2^chunk_rank).
+ * lsp::dspu::FFTCrossover is this class with a real gain curve per band (FFTCrossover.cpp:124-140).
+ *   b200conv_ss_create          N x SpectralSplitter::init(max_rank, handlers) (:64-130); ranks 7..14
+ *   b200conv_ss_set_rank        set_rank (:271-278), for the whole batch; ignored when equal or above
+ *                               the maximum; the bound tables are rank-specific: bind again afterwards
+ *   b200conv_ss_set_chunk_rank  set_chunk_rank (:280-287): <= 0 = the transform rank, else clamped to [5, rank]
+ *   b200conv_ss_set_phase       set_phase (:264-268), per instance, clamped to [0, 1]; like every setter
+ *                               it takes effect at the next process call, which clears that instance's
+ *                               buffers (update_settings, :227-245)
+ *   b200conv_ss_bind_complex    the reference binds HOST callbacks per handler: a function on the packed
+ *   b200conv_ss_bind_gain       complex spectrum (spectral_splitter_func_t, SpectralSplitter.h:44) and a
+ *   b200conv_ss_bind_sink       sink for the processed samples (spectral_splitter_sink_t, :60).  On the
+ *   b200conv_ss_unbind(_all)    device the function is a per-(instance, handler) table -- 2^rank packed
+ *                               complex bins, or 2^rank real gains (FFTCrossover's band) -- or absent
+ *                               (bind_sink: the input frames themselves, :327), and the sink of handler h
+ *                               is row h of the output.  bind clears the handler's output buffer (:175-176);
+ *                               unbind of an unbound handler fails (STATUS_NOT_BOUND, :190-191)
+ *   b200conv_ss_process_*       SpectralSplitter::process(src, count) (:296-383) for all instances in ONE
+ *                               launch: dst[h * band_stride + instance * dst_stride + i]; rows of handlers
+ *                               that are not bound are left untouched; an instance with nothing bound does
+ *                               nothing at all (:301-302)
+ *   b200conv_ss_clear           clear() (:247-260);  b200conv_ss_latency  latency() = 2^chunk_rank (:289-296) */
+typedef struct b200conv_ss b200conv_ss_t;
+
+int     b200conv_ss_create(b200conv_ss_t **out, int device, size_t instances, size_t max_rank, size_t handlers);
+void    b200conv_ss_free(b200conv_ss_t *s);
+int     b200conv_ss_set_rank(b200conv_ss_t *s, size_t rank);
+int     b200conv_ss_set_chunk_rank(b200conv_ss_t *s, long rank);
+int     b200conv_ss_set_phase(b200conv_ss_t *s, size_t idx, float phase);
+int     b200conv_ss_bind_complex(b200conv_ss_t *s, size_t idx, size_t handler, const float *table);
+int     b200conv_ss_bind_gain(b200conv_ss_t *s, size_t idx, size_t handler, const float *gain);
+int     b200conv_ss_bind_sink(b200conv_ss_t *s, size_t idx, size_t handler);
+int     b200conv_ss_unbind(b200conv_ss_t *s, size_t idx, size_t handler);
+int     b200conv_ss_unbind_all(b200conv_ss_t *s, size_t idx);
+size_t  b200conv_ss_bindings(const b200conv_ss_t *s, size_t idx);
+int     b200conv_ss_process_device(b200conv_ss_t *s, float *dst, size_t band_stride, size_t dst_stride,
+                                   const float *src, size_t src_stride, size_t count, void *stream);
+int     b200conv_ss_process_planar(b200conv_ss_t *s, float *dst, const float *src, size_t stride, size_t count);
+int     b200conv_ss_clear(b200conv_ss_t *s);
+int     b200conv_ss_sync(b200conv_ss_t *s);
+void   *b200conv_ss_stream(b200conv_ss_t *s);
+size_t  b200conv_ss_rank(const b200conv_ss_t *s);
+size_t  b200conv_ss_chunk_rank(const b200conv_ss_t *s);
+size_t  b200conv_ss_latency(const b200conv_ss_t *s);
+size_t  b200conv_ss_instances(const b200conv_ss_t *s);
+size_t  b200conv_ss_handlers(const b200conv_ss_t *s);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 
 const char *b200conv_last_error(void);      /* thread-local text of the last failure */

@@ -139,6 +139,27 @@ _SIGNATURES = {
     "b200conv_sp_latency": (_SZ, [_VP]),
     "b200conv_sp_remaining": (_SZ, [_VP, _SZ]),
     "b200conv_sp_instances": (_SZ, [_VP]),
+    "b200conv_ss_create": (ctypes.c_int, [ctypes.POINTER(_VP), ctypes.c_int, _SZ, _SZ, _SZ]),
+    "b200conv_ss_free": (None, [_VP]),
+    "b200conv_ss_set_rank": (ctypes.c_int, [_VP, _SZ]),
+    "b200conv_ss_set_chunk_rank": (ctypes.c_int, [_VP, ctypes.c_long]),
+    "b200conv_ss_set_phase": (ctypes.c_int, [_VP, _SZ, ctypes.c_float]),
+    "b200conv_ss_bind_complex": (ctypes.c_int, [_VP, _SZ, _SZ, _FP]),
+    "b200conv_ss_bind_gain": (ctypes.c_int, [_VP, _SZ, _SZ, _FP]),
+    "b200conv_ss_bind_sink": (ctypes.c_int, [_VP, _SZ, _SZ]),
+    "b200conv_ss_unbind": (ctypes.c_int, [_VP, _SZ, _SZ]),
+    "b200conv_ss_unbind_all": (ctypes.c_int, [_VP, _SZ]),
+    "b200conv_ss_bindings": (_SZ, [_VP, _SZ]),
+    "b200conv_ss_process_device": (ctypes.c_int, [_VP, _VP, _SZ, _SZ, _VP, _SZ, _SZ, _VP]),
+    "b200conv_ss_process_planar": (ctypes.c_int, [_VP, _VP, _VP, _SZ, _SZ]),
+    "b200conv_ss_clear": (ctypes.c_int, [_VP]),
+    "b200conv_ss_sync": (ctypes.c_int, [_VP]),
+    "b200conv_ss_stream": (_VP, [_VP]),
+    "b200conv_ss_rank": (_SZ, [_VP]),
+    "b200conv_ss_chunk_rank": (_SZ, [_VP]),
+    "b200conv_ss_latency": (_SZ, [_VP]),
+    "b200conv_ss_instances": (_SZ, [_VP]),
+    "b200conv_ss_handlers": (_SZ, [_VP]),
     "b200conv_last_error": (ctypes.c_char_p, []),
     "b200conv_version": (ctypes.c_char_p, []),
 }
@@ -572,3 +593,91 @@ class SpectralProcessorBatch:
 
     def stream(self):
         return lib().b200conv_sp_stream(self._h)
+
+
+class SpectralSplitterBatch:
+    """``instances`` x ``lsp::dspu::SpectralSplitter`` on one GPU (``b200conv_ss_*``): same method names
+    and meaning as the reference class; the host callbacks of the reference are replaced per handler
+    by a spectral table (``bind_complex`` / ``bind_gain`` -- the latter is ``FFTCrossover``'s band) or by
+    nothing (``bind_sink``), and the sink of handler ``h`` is row ``h`` of the output."""
+
+    def __init__(self, instances, max_rank, handlers, device=-1):
+        self._h = _VP()
+        _check(lib().b200conv_ss_create(ctypes.byref(self._h), device, instances, max_rank, handlers))
+        self.instances = instances
+        self.handlers = handlers
+
+    def close(self):
+        if self._h:
+            lib().b200conv_ss_free(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_rank(self, rank):
+        _check(lib().b200conv_ss_set_rank(self._h, rank))
+
+    def set_chunk_rank(self, rank):
+        _check(lib().b200conv_ss_set_chunk_rank(self._h, rank))
+
+    def set_phase(self, idx, phase):
+        _check(lib().b200conv_ss_set_phase(self._h, idx, phase))
+
+    def rank(self):
+        return int(lib().b200conv_ss_rank(self._h))
+
+    def chunk_rank(self):
+        return int(lib().b200conv_ss_chunk_rank(self._h))
+
+    def latency(self):
+        return int(lib().b200conv_ss_latency(self._h))
+
+    def bindings(self, idx):
+        return int(lib().b200conv_ss_bindings(self._h, idx))
+
+    def bind_complex(self, idx, handler, table):
+        t = np.ascontiguousarray(table, dtype=np.complex64).view(np.float32)
+        if t.size != 2 << self.rank():
+            raise ValueError("table must hold 2**rank complex bins")
+        _check(lib().b200conv_ss_bind_complex(self._h, idx, handler, _ptr(t)))
+
+    def bind_gain(self, idx, handler, gain):
+        g = np.ascontiguousarray(gain, dtype=np.float32)
+        if g.size != 1 << self.rank():
+            raise ValueError("gain must hold 2**rank values")
+        _check(lib().b200conv_ss_bind_gain(self._h, idx, handler, _ptr(g)))
+
+    def bind_sink(self, idx, handler):
+        _check(lib().b200conv_ss_bind_sink(self._h, idx, handler))
+
+    def unbind(self, idx, handler):
+        _check(lib().b200conv_ss_unbind(self._h, idx, handler))
+
+    def unbind_all(self, idx):
+        _check(lib().b200conv_ss_unbind_all(self._h, idx))
+
+    def clear(self):
+        _check(lib().b200conv_ss_clear(self._h))
+
+    def process(self, src):
+        """src: [instances][samples] float32 (host) -> [handlers][instances][samples] (synchronous);
+        rows of handlers that are not bound stay zero."""
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        if src.ndim != 2 or src.shape[0] != self.instances:
+            raise ValueError("expected [instances][samples]")
+        out = np.zeros((self.handlers,) + src.shape, dtype=np.float32)
+        _check(lib().b200conv_ss_process_planar(self._h, out.ctypes.data, src.ctypes.data, src.shape[1], src.shape[1]))
+        return out
+
+    def process_device(self, dst_ptr, band_stride, dst_stride, src_ptr, src_stride, samples, stream=None):
+        _check(lib().b200conv_ss_process_device(self._h, dst_ptr, band_stride, dst_stride, src_ptr, src_stride, samples, stream))
+
+    def sync(self):
+        _check(lib().b200conv_ss_sync(self._h))
+
+    def stream(self):
+        return lib().b200conv_ss_stream(self._h)

@@ -3115,6 +3115,7 @@ extern "C" int b200conv_chirp_linear_convolutions(int device, float *result, siz
 #include "equalizer.cuh"
 #include "spectral.cuh"
 #include "spectral_host.cuh"
+#include "splitter.cuh"
 
 #ifdef B200CONV_TIMING
 /* developer instrumentation: copies the per-CTA timestamps of the last k_frame launch */
