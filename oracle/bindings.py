@@ -479,3 +479,20 @@ class CpuSpectralSplitter:
     def run(self, src, step):
         src = np.ascontiguousarray(src, dtype=np.float32)
         return np.concatenate([self.process(src[i:i + step]) for i in range(0, src.size, step)], axis=1)
+
+
+def crossover_band_curve(rank, sample_rate, hpf=None, lpf=None, gain=1.0, flatten=1.0):
+    """The real gain curve (``2**rank`` bins) of one ``FFTCrossover`` band: the reference's own
+    ``crossover::hipass_fft_set / lopass_fft_apply / lopass_fft_set`` (misc/fft_crossover.cpp compiled
+    verbatim) combined as ``FFTCrossover::update_band`` does (FFTCrossover.cpp:458-480).
+    ``hpf`` / ``lpf``: ``(frequency, slope in dB/oct, negative)`` or None."""
+    lib = CpuSpectralSplitter.lib()
+    lib.refx_band_curve.argtypes = [_FP, _SZ, ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                    ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+    lib.refx_band_curve.restype = None
+    curve = np.zeros(1 << rank, dtype=np.float32)
+    h = hpf if hpf is not None else (0.0, 0.0)
+    l = lpf if lpf is not None else (0.0, 0.0)
+    lib.refx_band_curve(_ptr(curve), rank, float(sample_rate), int(hpf is not None), h[0], h[1],
+                        int(lpf is not None), l[0], l[1], gain, flatten)
+    return curve

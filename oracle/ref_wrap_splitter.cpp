@@ -135,3 +135,40 @@ extern "C"
         r->out          = nullptr;
     }
 }
+
+/* ---- FFTCrossover's band curves ---------------------------------------------------------------
+ * lsp::dspu::FFTCrossover (src/main/util/FFTCrossover.cpp) is a SpectralSplitter whose band function
+ * multiplies the spectrum by a real curve vFFT (:124-140).  The class itself cannot be compiled from
+ * a few files (FFTCrossover.h includes Crossover.h -> Filter.h / FilterBank.h, which need lsp-dsp-lib's
+ * biquad types), but the curve functions can: src/main/misc/fft_crossover.cpp is compiled VERBATIM,
+ * and refx_band_curve below restates the dozen lines of FFTCrossover::update_band (:458-480) that
+ * combine them. */
+#include <lsp-plug.in/dsp-units/misc/fft_crossover.h>
+
+extern "C" void refx_band_curve(float *curve, size_t rank, float sample_rate, int hpf, float hpf_freq, float hpf_slope,
+                                int lpf, float lpf_freq, float lpf_slope, float gain, float flatten)
+{
+    using namespace lsp::dspu;
+    const size_t bins = size_t(1) << rank;
+    if (hpf)
+    {
+        crossover::hipass_fft_set(curve, hpf_freq, hpf_slope, sample_rate, rank);           /* :468 */
+        if (lpf)
+            crossover::lopass_fft_apply(curve, lpf_freq, lpf_slope, sample_rate, rank);     /* :470 */
+    }
+    else if (lpf)
+        crossover::lopass_fft_set(curve, lpf_freq, lpf_slope, sample_rate, rank);           /* :477 */
+    else
+    {
+        for (size_t i = 0; i < bins; ++i)                                                   /* :482 dsp::fill */
+            curve[i]    = flatten * gain;
+        return;
+    }
+    for (size_t i = 0; i < bins; ++i)                                                       /* :472-473,478-479 */
+    {
+        /* dsp::limit1(vFFT, 0.0f, fFlatten, bins): clamp to [0, flatten]; dsp::mul_k2(vFFT, fGain, bins) */
+        float v     = curve[i];
+        v           = (v < 0.0f) ? 0.0f : ((v > flatten) ? flatten : v);
+        curve[i]    = v * gain;
+    }
+}

@@ -164,3 +164,36 @@ def test_settings_rebinding_device_api_and_errors(pkg):
     w0 = m7.process(x[0, :2000])
     assert _close(y[0, 0], w0[0]) and _close(y[1, 0], w0[1])
     ss.close()
+
+
+def test_fft_crossover_with_the_reference_band_curves(pkg):
+    """lsp::dspu::FFTCrossover = SpectralSplitter + one real curve per band (FFTCrossover.cpp:124-140).
+    The curves come from the reference's own crossover::*_fft_* functions (misc/fft_crossover.cpp
+    compiled verbatim, combined as FFTCrossover::update_band does, :458-480); the device splits a
+    stereo signal into three bands with them, in 1024-sample blocks, and must agree with the
+    reference splitter running the same curves."""
+    if not CpuSpectralSplitter.available():
+        pytest.skip("oracle/_ref has not been built")
+    from oracle.bindings import crossover_band_curve
+    rank, sr, n, ch = 12, 48000, 40000, 2
+    curves = [crossover_band_curve(rank, sr, lpf=(250.0, -24.0)),
+              crossover_band_curve(rank, sr, hpf=(250.0, -24.0), lpf=(4000.0, -48.0), gain=0.8),
+              crossover_band_curve(rank, sr, hpf=(4000.0, -48.0), flatten=0.9)]
+    x = np.stack([synth.noise(90 + c, n) for c in range(ch)])
+    ss = pkg.SpectralSplitterBatch(ch, rank, 3, device=0)
+    ss.set_phase(1, 0.5)                                # FFTCrossover::set_phase: channels de-phased
+    refs = []
+    for c in range(ch):
+        ref = CpuSpectralSplitter(rank, 3)
+        ref.set_phase(0.5 * c)
+        for h, curve in enumerate(curves):
+            ss.bind_gain(c, h, curve)
+            ref.bind_gain(h, curve)
+        refs.append(ref)
+    got = np.concatenate([ss.process(x[:, i:i + 1024]) for i in range(0, n, 1024)], axis=2)
+    assert ss.latency() == 1 << rank
+    for c in range(ch):
+        want = refs[c].run(x[c], 1024)
+        for h in range(3):
+            assert _close(got[h, c], want[h].astype(np.float64)), (c, h)
+    ss.close()

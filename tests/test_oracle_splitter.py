@@ -75,3 +75,29 @@ def test_nothing_bound_is_a_no_op_and_bind_checks():
     assert ss.bind_sink(5) != 0                 # STATUS_OVERFLOW
     assert ss.unbind(1) != 0                    # STATUS_NOT_BOUND
     assert ss.bind_sink(1) == 0 and ss.bindings() == 1
+
+
+def test_crossover_curves_of_the_reference_split_the_signal():
+    """FFTCrossover = SpectralSplitter + one real curve per band (FFTCrossover.cpp:124-140,458-480).
+    Three bands built with the reference's own curve functions: LPF 300 Hz | HPF 300 Hz + LPF 3 kHz |
+    HPF 3 kHz, -24 dB/oct.  hipass(f) + lopass(f) = 1 at every frequency, so the bands of a two-way
+    split add up to the delayed input."""
+    from oracle.bindings import crossover_band_curve
+    rank, sr, n = 12, 48000, 30000
+    N = 1 << rank
+    lo = crossover_band_curve(rank, sr, lpf=(300.0, -24.0))
+    mid = crossover_band_curve(rank, sr, hpf=(300.0, -24.0), lpf=(3000.0, -24.0))
+    hi = crossover_band_curve(rank, sr, hpf=(3000.0, -24.0))
+    lo2 = crossover_band_curve(rank, sr, lpf=(3000.0, -24.0))
+    assert lo.shape == (N,) and np.all(lo >= 0) and np.all(hi >= 0) and abs(lo[0] - 1.0) < 1e-6 and hi[0] == 0.0
+    assert np.max(np.abs(lo2[1:] + hi[1:] - 1.0)) < 1e-6            # a two-way split is complementary
+    assert np.allclose(lo[1:N // 2], lo[N - 1:N // 2:-1])             # symmetric: a real impulse response
+    src = synth.noise(77, n)
+    ss = CpuSpectralSplitter(rank, 3)
+    for h, curve in enumerate((lo2, hi, mid)):
+        ss.bind_gain(h, curve)
+    out = ss.run(src, 1024)
+    lat = ss.latency()
+    # bin 0: lopass 1 + hipass 0
+    assert np.max(np.abs(out[0, lat:] + out[1, lat:] - src[:n - lat])) <= 3e-5
+    assert np.max(np.abs(out[2])) > 0.01
