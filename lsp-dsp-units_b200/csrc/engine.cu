@@ -720,6 +720,10 @@ struct b200conv_batch
     uint32_t               *d_ring_head = nullptr;  /* k_frame: frames published per instance; [n] = chain head (StepArgs::chain_head) */
     bool                    chain_valid = false;    /* the device word will hold chain_next once everything enqueued has run */
     uint32_t                chain_next  = 0;
+    int                     opt_chain_ahead = 1;    /* ranks 14..16: the MAC of the NEXT block is launched behind this block's inverse transform */
+    bool                    ahead_valid = false;    /* partitions q >= 1 of block ahead_t are (being) summed into its row slot */
+    uint64_t                ahead_t     = 0;
+    uint32_t                ahead_splits = 0;
     uint32_t               *h_error     = nullptr;  /* page-locked, device-mapped: a bounded in-kernel wait gave up */
     std::vector<uint32_t>   h_ring_head;
 
@@ -894,6 +898,7 @@ static int upload_tables(Batch *b, cudaStream_t st)
         return B200CONV_OK;
     hist_reset(st, b->device);          /* the copies below are full dependencies */
     b->chain_valid = false;
+    b->ahead_valid = false;
     for (size_t i = 0; i < b->n; ++i)
     {
         b->h_ring_head[i]   = uint32_t(b->inst[i].frames);
@@ -1623,6 +1628,7 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             CU(launch_inv(a, nact * tf, st));
             hist_unknown(st, b->device);
             b->chain_valid  = false;
+            b->ahead_valid  = false;
             b->stats.launches       += 3;
             b->stats.mac_launches   += 1;
             b->stats.mac_algo_bytes += per_frame_bytes * tf;
@@ -1691,6 +1697,68 @@ static int process_uniform(Batch *b, float *dst, size_t dst_stride, const float 
             MacPlan sp      = plan;
             sp.sh.bias      = 0;
             b->pend_ready   = false;
+            const bool ahead = (b->rank >= 14) && (b->opt_pdl != 0) && (!b->profiling) && (b->opt_chain_ahead != 0) && (frames == 1);
+            if (ahead)
+            {
+                /* Block-by-block callers at ranks 14..16: partitions q >= 1 of block t need complete frames
+                 * only, so their MAC is launched one block AHEAD -- behind the inverse transform of block
+                 * t - 1 -- into a row slot of its own, and streams under that inverse transform and under
+                 * the transform of block t; partition 0 is added by the inverse transform of block t
+                 * (STEP_Q0_IN_INV).  Stream order per call:  k_fwd(t)  k_inv(t)  k_mac(t + 1).
+                 * What orders them: chain_head ("frames < x are final", published by k_inv(t) once
+                 * k_fwd(t) has completed; k_mac(t + 1) polls it), row slots t mod FRAME_SLOTS, and one
+                 * CTA of every kernel that waits for the launch before it as its last instruction. */
+                const uint64_t t    = a.t_base + a.frame0;
+                const uint32_t t32  = uint32_t(t);
+                uint32_t *head      = b->d_ring_head + b->n;
+                auto mac_ahead = [&](uint64_t t_of, bool pdl) -> cudaError_t
+                {
+                    StepArgs am     = a;
+                    am.t_base       = t_of - a.frame0;
+                    am.ypart        = ypart_slot(b, uint32_t(t_of));
+                    am.flags       |= STEP_FROM_Q1 | STEP_AHEAD;
+                    am.chain_head   = head;
+                    return launch_mac(b, am, sp, nact, st, false, false, pdl);
+                };
+                if (!(b->ahead_valid && (b->ahead_t == t) && (b->ahead_splits == sp.splits)))
+                {
+                    /* cold start (or a MAC launched ahead for a block that never came): seed the chain head by
+                     * a copy and launch this block's MAC without the attribute -- both full dependencies */
+                    CU(cudaMemcpyAsync(head, &t32, sizeof(t32), cudaMemcpyHostToDevice, st));
+                    CU(mac_ahead(t, false));
+                    b->stats.launches += 1;
+                }
+                bool early = false, serial = false, dst_clash = false;
+                {
+                    const bool capable = (b->opt_early_src == 2) || ((b->opt_early_src == 1) && (st == b->stream));
+                    const BlockRows in  = { reinterpret_cast<uintptr_t>(src + f * F), stride * sizeof(float), F * sizeof(float), b->n };
+                    const BlockRows out = { reinterpret_cast<uintptr_t>(dst + f * F), dst_stride * sizeof(float), F * sizeof(float), b->n };
+                    hist_launch(st, b->device, capable, in, out, &early, &serial, &dst_clash);
+                }
+                StepArgs ai     = a;
+                ai.ypart        = ypart_slot(b, t32);
+                TRY(attach_park(b, ai, nact, st));      /* (may synchronise) */
+                StepArgs af     = a;
+                if (early)
+                    af.flags       |= STEP_EARLY_SRC;
+                CU(launch_fwd(af, nact, st, !serial));
+                ai.flags       |= STEP_Q0_IN_INV;
+                ai.chain_head   = head;
+                CU(launch_inv(ai, nact, st, true, b->d_tickets));
+                CU(mac_ahead(t + 1, true));
+                b->ahead_valid  = true;
+                b->ahead_t      = t + 1;
+                b->ahead_splits = sp.splits;
+                b->chain_valid  = true;
+                b->chain_next   = t32 + 1u;
+                b->stats.launches       += 3;
+                b->stats.mac_launches   += 1;
+                b->stats.mac_algo_bytes += per_frame_bytes;
+                b->stats.frames         += nact;
+                f              += 1;
+                continue;
+            }
+            b->ahead_valid  = false;
             hist_reset(st, b->device);
             /* Ranks 14..16: the three kernels of a block are chained with programmatic serialisation --
              * the partition stream of q >= 1 runs beside the block's own transform (which only the
@@ -1979,6 +2047,7 @@ static int process_general_fused(Batch *b, float *dst, size_t dst_stride, const 
 
     hist_unknown(st, b->device);
     b->chain_valid = false;
+    b->ahead_valid = false;
     b->uniform_stale = true;    /* per-instance frame counters moved independently of t_batch */
     b->pend_ready = false;
     return B200CONV_OK;
@@ -2194,6 +2263,7 @@ static int process_general_staged(Batch *b, float *dst, size_t dst_stride, const
      * k_frame launch, which refreshes the tables first (uniform_stale) */
     hist_unknown(st, b->device);
     b->chain_valid = false;
+    b->ahead_valid = false;
     b->uniform_stale = true;
     b->pend_ready = false;
     return B200CONV_OK;
@@ -2610,6 +2680,7 @@ extern "C" int b200conv_set_option(b200conv_batch_t *b, const char *name, int va
     if ((b == nullptr) || (name == nullptr))
         return fail(B200CONV_ERR_ARG, "b200conv_set_option: bad arguments");
     if (!strcmp(name, "mac_splits") && (value >= 0) && (value <= 32))       b->tune_splits = value;
+    else if (!strcmp(name, "chain_ahead") && (value >= 0) && (value <= 1)) { b->opt_chain_ahead = value; b->ahead_valid = false; }
     else if (!strcmp(name, "mac_tile") && ((value == 0) || (value == 256) || (value == 512) || (value == 1024))) g_tune_tile = value;
     else if (!strcmp(name, "mac_stages") && ((value == 0) || ((value >= 2) && (value <= 12)))) b->tune_stages = value;
     else if (!strcmp(name, "fused") && (value >= 0) && (value <= 1))        b->opt_fused = value;

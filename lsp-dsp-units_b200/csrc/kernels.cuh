@@ -131,6 +131,14 @@ enum { INV_FULL = 1, STEP_FROM_Q1 = 2, STEP_HEAD_ONLY = 4,
                                flight writes or reads (a buffer re-used every call, a cascade's hand-over
                                block): this launch keeps the full griddepcontrol.wait before its first
                                shared write, i.e. its tail starts after every earlier launch has completed */,
+       STEP_AHEAD = 512 /* k_mac of the three-kernel block (ranks 14..16), launched one block AHEAD (behind the
+                           inverse transform of block t - 1, with STEP_FROM_Q1): partitions q >= 1 of block t need
+                           complete frames only, so it streams under that inverse transform and under the transform
+                           of block t.  Its rows go to a slot of their own (no wait in front of the row write), what
+                           it reads is ordered by chain_head, and only CTA (0, 0) waits for the launches before it,
+                           as its last instruction (completion order) */,
+       STEP_Q0_IN_INV = 1024 /* k_inv / k_inv_half: add partition 0 -- G_0 times the block's own spectrum -- while
+                                summing the partial rows (the MAC ran ahead, STEP_AHEAD), and publish chain_head */,
        STEP_EARLY_SRC = 32 /* k_frame: the input block may be read before griddepcontrol.wait -- set by
                               the host only when the predecessor on the stream is this batch's own pending
                               k_mac and the input is a caller-owned HOST block no kernel writes */ };
@@ -932,8 +940,12 @@ k_fwd(const StepArgs a)
         __syncthreads();
     }
     /* (three-kernel path with programmatic serialisation: the table staging above overlaps the
-     * previous launch; everything below reads what earlier launches wrote) */
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+     * previous launch; everything below reads what earlier launches wrote -- unless the host knows
+     * that no launch in flight writes the input block, STEP_EARLY_SRC: then the transform runs under
+     * the MAC that was launched ahead, and one CTA waits at the very end for completion order) */
+    const bool early_src = (a.flags & STEP_EARLY_SRC) != 0;
+    if (!early_src)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     /* grid-stride over the jobs: a launch over many frames (IR ingest, multi-frame calls) keeps
      * one resident set of CTAs and stages the twiddle table once per CTA; these launches are
      * throughput-bound, so every twiddle comes from the shared-memory copy (one load per butterfly) */
@@ -943,6 +955,8 @@ k_fwd(const StepArgs a)
         fwd_body<RANK, C::PP, 0, false, true, 0, !C::TWS>(A, B, job.src, job.spec, a.tw, tw, threadIdx.x);
         __syncthreads();            /* the work buffers are reused by the next job */
     }
+    if (early_src && (blockIdx.x == 0) && (threadIdx.x == 0))
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 /* k_fwd_half : ranks 13..16 with few frames per launch.  One CTA transforms a whole frame in k_fwd,
@@ -960,7 +974,9 @@ k_fwd_half(const StepArgs a)
     float2 *twc             = sm + C::WORK;
     stage_compact_twiddles<C>(twc, a.tw, threadIdx.x);
     __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool early_src = (a.flags & STEP_EARLY_SRC) != 0;     /* see k_fwd */
+    if (!early_src)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     CHAIN_STAMP(4096 + blockIdx.x, 0);
     for (uint32_t w = blockIdx.x; w < 2 * a.n_jobs; w += gridDim.x)
     {
@@ -970,6 +986,8 @@ k_fwd_half(const StepArgs a)
         __syncthreads();
     }
     CHAIN_STAMP(4096 + blockIdx.x, 1);
+    if (early_src && (blockIdx.x == 0) && (threadIdx.x == 0))
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -987,8 +1005,10 @@ enum { INV_OLA = 1, INV_PRESUMMED = 2, INV_STAGED = 4 };
 template <int RANK, bool PP, int RG = 8, int TT = 0, int MODE = 0, bool WM = (RANK >= 12), int NHO = 0, bool TWC = false>     /* RG: partial rows loaded per round (registers) */
 __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp, uint32_t splits,
                                          float *dst, const float2 *twg, const float2 *tw, bool full, int tid,
-                                         int only_pass = -1)
+                                         int only_pass = -1, const float2 *g0 = nullptr, const float2 *x0 = nullptr)
 {
+    /* g0, x0 (rows summed from global memory only, !PP): one more term, g0[k] * x0[k] -- partition 0
+     * against the block's own spectrum (STEP_Q0_IN_INV); bin 0 packs two real values (DC, Nyquist) */
     const float2 *twx       = TWC ? twg : tw;      /* TWC: `tw` is the compact pass table (fft_smem) */
     /* only_pass (one resident half, NH == 1; k_inv_half): 0 = the odd bins' half, 1 = the even
      * bins' half; either way dst receives that half's F scaled samples and nothing is combined */
@@ -1090,6 +1110,24 @@ __device__ __forceinline__ void inv_body(float2 *A, float2 *B, const float2 *yp,
                     {
                         yk[u]       = cadd(yk[u], __ldcg(row + k[u]));
                         ym[u]       = cadd(ym[u], __ldcg(row + km[u]));
+                    }
+                }
+                if (g0 != nullptr)
+                {
+                    float2 gk[UB], xk[UB], gm[UB], xm[UB];
+                    #pragma unroll
+                    for (int u = 0; u < UB; ++u)
+                    {
+                        gk[u]       = __ldcg(g0 + k[u]);
+                        xk[u]       = __ldcg(x0 + k[u]);
+                        gm[u]       = __ldcg(g0 + km[u]);
+                        xm[u]       = __ldcg(x0 + km[u]);
+                    }
+                    #pragma unroll
+                    for (int u = 0; u < UB; ++u)
+                    {
+                        yk[u]       = cadd(yk[u], (k[u] == 0) ? make_float2(gk[u].x * xk[u].x, gk[u].y * xk[u].y) : cmul(gk[u], xk[u]));
+                        ym[u]       = cadd(ym[u], cmul(gm[u], xm[u]));
                     }
                 }
             }
@@ -1235,11 +1273,20 @@ k_inv(const StepArgs a)
         __syncthreads();
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");     /* the partial rows of the launch before */
+    if ((a.flags & STEP_Q0_IN_INV) && (a.chain_head != nullptr) && (blockIdx.x == 0) && (threadIdx.x == 0))
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.chain_head), "r"(uint32_t(a.t_base + a.frame0) + 1u) : "memory");
     for (uint32_t j = blockIdx.x; j < a.n_jobs; j += gridDim.x)
     {
         const Job job           = fetch_job(a, j);
+        const float2 *g0        = nullptr;
+        if ((!C::PP) && (a.flags & STEP_Q0_IN_INV))
+        {
+            const InstDesc &d       = a.inst[job.inst];
+            if ((d.q_lo == 0) && (d.nq > 0))
+                g0                      = d.G;          /* row 0 = partition 0 */
+        }
         inv_body<RANK, C::PP, RG, 0, 0, true, 0, !C::TWS>(A, B, a.ypart + uint64_t(j) * rows_per_job(a) * C::M, rows_per_job(a),
-                                                          job.dst, a.tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x);
+                                                          job.dst, a.tw, tw, (a.flags & INV_FULL) != 0, threadIdx.x, -1, g0, job.spec);
         __syncthreads();
     }
 }
@@ -1263,13 +1310,24 @@ k_inv_half(const StepArgs a, uint32_t *tickets)
     CHAIN_STAMP(4096 + 512 + blockIdx.x, 0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     CHAIN_STAMP(4096 + 512 + blockIdx.x, 1);
+    if ((a.flags & STEP_Q0_IN_INV) && (a.chain_head != nullptr) && (blockIdx.x == 0) && (threadIdx.x == 0))
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.chain_head), "r"(uint32_t(a.t_base + a.frame0) + 1u) : "memory");
     const uint32_t rows = rows_per_job(a);
     for (uint32_t w = blockIdx.x; w < 2 * a.n_jobs; w += gridDim.x)
     {
         const uint32_t j = w >> 1, half = w & 1u;       /* half 0: odd bins, half 1: even bins */
+        const float2 *g0 = nullptr, *x0 = nullptr;
+        if (a.flags & STEP_Q0_IN_INV)
+        {
+            const Job jq            = fetch_job(a, j);
+            const InstDesc &d       = a.inst[jq.inst];
+            if ((d.q_lo == 0) && (d.nq > 0))
+                g0                      = d.G;          /* row 0 = partition 0 */
+            x0                      = jq.spec;
+        }
         inv_body<RANK, false, 8, 0, 0, true, 1, true>(sm, nullptr, a.ypart + uint64_t(j) * rows * C::M, rows,
                                                       a.park + (uint64_t(j) * 2 + half) * C::M, a.tw, twc, false,
-                                                      threadIdx.x, int(half));
+                                                      threadIdx.x, int(half), g0, x0);
         if (tickets != nullptr)
         {
             /* the second half of a frame to finish combines: y[i] = e[i] + o[i] (and e[i] - o[i] for
@@ -1823,11 +1881,14 @@ k_mac(const StepArgs a, const MacShape sh)
         acc[0].y    = dny;
     }
 
-    /* launched early: the previous launch may still be reading the rows this one replaces */
+    /* launched early: the previous launch may still be reading the rows this one replaces
+     * (STEP_AHEAD: it cannot -- the rows have a slot of their own, free once chain_head says so) */
     CHAIN_STAMP(blockIdx.x + gridDim.x * blockIdx.y, 1);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool ahead = (a.flags & STEP_AHEAD) != 0;
+    if (!ahead)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     CHAIN_STAMP(blockIdx.x + gridDim.x * blockIdx.y, 2);
-    if ((a.chain_head != nullptr) && (blockIdx.x == 0) && (blockIdx.y == 0) && (tid == 0))
+    if ((!ahead) && (a.chain_head != nullptr) && (blockIdx.x == 0) && (blockIdx.y == 0) && (tid == 0))
         asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.chain_head), "r"(uint32_t(a.t_base + a.frame0) + 1u) : "memory");
 
     float4 *yp      = reinterpret_cast<float4 *>(a.ypart + (uint64_t(jobi) * rows_per_job(a) + a.row0 + split) * M
@@ -1839,6 +1900,9 @@ k_mac(const StepArgs a, const MacShape sh)
     if (a.fold_tickets != nullptr)
         fold_rows(a.fold_tickets + jobi, a.ypart + (uint64_t(jobi) * rows_per_job(a) + a.row0) * M, a.splits,
                   a.splits * gridDim.y, M, tid, T);
+    /* STEP_AHEAD: this launch completes after every launch before it (stream order for what follows) */
+    if (ahead && (blockIdx.x == 0) && (blockIdx.y == 0) && (tid == 0))
+        asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 /* ------------------------------------------------------------------------------------------- */

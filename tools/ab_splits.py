@@ -6,12 +6,12 @@ import torch
 import __graft_entry__ as ge, synth
 pkg = ge.load()
 for rank in (16, 15, 14):
-    for tile in (0, 512, 256):
-      for splits in (0,):
+    for tile in (0,):
+      for splits in (0, -1):
         n, taps = 64, 480000
         F = 1 << (rank - 1)
         b = pkg.ConvolverBatch(n, 0)
-        b.set_option("mac_splits", splits); b.set_option("mac_tile", tile)
+        b.set_option("mac_splits", 0); b.set_option("mac_tile", tile); b.set_option("chain_ahead", 1 if splits == 0 else 0)
         ir = synth.decaying_ir(0, taps)
         b.init_many(list(range(n)), [ir] * n, rank, [0.0] * n)
         frames = 24
@@ -29,5 +29,5 @@ for rank in (16, 15, 14):
             for _ in range(3): run()
             e1.record(st)
         torch.cuda.synchronize()
-        print("rank", rank, "tile", tile, "splits", splits if splits else "auto", "us/block %.2f" % (e0.elapsed_time(e1) * 1e3 / (3 * frames)), flush=True)
+        print("rank", rank, "chain_ahead", 1 if splits == 0 else 0, "us/block %.2f" % (e0.elapsed_time(e1) * 1e3 / (3 * frames)), flush=True)
         b.close()
