@@ -6,7 +6,7 @@ import torch
 import __graft_entry__ as ge, synth
 pkg = ge.load()
 for rank in (16, 15, 14):
-    for tile in (0,):
+    for tile in (0, 512):
       for splits in (0, -1):
         n, taps = 64, 480000
         F = 1 << (rank - 1)
@@ -29,5 +29,5 @@ for rank in (16, 15, 14):
             for _ in range(3): run()
             e1.record(st)
         torch.cuda.synchronize()
-        print("rank", rank, "chain_ahead", 1 if splits == 0 else 0, "us/block %.2f" % (e0.elapsed_time(e1) * 1e3 / (3 * frames)), flush=True)
+        print("rank", rank, "tile", tile, "chain_ahead", 1 if splits == 0 else 0, "us/block %.2f" % (e0.elapsed_time(e1) * 1e3 / (3 * frames)), flush=True)
         b.close()
