@@ -1080,3 +1080,49 @@ def test_smaller_mac_bin_tiles(pkg):
         assert rel_err(outs[0][c], want) <= TOL
         assert rel_err(outs[1][c], want) <= TOL
         assert rel_err(outs[1][c], outs[0][c].astype(np.float64)) <= 2e-6
+
+
+@pytest.mark.parametrize("rank", [14, 15])
+def test_mac_launched_ahead_survives_other_call_sizes_and_reinit(pkg, rank):
+    """Ranks 14..16, whole-frame calls: the MAC of block t + 1 is launched behind block t (option
+    "chain_ahead").  A block that then does not come as a whole frame (partial calls, a multi-frame
+    call), or comes after an instance was re-initialised, must not use those rows; the answer is
+    always the convolution, and equal to rounding to the schedule without the look-ahead."""
+    torch = pytest.importorskip("torch")
+    F = 1 << (rank - 1)
+    n, taps = 3, 5 * F + 77
+    irs = [synth.decaying_ir(c, taps) for c in range(3)]
+    sizes = [F, F, 100, F - 100, F, 2 * F, F, F, 7, F, F - 7, F, F]
+    total = sum(sizes)
+    x = np.stack([synth.noise(900 + c, total) for c in range(n)])
+    outs = []
+    for ahead in (1, 0):
+        b = pkg.ConvolverBatch(n, 0)
+        b.set_option("chain_ahead", ahead)
+        for c in range(n):
+            assert b.init(c, irs[c], rank, 0.0)
+        src = torch.from_numpy(x).cuda()
+        dst = torch.zeros_like(src)
+        pos = 0
+        for s in sizes:
+            b.process_device(dst.data_ptr() + 4 * pos, src.data_ptr() + 4 * pos, total, s)
+            pos += s
+        b.sync()
+        out = dst.cpu().numpy()
+        for c in range(n):
+            assert rel_err(out[c], direct_convolve(x[c], irs[c], total)) <= TOL, (ahead, c)
+        # re-initialise one instance between two whole-frame calls: its history restarts, the others carry on
+        assert b.init(1, irs[2], rank, 0.0)
+        tail = np.stack([synth.noise(950 + c, 3 * F) for c in range(n)])
+        src2 = torch.from_numpy(tail).cuda()
+        dst2 = torch.zeros_like(src2)
+        for i in range(3):
+            b.process_device(dst2.data_ptr() + 4 * i * F, src2.data_ptr() + 4 * i * F, 3 * F, F)
+        b.sync()
+        out2 = dst2.cpu().numpy()
+        assert rel_err(out2[1], direct_convolve(tail[1], irs[2], 3 * F)) <= TOL
+        want0 = direct_convolve(np.concatenate([x[0], tail[0]]), irs[0], total + 3 * F)[total:]
+        assert rel_err(out2[0], want0) <= TOL
+        outs.append(np.concatenate([out, out2], axis=1))
+        b.close()
+    assert rel_err(outs[0][2], outs[1][2].astype(np.float64)) <= 2e-6
