@@ -227,6 +227,12 @@ void   *b200conv_stream(b200conv_batch_t *h);
  *                 stream, where the library knows everything that is enqueued; 2 = on a caller's
  *                 stream too -- the caller promises that no kernel it enqueues between two calls
  *                 signals programmatic launch completion before it has written the input block
+ *   "chain_ahead" ranks 14..16, whole-frame calls of one frame: 1 (default) = the partition sum of
+ *                 block t + 1 (partitions q >= 1 need complete frames only) is launched behind the
+ *                 inverse transform of block t and streams under it and under the transform of block
+ *                 t + 1; partition 0 is added by that block's inverse transform.  Rows computed ahead
+ *                 for a block that then arrives differently are simply not used; 0 = off
+ *   "mac_tile"    developer knob, ranks 14..16, process-wide: bins per k_mac CTA (0 = 1024, 512, 256)
  *   "zero_copy"   1 (default) = b200conv_process_planar lets the kernels read / write page-locked
  *                 host matrices directly (no staging copies); 0 = always stage */
 int     b200conv_set_option(b200conv_batch_t *h, const char *name, int value);
